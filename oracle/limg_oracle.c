@@ -275,8 +275,10 @@ void lo_fit(const uint32_t *pixels, size_t n, int ch, lo_decomp *out)
         float px[4], toPx[4];
         px_to_f4(pixels[i], px);
 
+        /* Reference quirk (limg_factorization.h:745-758): the estimate pointer is rewound but never advanced in this
+         * loop, so every pixel is measured against the A+B estimate of pixel 0. Reproduced, not fixed. */
         for (int c = 0; c < 4; c++)
-          toPx[c] = px[c] - est[i * 4 + c];
+          toPx[c] = px[c] - est[c];
 
         const float facC = dp4(toPx, dirC) * invLenC;
         minC = sse_min(minC, facC);
