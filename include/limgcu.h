@@ -1,0 +1,156 @@
+/* include/limgcu.h -- C ABI of the B200-native (sm_100a) limg encode/decode hot path.
+ *
+ * This is the drop-in boundary a reference maintainer binds against: plain C,
+ * plain pointers and sizes, no torch / C++ types. Two layers:
+ *
+ *   limgcu_*        device-buffer entry points. All `d_` pointers are CUDA device memory of the context's
+ *                   device; work is enqueued on the context's stream and is stream ordered. No hidden
+ *                   synchronisation except where a function returns a host value (documented per function).
+ *   limgcu_host_*   host-buffer entry points with the reference's argument meaning (H2D, kernels, D2H inside).
+ *                   include/limg.h declares the reference's own C++ signatures on top of these.
+ *
+ * There is NO CPU fallback: every entry point fails with LIMGCU_ERROR_NO_DEVICE / a CUDA error if the
+ * kernels cannot run.
+ *
+ * Reference interfaces replaced (file:line relative to the reference's src/):
+ *   limg_blocked_encode3d_test        limg.h:46,  limg.cpp:2329-2453   -> limgcu_blocked_encode3d / limgcu_host_blocked_encode3d
+ *   limg_encode3d_test                limg.h:35,  limg.cpp:2175-2265   -> limgcu_encode3d / limgcu_host_encode3d
+ *   limg_encode3d_test_perf           limg.h:37,  limg.cpp:2267-2327   -> limgcu_encode3d with no output planes
+ *   limg_decode_block_from_factors_3d limg_decode.h:326-340 (static)   -> limgcu_decode / limgcu_host_decode
+ *   limg_compare                      limg.h:48,  limg.cpp:2455-2491   -> limgcu_compare / limgcu_host_compare
+ *   limg_encode3d_blocked_test_y_range (pass 1) limg.cpp:1088-1119     -> limgcu_pass1
+ *   limg_encode_find_block_3d + drivers         limg.cpp:1390-1496,1814-1878 -> limgcu_merge
+ */
+#ifndef LIMGCU_H
+#define LIMGCU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Same numeric values as the reference's enum limg_result (limg.h:9-18), plus device errors. */
+enum
+{
+  LIMGCU_SUCCESS = 0,
+  LIMGCU_ERROR_GENERIC = 100,
+  LIMGCU_ERROR_INVALID_PARAMETER = 101,
+  LIMGCU_ERROR_ARGUMENT_NULL = 102,
+  LIMGCU_ERROR_OUT_OF_BOUNDS = 103,
+  LIMGCU_ERROR_MEMORY_ALLOCATION_FAILURE = 104,
+  LIMGCU_ERROR_NO_DEVICE = 200,
+  LIMGCU_ERROR_CUDA = 201
+};
+
+/* Per-block / per-area decomposition (reference: limg_encode_3d_output<channels>, limg_internal.h:343-353).
+ * Channel-agnostic: four slots, unused slots zero. 64 bytes. */
+typedef struct limgcu_decomp
+{
+  float avg[4];
+  int16_t dirA_min[4], dirA_max[4];
+  int16_t dirB_offset[4], dirB_mag[4];
+  int16_t dirC_offset[4], dirC_mag[4];
+} limgcu_decomp;
+
+/* One area of the area table, in the reference's emission order: large merges (stage 0), remaining merges
+ * (stage 1), leftover 8x8 blocks in raster order (stage 2). The area's pixels are addressed row-major inside
+ * its pixel rectangle ("area-contiguous order", limg.cpp:1752-1753). 120 bytes. */
+typedef struct limgcu_area
+{
+  uint32_t ox, oy, rx, ry;          /* rectangle in 8x8-block units */
+  uint32_t stage;
+  uint32_t px_x, px_y, px_w, px_h;  /* pixel rectangle after the edge fit (limg.cpp:1722-1739) */
+  uint8_t shift[3];                 /* bits dropped per factor, 0..8 (8 = factor dropped) */
+  uint8_t pad;
+  uint64_t ditherBefore, ditherAfter; /* dither chain state around this area (limg_internal.h:711, limg.cpp:1539-1549) */
+  limgcu_decomp decomp;
+} limgcu_area;
+
+/* The reference's limg_blocked_encode3d_info (limg.h:39-44): sizeX*sizeY elements each. Any pointer may be NULL
+ * (plane skipped). pBlockError is accepted and never written, exactly like the reference's 3D paths. */
+typedef struct limgcu_planes
+{
+  uint32_t *pDecoded;
+  uint8_t *pFactorsA, *pFactorsB, *pFactorsC, *pBlockError, *pBitsPerPixel;
+  uint32_t *pShiftABCX, *pColAMin, *pColAMax, *pColBMin, *pColBMax, *pColCMin, *pColCMax, *pBlockIndex;
+} limgcu_planes;
+
+/* Compact encoder output ("the stream"): area table + block->area map + three factor planes in image layout holding the
+ * RIGHT-ALIGNED codes (enc = dithered factor >> shift; a dropped factor keeps its raw byte, Q7). All device pointers;
+ * areas / block_to_area need blockX*blockY entries. Any of the members may be NULL. */
+typedef struct limgcu_stream
+{
+  limgcu_area *areas;
+  uint32_t *area_count;     /* one uint32 in device memory */
+  uint32_t *block_to_area;
+  uint8_t *codesA, *codesB, *codesC;
+} limgcu_stream;
+
+enum
+{
+  LIMGCU_FLAG_FAST_BIT_CRUSH = 1u << 0,  /* reference `fastBitCrushing` (limg.h:46); clear = --accurate-bit-crushing */
+  LIMGCU_FLAG_NO_MERGE = 1u << 1         /* every 8x8 block is its own area (limg_encode3d_test) */
+};
+
+typedef struct limgcu_ctx limgcu_ctx;
+
+/* context ------------------------------------------------------------------------------------------------------- */
+int limgcu_create(int device, limgcu_ctx **out);
+void limgcu_destroy(limgcu_ctx *ctx);
+const char *limgcu_last_error(const limgcu_ctx *ctx);
+int limgcu_device_count(void);
+/* x86 RSQRTPS table the fit emulates (2048 entries, see limg_b200/csrc/rsqrt_lut.h). NULL restores the built-in table. */
+int limgcu_set_rsqrt_lut(limgcu_ctx *ctx, const uint16_t *lut2048);
+void *limgcu_stream_handle(limgcu_ctx *ctx); /* cudaStream_t */
+int limgcu_sync(limgcu_ctx *ctx);
+/* number of kernels launched through this context since creation (bench.py's gpu_launches) */
+uint64_t limgcu_launch_count(const limgcu_ctx *ctx);
+/* milliseconds the kernels of one named phase took during the last limgcu_*encode3d call when profiling was enabled
+ * (phase: 0 pass1, 1 predicate windows, 2 merge scan, 3 area encode, 4 dither scan, 5 finalize). Synchronises. */
+int limgcu_enable_phase_timing(limgcu_ctx *ctx, int enable);
+float limgcu_phase_ms(limgcu_ctx *ctx, int phase);
+
+/* device-buffer entry points ------------------------------------------------------------------------------------ */
+
+/* pass 1: three-factor fit of every 8x8 block -> blockX*blockY records (limg.cpp:1088-1119). */
+int limgcu_pass1(limgcu_ctx *ctx, const uint32_t *d_src, size_t sizeX, size_t sizeY, int hasAlpha, limgcu_decomp *d_table);
+
+/* area expansion: pass-1 table -> emission-ordered area rectangles (ox,oy,rx,ry,stage and the pixel rectangle filled in)
+ * + block->area map (limg.cpp:1390-1496, 1814-1878). sizeX/sizeY are needed for the edge fit of the pixel rectangles. */
+int limgcu_merge(limgcu_ctx *ctx, const limgcu_decomp *d_table, size_t sizeX, size_t sizeY, int hasAlpha,
+                 limgcu_area *d_areas, uint32_t *d_area_count, uint32_t *d_block_to_area);
+
+/* the whole encode path. `stream` and/or `planes` (device pointers inside) select what is written. */
+int limgcu_blocked_encode3d(limgcu_ctx *ctx, const uint32_t *d_src, size_t sizeX, size_t sizeY, int hasAlpha, uint32_t errorFactor, uint32_t flags,
+                            const limgcu_stream *stream, const limgcu_planes *planes);
+
+/* streaming reconstruction of a stream produced by limgcu_blocked_encode3d (or by the reference). */
+int limgcu_decode(limgcu_ctx *ctx, const limgcu_area *d_areas, const uint32_t *d_block_to_area, const uint8_t *d_codesA, const uint8_t *d_codesB, const uint8_t *d_codesC,
+                  size_t sizeX, size_t sizeY, int hasAlpha, uint32_t *d_dst);
+
+/* rebuilds block_to_area from an area table that was produced elsewhere (e.g. by the reference). */
+int limgcu_build_block_map(limgcu_ctx *ctx, const limgcu_area *d_areas, uint32_t area_count, size_t sizeX, size_t sizeY, uint32_t *d_block_to_area);
+
+/* limg_compare on device images; synchronises and returns host values. */
+int limgcu_compare(limgcu_ctx *ctx, const uint32_t *d_a, const uint32_t *d_b, size_t sizeX, size_t sizeY, int hasAlpha, double *psnr, double *mse, double *maxError);
+
+/* host-buffer entry points (reference argument meaning) ----------------------------------------------------------- */
+
+int limgcu_host_blocked_encode3d(limgcu_ctx *ctx, const uint32_t *pIn, size_t sizeX, size_t sizeY, int hasAlpha, const limgcu_planes *pInfo, uint32_t errorFactor, int fastBitCrushing);
+int limgcu_host_encode3d(limgcu_ctx *ctx, const uint32_t *pIn, size_t sizeX, size_t sizeY, int hasAlpha, const limgcu_planes *pInfo, uint32_t errorFactor, int fastBitCrushing);
+/* host stream out: areas (capacity blockX*blockY), *area_count, codes in image layout; any may be NULL. */
+int limgcu_host_encode_stream(limgcu_ctx *ctx, const uint32_t *pIn, size_t sizeX, size_t sizeY, int hasAlpha, uint32_t errorFactor, uint32_t flags,
+                              limgcu_area *areas, uint32_t *area_count, uint8_t *codesA, uint8_t *codesB, uint8_t *codesC, uint32_t *pDecoded);
+int limgcu_host_decode(limgcu_ctx *ctx, const limgcu_area *areas, uint32_t area_count, const uint8_t *codesA, const uint8_t *codesB, const uint8_t *codesC,
+                       size_t sizeX, size_t sizeY, int hasAlpha, uint32_t *pOut);
+int limgcu_host_pass1(limgcu_ctx *ctx, const uint32_t *pIn, size_t sizeX, size_t sizeY, int hasAlpha, limgcu_decomp *table);
+int limgcu_host_merge(limgcu_ctx *ctx, const limgcu_decomp *table, size_t sizeX, size_t sizeY, int hasAlpha, limgcu_area *areas, uint32_t *area_count);
+double limgcu_host_compare(limgcu_ctx *ctx, const uint32_t *pImageA, const uint32_t *pImageB, size_t sizeX, size_t sizeY, int hasAlpha, double *pMeanSquaredError, double *pMaxPossibleSquaredError);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* LIMGCU_H */

@@ -1,0 +1,226 @@
+// limg_b200/csrc/kernels_fit.cuh -- pass 1 (per-8x8-block fit) and the per-area encode kernels
+// (gather -> refit -> projection -> shift search). One warp per small area, one CTA per large area.
+#pragma once
+
+#include "group.cuh"
+
+namespace limg
+{
+
+#define LIMG_SMALL_AREA_PX 256   // <= 4 blocks: one warp, everything in shared memory
+#define LIMG_CTA_AREA_CAP 4096   // <= 64 blocks: one CTA, pixels + factors in shared memory; above: global scratch
+#define LIMG_CTA_STAGE_PX 1024
+#define LIMG_ENCODE_THREADS 256
+
+// per-area bookkeeping produced by k_area_prepare
+struct AreaWork
+{
+  uint32_t n;          // pixels
+  uint32_t scratchOff; // exclusive scan of n (area-contiguous scratch for large areas)
+};
+
+__device__ __forceinline__ void load_lut(uint16_t *sLut, const uint16_t *__restrict__ gLut)
+{
+  for (int i = threadIdx.x; i < 2048 / 2; i += blockDim.x)
+    reinterpret_cast<uint32_t *>(sLut)[i] = reinterpret_cast<const uint32_t *>(gLut)[i];
+}
+
+__device__ __forceinline__ void store_decomp(limgcu_decomp *dst, const limgcu_decomp &d)
+{
+  *dst = d;
+}
+
+// ---------------------------------------------------------------------------------------------
+// pass 1: one warp per 8x8 block (limg.cpp:1088-1119)
+// ---------------------------------------------------------------------------------------------
+
+template <int CH>
+__global__ void __launch_bounds__(256) k_pass1(const uint32_t *__restrict__ src, int W, int H, int BX, int BY, const uint16_t *__restrict__ gLut, limgcu_decomp *__restrict__ table)
+{
+  __shared__ uint16_t sLut[2048];
+  __shared__ uint32_t sPx[8][64];
+  __shared__ float4 sStage[8][64];
+  __shared__ GroupScratch<1> sGs[8];
+
+  load_lut(sLut, gLut);
+  __syncthreads();
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x * 8 + warp;
+
+  if (b >= BX * BY)
+    return;
+
+  const int by = b / BX, bx = b - by * BX;
+  const int x0 = bx * LIMG_BLOCK, y0 = by * LIMG_BLOCK;
+  const int w = min(LIMG_BLOCK, W - x0), h = min(LIMG_BLOCK, H - y0);
+  const uint32_t n = (uint32_t)(w * h);
+
+  for (uint32_t i = lane; i < n; i += 32)
+  {
+    const int row = i / w, col = i - row * w;
+    sPx[warp][i] = src[(size_t)(y0 + row) * W + x0 + col];
+  }
+
+  __syncwarp();
+
+  limgcu_decomp d;
+  uint32_t parity = 0;
+  group_fit<CH, 1>(sPx[warp], n, sLut, sStage[warp], 64, &sGs[warp], parity, d);
+
+  if (lane == 0)
+    store_decomp(&table[b], d);
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-area encode: gather, refit (merged areas), projection, shift search -> decomposition + shifts + dither demand
+// (limg.cpp:1717-1772, 1498-1535)
+// ---------------------------------------------------------------------------------------------
+
+struct EncodeArgs
+{
+  const uint32_t *src;
+  int W, H, BX, BY;
+  const uint16_t *lut;
+  const limgcu_decomp *table; // pass-1 table (leftover areas keep their fit)
+  limgcu_area *areas;
+  const uint32_t *areaCount;
+  const AreaWork *work;
+  uint64_t *ditherDemand;     // per area: pixels consumed from the dither chain
+  uint32_t *scratchPx, *scratchFac;
+  uint32_t *workCounter;      // dynamic scheduling
+  const uint32_t *list;       // area indices of this size class
+  const uint32_t *listCount;
+  CrushParams cp;
+};
+
+template <int CH, int WARPS>
+__device__ void encode_area_group(const EncodeArgs &a, uint32_t k, uint32_t *px, uint32_t *fac, const uint16_t *lut, float4 *stage, int stagePx, GroupScratch<WARPS> *gs)
+{
+  constexpr int THREADS = WARPS * 32;
+  const int t = group_tid<WARPS>();
+  limgcu_area *area = &a.areas[k];
+  const uint32_t pw = area->px_w, ph = area->px_h, pxX = area->px_x, pxY = area->px_y;
+  const uint32_t n = pw * ph;
+  uint32_t parity = 0;
+
+  // gather into area-contiguous order (limg.cpp:1752-1753)
+  for (uint32_t i = t; i < n; i += THREADS)
+  {
+    const uint32_t row = i / pw, col = i - row * pw;
+    px[i] = a.src[(size_t)(pxY + row) * a.W + pxX + col];
+  }
+
+  group_sync<WARPS>();
+
+  limgcu_decomp d;
+
+  if (area->stage == 2)
+    d = a.table[(size_t)area->oy * a.BX + area->ox]; // leftovers keep the pass-1 decomposition (limg.cpp:1875)
+  else
+    group_fit<CH, WARPS>(px, n, lut, stage, stagePx, gs, parity, d);
+
+  Proj p;
+  init_proj<CH>(d, p);
+
+  for (uint32_t i = t; i < n; i += THREADS)
+    fac[i] = project_px<CH>(p, px[i]);
+
+  group_sync<WARPS>();
+
+  int shift[3] = { 0, 0, 0 };
+
+  if (a.cp.crushBits)
+  {
+    auto trial = [&](int sa, int sb, int sc, uint64_t &err) -> bool {
+      return group_trial<CH, WARPS>(px, fac, n, d, sa, sb, sc, a.cp, gs, parity, err);
+    };
+    search_shifts(trial, a.cp.fast != 0, shift);
+  }
+
+  if (t == 0)
+  {
+    area->decomp = d;
+    area->shift[0] = (uint8_t)shift[0];
+    area->shift[1] = (uint8_t)shift[1];
+    area->shift[2] = (uint8_t)shift[2];
+    area->pad = 0;
+    uint32_t planes = 0;
+    for (int i = 0; i < 3; i++)
+      planes += (shift[i] != 0 && shift[i] != 8) ? 1u : 0u;
+    a.ditherDemand[k] = (uint64_t)planes * n; // Q13: only planes with 0 < shift < 8 consume the chain
+  }
+
+  group_sync<WARPS>();
+}
+
+template <int CH>
+__global__ void __launch_bounds__(LIMG_ENCODE_THREADS) k_encode_small(EncodeArgs a)
+{
+  constexpr int WPB = LIMG_ENCODE_THREADS / 32;
+  __shared__ uint16_t sLut[2048];
+  __shared__ uint32_t sPx[WPB][LIMG_SMALL_AREA_PX];
+  __shared__ uint32_t sFac[WPB][LIMG_SMALL_AREA_PX];
+  __shared__ float4 sStage[WPB][64];
+  __shared__ GroupScratch<1> sGs[WPB];
+
+  load_lut(sLut, a.lut);
+  __syncthreads();
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t count = *a.listCount;
+
+  while (true)
+  {
+    uint32_t j = 0;
+
+    if (lane == 0)
+      j = atomicAdd(a.workCounter, 1u);
+
+    j = __shfl_sync(0xFFFFFFFFu, j, 0);
+
+    if (j >= count)
+      break;
+
+    encode_area_group<CH, 1>(a, a.list[j], sPx[warp], sFac[warp], sLut, sStage[warp], 64, &sGs[warp]);
+  }
+}
+
+template <int CH>
+__global__ void __launch_bounds__(LIMG_ENCODE_THREADS) k_encode_large(EncodeArgs a)
+{
+  constexpr int WARPS = LIMG_ENCODE_THREADS / 32;
+  extern __shared__ __align__(16) unsigned char dynSmem[];
+  uint16_t *sLut = reinterpret_cast<uint16_t *>(dynSmem);
+  float4 *sStage = reinterpret_cast<float4 *>(dynSmem + 4096);
+  uint32_t *sPx = reinterpret_cast<uint32_t *>(dynSmem + 4096 + LIMG_CTA_STAGE_PX * 16);
+  uint32_t *sFac = sPx + LIMG_CTA_AREA_CAP;
+  __shared__ GroupScratch<WARPS> sGs;
+  __shared__ uint32_t sJob;
+
+  load_lut(sLut, a.lut);
+  __syncthreads();
+
+  const uint32_t count = *a.listCount;
+
+  while (true)
+  {
+    if (threadIdx.x == 0)
+      sJob = atomicAdd(a.workCounter, 1u);
+
+    __syncthreads();
+    const uint32_t j = sJob;
+    __syncthreads();
+
+    if (j >= count)
+      break;
+
+    const uint32_t k = a.list[j];
+    const AreaWork w = a.work[k];
+    uint32_t *px = w.n <= LIMG_CTA_AREA_CAP ? sPx : a.scratchPx + w.scratchOff;
+    uint32_t *fac = w.n <= LIMG_CTA_AREA_CAP ? sFac : a.scratchFac + w.scratchOff;
+    encode_area_group<CH, WARPS>(a, k, px, fac, sLut, sStage, LIMG_CTA_STAGE_PX, &sGs);
+  }
+}
+
+} // namespace limg

@@ -1,0 +1,780 @@
+// limg_b200/csrc/kernels_merge.cuh -- area expansion (limg.cpp:1121-1135, 1137-1269, 1277-1496, 1814-1878).
+//
+// The reference's merge is a serial greedy raster scan whose only inputs are the pass-1 table and the scan order
+// (SURVEY.md Q2): the predicate "candidate block matches seed block" is a pure function of two pass-1 records.
+// B200 design:
+//   1. k_pred_records : one thread per block derives the predicate-side state of its record once (the divisions).
+//   2. k_pred_window  : for EVERY block as a hypothetical seed, all 63 predicates against the 8x8 window to its lower right are
+//                       evaluated in parallel (one thread per pair) -> one 64-bit match word per block.
+//   3. k_merge_scan   : one persistent CTA replays the reference's scan order. Warp 0 walks candidate seeds with pure bit
+//                       arithmetic on (match word & ~in-use window); growth that leaves the window and the four-way
+//                       centre-third regrowth evaluate their strips on demand, one warp per predicate (27 lanes = the 27
+//                       samples), across all warps of the CTA. The accept order is the reference's, so the area map is identical.
+//   4. k_area_prepare : leftover blocks (raster order), pixel rectangles, block->area map, size classes, scratch offsets.
+#pragma once
+
+#include "group.cuh"
+#include "kernels_fit.cuh"
+
+namespace limg
+{
+
+// predicate-side view of one pass-1 record (limg_init_color_error_state_3d + the loop at limg.cpp:1150-1161, 1201-1212)
+struct __align__(16) PredRec
+{
+  float avg[4];
+  float minA[4], offB[4], offC[4]; // as float
+  float nA[4], nB[4], nC[4];
+  float inv[3];                    // 1 / dot(n, n) or 0
+  float invLen[3];                 // 1 / lenSq, entries 1 and 2 doubled
+  float sumLen;                    // lenSq[0] + lenSq[1] + lenSq[2]
+  float pad;
+};
+
+template <int CH>
+__global__ void k_pred_records(const limgcu_decomp *__restrict__ table, int count, PredRec *__restrict__ rec)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+
+  if (i >= count)
+    return;
+
+  const limgcu_decomp d = table[i];
+  Proj p;
+  init_proj<CH>(d, p);
+  PredRec r;
+  const float nA[4] = { p.nA.x, p.nA.y, p.nA.z, p.nA.w }, nB[4] = { p.nB.x, p.nB.y, p.nB.z, p.nB.w }, nC[4] = { p.nC.x, p.nC.y, p.nC.z, p.nC.w };
+  const float w[4] = { 2, 4, 3, 3 };
+  float len[3] = { 3, 3, 3 }; // limg.cpp:1145
+
+#pragma unroll
+  for (int c = 0; c < 4; c++)
+  {
+    r.avg[c] = d.avg[c];
+    r.minA[c] = (float)d.dirA_min[c];
+    r.offB[c] = (float)d.dirB_offset[c];
+    r.offC[c] = (float)d.dirC_offset[c];
+    r.nA[c] = nA[c];
+    r.nB[c] = nB[c];
+    r.nC[c] = nC[c];
+
+    if (c < CH)
+    {
+      len[0] = fadd(len[0], fmul(fmul(nA[c], nA[c]), w[c]));
+      len[1] = fadd(len[1], fmul(fmul(nB[c], nB[c]), w[c]));
+      len[2] = fadd(len[2], fmul(fmul(nC[c], nC[c]), w[c]));
+    }
+  }
+
+  r.inv[0] = p.invA;
+  r.inv[1] = p.invB;
+  r.inv[2] = p.invC;
+  r.invLen[0] = frcp1(len[0]);
+  r.invLen[1] = fmul(frcp1(len[1]), 2.0f);
+  r.invLen[2] = fmul(frcp1(len[2]), 2.0f);
+  r.sumLen = fadd(fadd(len[0], len[1]), len[2]);
+  r.pad = 0.0f;
+  rec[i] = r;
+}
+
+// limg_color_error_state_3d_get_factors (limg_factorization.h:9-41): sequential dot products starting from 0.
+template <int CH>
+__device__ __forceinline__ float factor_term(const float color[4], const PredRec &s, const float invLen[3])
+{
+  float t[4], est[4];
+  float dA = 0.0f, dB = 0.0f, dC = 0.0f;
+
+#pragma unroll
+  for (int i = 0; i < CH; i++)
+  {
+    t[i] = fsub(color[i], s.minA[i]);
+    dA = fadd(dA, fmul(t[i], s.nA[i]));
+  }
+
+  const float facA = fmul(dA, s.inv[0]);
+
+#pragma unroll
+  for (int i = 0; i < CH; i++)
+  {
+    est[i] = fadd(s.minA[i], fmul(facA, s.nA[i]));
+    t[i] = fsub(fsub(color[i], est[i]), s.offB[i]);
+    dB = fadd(dB, fmul(t[i], s.nB[i]));
+  }
+
+  const float facB = fmul(dB, s.inv[1]);
+
+#pragma unroll
+  for (int i = 0; i < CH; i++)
+  {
+    est[i] = fadd(est[i], fmul(facB, s.nB[i]));
+    t[i] = fsub(fsub(color[i], est[i]), s.offC[i]);
+    dC = fadd(dC, fmul(t[i], s.nC[i]));
+  }
+
+  const float facC = fmul(dC, s.inv[2]);
+  // fabsf(fac_a) * inv[0] + fabsf(0.5f - fac_b) * inv[1] + fabsf(0.5f - fac_c) * inv[2]
+  return fadd(fadd(fmul(fabsf(facA), invLen[0]), fmul(fabsf(fsub(0.5f, facB)), invLen[1])), fmul(fabsf(fsub(0.5f, facC)), invLen[2]));
+}
+
+// returns 1 (early accept), 0 (ratio reject) or -1 (needs the 27-sample score)
+template <int CH>
+__device__ __forceinline__ int predicate_quick(const PredRec &a, const PredRec &b)
+{
+  const float w[4] = { 2, 4, 3, 3 };
+  float avgDiffSq = 0.0f;
+
+#pragma unroll
+  for (int i = 0; i < CH; i++)
+  {
+    const float diff = fsub(a.avg[i], b.avg[i]);
+    avgDiffSq = fadd(avgDiffSq, fmul(fmul(diff, diff), w[i]));
+  }
+
+  const float acceptAvg = (float)(16 * 3 * CH), acceptRange = (float)(200 * 3 * CH);
+
+  if (avgDiffSq < acceptAvg && a.sumLen < acceptRange && b.sumLen < acceptRange)
+    return 1;
+
+  const float ratio = __fdiv_rn(fadd(a.sumLen, 1.0f), fadd(b.sumLen, 1.0f));
+  const float maxRatio = 1.375f;
+
+  if (ratio > maxRatio || ratio < (1.f / maxRatio))
+    return 0;
+
+  return -1;
+}
+
+template <int CH>
+__device__ __forceinline__ float sample_term(const PredRec &a, const PredRec &b, int k)
+{
+  const int z = k / 9, y = (k / 3) % 3, x = k % 3;
+  const float xf = x * 0.5f, yf = y * 0.5f, zf = z * 0.5f;
+  float color[4];
+
+#pragma unroll
+  for (int i = 0; i < CH; i++)
+    color[i] = fadd(fadd(fmul(b.nA[i], xf), fmul(b.nB[i], yf)), fmul(b.nC[i], zf));
+
+  return factor_term<CH>(color, a, a.invLen);
+}
+
+// one thread evaluates the whole predicate (limg.cpp:1137-1269). a = seed, b = candidate.
+template <int CH>
+__device__ bool predicate_thread(const PredRec &a, const PredRec &b)
+{
+  const int q = predicate_quick<CH>(a, b);
+
+  if (q >= 0)
+    return q != 0;
+
+  // Q1: the second term of every iteration projects avg(a) into b: loop invariant, but part of the ordered sum.
+  const float constTerm = factor_term<CH>(a.avg, b, b.invLen);
+  float sum = 0.0f;
+
+  for (int k = 0; k < 27; k++)
+  {
+    sum = fadd(sum, sample_term<CH>(a, b, k));
+    sum = fadd(sum, constTerm);
+  }
+
+  return fmul(sum, 1.f / (3 * 3 * 3)) < 3.0f;
+}
+
+// one warp evaluates one predicate: lane k < 27 computes sample k, the ordered sum is replayed by every lane.
+template <int CH>
+__device__ bool predicate_warp(const PredRec &a, const PredRec &b)
+{
+  const int q = predicate_quick<CH>(a, b);
+
+  if (q >= 0)
+    return q != 0;
+
+  const int lane = threadIdx.x & 31;
+  const float constTerm = factor_term<CH>(a.avg, b, b.invLen);
+  const float term = sample_term<CH>(a, b, lane < 27 ? lane : 0);
+  float sum = 0.0f;
+
+#pragma unroll
+  for (int k = 0; k < 27; k++)
+  {
+    sum = fadd(sum, __shfl_sync(0xFFFFFFFFu, term, k));
+    sum = fadd(sum, constTerm);
+  }
+
+  return fmul(sum, 1.f / (3 * 3 * 3)) < 3.0f;
+}
+
+// match word of every block: bit (dy * 8 + dx) = predicate(seed = block, candidate = block + (dx, dy)), 0 outside the grid.
+template <int CH>
+__global__ void __launch_bounds__(256) k_pred_window(const PredRec *__restrict__ rec, int BX, int BY, uint32_t *__restrict__ window /* 2 words per block */)
+{
+  const int pair = blockIdx.x * 8 + (threadIdx.x >> 5); // (seed, half) pairs: 8 per CTA
+  const int seed = pair >> 1, half = pair & 1;
+
+  if (seed >= BX * BY)
+    return;
+
+  const int lane = threadIdx.x & 31;
+  const int o = half * 32 + lane;
+  const int dx = o & 7, dy = o >> 3;
+  const int sy = seed / BX, sx = seed - sy * BX;
+  bool m = false;
+
+  if (o == 0)
+    m = true;
+  else if (sx + dx < BX && sy + dy < BY)
+    m = predicate_thread<CH>(rec[seed], rec[(size_t)(sy + dy) * BX + sx + dx]);
+
+  const uint32_t bits = __ballot_sync(0xFFFFFFFFu, m);
+
+  if (lane == 0)
+    window[(size_t)seed * 2 + half] = bits;
+}
+
+// ---------------------------------------------------------------------------------------------
+// sequential scan
+// ---------------------------------------------------------------------------------------------
+
+#define LIMG_MERGE_THREADS 1024
+#define LIMG_MERGE_WARPS (LIMG_MERGE_THREADS / 32)
+
+struct MergeMailbox
+{
+  int kind; // 0 quit, 1 evaluate strip
+  int seed;
+  int x0, y0, w, h;
+  int result;
+};
+
+__device__ __forceinline__ void named_bar_sync(int id, int count)
+{
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+
+struct MergeArgs
+{
+  const PredRec *rec;
+  const uint32_t *window;
+  int BX, BY, wordsPerRow;
+  limgcu_area *areas;
+  uint32_t *mergedCount; // number of stage 0 + stage 1 areas
+  uint32_t *usedOut;     // BY * wordsPerRow words: in-use mask after both merge stages
+  uint32_t *stats;       // [8] optional counters
+};
+
+template <int CH>
+struct MergeScan
+{
+  const MergeArgs &a;
+  uint32_t *used;       // shared: BY rows of wordsPerRow words (+1 pad word per row inside wordsPerRow)
+  MergeMailbox *mail;
+  int lane;
+
+  __device__ __forceinline__ uint32_t used_bits8(int x, int y) const
+  {
+    // 8 in-use bits of row y starting at column x; rows outside the grid read as in use.
+    if (y >= a.BY)
+      return 0xFFu;
+
+    const uint32_t *row = used + (size_t)y * a.wordsPerRow;
+    const int w0 = x >> 5, s = x & 31;
+    return __funnelshift_r(row[w0], row[w0 + 1], s) & 0xFFu;
+  }
+
+  __device__ __forceinline__ bool is_used(int x, int y) const
+  {
+    return (used[(size_t)y * a.wordsPerRow + (x >> 5)] >> (x & 31)) & 1u;
+  }
+
+  // all blocks of the strip unused? (warp cooperative, uniform result)
+  __device__ bool strip_unused(int x0, int y0, int w, int h) const
+  {
+    bool any = false;
+
+    for (int e = lane; e < w * h; e += 32)
+    {
+      const int yy = y0 + e / w, xx = x0 + e % w;
+      any |= is_used(xx, yy);
+    }
+
+    return !__any_sync(0xFFFFFFFFu, any);
+  }
+
+  // all blocks of the strip match the seed? evaluated by every warp of the CTA (one predicate per warp at a time).
+  __device__ bool strip_matches(int seed, int x0, int y0, int w, int h)
+  {
+    if (lane == 0)
+    {
+      mail->kind = 1;
+      mail->seed = seed;
+      mail->x0 = x0; mail->y0 = y0; mail->w = w; mail->h = h;
+      mail->result = 1;
+    }
+
+    __syncwarp();
+    named_bar_sync(1, LIMG_MERGE_THREADS);
+    evaluate_strip(a, mail, 0);
+    named_bar_sync(2, LIMG_MERGE_THREADS);
+    return mail->result != 0;
+  }
+
+  static __device__ void evaluate_strip(const MergeArgs &a, MergeMailbox *mail, int warp)
+  {
+    const int count = mail->w * mail->h;
+    const PredRec seed = a.rec[mail->seed];
+
+    for (int e = warp; e < count; e += LIMG_MERGE_WARPS)
+    {
+      if (*(volatile int *)&mail->result == 0)
+        break;
+
+      const int yy = mail->y0 + e / mail->w, xx = mail->x0 + e % mail->w;
+
+      if (!predicate_warp<CH>(seed, a.rec[(size_t)yy * a.BX + xx]) && (threadIdx.x & 31) == 0)
+        atomicAnd(&mail->result, 0);
+    }
+  }
+
+  __device__ bool strip_joins(int seed, int x0, int y0, int w, int h)
+  {
+    return strip_unused(x0, y0, w, h) && strip_matches(seed, x0, y0, w, h);
+  }
+
+  // generic alternating growth with on-demand predicates (limg.cpp:1294-1388); the seed is the rectangle's top-left block.
+  __device__ void grow_generic(int &ox, int &oy, int &rx, int &ry, bool right, bool down, bool fourWay)
+  {
+    const int seed = oy * a.BX + ox;
+    bool up = fourWay, left = fourWay;
+
+    while (right || down || up || left)
+    {
+      if (right)
+      {
+        if (ox + rx + 1 < a.BX && strip_joins(seed, ox + rx, oy, 1, ry)) rx++; else right = false;
+      }
+
+      if (down)
+      {
+        if (oy + ry + 1 < a.BY && strip_joins(seed, ox, oy + ry, rx, 1)) ry++; else down = false;
+      }
+
+      if (up)
+      {
+        if (oy > 0 && strip_joins(seed, ox, oy - 1, rx, 1)) { oy--; ry++; } else up = false;
+      }
+
+      if (left)
+      {
+        if (ox > 0 && strip_joins(seed, ox - 1, oy, 1, ry)) { ox--; rx++; } else left = false;
+      }
+    }
+  }
+
+  // right/down growth of a 1x1 seed: bit arithmetic inside the 8x8 window, on-demand strips beyond it.
+  __device__ void grow_seed(int x, int y, int &rx, int &ry)
+  {
+    const uint32_t *wp = a.window + (size_t)(y * a.BX + x) * 2;
+    const uint64_t match = (uint64_t)wp[0] | ((uint64_t)wp[1] << 32);
+
+    // in-use window: lane r < 8 fetches row y + r
+    uint32_t rowBits = lane < 8 ? used_bits8(x, y + lane) : 0u;
+    uint32_t lo = 0, hi = 0;
+
+#pragma unroll
+    for (int r = 0; r < 4; r++)
+    {
+      lo |= __shfl_sync(0xFFFFFFFFu, rowBits, r) << (8 * r);
+      hi |= __shfl_sync(0xFFFFFFFFu, rowBits, r + 4) << (8 * r);
+    }
+
+    const uint64_t avail = match & ~((uint64_t)lo | ((uint64_t)hi << 32));
+    const int seed = y * a.BX + x;
+    bool right = true, down = true;
+    rx = 1;
+    ry = 1;
+
+    while (right || down)
+    {
+      if (right)
+      {
+        bool ok = x + rx + 1 < a.BX;
+
+        if (ok)
+        {
+          if (rx < 8)
+          {
+            // column rx, rows [0, min(ry, 8)) from the window, rows beyond on demand
+            const int rows = min(ry, 8);
+            const uint64_t mask = (0x0101010101010101ull << rx) & (rows >= 8 ? ~0ull : ((1ull << (8 * rows)) - 1));
+            ok = (avail & mask) == mask;
+
+            if (ok && ry > 8)
+              ok = strip_joins(seed, x + rx, y + 8, 1, ry - 8);
+          }
+          else
+          {
+            ok = strip_joins(seed, x + rx, y, 1, ry);
+          }
+        }
+
+        if (ok) rx++; else right = false;
+      }
+
+      if (down)
+      {
+        bool ok = y + ry + 1 < a.BY;
+
+        if (ok)
+        {
+          if (ry < 8)
+          {
+            const int cols = min(rx, 8);
+            const uint64_t mask = (uint64_t)((1u << cols) - 1u) << (8 * ry);
+            ok = (avail & mask) == mask;
+
+            if (ok && rx > 8)
+              ok = strip_joins(seed, x + 8, y + ry, rx - 8, 1);
+          }
+          else
+          {
+            ok = strip_joins(seed, x, y + ry, rx, 1);
+          }
+        }
+
+        if (ok) ry++; else down = false;
+      }
+    }
+  }
+
+  __device__ void mark_used(int ox, int oy, int rx, int ry)
+  {
+    for (int r = lane; r < ry; r += 32)
+    {
+      uint32_t *row = used + (size_t)(oy + r) * a.wordsPerRow;
+
+      for (int xx = ox; xx < ox + rx;)
+      {
+        const int w0 = xx >> 5, b0 = xx & 31;
+        const int cnt = min(32 - b0, ox + rx - xx);
+        const uint32_t m = (cnt == 32 ? 0xFFFFFFFFu : ((1u << cnt) - 1u)) << b0;
+        row[w0] |= m;
+        xx += cnt;
+      }
+    }
+
+    __syncwarp();
+  }
+
+  // stage 0: large merges (>= 3x3, centre-third retry); stage 1: anything larger than 1x1.
+  __device__ uint32_t run_stage(int stage, uint32_t count)
+  {
+    uint32_t seeds = 0, centreTries = 0, centreHits = 0;
+
+    for (int y = 0; y < a.BY; y++)
+    {
+      int x = 0;
+
+      while (x < a.BX)
+      {
+        // next candidate seed in this row at column >= x: unused and passing the stage's necessary condition on the match word
+        {
+          int found = -1;
+
+          for (int base = x & ~31; base < a.BX && found < 0; base += 32)
+          {
+            const int xx = base + lane;
+            bool cand = false;
+
+            if (xx >= x && xx < a.BX && !is_used(xx, y))
+            {
+              const uint32_t w0 = a.window[(size_t)(y * a.BX + xx) * 2];
+              cand = stage == 0 ? ((w0 & 0x070707u) == 0x070707u) : ((w0 & 0x0102u) != 0);
+            }
+
+            const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, cand);
+
+            if (ballot)
+              found = base + __ffs(ballot) - 1;
+          }
+
+          if (found < 0)
+            break;
+
+          x = found;
+        }
+
+        seeds++;
+        int rx, ry;
+        grow_seed(x, y, rx, ry);
+
+        int eox = x, eoy = y, erx = rx, ery = ry;
+        bool take = false, rescan = false;
+
+        if (stage == 0)
+        {
+          if (rx >= 3 && ry >= 3) // Q4
+          {
+            int cox = x + rx / 3, coy = y + ry / 3, crx = rx / 3, cry = ry / 3;
+            grow_generic(cox, coy, crx, cry, true, true, true);
+            centreTries++;
+
+            if (crx * cry > rx * ry)
+            {
+              eox = cox; eoy = coy; erx = crx; ery = cry;
+              rescan = true;
+              centreHits++;
+            }
+
+            take = true;
+          }
+        }
+        else
+        {
+          take = rx > 1 || ry > 1;
+        }
+
+        if (!take)
+        {
+          x++;
+          continue;
+        }
+
+        mark_used(eox, eoy, erx, ery);
+
+        if (lane == 0)
+        {
+          limgcu_area *out = &a.areas[count];
+          out->ox = eox; out->oy = eoy; out->rx = erx; out->ry = ery;
+          out->stage = stage;
+        }
+
+        count++;
+
+        if (!rescan)
+          x += rx;
+      }
+    }
+
+    if (lane == 0 && a.stats)
+    {
+      a.stats[stage * 3 + 0] = seeds;
+      a.stats[stage * 3 + 1] = centreTries;
+      a.stats[stage * 3 + 2] = centreHits;
+    }
+
+    return count;
+  }
+};
+
+template <int CH>
+__global__ void __launch_bounds__(LIMG_MERGE_THREADS) k_merge_scan(MergeArgs a)
+{
+  extern __shared__ __align__(16) unsigned char dynSmem[];
+  uint32_t *used = reinterpret_cast<uint32_t *>(dynSmem);
+  __shared__ MergeMailbox mail;
+
+  const int total = a.BY * a.wordsPerRow;
+
+  for (int i = threadIdx.x; i < total; i += blockDim.x)
+    used[i] = 0;
+
+  __syncthreads();
+
+  const int warp = threadIdx.x >> 5;
+
+  if (warp == 0)
+  {
+    MergeScan<CH> scan{ a, used, &mail, (int)(threadIdx.x & 31) };
+    uint32_t count = scan.run_stage(0, 0);
+    count = scan.run_stage(1, count);
+
+    if (scan.lane == 0)
+    {
+      *a.mergedCount = count;
+      mail.kind = 0;
+    }
+
+    __syncwarp();
+    named_bar_sync(1, LIMG_MERGE_THREADS); // release the helpers
+  }
+  else
+  {
+    while (true)
+    {
+      named_bar_sync(1, LIMG_MERGE_THREADS);
+
+      if (mail.kind == 0)
+        break;
+
+      MergeScan<CH>::evaluate_strip(a, &mail, warp);
+      named_bar_sync(2, LIMG_MERGE_THREADS);
+    }
+  }
+
+  __syncthreads();
+
+  for (int i = threadIdx.x; i < total; i += blockDim.x)
+    a.usedOut[i] = used[i];
+}
+
+// ---------------------------------------------------------------------------------------------
+// after the scan: leftovers, geometry, block map, size classes (single CTA, 1024 threads)
+// ---------------------------------------------------------------------------------------------
+
+struct PrepareArgs
+{
+  int W, H, BX, BY, wordsPerRow;
+  limgcu_area *areas;
+  const uint32_t *mergedCount;
+  const uint32_t *used;
+  uint32_t *areaCount;
+  uint32_t *blockToArea;
+  AreaWork *work;
+  uint32_t *smallList, *largeList;
+  uint32_t *smallCount, *largeCount;
+  int noMerge; // every block is its own area (limg_encode3d_test): mergedCount is ignored
+};
+
+__device__ __forceinline__ uint32_t block_exclusive_scan_1024(uint32_t v, uint32_t *warpSums /* [33] */, uint32_t &total)
+{
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t incl = v;
+
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1)
+  {
+    const uint32_t n = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+    if (lane >= o) incl += n;
+  }
+
+  if (lane == 31)
+    warpSums[warp] = incl;
+
+  __syncthreads();
+
+  if (warp == 0)
+  {
+    uint32_t s = warpSums[lane];
+    uint32_t si = s;
+
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1)
+    {
+      const uint32_t n = __shfl_up_sync(0xFFFFFFFFu, si, o);
+      if (lane >= o) si += n;
+    }
+
+    warpSums[lane] = si - s;
+
+    if (lane == 31)
+      warpSums[32] = si;
+  }
+
+  __syncthreads();
+  const uint32_t r = warpSums[warp] + incl - v;
+  total = warpSums[32];
+  __syncthreads();
+  return r;
+}
+
+__global__ void __launch_bounds__(1024) k_area_prepare(PrepareArgs a)
+{
+  __shared__ uint32_t warpSums[33];
+  __shared__ uint32_t sSmall, sLarge;
+  const int nBlocks = a.BX * a.BY;
+  const uint32_t merged = a.noMerge ? 0u : *a.mergedCount;
+
+  if (threadIdx.x == 0)
+  {
+    sSmall = 0;
+    sLarge = 0;
+  }
+
+  // 1. leftovers in raster order (limg.cpp:1860-1878)
+  uint32_t carry = merged;
+
+  for (int base = 0; base < nBlocks; base += 1024)
+  {
+    const int b = base + threadIdx.x;
+    uint32_t isLeft = 0;
+    int by = 0, bx = 0;
+
+    if (b < nBlocks)
+    {
+      by = b / a.BX;
+      bx = b - by * a.BX;
+      isLeft = a.noMerge ? 1u : (((a.used[(size_t)by * a.wordsPerRow + (bx >> 5)] >> (bx & 31)) & 1u) ^ 1u);
+    }
+
+    uint32_t total;
+    const uint32_t pos = block_exclusive_scan_1024(isLeft, warpSums, total);
+
+    if (isLeft)
+    {
+      limgcu_area *out = &a.areas[carry + pos];
+      out->ox = bx; out->oy = by; out->rx = 1; out->ry = 1;
+      out->stage = 2;
+    }
+
+    carry += total;
+  }
+
+  const uint32_t count = carry;
+
+  if (threadIdx.x == 0)
+    *a.areaCount = count;
+
+  __syncthreads();
+
+  // 2. geometry, block map, size class, scratch offsets
+  uint32_t offCarry = 0;
+
+  for (uint32_t base = 0; base < count; base += 1024)
+  {
+    const uint32_t k = base + threadIdx.x;
+    uint32_t n = 0;
+
+    if (k < count)
+    {
+      limgcu_area *ar = &a.areas[k];
+      const uint32_t ox = ar->ox, oy = ar->oy, rx = ar->rx, ry = ar->ry;
+      uint32_t pw = rx * LIMG_BLOCK, ph = ry * LIMG_BLOCK;
+
+      if (ox + rx == (uint32_t)a.BX && (a.W % LIMG_BLOCK)) pw = pw - LIMG_BLOCK + a.W % LIMG_BLOCK; // limg.cpp:1725-1739
+      if (oy + ry == (uint32_t)a.BY && (a.H % LIMG_BLOCK)) ph = ph - LIMG_BLOCK + a.H % LIMG_BLOCK;
+
+      ar->px_x = ox * LIMG_BLOCK; ar->px_y = oy * LIMG_BLOCK; ar->px_w = pw; ar->px_h = ph;
+      n = pw * ph;
+
+      for (uint32_t yy = oy; yy < oy + ry; yy++)
+        for (uint32_t xx = ox; xx < ox + rx; xx++)
+          a.blockToArea[(size_t)yy * a.BX + xx] = k;
+
+      if (n <= LIMG_SMALL_AREA_PX)
+        a.smallList[atomicAdd(&sSmall, 1u)] = k;
+      else
+        a.largeList[atomicAdd(&sLarge, 1u)] = k;
+    }
+
+    uint32_t total;
+    const uint32_t off = block_exclusive_scan_1024(n, warpSums, total);
+
+    if (k < count)
+    {
+      a.work[k].n = n;
+      a.work[k].scratchOff = offCarry + off;
+    }
+
+    offCarry += total;
+  }
+
+  __syncthreads();
+
+  if (threadIdx.x == 0)
+  {
+    *a.smallCount = sSmall;
+    *a.largeCount = sLarge;
+  }
+}
+
+} // namespace limg

@@ -1,0 +1,742 @@
+// limg_b200/csrc/limgcu.cu -- context + C ABI (include/limgcu.h) over the sm_100a kernels.
+// There is no CPU path in this file: every entry point either launches the kernels or fails.
+#include "kernels_fit.cuh"
+#include "kernels_merge.cuh"
+#include "kernels_stream.cuh"
+#include "rsqrt_lut.h"
+
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <math.h>
+#include <new>
+
+using namespace limg;
+
+enum { PHASE_PASS1 = 0, PHASE_WINDOW, PHASE_SCAN, PHASE_ENCODE, PHASE_DITHER, PHASE_FINALIZE, PHASE_COUNT };
+
+struct limgcu_ctx
+{
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  char err[512] = { 0 };
+  uint64_t launches = 0;
+  int smCount = 148;
+
+  uint16_t *dLut = nullptr;
+  LcgJumpTable jt;
+
+  // per-image working set, grown on demand
+  size_t capBlocks = 0, capPixels = 0, capUsedWords = 0;
+  limgcu_decomp *dTable = nullptr;
+  PredRec *dRec = nullptr;
+  uint32_t *dWindow = nullptr;
+  limgcu_area *dAreas = nullptr;
+  uint32_t *dBlockToArea = nullptr;
+  AreaWork *dWork = nullptr;
+  uint32_t *dSmallList = nullptr, *dLargeList = nullptr;
+  uint64_t *dDemand = nullptr;
+  uint32_t *dUsed = nullptr;
+  uint32_t *dScratchPx = nullptr, *dScratchFac = nullptr;
+  uint32_t *dCounters = nullptr; // [16]: 0 merged, 1 areaCount, 2 smallCount, 3 largeCount, 4 workSmall, 5 workLarge, 8.. stats
+  unsigned long long *dCompare = nullptr;
+
+  // host-buffer staging
+  size_t capStagePixels = 0;
+  uint32_t *dSrc = nullptr;
+  uint32_t *dPlaneU32[9] = { nullptr };
+  uint8_t *dPlaneU8[7] = { nullptr }; // factors A,B,C, bpp, codes A,B,C
+
+  bool timing = false;
+  cudaEvent_t ev[PHASE_COUNT + 1] = { nullptr };
+  float phaseMs[PHASE_COUNT] = { 0 };
+};
+
+static int fail(limgcu_ctx *ctx, int code, const char *what, cudaError_t e)
+{
+  if (ctx)
+    snprintf(ctx->err, sizeof(ctx->err), "%s: %s", what, e == cudaSuccess ? "" : cudaGetErrorString(e));
+
+  if (e == cudaErrorMemoryAllocation)
+    return LIMGCU_ERROR_MEMORY_ALLOCATION_FAILURE;
+
+  return code;
+}
+
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(ctx, LIMGCU_ERROR_CUDA, #call, e_); } while (0)
+#define CKL(what) do { ctx->launches++; cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) return fail(ctx, LIMGCU_ERROR_CUDA, what, e_); } while (0)
+#define NEED(p) do { if ((p) == nullptr) return fail(ctx, LIMGCU_ERROR_ARGUMENT_NULL, #p " is null", cudaSuccess); } while (0)
+
+template <class T>
+static cudaError_t regrow(T *&p, size_t count)
+{
+  if (p)
+    cudaFree(p);
+
+  p = nullptr;
+  return cudaMalloc(reinterpret_cast<void **>(&p), count * sizeof(T));
+}
+
+static int ensure_capacity(limgcu_ctx *ctx, size_t W, size_t H)
+{
+  const size_t BX = (W + 7) / 8, BY = (H + 7) / 8;
+  const size_t blocks = BX * BY, pixels = W * H;
+  const size_t usedWords = BY * ((BX + 31) / 32 + 1);
+
+  if (blocks > ctx->capBlocks)
+  {
+    CK(regrow(ctx->dTable, blocks));
+    CK(regrow(ctx->dRec, blocks));
+    CK(regrow(ctx->dWindow, blocks * 2));
+    CK(regrow(ctx->dAreas, blocks));
+    CK(regrow(ctx->dBlockToArea, blocks));
+    CK(regrow(ctx->dWork, blocks));
+    CK(regrow(ctx->dSmallList, blocks));
+    CK(regrow(ctx->dLargeList, blocks));
+    CK(regrow(ctx->dDemand, blocks));
+    ctx->capBlocks = blocks;
+  }
+
+  if (usedWords > ctx->capUsedWords)
+  {
+    CK(regrow(ctx->dUsed, usedWords));
+    ctx->capUsedWords = usedWords;
+  }
+
+  if (pixels > ctx->capPixels)
+  {
+    CK(regrow(ctx->dScratchPx, pixels));
+    CK(regrow(ctx->dScratchFac, pixels));
+    ctx->capPixels = pixels;
+  }
+
+  return LIMGCU_SUCCESS;
+}
+
+static int ensure_staging(limgcu_ctx *ctx, size_t pixels)
+{
+  if (pixels <= ctx->capStagePixels)
+    return LIMGCU_SUCCESS;
+
+  CK(regrow(ctx->dSrc, pixels));
+
+  for (auto &p : ctx->dPlaneU32)
+    CK(regrow(p, pixels));
+
+  for (auto &p : ctx->dPlaneU8)
+    CK(regrow(p, pixels));
+
+  ctx->capStagePixels = pixels;
+  return LIMGCU_SUCCESS;
+}
+
+static bool aligned32(const void *p) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) & 31) == 0; }
+
+extern "C" int limgcu_device_count(void)
+{
+  int n = 0;
+
+  if (cudaGetDeviceCount(&n) != cudaSuccess)
+    return 0;
+
+  return n;
+}
+
+extern "C" int limgcu_create(int device, limgcu_ctx **out)
+{
+  if (out == nullptr)
+    return LIMGCU_ERROR_ARGUMENT_NULL;
+
+  *out = nullptr;
+  int n = 0;
+
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0)
+    return LIMGCU_ERROR_NO_DEVICE; // no CPU fallback, by design
+
+  if (device < 0 || device >= n)
+    return LIMGCU_ERROR_INVALID_PARAMETER;
+
+  limgcu_ctx *ctx = new (std::nothrow) limgcu_ctx();
+
+  if (ctx == nullptr)
+    return LIMGCU_ERROR_MEMORY_ALLOCATION_FAILURE;
+
+  ctx->device = device;
+
+  auto bail = [&](int code) {
+    limgcu_destroy(ctx);
+    return code;
+  };
+
+  if (cudaSetDevice(device) != cudaSuccess) return bail(LIMGCU_ERROR_CUDA);
+  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(LIMGCU_ERROR_CUDA);
+  cudaDeviceGetAttribute(&ctx->smCount, cudaDevAttrMultiProcessorCount, device);
+
+  if (cudaMalloc(&ctx->dLut, 2048 * sizeof(uint16_t)) != cudaSuccess) return bail(LIMGCU_ERROR_MEMORY_ALLOCATION_FAILURE);
+  if (cudaMemcpy(ctx->dLut, LIMG_RSQRT_LUT, 2048 * sizeof(uint16_t), cudaMemcpyHostToDevice) != cudaSuccess) return bail(LIMGCU_ERROR_CUDA);
+  if (cudaMalloc(&ctx->dCounters, 32 * sizeof(uint32_t)) != cudaSuccess) return bail(LIMGCU_ERROR_MEMORY_ALLOCATION_FAILURE);
+  if (cudaMalloc(&ctx->dCompare, sizeof(unsigned long long)) != cudaSuccess) return bail(LIMGCU_ERROR_MEMORY_ALLOCATION_FAILURE);
+
+  // LCG jump table: f^(2^j)(h) = mul[j] * h + add[j]
+  ctx->jt.mul[0] = LIMG_LCG_MUL;
+  ctx->jt.add[0] = 1;
+
+  for (int j = 1; j < 64; j++)
+  {
+    ctx->jt.mul[j] = ctx->jt.mul[j - 1] * ctx->jt.mul[j - 1];
+    ctx->jt.add[j] = ctx->jt.add[j - 1] * (ctx->jt.mul[j - 1] + 1);
+  }
+
+  for (auto &e : ctx->ev)
+    if (cudaEventCreate(&e) != cudaSuccess) return bail(LIMGCU_ERROR_CUDA);
+
+  cudaFuncSetAttribute(k_encode_large<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 + LIMG_CTA_STAGE_PX * 16 + 2 * LIMG_CTA_AREA_CAP * 4);
+  cudaFuncSetAttribute(k_encode_large<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 + LIMG_CTA_STAGE_PX * 16 + 2 * LIMG_CTA_AREA_CAP * 4);
+  cudaFuncSetAttribute(k_merge_scan<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(k_merge_scan<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+
+  *out = ctx;
+  return LIMGCU_SUCCESS;
+}
+
+extern "C" void limgcu_destroy(limgcu_ctx *ctx)
+{
+  if (ctx == nullptr)
+    return;
+
+  cudaSetDevice(ctx->device);
+
+  if (ctx->stream)
+    cudaStreamSynchronize(ctx->stream);
+
+  void *ptrs[] = { ctx->dLut, ctx->dTable, ctx->dRec, ctx->dWindow, ctx->dAreas, ctx->dBlockToArea, ctx->dWork, ctx->dSmallList, ctx->dLargeList, ctx->dDemand,
+                   ctx->dUsed, ctx->dScratchPx, ctx->dScratchFac, ctx->dCounters, ctx->dCompare, ctx->dSrc };
+
+  for (void *p : ptrs)
+    if (p) cudaFree(p);
+
+  for (auto p : ctx->dPlaneU32) if (p) cudaFree(p);
+  for (auto p : ctx->dPlaneU8) if (p) cudaFree(p);
+  for (auto e : ctx->ev) if (e) cudaEventDestroy(e);
+
+  if (ctx->stream)
+    cudaStreamDestroy(ctx->stream);
+
+  delete ctx;
+}
+
+extern "C" const char *limgcu_last_error(const limgcu_ctx *ctx) { return ctx ? ctx->err : "null context"; }
+extern "C" void *limgcu_stream_handle(limgcu_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+extern "C" uint64_t limgcu_launch_count(const limgcu_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" int limgcu_sync(limgcu_ctx *ctx)
+{
+  NEED(ctx);
+  CK(cudaStreamSynchronize(ctx->stream));
+  return LIMGCU_SUCCESS;
+}
+
+extern "C" int limgcu_set_rsqrt_lut(limgcu_ctx *ctx, const uint16_t *lut2048)
+{
+  NEED(ctx);
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaMemcpyAsync(ctx->dLut, lut2048 ? lut2048 : LIMG_RSQRT_LUT, 2048 * sizeof(uint16_t), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return LIMGCU_SUCCESS;
+}
+
+extern "C" int limgcu_enable_phase_timing(limgcu_ctx *ctx, int enable)
+{
+  NEED(ctx);
+  ctx->timing = enable != 0;
+  return LIMGCU_SUCCESS;
+}
+
+extern "C" float limgcu_phase_ms(limgcu_ctx *ctx, int phase)
+{
+  if (ctx == nullptr || phase < 0 || phase >= PHASE_COUNT)
+    return -1.0f;
+
+  return ctx->phaseMs[phase];
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// stages
+// ---------------------------------------------------------------------------------------------------------------
+
+static int check_image(limgcu_ctx *ctx, size_t W, size_t H)
+{
+  if (W == 0 || H == 0 || W > 65528 || H > 65528)
+    return fail(ctx, LIMGCU_ERROR_INVALID_PARAMETER, "image size out of range (1..65528)", cudaSuccess);
+
+  return LIMGCU_SUCCESS;
+}
+
+static int launch_pass1(limgcu_ctx *ctx, const uint32_t *dSrc, size_t W, size_t H, int hasAlpha, limgcu_decomp *dTable)
+{
+  const int BX = (int)((W + 7) / 8), BY = (int)((H + 7) / 8);
+  const int grid = (BX * BY + 7) / 8;
+
+  if (hasAlpha)
+    k_pass1<4><<<grid, 256, 0, ctx->stream>>>(dSrc, (int)W, (int)H, BX, BY, ctx->dLut, dTable);
+  else
+    k_pass1<3><<<grid, 256, 0, ctx->stream>>>(dSrc, (int)W, (int)H, BX, BY, ctx->dLut, dTable);
+
+  CKL("k_pass1");
+  return LIMGCU_SUCCESS;
+}
+
+extern "C" int limgcu_pass1(limgcu_ctx *ctx, const uint32_t *d_src, size_t sizeX, size_t sizeY, int hasAlpha, limgcu_decomp *d_table)
+{
+  NEED(ctx); NEED(d_src); NEED(d_table);
+  int rc = check_image(ctx, sizeX, sizeY);
+  if (rc) return rc;
+  CK(cudaSetDevice(ctx->device));
+  return launch_pass1(ctx, d_src, sizeX, sizeY, hasAlpha, d_table);
+}
+
+// pass-1 table -> area rectangles (+ leftovers, geometry, block map, size classes). dAreas / dBlockToArea may be the context's own.
+static int launch_merge(limgcu_ctx *ctx, const limgcu_decomp *dTable, size_t W, size_t H, int hasAlpha, limgcu_area *dAreas, uint32_t *dBlockToArea, bool noMerge)
+{
+  const int BX = (int)((W + 7) / 8), BY = (int)((H + 7) / 8);
+  const int blocks = BX * BY;
+  const int wordsPerRow = (BX + 31) / 32 + 1;
+
+  CK(cudaMemsetAsync(ctx->dCounters, 0, 32 * sizeof(uint32_t), ctx->stream));
+
+  if (ctx->timing) CK(cudaEventRecord(ctx->ev[PHASE_WINDOW], ctx->stream));
+
+  if (!noMerge)
+  {
+    const size_t usedBytes = (size_t)BY * wordsPerRow * sizeof(uint32_t);
+
+    if (usedBytes > 200 * 1024)
+      return fail(ctx, LIMGCU_ERROR_OUT_OF_BOUNDS, "image too large for the shared-memory in-use mask of the merge scan", cudaSuccess);
+
+    if (hasAlpha)
+    {
+      k_pred_records<4><<<(blocks + 255) / 256, 256, 0, ctx->stream>>>(dTable, blocks, ctx->dRec);
+      CKL("k_pred_records");
+      k_pred_window<4><<<(blocks * 2 + 7) / 8, 256, 0, ctx->stream>>>(ctx->dRec, BX, BY, ctx->dWindow);
+      CKL("k_pred_window");
+    }
+    else
+    {
+      k_pred_records<3><<<(blocks + 255) / 256, 256, 0, ctx->stream>>>(dTable, blocks, ctx->dRec);
+      CKL("k_pred_records");
+      k_pred_window<3><<<(blocks * 2 + 7) / 8, 256, 0, ctx->stream>>>(ctx->dRec, BX, BY, ctx->dWindow);
+      CKL("k_pred_window");
+    }
+
+    if (ctx->timing) CK(cudaEventRecord(ctx->ev[PHASE_SCAN], ctx->stream));
+
+    MergeArgs m;
+    m.rec = ctx->dRec; m.window = ctx->dWindow; m.BX = BX; m.BY = BY; m.wordsPerRow = wordsPerRow;
+    m.areas = dAreas; m.mergedCount = ctx->dCounters + 0; m.usedOut = ctx->dUsed; m.stats = ctx->dCounters + 8;
+
+    if (hasAlpha)
+      k_merge_scan<4><<<1, LIMG_MERGE_THREADS, usedBytes, ctx->stream>>>(m);
+    else
+      k_merge_scan<3><<<1, LIMG_MERGE_THREADS, usedBytes, ctx->stream>>>(m);
+
+    CKL("k_merge_scan");
+  }
+  else if (ctx->timing)
+  {
+    CK(cudaEventRecord(ctx->ev[PHASE_SCAN], ctx->stream));
+  }
+
+  PrepareArgs p;
+  p.W = (int)W; p.H = (int)H; p.BX = BX; p.BY = BY; p.wordsPerRow = wordsPerRow;
+  p.areas = dAreas; p.mergedCount = ctx->dCounters + 0; p.used = ctx->dUsed; p.areaCount = ctx->dCounters + 1;
+  p.blockToArea = dBlockToArea; p.work = ctx->dWork; p.smallList = ctx->dSmallList; p.largeList = ctx->dLargeList;
+  p.smallCount = ctx->dCounters + 2; p.largeCount = ctx->dCounters + 3; p.noMerge = noMerge ? 1 : 0;
+  k_area_prepare<<<1, 1024, 0, ctx->stream>>>(p);
+  CKL("k_area_prepare");
+  return LIMGCU_SUCCESS;
+}
+
+extern "C" int limgcu_merge(limgcu_ctx *ctx, const limgcu_decomp *d_table, size_t sizeX, size_t sizeY, int hasAlpha, limgcu_area *d_areas, uint32_t *d_area_count, uint32_t *d_block_to_area)
+{
+  NEED(ctx); NEED(d_table); NEED(d_areas);
+  int rc = check_image(ctx, sizeX, sizeY);
+  if (rc) return rc;
+  CK(cudaSetDevice(ctx->device));
+  rc = ensure_capacity(ctx, sizeX, sizeY);
+  if (rc) return rc;
+  rc = launch_merge(ctx, d_table, sizeX, sizeY, hasAlpha, d_areas, d_block_to_area ? d_block_to_area : ctx->dBlockToArea, false);
+  if (rc) return rc;
+
+  if (d_area_count)
+    CK(cudaMemcpyAsync(d_area_count, ctx->dCounters + 1, sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream));
+
+  return LIMGCU_SUCCESS;
+}
+
+extern "C" int limgcu_blocked_encode3d(limgcu_ctx *ctx, const uint32_t *d_src, size_t sizeX, size_t sizeY, int hasAlpha, uint32_t errorFactor, uint32_t flags,
+                                       const limgcu_stream *stream, const limgcu_planes *planes)
+{
+  NEED(ctx); NEED(d_src);
+  int rc = check_image(ctx, sizeX, sizeY);
+  if (rc) return rc;
+  CK(cudaSetDevice(ctx->device));
+  rc = ensure_capacity(ctx, sizeX, sizeY);
+  if (rc) return rc;
+
+  const int W = (int)sizeX, H = (int)sizeY, BX = (W + 7) / 8;
+  limgcu_area *dAreas = (stream && stream->areas) ? stream->areas : ctx->dAreas;
+  uint32_t *dBlockToArea = (stream && stream->block_to_area) ? stream->block_to_area : ctx->dBlockToArea;
+  const bool noMerge = (flags & LIMGCU_FLAG_NO_MERGE) != 0;
+
+  if (ctx->timing) CK(cudaEventRecord(ctx->ev[PHASE_PASS1], ctx->stream));
+
+  rc = launch_pass1(ctx, d_src, sizeX, sizeY, hasAlpha, ctx->dTable);
+  if (rc) return rc;
+
+  rc = launch_merge(ctx, ctx->dTable, sizeX, sizeY, hasAlpha, dAreas, dBlockToArea, noMerge);
+  if (rc) return rc;
+
+  if (ctx->timing) CK(cudaEventRecord(ctx->ev[PHASE_ENCODE], ctx->stream));
+
+  EncodeArgs e;
+  e.src = d_src; e.W = W; e.H = H; e.BX = BX; e.BY = (H + 7) / 8; e.lut = ctx->dLut; e.table = ctx->dTable;
+  e.areas = dAreas; e.areaCount = ctx->dCounters + 1; e.work = ctx->dWork; e.ditherDemand = ctx->dDemand;
+  e.scratchPx = ctx->dScratchPx; e.scratchFac = ctx->dScratchFac;
+  e.cp = make_crush_params(errorFactor, (flags & LIMGCU_FLAG_FAST_BIT_CRUSH) ? 1 : 0);
+
+  {
+    EncodeArgs s = e;
+    s.workCounter = ctx->dCounters + 4; s.list = ctx->dSmallList; s.listCount = ctx->dCounters + 2;
+    EncodeArgs l = e;
+    l.workCounter = ctx->dCounters + 5; l.list = ctx->dLargeList; l.listCount = ctx->dCounters + 3;
+    const int gridLarge = ctx->smCount * 4, gridSmall = ctx->smCount * 6;
+    const size_t smemLarge = 4096 + LIMG_CTA_STAGE_PX * 16 + 2 * LIMG_CTA_AREA_CAP * 4;
+
+    // large areas first: they are the long poles
+    if (hasAlpha)
+    {
+      k_encode_large<4><<<gridLarge, LIMG_ENCODE_THREADS, smemLarge, ctx->stream>>>(l);
+      CKL("k_encode_large");
+      k_encode_small<4><<<gridSmall, LIMG_ENCODE_THREADS, 0, ctx->stream>>>(s);
+      CKL("k_encode_small");
+    }
+    else
+    {
+      k_encode_large<3><<<gridLarge, LIMG_ENCODE_THREADS, smemLarge, ctx->stream>>>(l);
+      CKL("k_encode_large");
+      k_encode_small<3><<<gridSmall, LIMG_ENCODE_THREADS, 0, ctx->stream>>>(s);
+      CKL("k_encode_small");
+    }
+  }
+
+  if (ctx->timing) CK(cudaEventRecord(ctx->ev[PHASE_DITHER], ctx->stream));
+
+  k_dither_scan<<<1, 1024, 0, ctx->stream>>>(dAreas, ctx->dCounters + 1, ctx->dDemand, ctx->jt, 0);
+  CKL("k_dither_scan");
+
+  if (ctx->timing) CK(cudaEventRecord(ctx->ev[PHASE_FINALIZE], ctx->stream));
+
+  FinalizeArgs f;
+  memset(&f, 0, sizeof(f));
+  f.src = d_src; f.W = W; f.H = H; f.BX = BX; f.areas = dAreas; f.blockToArea = dBlockToArea;
+  f.codesA = stream ? stream->codesA : nullptr; f.codesB = stream ? stream->codesB : nullptr; f.codesC = stream ? stream->codesC : nullptr;
+
+  if (planes)
+    f.planes = *planes;
+
+  f.planes.pBlockError = nullptr; // never written (Q12)
+  f.jt = ctx->jt;
+  f.vec = (W % 8 == 0) && aligned32(d_src) && aligned32(f.codesA) && aligned32(f.codesB) && aligned32(f.codesC) && aligned32(f.planes.pDecoded) &&
+          aligned32(f.planes.pFactorsA) && aligned32(f.planes.pFactorsB) && aligned32(f.planes.pFactorsC) && aligned32(f.planes.pBitsPerPixel) &&
+          aligned32(f.planes.pShiftABCX) && aligned32(f.planes.pColAMin) && aligned32(f.planes.pColAMax) && aligned32(f.planes.pColBMin) &&
+          aligned32(f.planes.pColBMax) && aligned32(f.planes.pColCMin) && aligned32(f.planes.pColCMax) && aligned32(f.planes.pBlockIndex);
+
+  const bool anyOut = f.codesA || f.codesB || f.codesC || f.planes.pDecoded || f.planes.pFactorsA || f.planes.pFactorsB || f.planes.pFactorsC ||
+                      f.planes.pBitsPerPixel || f.planes.pShiftABCX || f.planes.pColAMin || f.planes.pColAMax || f.planes.pColBMin || f.planes.pColBMax ||
+                      f.planes.pColCMin || f.planes.pColCMax || f.planes.pBlockIndex;
+
+  if (anyOut) // limg_encode3d_test_perf writes nothing (limg.cpp:2141-2173)
+  {
+    const long long segs = (long long)((W + 7) / 8) * H;
+    const int grid = (int)((segs + 255) / 256);
+
+    if (hasAlpha)
+      k_finalize<4><<<grid, 256, 0, ctx->stream>>>(f);
+    else
+      k_finalize<3><<<grid, 256, 0, ctx->stream>>>(f);
+
+    CKL("k_finalize");
+  }
+
+  if (stream && stream->area_count)
+    CK(cudaMemcpyAsync(stream->area_count, ctx->dCounters + 1, sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream));
+
+  if (ctx->timing)
+  {
+    CK(cudaEventRecord(ctx->ev[PHASE_COUNT], ctx->stream));
+    CK(cudaEventSynchronize(ctx->ev[PHASE_COUNT]));
+
+    for (int i = 0; i < PHASE_COUNT; i++)
+      CK(cudaEventElapsedTime(&ctx->phaseMs[i], ctx->ev[i], ctx->ev[i + 1]));
+  }
+
+  return LIMGCU_SUCCESS;
+}
+
+extern "C" int limgcu_build_block_map(limgcu_ctx *ctx, const limgcu_area *d_areas, uint32_t area_count, size_t sizeX, size_t sizeY, uint32_t *d_block_to_area)
+{
+  NEED(ctx); NEED(d_areas); NEED(d_block_to_area);
+  CK(cudaSetDevice(ctx->device));
+
+  if (area_count)
+  {
+    k_block_map<<<(area_count + 255) / 256, 256, 0, ctx->stream>>>(d_areas, area_count, (int)((sizeX + 7) / 8), d_block_to_area);
+    CKL("k_block_map");
+  }
+
+  (void)sizeY;
+  return LIMGCU_SUCCESS;
+}
+
+extern "C" int limgcu_decode(limgcu_ctx *ctx, const limgcu_area *d_areas, const uint32_t *d_block_to_area, const uint8_t *d_codesA, const uint8_t *d_codesB, const uint8_t *d_codesC,
+                             size_t sizeX, size_t sizeY, int hasAlpha, uint32_t *d_dst)
+{
+  NEED(ctx); NEED(d_areas); NEED(d_block_to_area); NEED(d_codesA); NEED(d_codesB); NEED(d_codesC); NEED(d_dst);
+  int rc = check_image(ctx, sizeX, sizeY);
+  if (rc) return rc;
+  CK(cudaSetDevice(ctx->device));
+
+  const int W = (int)sizeX, H = (int)sizeY, BX = (W + 7) / 8;
+  const long long segs = (long long)BX * H;
+  const int grid = (int)((segs + 255) / 256);
+  const int vec = (W % 8 == 0) && aligned32(d_codesA) && aligned32(d_codesB) && aligned32(d_codesC) && aligned32(d_dst);
+
+  if (hasAlpha)
+    k_decode<4><<<grid, 256, 0, ctx->stream>>>(d_areas, d_block_to_area, d_codesA, d_codesB, d_codesC, W, H, BX, d_dst, vec);
+  else
+    k_decode<3><<<grid, 256, 0, ctx->stream>>>(d_areas, d_block_to_area, d_codesA, d_codesB, d_codesC, W, H, BX, d_dst, vec);
+
+  CKL("k_decode");
+  return LIMGCU_SUCCESS;
+}
+
+extern "C" int limgcu_compare(limgcu_ctx *ctx, const uint32_t *d_a, const uint32_t *d_b, size_t sizeX, size_t sizeY, int hasAlpha, double *psnr, double *mse, double *maxError)
+{
+  NEED(ctx); NEED(d_a); NEED(d_b);
+  CK(cudaSetDevice(ctx->device));
+  const size_t n = sizeX * sizeY;
+  CK(cudaMemsetAsync(ctx->dCompare, 0, sizeof(unsigned long long), ctx->stream));
+  const int grid = (int)((n + 255) / 256 < (size_t)ctx->smCount * 8 ? (n + 255) / 256 : (size_t)ctx->smCount * 8);
+
+  if (hasAlpha)
+    k_compare<4><<<grid > 0 ? grid : 1, 256, 0, ctx->stream>>>(d_a, d_b, n, ctx->dCompare);
+  else
+    k_compare<3><<<grid > 0 ? grid : 1, 256, 0, ctx->stream>>>(d_a, d_b, n, ctx->dCompare);
+
+  CKL("k_compare");
+  unsigned long long total = 0;
+  CK(cudaMemcpyAsync(&total, ctx->dCompare, sizeof(total), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+
+  const double maxE = hasAlpha ? 780300.0 : 585225.0; // limg_color_error(0x00000000, 0xFFFFFFFF)
+  const double m = (double)total / (double)n;
+
+  if (mse) *mse = m;
+  if (maxError) *maxError = maxE;
+  if (psnr) *psnr = 10.0 * log10(maxE / m);
+
+  return LIMGCU_SUCCESS;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host-buffer entry points
+// ---------------------------------------------------------------------------------------------------------------
+
+static int host_encode(limgcu_ctx *ctx, const uint32_t *pIn, size_t W, size_t H, int hasAlpha, const limgcu_planes *pInfo, uint32_t errorFactor, uint32_t flags,
+                       limgcu_area *areas, uint32_t *areaCount, uint8_t *codesA, uint8_t *codesB, uint8_t *codesC)
+{
+  NEED(ctx); NEED(pIn);
+  int rc = check_image(ctx, W, H);
+  if (rc) return rc;
+  CK(cudaSetDevice(ctx->device));
+  const size_t n = W * H;
+  rc = ensure_staging(ctx, n);
+  if (rc) return rc;
+  rc = ensure_capacity(ctx, W, H);
+  if (rc) return rc;
+
+  CK(cudaMemcpyAsync(ctx->dSrc, pIn, n * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+
+  limgcu_planes dev;
+  memset(&dev, 0, sizeof(dev));
+  uint32_t **devU32[9] = { &dev.pDecoded, &dev.pShiftABCX, &dev.pColAMin, &dev.pColAMax, &dev.pColBMin, &dev.pColBMax, &dev.pColCMin, &dev.pColCMax, &dev.pBlockIndex };
+  uint32_t *hostU32[9] = { nullptr };
+  uint8_t **devU8[4] = { &dev.pFactorsA, &dev.pFactorsB, &dev.pFactorsC, &dev.pBitsPerPixel };
+  uint8_t *hostU8[4] = { nullptr };
+
+  if (pInfo)
+  {
+    uint32_t *h32[9] = { pInfo->pDecoded, pInfo->pShiftABCX, pInfo->pColAMin, pInfo->pColAMax, pInfo->pColBMin, pInfo->pColBMax, pInfo->pColCMin, pInfo->pColCMax, pInfo->pBlockIndex };
+    uint8_t *h8[4] = { pInfo->pFactorsA, pInfo->pFactorsB, pInfo->pFactorsC, pInfo->pBitsPerPixel };
+
+    for (int i = 0; i < 9; i++) { hostU32[i] = h32[i]; if (h32[i]) *devU32[i] = ctx->dPlaneU32[i]; }
+    for (int i = 0; i < 4; i++) { hostU8[i] = h8[i]; if (h8[i]) *devU8[i] = ctx->dPlaneU8[i]; }
+  }
+
+  limgcu_stream st;
+  memset(&st, 0, sizeof(st));
+  st.codesA = codesA ? ctx->dPlaneU8[4] : nullptr;
+  st.codesB = codesB ? ctx->dPlaneU8[5] : nullptr;
+  st.codesC = codesC ? ctx->dPlaneU8[6] : nullptr;
+
+  rc = limgcu_blocked_encode3d(ctx, ctx->dSrc, W, H, hasAlpha, errorFactor, flags, &st, &dev);
+  if (rc) return rc;
+
+  for (int i = 0; i < 9; i++)
+    if (hostU32[i]) CK(cudaMemcpyAsync(hostU32[i], ctx->dPlaneU32[i], n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+
+  for (int i = 0; i < 4; i++)
+    if (hostU8[i]) CK(cudaMemcpyAsync(hostU8[i], ctx->dPlaneU8[i], n, cudaMemcpyDeviceToHost, ctx->stream));
+
+  if (codesA) CK(cudaMemcpyAsync(codesA, ctx->dPlaneU8[4], n, cudaMemcpyDeviceToHost, ctx->stream));
+  if (codesB) CK(cudaMemcpyAsync(codesB, ctx->dPlaneU8[5], n, cudaMemcpyDeviceToHost, ctx->stream));
+  if (codesC) CK(cudaMemcpyAsync(codesC, ctx->dPlaneU8[6], n, cudaMemcpyDeviceToHost, ctx->stream));
+
+  uint32_t count = 0;
+  CK(cudaMemcpyAsync(&count, ctx->dCounters + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+
+  if (areas)
+  {
+    CK(cudaMemcpyAsync(areas, ctx->dAreas, (size_t)count * sizeof(limgcu_area), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+  }
+
+  if (areaCount)
+    *areaCount = count;
+
+  return LIMGCU_SUCCESS;
+}
+
+extern "C" int limgcu_host_blocked_encode3d(limgcu_ctx *ctx, const uint32_t *pIn, size_t sizeX, size_t sizeY, int hasAlpha, const limgcu_planes *pInfo, uint32_t errorFactor, int fastBitCrushing)
+{
+  return host_encode(ctx, pIn, sizeX, sizeY, hasAlpha, pInfo, errorFactor, fastBitCrushing ? LIMGCU_FLAG_FAST_BIT_CRUSH : 0, nullptr, nullptr, nullptr, nullptr, nullptr);
+}
+
+extern "C" int limgcu_host_encode3d(limgcu_ctx *ctx, const uint32_t *pIn, size_t sizeX, size_t sizeY, int hasAlpha, const limgcu_planes *pInfo, uint32_t errorFactor, int fastBitCrushing)
+{
+  limgcu_planes p;
+  memset(&p, 0, sizeof(p));
+
+  if (pInfo)
+  {
+    p = *pInfo;
+    p.pBitsPerPixel = nullptr; // limg_encode3d_info (limg.h:29-33) has no bits-per-pixel / block-index planes
+    p.pBlockIndex = nullptr;
+    p.pBlockError = nullptr;
+  }
+
+  return host_encode(ctx, pIn, sizeX, sizeY, hasAlpha, pInfo ? &p : nullptr, errorFactor, (fastBitCrushing ? LIMGCU_FLAG_FAST_BIT_CRUSH : 0) | LIMGCU_FLAG_NO_MERGE, nullptr, nullptr, nullptr, nullptr, nullptr);
+}
+
+extern "C" int limgcu_host_encode_stream(limgcu_ctx *ctx, const uint32_t *pIn, size_t sizeX, size_t sizeY, int hasAlpha, uint32_t errorFactor, uint32_t flags,
+                                         limgcu_area *areas, uint32_t *area_count, uint8_t *codesA, uint8_t *codesB, uint8_t *codesC, uint32_t *pDecoded)
+{
+  limgcu_planes p;
+  memset(&p, 0, sizeof(p));
+  p.pDecoded = pDecoded;
+  return host_encode(ctx, pIn, sizeX, sizeY, hasAlpha, &p, errorFactor, flags, areas, area_count, codesA, codesB, codesC);
+}
+
+extern "C" int limgcu_host_decode(limgcu_ctx *ctx, const limgcu_area *areas, uint32_t area_count, const uint8_t *codesA, const uint8_t *codesB, const uint8_t *codesC,
+                                  size_t sizeX, size_t sizeY, int hasAlpha, uint32_t *pOut)
+{
+  NEED(ctx); NEED(areas); NEED(codesA); NEED(codesB); NEED(codesC); NEED(pOut);
+  int rc = check_image(ctx, sizeX, sizeY);
+  if (rc) return rc;
+  CK(cudaSetDevice(ctx->device));
+  const size_t n = sizeX * sizeY;
+  rc = ensure_staging(ctx, n);
+  if (rc) return rc;
+  rc = ensure_capacity(ctx, sizeX, sizeY);
+  if (rc) return rc;
+
+  if ((size_t)area_count > ctx->capBlocks)
+    return fail(ctx, LIMGCU_ERROR_OUT_OF_BOUNDS, "more areas than blocks", cudaSuccess);
+
+  CK(cudaMemcpyAsync(ctx->dAreas, areas, (size_t)area_count * sizeof(limgcu_area), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->dPlaneU8[4], codesA, n, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->dPlaneU8[5], codesB, n, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->dPlaneU8[6], codesC, n, cudaMemcpyHostToDevice, ctx->stream));
+  rc = limgcu_build_block_map(ctx, ctx->dAreas, area_count, sizeX, sizeY, ctx->dBlockToArea);
+  if (rc) return rc;
+  rc = limgcu_decode(ctx, ctx->dAreas, ctx->dBlockToArea, ctx->dPlaneU8[4], ctx->dPlaneU8[5], ctx->dPlaneU8[6], sizeX, sizeY, hasAlpha, ctx->dPlaneU32[0]);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(pOut, ctx->dPlaneU32[0], n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return LIMGCU_SUCCESS;
+}
+
+extern "C" int limgcu_host_pass1(limgcu_ctx *ctx, const uint32_t *pIn, size_t sizeX, size_t sizeY, int hasAlpha, limgcu_decomp *table)
+{
+  NEED(ctx); NEED(pIn); NEED(table);
+  int rc = check_image(ctx, sizeX, sizeY);
+  if (rc) return rc;
+  CK(cudaSetDevice(ctx->device));
+  const size_t n = sizeX * sizeY, blocks = ((sizeX + 7) / 8) * ((sizeY + 7) / 8);
+  rc = ensure_staging(ctx, n);
+  if (rc) return rc;
+  rc = ensure_capacity(ctx, sizeX, sizeY);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(ctx->dSrc, pIn, n * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+  rc = launch_pass1(ctx, ctx->dSrc, sizeX, sizeY, hasAlpha, ctx->dTable);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(table, ctx->dTable, blocks * sizeof(limgcu_decomp), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return LIMGCU_SUCCESS;
+}
+
+extern "C" int limgcu_host_merge(limgcu_ctx *ctx, const limgcu_decomp *table, size_t sizeX, size_t sizeY, int hasAlpha, limgcu_area *areas, uint32_t *area_count)
+{
+  NEED(ctx); NEED(table); NEED(areas); NEED(area_count);
+  int rc = check_image(ctx, sizeX, sizeY);
+  if (rc) return rc;
+  CK(cudaSetDevice(ctx->device));
+  const size_t blocks = ((sizeX + 7) / 8) * ((sizeY + 7) / 8);
+  rc = ensure_capacity(ctx, sizeX, sizeY);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(ctx->dTable, table, blocks * sizeof(limgcu_decomp), cudaMemcpyHostToDevice, ctx->stream));
+  rc = launch_merge(ctx, ctx->dTable, sizeX, sizeY, hasAlpha, ctx->dAreas, ctx->dBlockToArea, false);
+  if (rc) return rc;
+  uint32_t count = 0;
+  CK(cudaMemcpyAsync(&count, ctx->dCounters + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaMemcpyAsync(areas, ctx->dAreas, (size_t)count * sizeof(limgcu_area), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  *area_count = count;
+  return LIMGCU_SUCCESS;
+}
+
+extern "C" double limgcu_host_compare(limgcu_ctx *ctx, const uint32_t *pImageA, const uint32_t *pImageB, size_t sizeX, size_t sizeY, int hasAlpha, double *pMeanSquaredError, double *pMaxPossibleSquaredError)
+{
+  if (ctx == nullptr || pImageA == nullptr || pImageB == nullptr)
+    return NAN;
+
+  if (cudaSetDevice(ctx->device) != cudaSuccess)
+    return NAN;
+
+  const size_t n = sizeX * sizeY;
+
+  if (ensure_staging(ctx, n) != LIMGCU_SUCCESS)
+    return NAN;
+
+  if (cudaMemcpyAsync(ctx->dPlaneU32[0], pImageA, n * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) return NAN;
+  if (cudaMemcpyAsync(ctx->dPlaneU32[1], pImageB, n * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) return NAN;
+
+  double psnr = NAN;
+
+  if (limgcu_compare(ctx, ctx->dPlaneU32[0], ctx->dPlaneU32[1], sizeX, sizeY, hasAlpha, &psnr, pMeanSquaredError, pMaxPossibleSquaredError) != LIMGCU_SUCCESS)
+    return NAN;
+
+  return psnr;
+}
