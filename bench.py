@@ -1,0 +1,356 @@
+#!/usr/bin/env python
+"""bench.py -- limg encode/decode hot path on B200 (contract in the task statement, section 4).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+
+A step = one blocked encode (compact stream out: area table + three code planes) followed by one standalone decode of
+that stream, on one synthetic frame of the workload (default: BASELINE.json configs[1], one 3840x2160 RGB photo-like
+frame). With N > 1 (torchrun, one rank per GPU) every rank processes its own frame of the same shape (independent units,
+no data-path collective, "weak" scaling); value = frames * pixels of all ranks / max-over-ranks device time.
+
+  value      device-resident throughput (inputs in HBM before the timed region), CUDA events on the codec's stream
+  e2e        same step through the host-buffer C ABI entry points with pinned host buffers: H2D of the frame, D2H of the
+             stream, H2D of the stream, D2H of the decoded frame -- all inside the timed region
+  roofline   encode path at SURVEY.md 8(d)'s 7 algorithmic bytes per pixel against MEASURED_PEAKS.json's HBM copy bandwidth,
+             per-kernel-phase durations from CUDA events on the launching stream (limgcu phase timing), dominant kernel named
+  cpu_baseline  the reference itself (oracle/_ref/libref.so, kind "reference") or the C port (oracle/, kind "port") on the
+             box's host cores, bounded sample, rank 0 at N == 1 only
+
+--impl reference times the reference's own CPU implementation (limg_blocked_encode3d_test, all host threads through its thread
+pool) on the same workload and prints the same line with "impl": "reference".
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "encode+decode throughput"
+UNIT = "Mpixel/s"
+
+WORKLOADS = {
+    # name: (width, height, has_alpha, generator kind)
+    "c2_4k_photo": (3840, 2160, False, "photo"),
+    "c4_4k_flatui": (3840, 2160, False, "flatui"),
+    "c5_1080p_photo": (1920, 1080, False, "photo"),
+    "c1_512_gradient": (512, 512, False, "gradient"),
+    "c3_8k_rgba": (7680, 4320, True, "photo"),
+}
+
+
+def make_frame(workload: str, index: int) -> np.ndarray:
+    from limg_b200 import synth
+    w, h, alpha, kind = WORKLOADS[workload]
+    if kind == "photo":
+        seed = {"c2_4k_photo": 1, "c5_1080p_photo": 3, "c3_8k_rgba": 4}[workload] + index
+        return synth.photo_like(w, h, seed, 4 if alpha else 3)
+    if kind == "flatui":
+        return synth.flat_ui(w, h, 2 + index)
+    return synth.gradient_noise(w, h, 1234 + index)
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    FIELDS = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index: int):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for line in self.lines:
+            p = [x.strip() for x in line.split(",")]
+            if len(p) < 9:
+                continue
+            try:
+                sm.append(float(p[1])); mx.append(float(p[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def host_cores() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def cpu_baseline(workload: str, threads: int, budget_s: float = 20.0) -> dict:
+    """Times the reference (or the C port) on the host. Sample: whole frames of the workload, as many as fit ~budget_s."""
+    from oracle import ref
+    w, h, alpha, _ = WORKLOADS[workload]
+    img = make_frame(workload, 0)
+    mpx = w * h / 1e6
+    if ref.available():
+        ref.set_modes(True, False)
+        t = ref.time_blocked(img, alpha, 100, True, threads, 1, False)  # one frame, also the warm-up
+        reps = max(1, min(8, int(budget_s / max(t, 1e-3)) - 1))
+        t = ref.time_blocked(img, alpha, 100, True, threads, reps, False)
+        return {"value": mpx / t, "unit": UNIT, "cores": threads, "kind": "reference",
+                "sample": "%d x limg_blocked_encode3d_test (encode + in-encoder decode) of one %dx%d frame, %d-thread limg_thread_pool, LCG dither" % (reps, w, h, threads),
+                "seconds_per_frame": t}
+    from oracle import oracle as lo
+    crop = img[: min(h, 1080), : min(w, 1920)]
+    t0 = time.time()
+    lo.blocked_encode3d(np.ascontiguousarray(crop), alpha, 100, True)
+    t = time.time() - t0
+    return {"value": crop.size / 1e6 / t, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": "1 x oracle lo_blocked_encode3d on a %dx%d crop (scalar C port, 1 thread)" % (crop.shape[1], crop.shape[0]), "seconds_per_frame": t}
+
+
+def run_reference(args, rank: int, world: int):
+    """--impl reference: the reference's CPU path on the same workload; rank 0 only."""
+    if rank != 0:
+        return
+    from oracle import ref
+    w, h, alpha, _ = WORKLOADS[args.workload]
+    mpx = w * h / 1e6
+    threads = host_cores()
+    img = make_frame(args.workload, 0)
+    line = {"impl": "reference", "metric": METRIC, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32+i32", "data": "synthetic",
+            "config": {"workload": args.workload, "width": w, "height": h, "channels": 4 if alpha else 3, "error_factor": 100, "fast_bit_crushing": True,
+                       "step": "limg_blocked_encode3d_test: encode + in-encoder decode of one frame (the reference has no standalone decoder)"}}
+    if ref.available():
+        ref.set_modes(True, False)
+        ref.time_blocked(img, alpha, 100, True, threads, max(1, min(args.warmup, 1)), False)
+        times = [ref.time_blocked(img, alpha, 100, True, threads, 1, False) for _ in range(args.steps)]
+        kind, cores = "reference", threads
+        sample = "%d steps, each one full %dx%d frame through limg_blocked_encode3d_test with a %d-thread limg_thread_pool (oracle/_ref/libref.so, LCG dither)" % (args.steps, w, h, threads)
+    else:
+        from oracle import oracle as lo
+        crop = np.ascontiguousarray(img[: min(h, 1080), : min(w, 1920)])
+        mpx = crop.size / 1e6
+        times = []
+        for _ in range(max(1, min(args.steps, 3))):
+            t0 = time.time(); lo.blocked_encode3d(crop, alpha, 100, True); times.append(time.time() - t0)
+        kind, cores = "port", 1
+        sample = "%d steps, each a %dx%d crop through the scalar C port (oracle/liblimg_oracle.so); libref.so not present" % (len(times), crop.shape[1], crop.shape[0])
+    t = sum(times) / len(times)
+    value = mpx / t
+    line.update({"value": value, "ms_per_step": t * 1e3,
+                 "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+                 "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args, rank: int, local_rank: int, world: int):
+    import torch
+    import torch.distributed as dist
+    from limg_b200 import AREA_DTYPE, Codec
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    w, h, alpha, _ = WORKLOADS[args.workload]
+    npx = w * h
+    bx, by = (w + 7) // 8, (h + 7) // 8
+    codec = Codec(local_rank)
+    stream = torch.cuda.ExternalStream(codec.stream, device=dev)
+
+    frame = make_frame(args.workload, rank)  # every rank its own frame (independent unit)
+    d_src = torch.from_numpy(frame.view(np.int32)).to(dev)
+    d_codes = [torch.empty((h, w), dtype=torch.uint8, device=dev) for _ in range(3)]
+    d_areas = torch.empty(bx * by * AREA_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+    d_map = torch.empty(bx * by, dtype=torch.int32, device=dev)
+    d_count = torch.zeros(1, dtype=torch.int32, device=dev)
+    d_dec = torch.empty((h, w), dtype=torch.int32, device=dev)
+    d_flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    st = {"areas": d_areas.data_ptr(), "area_count": d_count.data_ptr(), "block_to_area": d_map.data_ptr(),
+          "codesA": d_codes[0].data_ptr(), "codesB": d_codes[1].data_ptr(), "codesC": d_codes[2].data_ptr()}
+
+    def step_device():
+        codec.blocked_encode3d_device(d_src.data_ptr(), w, h, alpha, 100, True, False, st, None)
+        codec.decode_device(d_areas.data_ptr(), d_map.data_ptr(), d_codes[0].data_ptr(), d_codes[1].data_ptr(), d_codes[2].data_ptr(), w, h, alpha, d_dec.data_ptr())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- device-resident timing -------------------------------------------------------------------------------
+    for _ in range(args.warmup):
+        step_device()
+    codec.sync()
+
+    sampler = ClockSampler(local_rank)
+    launches0 = codec.launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    sampler.start()
+    with torch.cuda.stream(stream):
+        for i in range(args.steps):
+            d_flush.fill_(i & 0xFF)  # L2 flush between timed iterations (not timed)
+            ev[i][0].record(stream)
+            codec.blocked_encode3d_device(d_src.data_ptr(), w, h, alpha, 100, True, False, st, None)
+            ev[i][1].record(stream)
+            codec.decode_device(d_areas.data_ptr(), d_map.data_ptr(), d_codes[0].data_ptr(), d_codes[1].data_ptr(), d_codes[2].data_ptr(), w, h, alpha, d_dec.data_ptr())
+            ev[i][2].record(stream)
+    codec.sync()
+    barrier()
+    clocks = sampler.stop()
+    launches = codec.launch_count() - launches0
+
+    enc_ms = [e[0].elapsed_time(e[1]) for e in ev]
+    dec_ms = [e[1].elapsed_time(e[2]) for e in ev]
+    total_ms = sum(enc_ms) + sum(dec_ms)
+
+    # ---- per-kernel-phase durations (CUDA events on the codec's stream, same workload, separate passes) ------------
+    codec.enable_phase_timing(True)
+    phase_acc = {}
+    reps = max(3, min(args.steps, 10))
+    for i in range(reps):
+        d_flush.fill_(i & 0xFF)
+        codec.blocked_encode3d_device(d_src.data_ptr(), w, h, alpha, 100, True, False, st, None)
+        for k, v in codec.phase_ms().items():
+            phase_acc[k] = phase_acc.get(k, 0.0) + v / reps
+    codec.enable_phase_timing(False)
+
+    # ---- end to end through the host-buffer C ABI, pinned host memory ----------------------------------------------
+    h_src = torch.from_numpy(frame.view(np.int32)).pin_memory()
+    h_codes = [torch.empty((h, w), dtype=torch.uint8).pin_memory() for _ in range(3)]
+    h_areas = torch.empty(bx * by * AREA_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
+    h_dec = torch.empty((h, w), dtype=torch.int32).pin_memory()
+    import ctypes as C
+    n_areas = C.c_uint32(0)
+    lib = codec.lib
+
+    def step_e2e():
+        rc = lib.limgcu_host_encode_stream(codec.h, h_src.data_ptr(), w, h, int(alpha), 100, 1, h_areas.data_ptr(), C.byref(n_areas),
+                                           h_codes[0].data_ptr(), h_codes[1].data_ptr(), h_codes[2].data_ptr(), None)
+        assert rc == 0, rc
+        rc = lib.limgcu_host_decode(codec.h, h_areas.data_ptr(), n_areas.value, h_codes[0].data_ptr(), h_codes[1].data_ptr(), h_codes[2].data_ptr(), w, h, int(alpha), h_dec.data_ptr())
+        assert rc == 0, rc
+
+    for _ in range(max(1, args.warmup)):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    area_bytes = n_areas.value * AREA_DTYPE.itemsize
+    h2d = npx * 4 + area_bytes + 3 * npx
+    d2h = area_bytes + 3 * npx + 4 + npx * 4
+
+    # ---- max over ranks -----------------------------------------------------------------------------------------------
+    t = torch.tensor([total_ms, sum(enc_ms), sum(dec_ms), e2e_s * 1e3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, enc_total, dec_total, e2e_ms = [float(x) for x in t.tolist()]
+
+    # self-check of the timed data against the round trip (cheap, outside the timed region)
+    psnr, _, _ = codec.compare_device(d_src.data_ptr(), d_dec.data_ptr(), w, h, alpha)
+
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        mpx_total = npx * world * args.steps / 1e6
+        value = mpx_total / (total_ms / 1e3)
+        enc_step_ms = enc_total / args.steps
+        dec_step_ms = dec_total / args.steps
+        enc_gbs = 7.0 * npx / (enc_step_ms * 1e-3) / 1e9
+        dec_gbs = 7.0 * npx / (dec_step_ms * 1e-3) / 1e9
+        dominant = max(phase_acc, key=phase_acc.get)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32+i32", "data": "synthetic",
+            "config": {"workload": args.workload, "width": w, "height": h, "channels": 4 if alpha else 3, "error_factor": 100, "fast_bit_crushing": True,
+                       "dither": "lcg", "frames_per_rank_per_step": 1, "parallelism": "independent frames, one per GPU" if world > 1 else "single GPU",
+                       "step": "limgcu_blocked_encode3d (stream out) + limgcu_decode", "l2": "flushed between timed steps (512 MiB fill, untimed)"},
+            "encode_mpixel_s": npx * world / 1e6 / (enc_step_ms * 1e-3), "decode_mpixel_s": npx * world / 1e6 / (dec_step_ms * 1e-3),
+            "encode_ms": enc_step_ms, "decode_ms": dec_step_ms, "psnr_db": psnr,
+            "clocks": clocks, "gpu_launches": int(launches),
+            "e2e": {"value": npx * world * args.steps / 1e6 / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "path": "limgcu_host_encode_stream + limgcu_host_decode, pinned host buffers"},
+            "roofline": {"bound": "hbm", "achieved": enc_gbs, "peak": peak, "unit": "GB/s", "frac": enc_gbs / peak, "traffic": None,
+                         "kernel": "encode path (all kernels of limgcu_blocked_encode3d), 7 algorithmic B/px", "peak_source": peak_src,
+                         "dominant_kernel": dominant, "dominant_share": phase_acc[dominant] / max(sum(phase_acc.values()), 1e-9),
+                         "phase_ms": {k: round(v, 4) for k, v in phase_acc.items()}},
+            "roofline_decode": {"bound": "hbm", "achieved": dec_gbs, "peak": peak, "unit": "GB/s", "frac": dec_gbs / peak, "traffic": None,
+                                "kernel": "k_decode, 7 algorithmic B/px"},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                line["cpu_baseline"] = cpu_baseline(args.workload, host_cores())
+            except Exception as e:  # the baseline is reported, never required for the GPU numbers
+                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": repr(e)}
+        print(json.dumps(line), flush=True)
+
+    codec.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2_4k_photo", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

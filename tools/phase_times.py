@@ -1,0 +1,20 @@
+import sys, time, json
+sys.path.insert(0,'.')
+import numpy as np, torch
+from limg_b200 import Codec, synth
+c = Codec(0)
+c.enable_phase_timing(True)
+for name in ("c1_512_gradient","c5_1080p_frame0","c2_4k_photo","c4_4k_flatui","c3_8k_rgba"):
+    img, alpha = synth.CONFIGS[name]()
+    h,w = img.shape
+    d = torch.from_numpy(img.view(np.int32)).cuda()
+    codes = [torch.empty((h,w),dtype=torch.uint8,device='cuda') for _ in range(3)]
+    dec = torch.empty((h,w),dtype=torch.int32,device='cuda')
+    stream = {"codesA":codes[0].data_ptr(),"codesB":codes[1].data_ptr(),"codesC":codes[2].data_ptr()}
+    for it in range(3):
+        t=time.time()
+        c.blocked_encode3d_device(d.data_ptr(), w, h, alpha, 100, True, False, stream, {"pDecoded": dec.data_ptr()})
+        c.sync(); dt=time.time()-t
+    ph = c.phase_ms()
+    tot = sum(ph.values())
+    print(name, "%dx%d"%(w,h), "total %.3f ms (wall %.3f) -> %.1f Mpx/s"%(tot, dt*1e3, w*h/tot/1e3), {k: round(v,3) for k,v in ph.items()})
