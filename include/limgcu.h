@@ -111,6 +111,8 @@ uint64_t limgcu_launch_count(const limgcu_ctx *ctx);
  * (phase: 0 pass1, 1 predicate windows, 2 merge scan, 3 area encode, 4 dither scan, 5 finalize). Synchronises. */
 int limgcu_enable_phase_timing(limgcu_ctx *ctx, int enable);
 float limgcu_phase_ms(limgcu_ctx *ctx, int phase);
+/* 32 internal counters of the last encode / merge (area counts, merge iterations ...), for profiling. Synchronises. */
+int limgcu_debug_counters(limgcu_ctx *ctx, uint32_t *out32);
 
 /* device-buffer entry points ------------------------------------------------------------------------------------ */
 

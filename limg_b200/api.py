@@ -67,6 +67,11 @@ class Codec:
     def phase_ms(self) -> dict:
         return {name: float(self.lib.limgcu_phase_ms(self.h, i)) for i, name in enumerate(PHASES)}
 
+    def debug_counters(self) -> np.ndarray:
+        out = np.zeros(32, np.uint32)
+        self._ck(self.lib.limgcu_debug_counters(self.h, _vp(out)), "limgcu_debug_counters")
+        return out
+
     # ---- host-buffer operators (reference argument meaning) -------------------------------------------------
 
     @staticmethod

@@ -6,10 +6,11 @@
 //   1. k_pred_records : one thread per block derives the predicate-side state of its record once (the divisions).
 //   2. k_pred_window  : for EVERY block as a hypothetical seed, all 63 predicates against the 8x8 window to its lower right are
 //                       evaluated in parallel (one thread per pair) -> one 64-bit match word per block.
-//   3. k_merge_scan   : one persistent CTA replays the reference's scan order. Warp 0 walks candidate seeds with pure bit
-//                       arithmetic on (match word & ~in-use window); growth that leaves the window and the four-way
-//                       centre-third regrowth evaluate their strips on demand, one warp per predicate (27 lanes = the 27
-//                       samples), across all warps of the CTA. The accept order is the reference's, so the area map is identical.
+//   3. k_merge_banded : one CTA per band of block rows replays the reference's scan order over its rows (see "banded scan"
+//                       below for why the concurrent bands converge to the sequential result). Inside a band warp 0 walks
+//                       candidate seeds with pure bit arithmetic on (match word & ~in-use window); growth that leaves the
+//                       window and the four-way centre-third regrowth evaluate their predicates on demand, one warp per
+//                       predicate (27 lanes = the 27 samples), across all warps of the CTA.
 //   4. k_area_prepare : leftover blocks (raster order), pixel rectangles, block->area map, size classes, scratch offsets.
 #pragma once
 
@@ -232,18 +233,29 @@ __global__ void __launch_bounds__(256) k_pred_window(const PredRec *__restrict__
 }
 
 // ---------------------------------------------------------------------------------------------
-// sequential scan
+// banded scan
+//
+// The reference's scan is sequential only through the in-use mask. The block rows are cut into bands, one CTA per band.
+// Band k replays the reference's scan over ITS rows against an input mask that holds the rectangles emitted by all bands
+// above it. All bands run concurrently from the previous iteration's rectangles; a band re-runs only when the input mask
+// changed inside the row range its last run actually read. Band 0 never depends on anything, so after iteration t bands
+// 0..t are final; in practice influence dies out after a few rows and a handful of iterations suffice. At the fixed point
+// every band saw exactly the mask the sequential scan would have shown it, so the emission lists, concatenated in band
+// order, ARE the reference's emission order. Stage 1 (remaining merges) repeats the procedure on top of the final stage-0 mask.
 // ---------------------------------------------------------------------------------------------
 
 #define LIMG_MERGE_THREADS 1024
 #define LIMG_MERGE_WARPS (LIMG_MERGE_THREADS / 32)
+#define LIMG_MERGE_MAX_BANDS 128
+#define LIMG_REGION_MAX 32
 
 struct MergeMailbox
 {
-  int kind; // 0 quit, 1 evaluate strip
+  int kind; // 0 quit, 1 evaluate strip (AND of predicates), 2 evaluate region bitmap
   int seed;
   int x0, y0, w, h;
   int result;
+  uint32_t regionBits[LIMG_REGION_MAX]; // kind 2: bit (row, col) = block unused-or-unknown AND matches
 };
 
 __device__ __forceinline__ void named_bar_sync(int id, int count)
@@ -256,23 +268,65 @@ struct MergeArgs
   const PredRec *rec;
   const uint32_t *window;
   int BX, BY, wordsPerRow;
+  int bandRows, numBands, listCap;
+  uint2 *lists;          // [numBands][2][listCap]: (ox | oy << 16, rx | ry << 16)
+  uint32_t *counts;      // [numBands][2]
+  uint32_t *snapshot;    // [numBands][BY * wordsPerRow]: input mask of the band's last run
+  uint32_t *sync;        // [0] barrier count, [1] barrier generation, [2] error flag, [8 + stage * (MAX_BANDS + 2) + iter] dirty flags
   limgcu_area *areas;
   uint32_t *mergedCount; // number of stage 0 + stage 1 areas
-  uint32_t *usedOut;     // BY * wordsPerRow words: in-use mask after both merge stages
-  uint32_t *stats;       // [8] optional counters
+  uint32_t *usedOut;     // BY * wordsPerRow words: in-use mask after both merge stages (zeroed by the host)
+  uint32_t *stats;       // [8] optional counters: iterations stage 0 / 1, band runs stage 0 / 1
 };
+
+__device__ __forceinline__ void grid_barrier(uint32_t *sync, uint32_t numBlocks)
+{
+  __syncthreads();
+
+  if (threadIdx.x == 0)
+  {
+    volatile uint32_t *gen = sync + 1;
+    const uint32_t g = *gen;
+    __threadfence();
+
+    if (atomicAdd(sync, 1u) == numBlocks - 1)
+    {
+      sync[0] = 0;
+      __threadfence();
+      *gen = g + 1;
+    }
+    else
+    {
+      while (*gen == g) { }
+    }
+
+    __threadfence();
+  }
+
+  __syncthreads();
+}
 
 template <int CH>
 struct MergeScan
 {
   const MergeArgs &a;
-  uint32_t *used;       // shared: BY rows of wordsPerRow words (+1 pad word per row inside wordsPerRow)
+  uint32_t *used;          // shared: BY rows of wordsPerRow words
+  const uint32_t *winBand; // shared: window words of the band's rows
   MergeMailbox *mail;
   int lane;
+  int bandY0, bandY1;
+  int readLo, readHi;      // rows whose in-use bits this run consulted
+  unsigned long long tSearch = 0, tGrow = 0, tPost = 0, tFour = 0;
+  uint32_t nSeeds = 0, nPost1 = 0, nPost2 = 0, nFour = 0;
+
+  __device__ __forceinline__ void touch_rows(int lo, int hi)
+  {
+    readLo = min(readLo, max(lo, 0));
+    readHi = max(readHi, min(hi, a.BY - 1));
+  }
 
   __device__ __forceinline__ uint32_t used_bits8(int x, int y) const
   {
-    // 8 in-use bits of row y starting at column x; rows outside the grid read as in use.
     if (y >= a.BY)
       return 0xFFu;
 
@@ -286,10 +340,16 @@ struct MergeScan
     return (used[(size_t)y * a.wordsPerRow + (x >> 5)] >> (x & 31)) & 1u;
   }
 
-  // all blocks of the strip unused? (warp cooperative, uniform result)
-  __device__ bool strip_unused(int x0, int y0, int w, int h) const
+  __device__ __forceinline__ uint64_t match_word(int x, int y) const
+  {
+    const uint32_t *wp = winBand + (size_t)((y - bandY0) * a.BX + x) * 2;
+    return (uint64_t)wp[0] | ((uint64_t)wp[1] << 32);
+  }
+
+  __device__ bool strip_unused(int x0, int y0, int w, int h)
   {
     bool any = false;
+    touch_rows(y0, y0 + h - 1);
 
     for (int e = lane; e < w * h; e += 32)
     {
@@ -300,39 +360,64 @@ struct MergeScan
     return !__any_sync(0xFFFFFFFFu, any);
   }
 
-  // all blocks of the strip match the seed? evaluated by every warp of the CTA (one predicate per warp at a time).
-  __device__ bool strip_matches(int seed, int x0, int y0, int w, int h)
+  __device__ void post(int kind, int seed, int x0, int y0, int w, int h)
   {
     if (lane == 0)
     {
-      mail->kind = 1;
+      mail->kind = kind;
       mail->seed = seed;
       mail->x0 = x0; mail->y0 = y0; mail->w = w; mail->h = h;
       mail->result = 1;
     }
 
+    if (kind == 2 && lane < LIMG_REGION_MAX)
+      mail->regionBits[lane] = 0;
+
+    const long long t0 = clock64();
     __syncwarp();
     named_bar_sync(1, LIMG_MERGE_THREADS);
-    evaluate_strip(a, mail, 0);
+    serve(a, mail, used, 0);
     named_bar_sync(2, LIMG_MERGE_THREADS);
-    return mail->result != 0;
+    tPost += clock64() - t0;
+    if (kind == 1) nPost1++; else nPost2++;
   }
 
-  static __device__ void evaluate_strip(const MergeArgs &a, MergeMailbox *mail, int warp)
+  // executed by every warp of the CTA for the posted request
+  static __device__ void serve(const MergeArgs &a, MergeMailbox *mail, const uint32_t *used, int warp)
   {
     const int count = mail->w * mail->h;
+    const int w = mail->w;
+    const int kind = mail->kind;
     const PredRec seed = a.rec[mail->seed];
 
     for (int e = warp; e < count; e += LIMG_MERGE_WARPS)
     {
-      if (*(volatile int *)&mail->result == 0)
-        break;
+      const int ry = e / w, rx = e - ry * w;
+      const int yy = mail->y0 + ry, xx = mail->x0 + rx;
 
-      const int yy = mail->y0 + e / mail->w, xx = mail->x0 + e % mail->w;
+      if (kind == 1)
+      {
+        if (*(volatile int *)&mail->result == 0)
+          break;
 
-      if (!predicate_warp<CH>(seed, a.rec[(size_t)yy * a.BX + xx]) && (threadIdx.x & 31) == 0)
-        atomicAnd(&mail->result, 0);
+        if (!predicate_warp<CH>(seed, a.rec[(size_t)yy * a.BX + xx]) && (threadIdx.x & 31) == 0)
+          atomicAnd(&mail->result, 0);
+      }
+      else
+      {
+        // region bitmap: blocks already in use can never join, skip their predicate
+        const bool inUse = (used[(size_t)yy * a.wordsPerRow + (xx >> 5)] >> (xx & 31)) & 1u;
+
+        if (!inUse && predicate_warp<CH>(seed, a.rec[(size_t)yy * a.BX + xx]) && (threadIdx.x & 31) == 0)
+          atomicOr(&mail->regionBits[ry], 1u << rx);
+      }
     }
+  }
+
+  __device__ bool strip_matches(int seed, int x0, int y0, int w, int h)
+  {
+    post(1, seed, x0, y0, w, h);
+    return mail->result != 0;
   }
 
   __device__ bool strip_joins(int seed, int x0, int y0, int w, int h)
@@ -340,32 +425,64 @@ struct MergeScan
     return strip_unused(x0, y0, w, h) && strip_matches(seed, x0, y0, w, h);
   }
 
-  // generic alternating growth with on-demand predicates (limg.cpp:1294-1388); the seed is the rectangle's top-left block.
-  __device__ void grow_generic(int &ox, int &oy, int &rx, int &ry, bool right, bool down, bool fourWay)
+  // region cache of the four-way regrowth: one parallel request evaluates every predicate of the neighbourhood at once
+  int rgX, rgY, rgW, rgH;
+
+  __device__ bool strip_joins_cached(int seed, int x0, int y0, int w, int h)
+  {
+    if (x0 >= rgX && y0 >= rgY && x0 + w <= rgX + rgW && y0 + h <= rgY + rgH)
+    {
+      if (!strip_unused(x0, y0, w, h))
+        return false;
+
+      bool ok = true;
+
+      if (lane < h)
+      {
+        const uint32_t m = (w >= 32 ? 0xFFFFFFFFu : ((1u << w) - 1u)) << (x0 - rgX);
+        ok = (mail->regionBits[y0 - rgY + lane] & m) == m;
+      }
+
+      return __all_sync(0xFFFFFFFFu, ok);
+    }
+
+    return strip_joins(seed, x0, y0, w, h);
+  }
+
+  // four-way alternating growth (limg.cpp:1294-1388); the seed is the rectangle's top-left block at entry.
+  __device__ void grow_four_way(int &ox, int &oy, int &rx, int &ry, int hintX, int hintY, int hintW, int hintH)
   {
     const int seed = oy * a.BX + ox;
-    bool up = fourWay, left = fourWay;
+    // neighbourhood request: the right/down rectangle the centre came from, plus a margin, clipped to 32 x 32
+    rgX = max(hintX - 3, 0);
+    rgY = max(hintY - 3, 0);
+    rgW = min(min(hintW + 6, LIMG_REGION_MAX), a.BX - rgX);
+    rgH = min(min(hintH + 6, LIMG_REGION_MAX), a.BY - rgY);
+    touch_rows(rgY, rgY + rgH - 1);
+    post(2, seed, rgX, rgY, rgW, rgH);
+
+    bool right = true, down = true, up = true, left = true;
 
     while (right || down || up || left)
     {
       if (right)
       {
-        if (ox + rx + 1 < a.BX && strip_joins(seed, ox + rx, oy, 1, ry)) rx++; else right = false;
+        if (ox + rx + 1 < a.BX && strip_joins_cached(seed, ox + rx, oy, 1, ry)) rx++; else right = false;
       }
 
       if (down)
       {
-        if (oy + ry + 1 < a.BY && strip_joins(seed, ox, oy + ry, rx, 1)) ry++; else down = false;
+        if (oy + ry + 1 < a.BY && strip_joins_cached(seed, ox, oy + ry, rx, 1)) ry++; else down = false;
       }
 
       if (up)
       {
-        if (oy > 0 && strip_joins(seed, ox, oy - 1, rx, 1)) { oy--; ry++; } else up = false;
+        if (oy > 0 && strip_joins_cached(seed, ox, oy - 1, rx, 1)) { oy--; ry++; } else up = false;
       }
 
       if (left)
       {
-        if (ox > 0 && strip_joins(seed, ox - 1, oy, 1, ry)) { ox--; rx++; } else left = false;
+        if (ox > 0 && strip_joins_cached(seed, ox - 1, oy, 1, ry)) { ox--; rx++; } else left = false;
       }
     }
   }
@@ -373,10 +490,7 @@ struct MergeScan
   // right/down growth of a 1x1 seed: bit arithmetic inside the 8x8 window, on-demand strips beyond it.
   __device__ void grow_seed(int x, int y, int &rx, int &ry)
   {
-    const uint32_t *wp = a.window + (size_t)(y * a.BX + x) * 2;
-    const uint64_t match = (uint64_t)wp[0] | ((uint64_t)wp[1] << 32);
-
-    // in-use window: lane r < 8 fetches row y + r
+    const uint64_t match = match_word(x, y);
     uint32_t rowBits = lane < 8 ? used_bits8(x, y + lane) : 0u;
     uint32_t lo = 0, hi = 0;
 
@@ -403,7 +517,6 @@ struct MergeScan
         {
           if (rx < 8)
           {
-            // column rx, rows [0, min(ry, 8)) from the window, rows beyond on demand
             const int rows = min(ry, 8);
             const uint64_t mask = (0x0101010101010101ull << rx) & (rows >= 8 ? ~0ull : ((1ull << (8 * rows)) - 1));
             ok = (avail & mask) == mask;
@@ -444,6 +557,8 @@ struct MergeScan
         if (ok) ry++; else down = false;
       }
     }
+
+    touch_rows(y, y + min(ry, 7)); // window rows consulted: up to the failing row (deeper rows go through strip_unused)
   }
 
   __device__ void mark_used(int ox, int oy, int rx, int ry)
@@ -465,18 +580,20 @@ struct MergeScan
     __syncwarp();
   }
 
-  // stage 0: large merges (>= 3x3, centre-third retry); stage 1: anything larger than 1x1.
-  __device__ uint32_t run_stage(int stage, uint32_t count)
+  // one stage over the band's rows. stage 0: large merges (>= 3x3, centre-third retry); stage 1: anything larger than 1x1.
+  __device__ uint32_t run_band(int stage, uint2 *list)
   {
-    uint32_t seeds = 0, centreTries = 0, centreHits = 0;
+    uint32_t count = 0;
+    touch_rows(bandY0, bandY1 - 1); // the candidate search reads the in-use bits of every row of the band
 
-    for (int y = 0; y < a.BY; y++)
+    for (int y = bandY0; y < bandY1; y++)
     {
       int x = 0;
 
       while (x < a.BX)
       {
-        // next candidate seed in this row at column >= x: unused and passing the stage's necessary condition on the match word
+        // next candidate seed of this row at column >= x: unused and passing the stage's necessary condition on its match word
+        const long long ts0 = clock64();
         {
           int found = -1;
 
@@ -487,7 +604,7 @@ struct MergeScan
 
             if (xx >= x && xx < a.BX && !is_used(xx, y))
             {
-              const uint32_t w0 = a.window[(size_t)(y * a.BX + xx) * 2];
+              const uint32_t w0 = winBand[(size_t)((y - bandY0) * a.BX + xx) * 2];
               cand = stage == 0 ? ((w0 & 0x070707u) == 0x070707u) : ((w0 & 0x0102u) != 0);
             }
 
@@ -497,15 +614,19 @@ struct MergeScan
               found = base + __ffs(ballot) - 1;
           }
 
+          tSearch += clock64() - ts0;
+
           if (found < 0)
             break;
 
           x = found;
         }
 
-        seeds++;
         int rx, ry;
+        nSeeds++;
+        const long long tg0 = clock64();
         grow_seed(x, y, rx, ry);
+        tGrow += clock64() - tg0;
 
         int eox = x, eoy = y, erx = rx, ery = ry;
         bool take = false, rescan = false;
@@ -515,14 +636,15 @@ struct MergeScan
           if (rx >= 3 && ry >= 3) // Q4
           {
             int cox = x + rx / 3, coy = y + ry / 3, crx = rx / 3, cry = ry / 3;
-            grow_generic(cox, coy, crx, cry, true, true, true);
-            centreTries++;
+            const long long tf0 = clock64();
+            grow_four_way(cox, coy, crx, cry, x, y, rx, ry);
+            tFour += clock64() - tf0;
+            nFour++;
 
             if (crx * cry > rx * ry)
             {
               eox = cox; eoy = coy; erx = crx; ery = cry;
               rescan = true;
-              centreHits++;
             }
 
             take = true;
@@ -543,9 +665,10 @@ struct MergeScan
 
         if (lane == 0)
         {
-          limgcu_area *out = &a.areas[count];
-          out->ox = eox; out->oy = eoy; out->rx = erx; out->ry = ery;
-          out->stage = stage;
+          if (count < (uint32_t)a.listCap)
+            list[count] = make_uint2((uint32_t)eox | ((uint32_t)eoy << 16), (uint32_t)erx | ((uint32_t)ery << 16));
+          else
+            a.sync[2] = 1; // list overflow: reported by the host as LIMGCU_ERROR_OUT_OF_BOUNDS
         }
 
         count++;
@@ -557,64 +680,215 @@ struct MergeScan
 
     if (lane == 0 && a.stats)
     {
-      a.stats[stage * 3 + 0] = seeds;
-      a.stats[stage * 3 + 1] = centreTries;
-      a.stats[stage * 3 + 2] = centreHits;
+      atomicAdd(&a.stats[4], nSeeds); atomicAdd(&a.stats[5], nPost1); atomicAdd(&a.stats[6], nPost2); atomicAdd(&a.stats[7], nFour);
+      atomicAdd(&a.stats[8], (uint32_t)(tSearch >> 10)); atomicAdd(&a.stats[9], (uint32_t)(tGrow >> 10)); atomicAdd(&a.stats[10], (uint32_t)(tPost >> 10)); atomicAdd(&a.stats[11], (uint32_t)(tFour >> 10));
     }
 
-    return count;
+    return min(count, (uint32_t)a.listCap);
   }
 };
 
+__device__ __forceinline__ void or_rect(uint32_t *mask, int wordsPerRow, uint2 r, bool atomic)
+{
+  const int ox = r.x & 0xFFFF, oy = r.x >> 16, rx = r.y & 0xFFFF, ry = r.y >> 16;
+
+  for (int row = 0; row < ry; row++)
+  {
+    uint32_t *m = mask + (size_t)(oy + row) * wordsPerRow;
+
+    for (int xx = ox; xx < ox + rx;)
+    {
+      const int w0 = xx >> 5, b0 = xx & 31;
+      const int cnt = min(32 - b0, ox + rx - xx);
+      const uint32_t bits = (cnt == 32 ? 0xFFFFFFFFu : ((1u << cnt) - 1u)) << b0;
+      atomicOr(&m[w0], bits);
+      xx += cnt;
+    }
+  }
+
+  (void)atomic;
+}
+
 template <int CH>
-__global__ void __launch_bounds__(LIMG_MERGE_THREADS) k_merge_scan(MergeArgs a)
+__global__ void __launch_bounds__(LIMG_MERGE_THREADS) k_merge_banded(MergeArgs a)
 {
   extern __shared__ __align__(16) unsigned char dynSmem[];
   uint32_t *used = reinterpret_cast<uint32_t *>(dynSmem);
+  const int maskWords = a.BY * a.wordsPerRow;
+  uint32_t *winBand = used + maskWords;
   __shared__ MergeMailbox mail;
+  __shared__ int sDirty;
+  __shared__ int sRange[2];
+  __shared__ uint32_t sCount;
 
-  const int total = a.BY * a.wordsPerRow;
+  const int k = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int bandY0 = k * a.bandRows, bandY1 = min(a.BY, bandY0 + a.bandRows);
+  uint32_t *snapshot = a.snapshot + (size_t)k * maskWords;
 
-  for (int i = threadIdx.x; i < total; i += blockDim.x)
-    used[i] = 0;
+  // the band's match words never change: shared memory
+  for (int i = threadIdx.x; i < (bandY1 - bandY0) * a.BX * 2; i += blockDim.x)
+    winBand[i] = a.window[(size_t)bandY0 * a.BX * 2 + i];
 
-  __syncthreads();
-
-  const int warp = threadIdx.x >> 5;
-
-  if (warp == 0)
+  for (int stage = 0; stage < 2; stage++)
   {
-    MergeScan<CH> scan{ a, used, &mail, (int)(threadIdx.x & 31) };
-    uint32_t count = scan.run_stage(0, 0);
-    count = scan.run_stage(1, count);
+    bool ran = false;
+    int readLo = a.BY, readHi = -1;
+    uint2 *myList = a.lists + ((size_t)k * 2 + stage) * a.listCap;
+    uint32_t *dirtyFlags = a.sync + 8 + stage * (LIMG_MERGE_MAX_BANDS + 2);
 
-    if (scan.lane == 0)
+    for (int iter = 0; iter <= a.numBands; iter++)
     {
-      *a.mergedCount = count;
-      mail.kind = 0;
-    }
+      // ---- phase A: input mask = rectangles of every band above (this stage) [+ all of stage 0 when in stage 1]
+      for (int i = threadIdx.x; i < maskWords; i += blockDim.x)
+        used[i] = 0;
 
-    __syncwarp();
-    named_bar_sync(1, LIMG_MERGE_THREADS); // release the helpers
-  }
-  else
-  {
-    while (true)
-    {
-      named_bar_sync(1, LIMG_MERGE_THREADS);
+      __syncthreads();
 
-      if (mail.kind == 0)
+      if (stage == 1)
+      {
+        for (int j = 0; j < a.numBands; j++)
+        {
+          const uint32_t n = a.counts[j * 2 + 0];
+          const uint2 *l = a.lists + ((size_t)j * 2 + 0) * a.listCap;
+
+          for (uint32_t i = threadIdx.x; i < n; i += blockDim.x)
+            or_rect(used, a.wordsPerRow, l[i], true);
+        }
+      }
+
+      for (int j = 0; j < k; j++)
+      {
+        const uint32_t n = a.counts[j * 2 + stage];
+        const uint2 *l = a.lists + ((size_t)j * 2 + stage) * a.listCap;
+
+        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x)
+          or_rect(used, a.wordsPerRow, l[i], true);
+      }
+
+      if (threadIdx.x == 0)
+        sDirty = ran ? 0 : 1;
+
+      __syncthreads();
+
+      if (ran && readHi >= readLo)
+      {
+        bool diff = false;
+
+        for (int i = readLo * a.wordsPerRow + threadIdx.x; i < (readHi + 1) * a.wordsPerRow; i += blockDim.x)
+          diff |= used[i] != snapshot[i];
+
+        if (diff)
+          sDirty = 1;
+      }
+
+      __syncthreads();
+      const bool dirty = sDirty != 0;
+
+      if (dirty)
+      {
+        for (int i = threadIdx.x; i < maskWords; i += blockDim.x)
+          snapshot[i] = used[i];
+      }
+
+      grid_barrier(a.sync, gridDim.x); // every band has read the lists of the previous iteration
+
+      // ---- phase B: dirty bands replay their rows
+      if (dirty)
+      {
+        if (warp == 0)
+        {
+          MergeScan<CH> scan{ a, used, winBand, &mail, lane, bandY0, bandY1, a.BY, -1 };
+          const uint32_t count = scan.run_band(stage, myList);
+
+          if (lane == 0)
+          {
+            sCount = count;
+            sRange[0] = scan.readLo;
+            sRange[1] = scan.readHi;
+            mail.kind = 0;
+            dirtyFlags[iter] = 1;
+
+            if (a.stats)
+              atomicAdd(&a.stats[2 + stage], 1u);
+          }
+
+          __syncwarp();
+          named_bar_sync(1, LIMG_MERGE_THREADS); // release the helpers
+        }
+        else
+        {
+          while (true)
+          {
+            named_bar_sync(1, LIMG_MERGE_THREADS);
+
+            if (mail.kind == 0)
+              break;
+
+            MergeScan<CH>::serve(a, &mail, used, warp);
+            named_bar_sync(2, LIMG_MERGE_THREADS);
+          }
+        }
+
+        __syncthreads();
+        ran = true;
+        readLo = sRange[0];
+        readHi = sRange[1];
+
+        if (threadIdx.x == 0)
+        {
+          a.counts[k * 2 + stage] = sCount;
+          __threadfence();
+        }
+      }
+
+      grid_barrier(a.sync, gridDim.x); // lists of this iteration are complete
+
+      if (*(volatile uint32_t *)&dirtyFlags[iter] == 0)
+      {
+        if (k == 0 && threadIdx.x == 0 && a.stats)
+          a.stats[stage] = iter;
+
         break;
-
-      MergeScan<CH>::evaluate_strip(a, &mail, warp);
-      named_bar_sync(2, LIMG_MERGE_THREADS);
+      }
     }
   }
 
-  __syncthreads();
+  // ---- emission order = band order, stage 0 then stage 1; in-use mask for the leftover pass
+  uint32_t before0 = 0, before1 = 0, total0 = 0, total1 = 0;
 
-  for (int i = threadIdx.x; i < total; i += blockDim.x)
-    a.usedOut[i] = used[i];
+  for (int j = 0; j < a.numBands; j++)
+  {
+    const uint32_t c0 = a.counts[j * 2 + 0], c1 = a.counts[j * 2 + 1];
+
+    if (j < k)
+    {
+      before0 += c0;
+      before1 += c1;
+    }
+
+    total0 += c0;
+    total1 += c1;
+  }
+
+  for (int stage = 0; stage < 2; stage++)
+  {
+    const uint32_t n = a.counts[k * 2 + stage];
+    const uint2 *l = a.lists + ((size_t)k * 2 + stage) * a.listCap;
+    const uint32_t base = stage == 0 ? before0 : total0 + before1;
+
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x)
+    {
+      const uint2 r = l[i];
+      limgcu_area *out = &a.areas[base + i];
+      out->ox = r.x & 0xFFFF; out->oy = r.x >> 16; out->rx = r.y & 0xFFFF; out->ry = r.y >> 16;
+      out->stage = stage;
+      or_rect(a.usedOut, a.wordsPerRow, r, true);
+    }
+  }
+
+  if (k == 0 && threadIdx.x == 0)
+    *a.mergedCount = total0 + total1;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -37,6 +37,10 @@ struct limgcu_ctx
   uint32_t *dSmallList = nullptr, *dLargeList = nullptr;
   uint64_t *dDemand = nullptr;
   uint32_t *dUsed = nullptr;
+  uint2 *dBandLists = nullptr;
+  uint32_t *dBandSnapshot = nullptr;
+  uint32_t *dBandState = nullptr; // [0..8 + 2 * (MAX_BANDS + 2)) barrier + flags, then counts [MAX_BANDS * 2]
+  size_t capBandLists = 0, capBandSnapshot = 0;
   uint32_t *dScratchPx = nullptr, *dScratchFac = nullptr;
   uint32_t *dCounters = nullptr; // [16]: 0 merged, 1 areaCount, 2 smallCount, 3 largeCount, 4 workSmall, 5 workLarge, 8.. stats
   unsigned long long *dCompare = nullptr;
@@ -101,6 +105,28 @@ static int ensure_capacity(limgcu_ctx *ctx, size_t W, size_t H)
   {
     CK(regrow(ctx->dUsed, usedWords));
     ctx->capUsedWords = usedWords;
+  }
+
+  {
+    const size_t bandRows = BY / 128 + 1 > 8 ? BY / 128 + 1 : 8;
+    const size_t numBands = (BY + bandRows - 1) / bandRows;
+    const size_t listCap = bandRows * BX * 2;
+    const size_t lists = numBands * 2 * listCap, snap = numBands * usedWords;
+
+    if (lists > ctx->capBandLists)
+    {
+      CK(regrow(ctx->dBandLists, lists));
+      ctx->capBandLists = lists;
+    }
+
+    if (snap > ctx->capBandSnapshot)
+    {
+      CK(regrow(ctx->dBandSnapshot, snap));
+      ctx->capBandSnapshot = snap;
+    }
+
+    if (ctx->dBandState == nullptr)
+      CK(regrow(ctx->dBandState, (size_t)1024));
   }
 
   if (pixels > ctx->capPixels)
@@ -192,8 +218,8 @@ extern "C" int limgcu_create(int device, limgcu_ctx **out)
 
   cudaFuncSetAttribute(k_encode_large<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 + LIMG_CTA_STAGE_PX * 16 + 2 * LIMG_CTA_AREA_CAP * 4);
   cudaFuncSetAttribute(k_encode_large<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 + LIMG_CTA_STAGE_PX * 16 + 2 * LIMG_CTA_AREA_CAP * 4);
-  cudaFuncSetAttribute(k_merge_scan<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-  cudaFuncSetAttribute(k_merge_scan<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(k_merge_banded<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(k_merge_banded<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
 
   *out = ctx;
   return LIMGCU_SUCCESS;
@@ -210,7 +236,7 @@ extern "C" void limgcu_destroy(limgcu_ctx *ctx)
     cudaStreamSynchronize(ctx->stream);
 
   void *ptrs[] = { ctx->dLut, ctx->dTable, ctx->dRec, ctx->dWindow, ctx->dAreas, ctx->dBlockToArea, ctx->dWork, ctx->dSmallList, ctx->dLargeList, ctx->dDemand,
-                   ctx->dUsed, ctx->dScratchPx, ctx->dScratchFac, ctx->dCounters, ctx->dCompare, ctx->dSrc };
+                   ctx->dUsed, ctx->dScratchPx, ctx->dScratchFac, ctx->dCounters, ctx->dCompare, ctx->dSrc, ctx->dBandLists, ctx->dBandSnapshot, ctx->dBandState };
 
   for (void *p : ptrs)
     if (p) cudaFree(p);
@@ -228,6 +254,14 @@ extern "C" void limgcu_destroy(limgcu_ctx *ctx)
 extern "C" const char *limgcu_last_error(const limgcu_ctx *ctx) { return ctx ? ctx->err : "null context"; }
 extern "C" void *limgcu_stream_handle(limgcu_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
 extern "C" uint64_t limgcu_launch_count(const limgcu_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" int limgcu_debug_counters(limgcu_ctx *ctx, uint32_t *out32)
+{
+  NEED(ctx); NEED(out32);
+  CK(cudaMemcpyAsync(out32, ctx->dCounters, 32 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return LIMGCU_SUCCESS;
+}
 
 extern "C" int limgcu_sync(limgcu_ctx *ctx)
 {
@@ -308,10 +342,13 @@ static int launch_merge(limgcu_ctx *ctx, const limgcu_decomp *dTable, size_t W, 
 
   if (!noMerge)
   {
+    const int bandRows = BY / 128 + 1 > 8 ? BY / 128 + 1 : 8;
+    const int numBands = (BY + bandRows - 1) / bandRows;
     const size_t usedBytes = (size_t)BY * wordsPerRow * sizeof(uint32_t);
+    const size_t smemBytes = usedBytes + (size_t)bandRows * BX * 2 * sizeof(uint32_t);
 
-    if (usedBytes > 200 * 1024)
-      return fail(ctx, LIMGCU_ERROR_OUT_OF_BOUNDS, "image too large for the shared-memory in-use mask of the merge scan", cudaSuccess);
+    if (smemBytes > 200 * 1024 || numBands > LIMG_MERGE_MAX_BANDS || numBands > ctx->smCount || BX > 65535 || BY > 65535)
+      return fail(ctx, LIMGCU_ERROR_OUT_OF_BOUNDS, "image too large for the shared-memory in-use mask of the banded merge", cudaSuccess);
 
     if (hasAlpha)
     {
@@ -330,16 +367,23 @@ static int launch_merge(limgcu_ctx *ctx, const limgcu_decomp *dTable, size_t W, 
 
     if (ctx->timing) CK(cudaEventRecord(ctx->ev[PHASE_SCAN], ctx->stream));
 
+    CK(cudaMemsetAsync(ctx->dBandState, 0, 1024 * sizeof(uint32_t), ctx->stream));
+    CK(cudaMemsetAsync(ctx->dUsed, 0, usedBytes, ctx->stream));
+
     MergeArgs m;
     m.rec = ctx->dRec; m.window = ctx->dWindow; m.BX = BX; m.BY = BY; m.wordsPerRow = wordsPerRow;
+    m.bandRows = bandRows; m.numBands = numBands; m.listCap = bandRows * BX * 2;
+    m.lists = ctx->dBandLists; m.counts = ctx->dBandState + 512; m.snapshot = ctx->dBandSnapshot; m.sync = ctx->dBandState;
     m.areas = dAreas; m.mergedCount = ctx->dCounters + 0; m.usedOut = ctx->dUsed; m.stats = ctx->dCounters + 8;
+    void *kargs[] = { &m };
 
+    // cooperative launch: every band CTA must be resident, the bands synchronise through a grid barrier
     if (hasAlpha)
-      k_merge_scan<4><<<1, LIMG_MERGE_THREADS, usedBytes, ctx->stream>>>(m);
+      CK(cudaLaunchCooperativeKernel((const void *)k_merge_banded<4>, dim3(numBands), dim3(LIMG_MERGE_THREADS), kargs, smemBytes, ctx->stream));
     else
-      k_merge_scan<3><<<1, LIMG_MERGE_THREADS, usedBytes, ctx->stream>>>(m);
+      CK(cudaLaunchCooperativeKernel((const void *)k_merge_banded<3>, dim3(numBands), dim3(LIMG_MERGE_THREADS), kargs, smemBytes, ctx->stream));
 
-    CKL("k_merge_scan");
+    CKL("k_merge_banded");
   }
   else if (ctx->timing)
   {
