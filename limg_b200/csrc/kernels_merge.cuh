@@ -232,6 +232,281 @@ __global__ void __launch_bounds__(256) k_pred_window(const PredRec *__restrict__
     window[(size_t)seed * 2 + half] = bits;
 }
 
+// Symmetric match window of every block c: bit (r, col) of its 16 x 16 bitmap = predicate(seed = c, candidate = c + (col - 8, r - 8)),
+// 0 outside the grid. It is what the four-way centre-third regrowth (limg.cpp:1426-1433) asks for: the centre seed sits inside
+// the right/down rectangle it came from, so the regrowth explores a neighbourhood on all four sides. The lower-right quadrant is
+// the 8 x 8 match word. Stored as 8 words per block (two 16-bit rows per word).
+template <int CH>
+__global__ void __launch_bounds__(256) k_pred_symwindow(const PredRec *__restrict__ rec, const uint32_t *__restrict__ window, int BX, int BY, uint32_t *__restrict__ sym)
+{
+  const int c = blockIdx.x;
+  const int cy = c / BX, cx = c - cy * BX;
+  const int r = threadIdx.x >> 4, col = threadIdx.x & 15;
+  const int dx = col - 8, dy = r - 8;
+  bool m = false;
+
+  if (dx >= 0 && dy >= 0)
+  {
+    const uint32_t w = window[(size_t)c * 2 + (dy >> 2)];
+    m = (w >> (8 * (dy & 3) + dx)) & 1u;
+  }
+  else if (cx + dx >= 0 && cx + dx < BX && cy + dy >= 0 && cy + dy < BY)
+  {
+    m = predicate_thread<CH>(rec[c], rec[(size_t)(cy + dy) * BX + cx + dx]);
+  }
+
+  const uint32_t b = __ballot_sync(0xFFFFFFFFu, m);
+
+  if ((threadIdx.x & 31) == 0)
+    sym[(size_t)c * 8 + (threadIdx.x >> 5)] = b;
+}
+
+// ---------------------------------------------------------------------------------------------
+// speculative windows: everything the scan is likely to ask for is evaluated up front, in parallel on the whole GPU.
+//   - seeds whose mask-free right/down growth leaves the 8x8 window get a 16x16 and, if that is left too, a 32x32 match bitmap;
+//   - seeds whose mask-free growth reaches 3x3 get the match bitmap of their centre-third seed over the neighbourhood the
+//     four-way regrowth explores (limg.cpp:1426-1433), keyed by the (rx, ry) the prediction assumed.
+// The scan uses a bitmap only when its assumptions hold and falls back to on-demand evaluation otherwise, so the bitmaps are a
+// pure accelerator: they never change the result.
+// ---------------------------------------------------------------------------------------------
+
+#define LIMG_NO_SLOT 0xFFFFFFFFu
+
+struct PlanArgs
+{
+  const PredRec *rec;
+  const uint32_t *window;
+  int BX, BY;
+  uint32_t *extSlot;   // per block: LIMG_NO_SLOT or slot | (size 32 ? 1u << 31 : 0)
+  uint32_t *extSeed;   // per slot: block index
+  uint32_t *extBits;   // per slot: 32 row words
+  uint32_t *ctrSlot;   // per block: LIMG_NO_SLOT or slot
+  uint4 *ctrHdr;       // per slot: x = rx0 | ry0 << 16 (assumed growth), y = rgX | rgY << 16, z = rgW | rgH << 16, w = centre block index
+  uint32_t *ctrBits;   // per slot: 32 row words
+  uint32_t *counters;  // [0] ext slots, [1] centre slots
+  uint32_t extCap, ctrCap;
+};
+
+// mask-free alternating right/down growth over `rows` (S x S match bitmap of the seed); returns true if it wanted to leave the bitmap
+__device__ __forceinline__ bool expand_unmasked(const uint32_t *rows, int S, int x, int y, int BX, int BY, int &rx, int &ry)
+{
+  bool right = true, down = true, hit = false;
+  rx = 1;
+  ry = 1;
+
+  while (right || down)
+  {
+    if (right)
+    {
+      bool ok = x + rx + 1 < BX;
+
+      if (ok && rx >= S) { hit = true; ok = false; }
+
+      if (ok)
+        for (int r = 0; r < ry; r++)
+          ok &= (rows[r] >> rx) & 1u;
+
+      if (ok) rx++; else right = false;
+    }
+
+    if (down)
+    {
+      bool ok = y + ry + 1 < BY;
+
+      if (ok && ry >= S) { hit = true; ok = false; }
+
+      if (ok)
+      {
+        const uint32_t m = rx >= 32 ? 0xFFFFFFFFu : ((1u << rx) - 1u);
+        ok = (rows[ry] & m) == m;
+      }
+
+      if (ok) ry++; else down = false;
+    }
+  }
+
+  return hit;
+}
+
+__device__ __forceinline__ void plan_centre(const PlanArgs &a, int seed, int x, int y, int rx, int ry)
+{
+  if (rx < 3 || ry < 3)
+    return;
+
+  const uint32_t slot = atomicAdd(&a.counters[1], 1u);
+
+  if (slot >= a.ctrCap)
+    return;
+
+  const int rgX = max(x - 3, 0), rgY = max(y - 3, 0);
+  const int rgW = min(min(rx + 6, 32), a.BX - rgX), rgH = min(min(ry + 6, 32), a.BY - rgY);
+  const int centre = (y + ry / 3) * a.BX + x + rx / 3;
+  a.ctrHdr[slot] = make_uint4((uint32_t)rx | ((uint32_t)ry << 16), (uint32_t)rgX | ((uint32_t)rgY << 16), (uint32_t)rgW | ((uint32_t)rgH << 16), (uint32_t)centre);
+  a.ctrSlot[seed] = slot;
+}
+
+__global__ void __launch_bounds__(256) k_plan_seeds(PlanArgs a)
+{
+  const int seed = blockIdx.x * blockDim.x + threadIdx.x;
+
+  if (seed >= a.BX * a.BY)
+    return;
+
+  const int y = seed / a.BX, x = seed - y * a.BX;
+  const uint32_t w0 = a.window[(size_t)seed * 2], w1 = a.window[(size_t)seed * 2 + 1];
+  uint32_t rows[8];
+
+#pragma unroll
+  for (int r = 0; r < 4; r++)
+  {
+    rows[r] = (w0 >> (8 * r)) & 0xFF;
+    rows[r + 4] = (w1 >> (8 * r)) & 0xFF;
+  }
+
+  int rx, ry;
+  const bool hit = expand_unmasked(rows, 8, x, y, a.BX, a.BY, rx, ry);
+  a.extSlot[seed] = LIMG_NO_SLOT;
+  a.ctrSlot[seed] = LIMG_NO_SLOT;
+
+  if (hit)
+  {
+    const uint32_t slot = atomicAdd(&a.counters[0], 1u);
+
+    if (slot < a.extCap)
+    {
+      a.extSeed[slot] = seed;
+      a.extSlot[seed] = slot;
+    }
+  }
+}
+
+template <int CH>
+__global__ void __launch_bounds__(256) k_plan_extend(PlanArgs a)
+{
+  __shared__ uint32_t rows[32];
+  __shared__ int sHit, sRx, sRy;
+  const uint32_t count = min(a.counters[0], a.extCap);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+  for (uint32_t slot = blockIdx.x; slot < count; slot += gridDim.x)
+  {
+    const int seed = (int)a.extSeed[slot];
+    const int y = seed / a.BX, x = seed - y * a.BX;
+    const PredRec s = a.rec[seed];
+    const uint32_t w0 = a.window[(size_t)seed * 2], w1 = a.window[(size_t)seed * 2 + 1];
+
+    if (threadIdx.x < 32)
+      rows[threadIdx.x] = 0;
+
+    __syncthreads();
+
+    // 16 x 16: thread t -> (dx, dy) = (t & 15, t >> 4); the 8 x 8 corner is known
+    {
+      const int dx = threadIdx.x & 15, dy = threadIdx.x >> 4;
+      bool m = false;
+
+      if (dx < 8 && dy < 8)
+        m = ((dy < 4 ? w0 >> (8 * dy) : w1 >> (8 * (dy - 4))) >> dx) & 1u;
+      else if (x + dx < a.BX && y + dy < a.BY)
+        m = predicate_thread<CH>(s, a.rec[(size_t)(y + dy) * a.BX + x + dx]);
+
+      const uint32_t b = __ballot_sync(0xFFFFFFFFu, m);
+
+      if (lane == 0)
+      {
+        rows[warp * 2] = b & 0xFFFF;
+        rows[warp * 2 + 1] = b >> 16;
+      }
+    }
+
+    __syncthreads();
+
+    if (threadIdx.x == 0)
+    {
+      int rx, ry;
+      sHit = expand_unmasked(rows, 16, x, y, a.BX, a.BY, rx, ry) ? 1 : 0;
+      sRx = rx;
+      sRy = ry;
+    }
+
+    __syncthreads();
+    int size = 16;
+
+    if (sHit)
+    {
+      // 32 x 32: four passes of eight rows; the 16 x 16 corner is known
+      size = 32;
+
+      for (int p = 0; p < 4; p++)
+      {
+        const int dy = p * 8 + warp, dx = lane;
+        bool m = false;
+
+        if (dx < 16 && dy < 16)
+          m = (rows[dy] >> dx) & 1u;
+        else if (x + dx < a.BX && y + dy < a.BY)
+          m = predicate_thread<CH>(s, a.rec[(size_t)(y + dy) * a.BX + x + dx]);
+
+        const uint32_t b = __ballot_sync(0xFFFFFFFFu, m);
+        __syncthreads(); // every read of rows[dy] (dy < 16) of this pass happened
+
+        if (lane == 0)
+          rows[dy] = b;
+
+        __syncthreads();
+      }
+
+      if (threadIdx.x == 0)
+      {
+        int rx, ry;
+        sHit = expand_unmasked(rows, 32, x, y, a.BX, a.BY, rx, ry) ? 1 : 0;
+        sRx = rx;
+        sRy = ry;
+      }
+
+      __syncthreads();
+    }
+
+    if (threadIdx.x < 32)
+      a.extBits[(size_t)slot * 32 + threadIdx.x] = rows[threadIdx.x];
+
+    if (threadIdx.x == 0)
+    {
+      a.extSlot[seed] = slot | (size == 32 ? 0x80000000u : 0u);
+
+    }
+
+    __syncthreads();
+  }
+}
+
+template <int CH>
+__global__ void __launch_bounds__(256) k_plan_centres(PlanArgs a)
+{
+  const uint32_t count = min(a.counters[1], a.ctrCap);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+  for (uint32_t slot = blockIdx.x; slot < count; slot += gridDim.x)
+  {
+    const uint4 h = a.ctrHdr[slot];
+    const int rgX = h.y & 0xFFFF, rgY = h.y >> 16, rgW = h.z & 0xFFFF, rgH = h.z >> 16;
+    const PredRec c = a.rec[h.w];
+
+    for (int row = warp; row < 32; row += 8)
+    {
+      bool m = false;
+
+      if (row < rgH && lane < rgW)
+        m = predicate_thread<CH>(c, a.rec[(size_t)(rgY + row) * a.BX + rgX + lane]);
+
+      const uint32_t b = __ballot_sync(0xFFFFFFFFu, m);
+
+      if (lane == 0)
+        a.ctrBits[(size_t)slot * 32 + row] = b;
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // banded scan
 //
@@ -267,6 +542,8 @@ struct MergeArgs
 {
   const PredRec *rec;
   const uint32_t *window;
+  const uint32_t *extSlot, *extBits, *ctrSlot, *ctrBits, *sym;
+  const uint4 *ctrHdr;
   int BX, BY, wordsPerRow;
   int bandRows, numBands, listCap;
   uint2 *lists;          // [numBands][2][listCap]: (ox | oy << 16, rx | ry << 16)
@@ -312,12 +589,16 @@ struct MergeScan
   const MergeArgs &a;
   uint32_t *used;          // shared: BY rows of wordsPerRow words
   const uint32_t *winBand; // shared: window words of the band's rows
+  const uint32_t *extBand, *ctrBand; // shared: speculative-window slots of the band's seeds
   MergeMailbox *mail;
   int lane;
   int bandY0, bandY1;
   int readLo, readHi;      // rows whose in-use bits this run consulted
   unsigned long long tSearch = 0, tGrow = 0, tPost = 0, tFour = 0;
-  uint32_t nSeeds = 0, nPost1 = 0, nPost2 = 0, nFour = 0;
+  uint32_t nSeeds = 0, nPost1 = 0, nPost2 = 0, nFour = 0, nPlanned = 0, nPostInFour = 0, nExtSeeds = 0;
+  bool inFour = false;
+  int curS = 0;
+  uint32_t nPostS8 = 0, nPostS16 = 0, nPostS32 = 0, nBigSeeds = 0;
 
   __device__ __forceinline__ void touch_rows(int lo, int hi)
   {
@@ -333,6 +614,16 @@ struct MergeScan
     const uint32_t *row = used + (size_t)y * a.wordsPerRow;
     const int w0 = x >> 5, s = x & 31;
     return __funnelshift_r(row[w0], row[w0 + 1], s) & 0xFFu;
+  }
+
+  __device__ __forceinline__ uint32_t used_bits32(int x, int y) const
+  {
+    if (y >= a.BY)
+      return 0xFFFFFFFFu;
+
+    const uint32_t *row = used + (size_t)y * a.wordsPerRow;
+    const int w0 = x >> 5, s = x & 31;
+    return __funnelshift_r(row[w0], row[w0 + 1], s);
   }
 
   __device__ __forceinline__ bool is_used(int x, int y) const
@@ -379,7 +670,7 @@ struct MergeScan
     serve(a, mail, used, 0);
     named_bar_sync(2, LIMG_MERGE_THREADS);
     tPost += clock64() - t0;
-    if (kind == 1) nPost1++; else nPost2++;
+    if (kind == 1) { nPost1++; if (inFour) nPostInFour++; else if (curS == 8) nPostS8++; else if (curS == 16) nPostS16++; else nPostS32++; } else nPost2++;
   }
 
   // executed by every warp of the CTA for the posted request
@@ -453,13 +744,23 @@ struct MergeScan
   __device__ void grow_four_way(int &ox, int &oy, int &rx, int &ry, int hintX, int hintY, int hintW, int hintH)
   {
     const int seed = oy * a.BX + ox;
-    // neighbourhood request: the right/down rectangle the centre came from, plus a margin, clipped to 32 x 32
-    rgX = max(hintX - 3, 0);
-    rgY = max(hintY - 3, 0);
-    rgW = min(min(hintW + 6, LIMG_REGION_MAX), a.BX - rgX);
-    rgH = min(min(hintH + 6, LIMG_REGION_MAX), a.BY - rgY);
+    // the centre seed's symmetric 16 x 16 match window covers [ox - 8, ox + 8) x [oy - 8, oy + 8); strips that leave it are
+    // evaluated on demand
+    rgX = ox - 8;
+    rgY = oy - 8;
+    rgW = 16;
+    rgH = 16;
     touch_rows(rgY, rgY + rgH - 1);
-    post(2, seed, rgX, rgY, rgW, rgH);
+    (void)hintX; (void)hintY; (void)hintW; (void)hintH;
+
+    if (lane < 16)
+    {
+      const uint32_t w = __ldg(&a.sym[(size_t)seed * 8 + (lane >> 1)]);
+      mail->regionBits[lane] = (w >> (16 * (lane & 1))) & 0xFFFFu;
+    }
+
+    __syncwarp();
+    nPlanned++;
 
     bool right = true, down = true, up = true, left = true;
 
@@ -487,22 +788,29 @@ struct MergeScan
     }
   }
 
-  // right/down growth of a 1x1 seed: bit arithmetic inside the 8x8 window, on-demand strips beyond it.
+  // right/down growth of a 1x1 seed. The seed's match bitmap (8x8 word, or the speculative 16x16 / 32x32 extension) lives one
+  // row per lane; growth inside it is ballots and shuffles, strips beyond it are evaluated on demand.
   __device__ void grow_seed(int x, int y, int &rx, int &ry)
   {
-    const uint64_t match = match_word(x, y);
-    uint32_t rowBits = lane < 8 ? used_bits8(x, y + lane) : 0u;
-    uint32_t lo = 0, hi = 0;
+    const int seed = y * a.BX + x;
+    const uint32_t slot = extBand[(y - bandY0) * a.BX + x];
+    int S = 8;
+    uint32_t rowBits;
 
-#pragma unroll
-    for (int r = 0; r < 4; r++)
+    if (slot == LIMG_NO_SLOT)
     {
-      lo |= __shfl_sync(0xFFFFFFFFu, rowBits, r) << (8 * r);
-      hi |= __shfl_sync(0xFFFFFFFFu, rowBits, r + 4) << (8 * r);
+      const uint64_t match = match_word(x, y);
+      rowBits = lane < 8 ? (uint32_t)(match >> (8 * lane)) & 0xFFu : 0u;
+    }
+    else
+    {
+      S = (slot >> 31) ? 32 : 16;
+      nExtSeeds++;
+      rowBits = lane < S ? __ldg(&a.extBits[(size_t)(slot & 0x7FFFFFFFu) * 32 + lane]) : 0u;
     }
 
-    const uint64_t avail = match & ~((uint64_t)lo | ((uint64_t)hi << 32));
-    const int seed = y * a.BX + x;
+    const uint32_t avail = lane < S ? (rowBits & ~used_bits32(x, y + lane)) : 0u;
+    curS = S;
     bool right = true, down = true;
     rx = 1;
     ry = 1;
@@ -515,14 +823,15 @@ struct MergeScan
 
         if (ok)
         {
-          if (rx < 8)
+          if (rx < S)
           {
-            const int rows = min(ry, 8);
-            const uint64_t mask = (0x0101010101010101ull << rx) & (rows >= 8 ? ~0ull : ((1ull << (8 * rows)) - 1));
-            ok = (avail & mask) == mask;
+            const int rows = min(ry, S);
+            const uint32_t need = rows >= 32 ? 0xFFFFFFFFu : ((1u << rows) - 1u);
+            const uint32_t have = __ballot_sync(0xFFFFFFFFu, (avail >> rx) & 1u);
+            ok = (have & need) == need;
 
-            if (ok && ry > 8)
-              ok = strip_joins(seed, x + rx, y + 8, 1, ry - 8);
+            if (ok && ry > S)
+              ok = strip_joins(seed, x + rx, y + S, 1, ry - S);
           }
           else
           {
@@ -539,14 +848,15 @@ struct MergeScan
 
         if (ok)
         {
-          if (ry < 8)
+          if (ry < S)
           {
-            const int cols = min(rx, 8);
-            const uint64_t mask = (uint64_t)((1u << cols) - 1u) << (8 * ry);
-            ok = (avail & mask) == mask;
+            const int cols = min(rx, S);
+            const uint32_t need = cols >= 32 ? 0xFFFFFFFFu : ((1u << cols) - 1u);
+            const uint32_t rowv = __shfl_sync(0xFFFFFFFFu, avail, ry);
+            ok = (rowv & need) == need;
 
-            if (ok && rx > 8)
-              ok = strip_joins(seed, x + 8, y + ry, rx - 8, 1);
+            if (ok && rx > S)
+              ok = strip_joins(seed, x + S, y + ry, rx - S, 1);
           }
           else
           {
@@ -558,7 +868,8 @@ struct MergeScan
       }
     }
 
-    touch_rows(y, y + min(ry, 7)); // window rows consulted: up to the failing row (deeper rows go through strip_unused)
+    if (rx > 8 || ry > 8) nBigSeeds++;
+    touch_rows(y, y + min(ry, S - 1)); // bitmap rows consulted: up to the failing row (deeper rows go through strip_unused)
   }
 
   __device__ void mark_used(int ox, int oy, int rx, int ry)
@@ -606,6 +917,21 @@ struct MergeScan
             {
               const uint32_t w0 = winBand[(size_t)((y - bandY0) * a.BX + xx) * 2];
               cand = stage == 0 ? ((w0 & 0x070707u) == 0x070707u) : ((w0 & 0x0102u) != 0);
+
+              if (cand)
+              {
+                // warm L1 with the speculative bitmaps this seed may consult
+                const uint32_t es = extBand[(y - bandY0) * a.BX + xx];
+                if (es != LIMG_NO_SLOT)
+                  asm volatile("prefetch.global.L1 [%0];" ::"l"(a.extBits + (size_t)(es & 0x7FFFFFFFu) * 32));
+
+                const uint32_t cs = stage == 0 ? ctrBand[(y - bandY0) * a.BX + xx] : LIMG_NO_SLOT;
+                if (cs != LIMG_NO_SLOT)
+                {
+                  asm volatile("prefetch.global.L1 [%0];" ::"l"(a.ctrHdr + cs));
+                  asm volatile("prefetch.global.L1 [%0];" ::"l"(a.ctrBits + (size_t)cs * 32));
+                }
+              }
             }
 
             const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, cand);
@@ -637,7 +963,9 @@ struct MergeScan
           {
             int cox = x + rx / 3, coy = y + ry / 3, crx = rx / 3, cry = ry / 3;
             const long long tf0 = clock64();
+            inFour = true;
             grow_four_way(cox, coy, crx, cry, x, y, rx, ry);
+            inFour = false;
             tFour += clock64() - tf0;
             nFour++;
 
@@ -680,7 +1008,7 @@ struct MergeScan
 
     if (lane == 0 && a.stats)
     {
-      atomicAdd(&a.stats[4], nSeeds); atomicAdd(&a.stats[5], nPost1); atomicAdd(&a.stats[6], nPost2); atomicAdd(&a.stats[7], nFour);
+      atomicAdd(&a.stats[4], nSeeds); atomicAdd(&a.stats[5], nPost1); atomicAdd(&a.stats[6], nPost2); atomicAdd(&a.stats[7], nFour); atomicAdd(&a.stats[12], nPlanned); atomicAdd(&a.stats[13], nPostInFour); atomicAdd(&a.stats[14], nExtSeeds); atomicAdd(&a.stats[15], nPostS8); atomicAdd(&a.stats[1], nPostS16); atomicAdd(&a.stats[0], nPostS32); atomicAdd(&a.stats[3], nBigSeeds);
       atomicAdd(&a.stats[8], (uint32_t)(tSearch >> 10)); atomicAdd(&a.stats[9], (uint32_t)(tGrow >> 10)); atomicAdd(&a.stats[10], (uint32_t)(tPost >> 10)); atomicAdd(&a.stats[11], (uint32_t)(tFour >> 10));
     }
 
@@ -716,6 +1044,8 @@ __global__ void __launch_bounds__(LIMG_MERGE_THREADS) k_merge_banded(MergeArgs a
   uint32_t *used = reinterpret_cast<uint32_t *>(dynSmem);
   const int maskWords = a.BY * a.wordsPerRow;
   uint32_t *winBand = used + maskWords;
+  uint32_t *extBand = winBand + (size_t)a.bandRows * a.BX * 2;
+  uint32_t *ctrBand = extBand + (size_t)a.bandRows * a.BX;
   __shared__ MergeMailbox mail;
   __shared__ int sDirty;
   __shared__ int sRange[2];
@@ -729,6 +1059,12 @@ __global__ void __launch_bounds__(LIMG_MERGE_THREADS) k_merge_banded(MergeArgs a
   // the band's match words never change: shared memory
   for (int i = threadIdx.x; i < (bandY1 - bandY0) * a.BX * 2; i += blockDim.x)
     winBand[i] = a.window[(size_t)bandY0 * a.BX * 2 + i];
+
+  for (int i = threadIdx.x; i < (bandY1 - bandY0) * a.BX; i += blockDim.x)
+  {
+    extBand[i] = a.extSlot[(size_t)bandY0 * a.BX + i];
+    ctrBand[i] = a.ctrSlot[(size_t)bandY0 * a.BX + i];
+  }
 
   for (int stage = 0; stage < 2; stage++)
   {
@@ -798,7 +1134,7 @@ __global__ void __launch_bounds__(LIMG_MERGE_THREADS) k_merge_banded(MergeArgs a
       {
         if (warp == 0)
         {
-          MergeScan<CH> scan{ a, used, winBand, &mail, lane, bandY0, bandY1, a.BY, -1 };
+          MergeScan<CH> scan{ a, used, winBand, extBand, ctrBand, &mail, lane, bandY0, bandY1, a.BY, -1 };
           const uint32_t count = scan.run_band(stage, myList);
 
           if (lane == 0)

@@ -41,6 +41,10 @@ struct limgcu_ctx
   uint32_t *dBandSnapshot = nullptr;
   uint32_t *dBandState = nullptr; // [0..8 + 2 * (MAX_BANDS + 2)) barrier + flags, then counts [MAX_BANDS * 2]
   size_t capBandLists = 0, capBandSnapshot = 0;
+  uint32_t *dExtSlot = nullptr, *dExtSeed = nullptr, *dExtBits = nullptr, *dCtrSlot = nullptr, *dCtrBits = nullptr, *dPlanCounters = nullptr;
+  uint4 *dCtrHdr = nullptr;
+  uint32_t *dSym = nullptr;
+  uint32_t extCap = 0, ctrCap = 0;
   uint32_t *dScratchPx = nullptr, *dScratchFac = nullptr;
   uint32_t *dCounters = nullptr; // [16]: 0 merged, 1 areaCount, 2 smallCount, 3 largeCount, 4 workSmall, 5 workLarge, 8.. stats
   unsigned long long *dCompare = nullptr;
@@ -98,6 +102,16 @@ static int ensure_capacity(limgcu_ctx *ctx, size_t W, size_t H)
     CK(regrow(ctx->dSmallList, blocks));
     CK(regrow(ctx->dLargeList, blocks));
     CK(regrow(ctx->dDemand, blocks));
+    ctx->extCap = (uint32_t)(blocks / 2 > 1024 ? blocks / 2 : 1024);
+    ctx->ctrCap = (uint32_t)(blocks / 2 > 1024 ? blocks / 2 : 1024);
+    CK(regrow(ctx->dSym, blocks * 8));
+    CK(regrow(ctx->dExtSlot, blocks));
+    CK(regrow(ctx->dCtrSlot, blocks));
+    CK(regrow(ctx->dExtSeed, (size_t)ctx->extCap));
+    CK(regrow(ctx->dExtBits, (size_t)ctx->extCap * 32));
+    CK(regrow(ctx->dCtrHdr, (size_t)ctx->ctrCap));
+    CK(regrow(ctx->dCtrBits, (size_t)ctx->ctrCap * 32));
+    if (ctx->dPlanCounters == nullptr) CK(regrow(ctx->dPlanCounters, (size_t)8));
     ctx->capBlocks = blocks;
   }
 
@@ -236,7 +250,8 @@ extern "C" void limgcu_destroy(limgcu_ctx *ctx)
     cudaStreamSynchronize(ctx->stream);
 
   void *ptrs[] = { ctx->dLut, ctx->dTable, ctx->dRec, ctx->dWindow, ctx->dAreas, ctx->dBlockToArea, ctx->dWork, ctx->dSmallList, ctx->dLargeList, ctx->dDemand,
-                   ctx->dUsed, ctx->dScratchPx, ctx->dScratchFac, ctx->dCounters, ctx->dCompare, ctx->dSrc, ctx->dBandLists, ctx->dBandSnapshot, ctx->dBandState };
+                   ctx->dUsed, ctx->dScratchPx, ctx->dScratchFac, ctx->dCounters, ctx->dCompare, ctx->dSrc, ctx->dBandLists, ctx->dBandSnapshot, ctx->dBandState,
+                   ctx->dExtSlot, ctx->dExtSeed, ctx->dExtBits, ctx->dCtrSlot, ctx->dCtrBits, ctx->dPlanCounters, ctx->dCtrHdr, ctx->dSym };
 
   for (void *p : ptrs)
     if (p) cudaFree(p);
@@ -259,6 +274,7 @@ extern "C" int limgcu_debug_counters(limgcu_ctx *ctx, uint32_t *out32)
 {
   NEED(ctx); NEED(out32);
   CK(cudaMemcpyAsync(out32, ctx->dCounters, 32 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  if (ctx->dPlanCounters) CK(cudaMemcpyAsync(out32 + 24, ctx->dPlanCounters, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   return LIMGCU_SUCCESS;
 }
@@ -345,7 +361,7 @@ static int launch_merge(limgcu_ctx *ctx, const limgcu_decomp *dTable, size_t W, 
     const int bandRows = BY / 128 + 1 > 8 ? BY / 128 + 1 : 8;
     const int numBands = (BY + bandRows - 1) / bandRows;
     const size_t usedBytes = (size_t)BY * wordsPerRow * sizeof(uint32_t);
-    const size_t smemBytes = usedBytes + (size_t)bandRows * BX * 2 * sizeof(uint32_t);
+    const size_t smemBytes = usedBytes + (size_t)bandRows * BX * 4 * sizeof(uint32_t);
 
     if (smemBytes > 200 * 1024 || numBands > LIMG_MERGE_MAX_BANDS || numBands > ctx->smCount || BX > 65535 || BY > 65535)
       return fail(ctx, LIMGCU_ERROR_OUT_OF_BOUNDS, "image too large for the shared-memory in-use mask of the banded merge", cudaSuccess);
@@ -356,6 +372,8 @@ static int launch_merge(limgcu_ctx *ctx, const limgcu_decomp *dTable, size_t W, 
       CKL("k_pred_records");
       k_pred_window<4><<<(blocks * 2 + 7) / 8, 256, 0, ctx->stream>>>(ctx->dRec, BX, BY, ctx->dWindow);
       CKL("k_pred_window");
+      k_pred_symwindow<4><<<blocks, 256, 0, ctx->stream>>>(ctx->dRec, ctx->dWindow, BX, BY, ctx->dSym);
+      CKL("k_pred_symwindow");
     }
     else
     {
@@ -363,6 +381,28 @@ static int launch_merge(limgcu_ctx *ctx, const limgcu_decomp *dTable, size_t W, 
       CKL("k_pred_records");
       k_pred_window<3><<<(blocks * 2 + 7) / 8, 256, 0, ctx->stream>>>(ctx->dRec, BX, BY, ctx->dWindow);
       CKL("k_pred_window");
+      k_pred_symwindow<3><<<blocks, 256, 0, ctx->stream>>>(ctx->dRec, ctx->dWindow, BX, BY, ctx->dSym);
+      CKL("k_pred_symwindow");
+    }
+
+    PlanArgs pl;
+    pl.rec = ctx->dRec; pl.window = ctx->dWindow; pl.BX = BX; pl.BY = BY;
+    pl.extSlot = ctx->dExtSlot; pl.extSeed = ctx->dExtSeed; pl.extBits = ctx->dExtBits;
+    pl.ctrSlot = ctx->dCtrSlot; pl.ctrHdr = ctx->dCtrHdr; pl.ctrBits = ctx->dCtrBits;
+    pl.counters = ctx->dPlanCounters; pl.extCap = ctx->extCap; pl.ctrCap = ctx->ctrCap;
+    CK(cudaMemsetAsync(ctx->dPlanCounters, 0, 8 * sizeof(uint32_t), ctx->stream));
+    k_plan_seeds<<<(blocks + 255) / 256, 256, 0, ctx->stream>>>(pl);
+    CKL("k_plan_seeds");
+
+    if (hasAlpha)
+    {
+      k_plan_extend<4><<<ctx->smCount * 8, 256, 0, ctx->stream>>>(pl);
+      CKL("k_plan_extend");
+    }
+    else
+    {
+      k_plan_extend<3><<<ctx->smCount * 8, 256, 0, ctx->stream>>>(pl);
+      CKL("k_plan_extend");
     }
 
     if (ctx->timing) CK(cudaEventRecord(ctx->ev[PHASE_SCAN], ctx->stream));
@@ -371,7 +411,9 @@ static int launch_merge(limgcu_ctx *ctx, const limgcu_decomp *dTable, size_t W, 
     CK(cudaMemsetAsync(ctx->dUsed, 0, usedBytes, ctx->stream));
 
     MergeArgs m;
-    m.rec = ctx->dRec; m.window = ctx->dWindow; m.BX = BX; m.BY = BY; m.wordsPerRow = wordsPerRow;
+    m.rec = ctx->dRec; m.window = ctx->dWindow;
+    m.extSlot = ctx->dExtSlot; m.extBits = ctx->dExtBits; m.ctrSlot = ctx->dCtrSlot; m.ctrBits = ctx->dCtrBits; m.ctrHdr = ctx->dCtrHdr; m.sym = ctx->dSym;
+    m.BX = BX; m.BY = BY; m.wordsPerRow = wordsPerRow;
     m.bandRows = bandRows; m.numBands = numBands; m.listCap = bandRows * BX * 2;
     m.lists = ctx->dBandLists; m.counts = ctx->dBandState + 512; m.snapshot = ctx->dBandSnapshot; m.sync = ctx->dBandState;
     m.areas = dAreas; m.mergedCount = ctx->dCounters + 0; m.usedOut = ctx->dUsed; m.stats = ctx->dCounters + 8;
