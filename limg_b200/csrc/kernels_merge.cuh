@@ -264,8 +264,6 @@ __global__ void __launch_bounds__(256) k_pred_symwindow(const PredRec *__restric
 // ---------------------------------------------------------------------------------------------
 // speculative windows: everything the scan is likely to ask for is evaluated up front, in parallel on the whole GPU.
 //   - seeds whose mask-free right/down growth leaves the 8x8 window get a 16x16 and, if that is left too, a 32x32 match bitmap;
-//   - seeds whose mask-free growth reaches 3x3 get the match bitmap of their centre-third seed over the neighbourhood the
-//     four-way regrowth explores (limg.cpp:1426-1433), keyed by the (rx, ry) the prediction assumed.
 // The scan uses a bitmap only when its assumptions hold and falls back to on-demand evaluation otherwise, so the bitmaps are a
 // pure accelerator: they never change the result.
 // ---------------------------------------------------------------------------------------------
@@ -280,11 +278,9 @@ struct PlanArgs
   uint32_t *extSlot;   // per block: LIMG_NO_SLOT or slot | (size 32 ? 1u << 31 : 0)
   uint32_t *extSeed;   // per slot: block index
   uint32_t *extBits;   // per slot: 32 row words
-  uint32_t *ctrSlot;   // per block: LIMG_NO_SLOT or slot
-  uint4 *ctrHdr;       // per slot: x = rx0 | ry0 << 16 (assumed growth), y = rgX | rgY << 16, z = rgW | rgH << 16, w = centre block index
-  uint32_t *ctrBits;   // per slot: 32 row words
-  uint32_t *counters;  // [0] ext slots, [1] centre slots
-  uint32_t extCap, ctrCap;
+  uint32_t *counters;  // [0] ext slots
+  uint32_t extCap;
+  uint16_t *unmasked;  // per block: rx | ry << 8 of the mask-free right/down growth inside the best available bitmap
 };
 
 // mask-free alternating right/down growth over `rows` (S x S match bitmap of the seed); returns true if it wanted to leave the bitmap
@@ -328,23 +324,6 @@ __device__ __forceinline__ bool expand_unmasked(const uint32_t *rows, int S, int
   return hit;
 }
 
-__device__ __forceinline__ void plan_centre(const PlanArgs &a, int seed, int x, int y, int rx, int ry)
-{
-  if (rx < 3 || ry < 3)
-    return;
-
-  const uint32_t slot = atomicAdd(&a.counters[1], 1u);
-
-  if (slot >= a.ctrCap)
-    return;
-
-  const int rgX = max(x - 3, 0), rgY = max(y - 3, 0);
-  const int rgW = min(min(rx + 6, 32), a.BX - rgX), rgH = min(min(ry + 6, 32), a.BY - rgY);
-  const int centre = (y + ry / 3) * a.BX + x + rx / 3;
-  a.ctrHdr[slot] = make_uint4((uint32_t)rx | ((uint32_t)ry << 16), (uint32_t)rgX | ((uint32_t)rgY << 16), (uint32_t)rgW | ((uint32_t)rgH << 16), (uint32_t)centre);
-  a.ctrSlot[seed] = slot;
-}
-
 __global__ void __launch_bounds__(256) k_plan_seeds(PlanArgs a)
 {
   const int seed = blockIdx.x * blockDim.x + threadIdx.x;
@@ -366,7 +345,7 @@ __global__ void __launch_bounds__(256) k_plan_seeds(PlanArgs a)
   int rx, ry;
   const bool hit = expand_unmasked(rows, 8, x, y, a.BX, a.BY, rx, ry);
   a.extSlot[seed] = LIMG_NO_SLOT;
-  a.ctrSlot[seed] = LIMG_NO_SLOT;
+  a.unmasked[seed] = (uint16_t)(rx | (ry << 8));
 
   if (hit)
   {
@@ -473,37 +452,11 @@ __global__ void __launch_bounds__(256) k_plan_extend(PlanArgs a)
     if (threadIdx.x == 0)
     {
       a.extSlot[seed] = slot | (size == 32 ? 0x80000000u : 0u);
+      a.unmasked[seed] = (uint16_t)(sRx | (sRy << 8));
 
     }
 
     __syncthreads();
-  }
-}
-
-template <int CH>
-__global__ void __launch_bounds__(256) k_plan_centres(PlanArgs a)
-{
-  const uint32_t count = min(a.counters[1], a.ctrCap);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-
-  for (uint32_t slot = blockIdx.x; slot < count; slot += gridDim.x)
-  {
-    const uint4 h = a.ctrHdr[slot];
-    const int rgX = h.y & 0xFFFF, rgY = h.y >> 16, rgW = h.z & 0xFFFF, rgH = h.z >> 16;
-    const PredRec c = a.rec[h.w];
-
-    for (int row = warp; row < 32; row += 8)
-    {
-      bool m = false;
-
-      if (row < rgH && lane < rgW)
-        m = predicate_thread<CH>(c, a.rec[(size_t)(rgY + row) * a.BX + rgX + lane]);
-
-      const uint32_t b = __ballot_sync(0xFFFFFFFFu, m);
-
-      if (lane == 0)
-        a.ctrBits[(size_t)slot * 32 + row] = b;
-    }
   }
 }
 
@@ -519,33 +472,20 @@ __global__ void __launch_bounds__(256) k_plan_centres(PlanArgs a)
 // order, ARE the reference's emission order. Stage 1 (remaining merges) repeats the procedure on top of the final stage-0 mask.
 // ---------------------------------------------------------------------------------------------
 
-#define LIMG_MERGE_THREADS 1024
+#define LIMG_MERGE_THREADS 512
 #define LIMG_MERGE_WARPS (LIMG_MERGE_THREADS / 32)
 #define LIMG_MERGE_MAX_BANDS 128
-#define LIMG_REGION_MAX 32
-
-struct MergeMailbox
-{
-  int kind; // 0 quit, 1 evaluate strip (AND of predicates), 2 evaluate region bitmap
-  int seed;
-  int x0, y0, w, h;
-  int result;
-  uint32_t regionBits[LIMG_REGION_MAX]; // kind 2: bit (row, col) = block unused-or-unknown AND matches
-};
-
-__device__ __forceinline__ void named_bar_sync(int id, int count)
-{
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
-}
+#define LIMG_ROW_CHUNK 128 // candidate seeds of one block row expanded concurrently
 
 struct MergeArgs
 {
   const PredRec *rec;
   const uint32_t *window;
-  const uint32_t *extSlot, *extBits, *ctrSlot, *ctrBits, *sym;
-  const uint4 *ctrHdr;
+  const uint32_t *extSlot, *extBits, *sym;
+  const uint16_t *unmasked;
   int BX, BY, wordsPerRow;
   int bandRows, numBands, listCap;
+  int rowChunk;          // candidate seeds of one block row expanded concurrently (<= LIMG_ROW_CHUNK)
   uint2 *lists;          // [numBands][2][listCap]: (ox | oy << 16, rx | ry << 16)
   uint32_t *counts;      // [numBands][2]
   uint32_t *snapshot;    // [numBands][BY * wordsPerRow]: input mask of the band's last run
@@ -553,7 +493,7 @@ struct MergeArgs
   limgcu_area *areas;
   uint32_t *mergedCount; // number of stage 0 + stage 1 areas
   uint32_t *usedOut;     // BY * wordsPerRow words: in-use mask after both merge stages (zeroed by the host)
-  uint32_t *stats;       // [8] optional counters: iterations stage 0 / 1, band runs stage 0 / 1
+  uint32_t *stats;       // [24] optional counters
 };
 
 __device__ __forceinline__ void grid_barrier(uint32_t *sync, uint32_t numBlocks)
@@ -583,22 +523,42 @@ __device__ __forceinline__ void grid_barrier(uint32_t *sync, uint32_t numBlocks)
   __syncthreads();
 }
 
+// what one seed would do against a given in-use mask
+struct SeedResult
+{
+  short x, rx, ry;       // right/down rectangle grown from the seed
+  short kind;            // 0 nothing to emit, 1 emit the right/down rectangle, 2 emit the centre-third regrowth (and examine the seed again)
+  short cox, coy, crx, cry; // four-way regrowth (valid when attempted)
+  short attempted;
+  short pad;
+};
+
+struct BandShared
+{
+  SeedResult res[LIMG_ROW_CHUNK];
+  short cand[LIMG_ROW_CHUNK];
+  uint2 accepted[LIMG_ROW_CHUNK + 32]; // rectangles committed in the current chunk round
+  int nCand, nextX;
+  int rangeLo, rangeHi;
+  uint32_t count;
+  int dirty;
+};
+
+// A band's scan. Every method is warp-cooperative: all 32 lanes call it with warp-uniform arguments. The in-use mask is only
+// modified by commit() (warp 0, between barriers); expansions read it.
 template <int CH>
-struct MergeScan
+struct BandScan
 {
   const MergeArgs &a;
   uint32_t *used;          // shared: BY rows of wordsPerRow words
-  const uint32_t *winBand; // shared: window words of the band's rows
-  const uint32_t *extBand, *ctrBand; // shared: speculative-window slots of the band's seeds
-  MergeMailbox *mail;
+  const uint32_t *winBand; // shared: match words of the band's rows
+  const uint32_t *extBand; // shared: extension-bitmap slots of the band's seeds
+  BandShared *sh;
   int lane;
   int bandY0, bandY1;
-  int readLo, readHi;      // rows whose in-use bits this run consulted
-  unsigned long long tSearch = 0, tGrow = 0, tPost = 0, tFour = 0;
-  uint32_t nSeeds = 0, nPost1 = 0, nPost2 = 0, nFour = 0, nPlanned = 0, nPostInFour = 0, nExtSeeds = 0;
-  bool inFour = false;
-  int curS = 0;
-  uint32_t nPostS8 = 0, nPostS16 = 0, nPostS32 = 0, nBigSeeds = 0;
+  int readLo, readHi;      // rows whose in-use bits this warp consulted
+  uint32_t nOnDemand, nSeeds, nFour, nInline;
+  bool cheapOnly, aborted; // a speculative expansion of a probably-swallowed candidate gives up instead of evaluating predicates on demand
 
   __device__ __forceinline__ void touch_rows(int lo, int hi)
   {
@@ -606,22 +566,20 @@ struct MergeScan
     readHi = max(readHi, min(hi, a.BY - 1));
   }
 
-  __device__ __forceinline__ uint32_t used_bits8(int x, int y) const
-  {
-    if (y >= a.BY)
-      return 0xFFu;
-
-    const uint32_t *row = used + (size_t)y * a.wordsPerRow;
-    const int w0 = x >> 5, s = x & 31;
-    return __funnelshift_r(row[w0], row[w0 + 1], s) & 0xFFu;
-  }
-
   __device__ __forceinline__ uint32_t used_bits32(int x, int y) const
   {
-    if (y >= a.BY)
+    // 32 in-use bits of row y starting at column x (x may be negative); everything outside the grid reads as in use
+    if (y < 0 || y >= a.BY)
       return 0xFFFFFFFFu;
 
     const uint32_t *row = used + (size_t)y * a.wordsPerRow;
+
+    if (x < 0)
+    {
+      const int s = -x; // 1..31
+      return (row[0] << s) | ((1u << s) - 1u);
+    }
+
     const int w0 = x >> 5, s = x & 31;
     return __funnelshift_r(row[w0], row[w0 + 1], s);
   }
@@ -629,12 +587,6 @@ struct MergeScan
   __device__ __forceinline__ bool is_used(int x, int y) const
   {
     return (used[(size_t)y * a.wordsPerRow + (x >> 5)] >> (x & 31)) & 1u;
-  }
-
-  __device__ __forceinline__ uint64_t match_word(int x, int y) const
-  {
-    const uint32_t *wp = winBand + (size_t)((y - bandY0) * a.BX + x) * 2;
-    return (uint64_t)wp[0] | ((uint64_t)wp[1] << 32);
   }
 
   __device__ bool strip_unused(int x0, int y0, int w, int h)
@@ -651,145 +603,59 @@ struct MergeScan
     return !__any_sync(0xFFFFFFFFu, any);
   }
 
-  __device__ void post(int kind, int seed, int x0, int y0, int w, int h)
+  // every block of the strip matches the seed? evaluated by this warp alone: short strips one predicate at a time with the 27
+  // samples spread over the lanes, long strips one predicate per lane.
+  __device__ bool strip_matches(const PredRec &seed, int x0, int y0, int w, int h)
   {
-    if (lane == 0)
+    const int count = w * h;
+
+    if (cheapOnly)
     {
-      mail->kind = kind;
-      mail->seed = seed;
-      mail->x0 = x0; mail->y0 = y0; mail->w = w; mail->h = h;
-      mail->result = 1;
+      aborted = true;
+      return false;
     }
 
-    if (kind == 2 && lane < LIMG_REGION_MAX)
-      mail->regionBits[lane] = 0;
+    nOnDemand += count;
 
-    const long long t0 = clock64();
-    __syncwarp();
-    named_bar_sync(1, LIMG_MERGE_THREADS);
-    serve(a, mail, used, 0);
-    named_bar_sync(2, LIMG_MERGE_THREADS);
-    tPost += clock64() - t0;
-    if (kind == 1) { nPost1++; if (inFour) nPostInFour++; else if (curS == 8) nPostS8++; else if (curS == 16) nPostS16++; else nPostS32++; } else nPost2++;
-  }
-
-  // executed by every warp of the CTA for the posted request
-  static __device__ void serve(const MergeArgs &a, MergeMailbox *mail, const uint32_t *used, int warp)
-  {
-    const int count = mail->w * mail->h;
-    const int w = mail->w;
-    const int kind = mail->kind;
-    const PredRec seed = a.rec[mail->seed];
-
-    for (int e = warp; e < count; e += LIMG_MERGE_WARPS)
+    if (count >= 6)
     {
-      const int ry = e / w, rx = e - ry * w;
-      const int yy = mail->y0 + ry, xx = mail->x0 + rx;
+      bool ok = true;
 
-      if (kind == 1)
+      for (int base = 0; base < count && ok; base += 32)
       {
-        if (*(volatile int *)&mail->result == 0)
-          break;
+        const int e = base + lane;
+        bool m = true;
 
-        if (!predicate_warp<CH>(seed, a.rec[(size_t)yy * a.BX + xx]) && (threadIdx.x & 31) == 0)
-          atomicAnd(&mail->result, 0);
-      }
-      else
-      {
-        // region bitmap: blocks already in use can never join, skip their predicate
-        const bool inUse = (used[(size_t)yy * a.wordsPerRow + (xx >> 5)] >> (xx & 31)) & 1u;
+        if (e < count)
+        {
+          const int yy = y0 + e / w, xx = x0 + e % w;
+          m = predicate_thread<CH>(seed, a.rec[(size_t)yy * a.BX + xx]);
+        }
 
-        if (!inUse && predicate_warp<CH>(seed, a.rec[(size_t)yy * a.BX + xx]) && (threadIdx.x & 31) == 0)
-          atomicOr(&mail->regionBits[ry], 1u << rx);
+        ok = __all_sync(0xFFFFFFFFu, m);
       }
+
+      return ok;
     }
+
+    for (int e = 0; e < count; e++)
+    {
+      const int yy = y0 + e / w, xx = x0 + e % w;
+
+      if (!predicate_warp<CH>(seed, a.rec[(size_t)yy * a.BX + xx]))
+        return false;
+    }
+
+    return true;
   }
 
-  __device__ bool strip_matches(int seed, int x0, int y0, int w, int h)
-  {
-    post(1, seed, x0, y0, w, h);
-    return mail->result != 0;
-  }
-
-  __device__ bool strip_joins(int seed, int x0, int y0, int w, int h)
+  __device__ bool strip_joins(const PredRec &seed, int x0, int y0, int w, int h)
   {
     return strip_unused(x0, y0, w, h) && strip_matches(seed, x0, y0, w, h);
   }
 
-  // region cache of the four-way regrowth: one parallel request evaluates every predicate of the neighbourhood at once
-  int rgX, rgY, rgW, rgH;
-
-  __device__ bool strip_joins_cached(int seed, int x0, int y0, int w, int h)
-  {
-    if (x0 >= rgX && y0 >= rgY && x0 + w <= rgX + rgW && y0 + h <= rgY + rgH)
-    {
-      if (!strip_unused(x0, y0, w, h))
-        return false;
-
-      bool ok = true;
-
-      if (lane < h)
-      {
-        const uint32_t m = (w >= 32 ? 0xFFFFFFFFu : ((1u << w) - 1u)) << (x0 - rgX);
-        ok = (mail->regionBits[y0 - rgY + lane] & m) == m;
-      }
-
-      return __all_sync(0xFFFFFFFFu, ok);
-    }
-
-    return strip_joins(seed, x0, y0, w, h);
-  }
-
-  // four-way alternating growth (limg.cpp:1294-1388); the seed is the rectangle's top-left block at entry.
-  __device__ void grow_four_way(int &ox, int &oy, int &rx, int &ry, int hintX, int hintY, int hintW, int hintH)
-  {
-    const int seed = oy * a.BX + ox;
-    // the centre seed's symmetric 16 x 16 match window covers [ox - 8, ox + 8) x [oy - 8, oy + 8); strips that leave it are
-    // evaluated on demand
-    rgX = ox - 8;
-    rgY = oy - 8;
-    rgW = 16;
-    rgH = 16;
-    touch_rows(rgY, rgY + rgH - 1);
-    (void)hintX; (void)hintY; (void)hintW; (void)hintH;
-
-    if (lane < 16)
-    {
-      const uint32_t w = __ldg(&a.sym[(size_t)seed * 8 + (lane >> 1)]);
-      mail->regionBits[lane] = (w >> (16 * (lane & 1))) & 0xFFFFu;
-    }
-
-    __syncwarp();
-    nPlanned++;
-
-    bool right = true, down = true, up = true, left = true;
-
-    while (right || down || up || left)
-    {
-      if (right)
-      {
-        if (ox + rx + 1 < a.BX && strip_joins_cached(seed, ox + rx, oy, 1, ry)) rx++; else right = false;
-      }
-
-      if (down)
-      {
-        if (oy + ry + 1 < a.BY && strip_joins_cached(seed, ox, oy + ry, rx, 1)) ry++; else down = false;
-      }
-
-      if (up)
-      {
-        if (oy > 0 && strip_joins_cached(seed, ox, oy - 1, rx, 1)) { oy--; ry++; } else up = false;
-      }
-
-      if (left)
-      {
-        if (ox > 0 && strip_joins_cached(seed, ox - 1, oy, 1, ry)) { ox--; rx++; } else left = false;
-      }
-    }
-  }
-
-  // right/down growth of a 1x1 seed. The seed's match bitmap (8x8 word, or the speculative 16x16 / 32x32 extension) lives one
-  // row per lane; growth inside it is ballots and shuffles, strips beyond it are evaluated on demand.
+  // right/down growth of a 1x1 seed (limg.cpp:1294-1343). The seed's match bitmap (8x8 word, or the speculative 16x16 / 32x32
+  // extension) lives one row per lane; growth inside it is ballots and shuffles, strips beyond it are evaluated on demand.
   __device__ void grow_seed(int x, int y, int &rx, int &ry)
   {
     const int seed = y * a.BX + x;
@@ -799,19 +665,19 @@ struct MergeScan
 
     if (slot == LIMG_NO_SLOT)
     {
-      const uint64_t match = match_word(x, y);
-      rowBits = lane < 8 ? (uint32_t)(match >> (8 * lane)) & 0xFFu : 0u;
+      const uint32_t *wp = winBand + (size_t)((y - bandY0) * a.BX + x) * 2;
+      rowBits = lane < 8 ? (wp[lane >> 2] >> (8 * (lane & 3))) & 0xFFu : 0u;
     }
     else
     {
       S = (slot >> 31) ? 32 : 16;
-      nExtSeeds++;
       rowBits = lane < S ? __ldg(&a.extBits[(size_t)(slot & 0x7FFFFFFFu) * 32 + lane]) : 0u;
     }
 
     const uint32_t avail = lane < S ? (rowBits & ~used_bits32(x, y + lane)) : 0u;
-    curS = S;
     bool right = true, down = true;
+    bool haveRec = false;
+    PredRec rec;
     rx = 1;
     ry = 1;
 
@@ -823,19 +689,19 @@ struct MergeScan
 
         if (ok)
         {
+          const int rows = min(ry, S);
+
           if (rx < S)
           {
-            const int rows = min(ry, S);
             const uint32_t need = rows >= 32 ? 0xFFFFFFFFu : ((1u << rows) - 1u);
             const uint32_t have = __ballot_sync(0xFFFFFFFFu, (avail >> rx) & 1u);
             ok = (have & need) == need;
-
-            if (ok && ry > S)
-              ok = strip_joins(seed, x + rx, y + S, 1, ry - S);
           }
-          else
+
+          if (ok && (rx >= S || ry > S))
           {
-            ok = strip_joins(seed, x + rx, y, 1, ry);
+            if (!haveRec) { rec = a.rec[seed]; haveRec = true; }
+            ok = rx >= S ? strip_joins(rec, x + rx, y, 1, ry) : strip_joins(rec, x + rx, y + S, 1, ry - S);
           }
         }
 
@@ -848,19 +714,19 @@ struct MergeScan
 
         if (ok)
         {
+          const int cols = min(rx, S);
+
           if (ry < S)
           {
-            const int cols = min(rx, S);
             const uint32_t need = cols >= 32 ? 0xFFFFFFFFu : ((1u << cols) - 1u);
             const uint32_t rowv = __shfl_sync(0xFFFFFFFFu, avail, ry);
             ok = (rowv & need) == need;
-
-            if (ok && rx > S)
-              ok = strip_joins(seed, x + S, y + ry, rx - S, 1);
           }
-          else
+
+          if (ok && (ry >= S || rx > S))
           {
-            ok = strip_joins(seed, x, y + ry, rx, 1);
+            if (!haveRec) { rec = a.rec[seed]; haveRec = true; }
+            ok = ry >= S ? strip_joins(rec, x, y + ry, rx, 1) : strip_joins(rec, x + S, y + ry, rx - S, 1);
           }
         }
 
@@ -868,8 +734,101 @@ struct MergeScan
       }
     }
 
-    if (rx > 8 || ry > 8) nBigSeeds++;
     touch_rows(y, y + min(ry, S - 1)); // bitmap rows consulted: up to the failing row (deeper rows go through strip_unused)
+  }
+
+  // four-way alternating growth from the centre third (limg.cpp:1294-1388, 1426-1433). The centre seed's symmetric 16 x 16 match
+  // window covers [ox - 8, ox + 8) x [oy - 8, oy + 8), one row per lane; strips that leave it are evaluated on demand.
+  __device__ void grow_four_way(int &ox, int &oy, int &rx, int &ry)
+  {
+    const int seed = oy * a.BX + ox;
+    const int rgX = ox - 8, rgY = oy - 8;
+    uint32_t avail = 0;
+
+    if (lane < 16)
+    {
+      const uint32_t w = __ldg(&a.sym[(size_t)seed * 8 + (lane >> 1)]);
+      avail = ((w >> (16 * (lane & 1))) & 0xFFFFu) & ~used_bits32(rgX, rgY + lane);
+    }
+
+    touch_rows(rgY, rgY + 15);
+    bool haveRec = false;
+    PredRec rec;
+    bool right = true, down = true, up = true, left = true;
+
+    // strip test: inside the window -> bits, otherwise on demand
+    auto joins = [&](int x0, int y0, int w, int h) -> bool {
+      if (x0 >= rgX && y0 >= rgY && x0 + w <= rgX + 16 && y0 + h <= rgY + 16)
+      {
+        const uint32_t m = ((1u << w) - 1u) << (x0 - rgX);
+        const int r0 = y0 - rgY;
+        const bool rowOk = (lane < r0 || lane >= r0 + h) || ((avail & m) == m);
+        return __all_sync(0xFFFFFFFFu, rowOk);
+      }
+
+      if (!haveRec) { rec = a.rec[seed]; haveRec = true; }
+      return strip_joins(rec, x0, y0, w, h);
+    };
+
+    while (right || down || up || left)
+    {
+      if (right)
+      {
+        if (ox + rx + 1 < a.BX && joins(ox + rx, oy, 1, ry)) rx++; else right = false;
+      }
+
+      if (down)
+      {
+        if (oy + ry + 1 < a.BY && joins(ox, oy + ry, rx, 1)) ry++; else down = false;
+      }
+
+      if (up)
+      {
+        if (oy > 0 && joins(ox, oy - 1, rx, 1)) { oy--; ry++; } else up = false;
+      }
+
+      if (left)
+      {
+        if (ox > 0 && joins(ox - 1, oy, 1, ry)) { ox--; rx++; } else left = false;
+      }
+    }
+  }
+
+  // what seed (x, y) does against the current mask (limg.cpp:1405-1486)
+  __device__ SeedResult expand(int x, int y, int stage, bool cheap = false)
+  {
+    SeedResult r;
+    int rx, ry;
+    nSeeds++;
+    cheapOnly = cheap;
+    aborted = false;
+    grow_seed(x, y, rx, ry);
+    r.x = (short)x; r.rx = (short)rx; r.ry = (short)ry;
+    r.kind = 0; r.attempted = 0; r.pad = 0;
+    r.cox = r.coy = r.crx = r.cry = 0;
+
+    if (stage == 0)
+    {
+      if (rx >= 3 && ry >= 3) // Q4
+      {
+        int cox = x + rx / 3, coy = y + ry / 3, crx = rx / 3, cry = ry / 3;
+        nFour++;
+        grow_four_way(cox, coy, crx, cry);
+        r.cox = (short)cox; r.coy = (short)coy; r.crx = (short)crx; r.cry = (short)cry;
+        r.attempted = 1;
+        r.kind = (crx * cry > rx * ry) ? 2 : 1;
+      }
+    }
+    else
+    {
+      r.kind = (rx > 1 || ry > 1) ? 1 : 0;
+    }
+
+    if (aborted)
+      r.kind = -1; // unknown: commit() expands the seed properly if it is still free when its turn comes
+
+    cheapOnly = false;
+    return r;
   }
 
   __device__ void mark_used(int ox, int oy, int rx, int ry)
@@ -891,128 +850,92 @@ struct MergeScan
     __syncwarp();
   }
 
-  // one stage over the band's rows. stage 0: large merges (>= 3x3, centre-third retry); stage 1: anything larger than 1x1.
-  __device__ uint32_t run_band(int stage, uint2 *list)
+  // does any rectangle committed in this chunk round touch the inclusive box [x0, x1] x [y0, y1]?
+  __device__ bool touches_accepted(int nAcc, int x0, int y0, int x1, int y1) const
   {
-    uint32_t count = 0;
-    touch_rows(bandY0, bandY1 - 1); // the candidate search reads the in-use bits of every row of the band
+    bool hit = false;
 
-    for (int y = bandY0; y < bandY1; y++)
+    for (int j = lane; j < nAcc; j += 32)
     {
-      int x = 0;
+      const uint2 r = sh->accepted[j];
+      const int ax = r.x & 0xFFFF, ay = r.x >> 16, aw = r.y & 0xFFFF, ah = r.y >> 16;
+      hit |= ax <= x1 && ax + aw > x0 && ay <= y1 && ay + ah > y0;
+    }
 
-      while (x < a.BX)
+    return __any_sync(0xFFFFFFFFu, hit);
+  }
+
+  // warp 0: commit the chunk's expansions in scan order. A result computed against the pre-chunk mask stands unless a rectangle
+  // committed earlier in this chunk touches what it probed; then (and after a centre-third hit, which re-examines the same seed)
+  // the seed is expanded again against the current mask, exactly as the sequential scan would have seen it.
+  __device__ void commit(int y, int stage, int nCand, uint2 *list, uint32_t &count)
+  {
+    int nAcc = 0;
+
+    for (int i = 0; i < nCand; i++)
+    {
+      const int x = sh->cand[i];
+
+      if (is_used(x, y))
+        continue;
+
+      SeedResult r = sh->res[i];
+      bool valid = r.kind >= 0 && !touches_accepted(nAcc, x, y, x + r.rx, y + r.ry);
+
+      if (valid && r.attempted)
+        valid = !touches_accepted(nAcc, r.cox - 1, r.coy - 1, r.cox + r.crx, r.coy + r.cry);
+
+      while (true)
       {
-        // next candidate seed of this row at column >= x: unused and passing the stage's necessary condition on its match word
-        const long long ts0 = clock64();
+        if (!valid)
         {
-          int found = -1;
-
-          for (int base = x & ~31; base < a.BX && found < 0; base += 32)
-          {
-            const int xx = base + lane;
-            bool cand = false;
-
-            if (xx >= x && xx < a.BX && !is_used(xx, y))
-            {
-              const uint32_t w0 = winBand[(size_t)((y - bandY0) * a.BX + xx) * 2];
-              cand = stage == 0 ? ((w0 & 0x070707u) == 0x070707u) : ((w0 & 0x0102u) != 0);
-
-              if (cand)
-              {
-                // warm L1 with the speculative bitmaps this seed may consult
-                const uint32_t es = extBand[(y - bandY0) * a.BX + xx];
-                if (es != LIMG_NO_SLOT)
-                  asm volatile("prefetch.global.L1 [%0];" ::"l"(a.extBits + (size_t)(es & 0x7FFFFFFFu) * 32));
-
-                const uint32_t cs = stage == 0 ? ctrBand[(y - bandY0) * a.BX + xx] : LIMG_NO_SLOT;
-                if (cs != LIMG_NO_SLOT)
-                {
-                  asm volatile("prefetch.global.L1 [%0];" ::"l"(a.ctrHdr + cs));
-                  asm volatile("prefetch.global.L1 [%0];" ::"l"(a.ctrBits + (size_t)cs * 32));
-                }
-              }
-            }
-
-            const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, cand);
-
-            if (ballot)
-              found = base + __ffs(ballot) - 1;
-          }
-
-          tSearch += clock64() - ts0;
-
-          if (found < 0)
-            break;
-
-          x = found;
+          nInline++;
+          r = expand(x, y, stage);
+          valid = true;
         }
 
-        int rx, ry;
-        nSeeds++;
-        const long long tg0 = clock64();
-        grow_seed(x, y, rx, ry);
-        tGrow += clock64() - tg0;
+        if (r.kind == 0)
+          break;
 
-        int eox = x, eoy = y, erx = rx, ery = ry;
-        bool take = false, rescan = false;
-
-        if (stage == 0)
-        {
-          if (rx >= 3 && ry >= 3) // Q4
-          {
-            int cox = x + rx / 3, coy = y + ry / 3, crx = rx / 3, cry = ry / 3;
-            const long long tf0 = clock64();
-            inFour = true;
-            grow_four_way(cox, coy, crx, cry, x, y, rx, ry);
-            inFour = false;
-            tFour += clock64() - tf0;
-            nFour++;
-
-            if (crx * cry > rx * ry)
-            {
-              eox = cox; eoy = coy; erx = crx; ery = cry;
-              rescan = true;
-            }
-
-            take = true;
-          }
-        }
-        else
-        {
-          take = rx > 1 || ry > 1;
-        }
-
-        if (!take)
-        {
-          x++;
-          continue;
-        }
-
+        const int eox = r.kind == 2 ? r.cox : x, eoy = r.kind == 2 ? r.coy : y;
+        const int erx = r.kind == 2 ? r.crx : r.rx, ery = r.kind == 2 ? r.cry : r.ry;
         mark_used(eox, eoy, erx, ery);
+        const uint2 packed = make_uint2((uint32_t)eox | ((uint32_t)eoy << 16), (uint32_t)erx | ((uint32_t)ery << 16));
 
         if (lane == 0)
         {
           if (count < (uint32_t)a.listCap)
-            list[count] = make_uint2((uint32_t)eox | ((uint32_t)eoy << 16), (uint32_t)erx | ((uint32_t)ery << 16));
+            list[count] = packed;
           else
             a.sync[2] = 1; // list overflow: reported by the host as LIMGCU_ERROR_OUT_OF_BOUNDS
+
+          if (nAcc < LIMG_ROW_CHUNK + 32)
+            sh->accepted[nAcc] = packed;
         }
 
+        __syncwarp();
         count++;
+        nAcc++;
 
-        if (!rescan)
-          x += rx;
+        if (nAcc >= LIMG_ROW_CHUNK + 32)
+          nAcc = LIMG_ROW_CHUNK + 32; // list full: every later result of this chunk is re-expanded (still exact)
+
+        if (r.kind == 2 && !is_used(x, y))
+        {
+          valid = false; // limg.cpp:1435-1438: the scan resumes at the same seed
+          continue;
+        }
+
+        break;
+      }
+
+      if (nAcc >= LIMG_ROW_CHUNK + 32)
+      {
+        // cannot track more rectangles: fall back to sequential handling of the rest of the chunk
+        for (int j = i + 1; j < nCand; j++)
+          sh->res[j].attempted = 1, sh->res[j].cox = 0, sh->res[j].coy = 0, sh->res[j].crx = (short)a.BX, sh->res[j].cry = (short)a.BY;
       }
     }
-
-    if (lane == 0 && a.stats)
-    {
-      atomicAdd(&a.stats[4], nSeeds); atomicAdd(&a.stats[5], nPost1); atomicAdd(&a.stats[6], nPost2); atomicAdd(&a.stats[7], nFour); atomicAdd(&a.stats[12], nPlanned); atomicAdd(&a.stats[13], nPostInFour); atomicAdd(&a.stats[14], nExtSeeds); atomicAdd(&a.stats[15], nPostS8); atomicAdd(&a.stats[1], nPostS16); atomicAdd(&a.stats[0], nPostS32); atomicAdd(&a.stats[3], nBigSeeds);
-      atomicAdd(&a.stats[8], (uint32_t)(tSearch >> 10)); atomicAdd(&a.stats[9], (uint32_t)(tGrow >> 10)); atomicAdd(&a.stats[10], (uint32_t)(tPost >> 10)); atomicAdd(&a.stats[11], (uint32_t)(tFour >> 10));
-    }
-
-    return min(count, (uint32_t)a.listCap);
   }
 };
 
@@ -1045,26 +968,25 @@ __global__ void __launch_bounds__(LIMG_MERGE_THREADS) k_merge_banded(MergeArgs a
   const int maskWords = a.BY * a.wordsPerRow;
   uint32_t *winBand = used + maskWords;
   uint32_t *extBand = winBand + (size_t)a.bandRows * a.BX * 2;
-  uint32_t *ctrBand = extBand + (size_t)a.bandRows * a.BX;
-  __shared__ MergeMailbox mail;
-  __shared__ int sDirty;
-  __shared__ int sRange[2];
-  __shared__ uint32_t sCount;
+  uint16_t *unmBand = reinterpret_cast<uint16_t *>(extBand + (size_t)a.bandRows * a.BX);
+  __shared__ BandShared sh;
 
   const int k = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int bandY0 = k * a.bandRows, bandY1 = min(a.BY, bandY0 + a.bandRows);
   uint32_t *snapshot = a.snapshot + (size_t)k * maskWords;
 
-  // the band's match words never change: shared memory
+  // the band's match words and extension slots never change: shared memory
   for (int i = threadIdx.x; i < (bandY1 - bandY0) * a.BX * 2; i += blockDim.x)
     winBand[i] = a.window[(size_t)bandY0 * a.BX * 2 + i];
 
   for (int i = threadIdx.x; i < (bandY1 - bandY0) * a.BX; i += blockDim.x)
   {
     extBand[i] = a.extSlot[(size_t)bandY0 * a.BX + i];
-    ctrBand[i] = a.ctrSlot[(size_t)bandY0 * a.BX + i];
+    unmBand[i] = a.unmasked[(size_t)bandY0 * a.BX + i];
   }
+
+  BandScan<CH> scan{ a, used, winBand, extBand, &sh, lane, bandY0, bandY1, a.BY, -1, 0, 0, 0, 0, false, false };
 
   for (int stage = 0; stage < 2; stage++)
   {
@@ -1103,7 +1025,7 @@ __global__ void __launch_bounds__(LIMG_MERGE_THREADS) k_merge_banded(MergeArgs a
       }
 
       if (threadIdx.x == 0)
-        sDirty = ran ? 0 : 1;
+        sh.dirty = ran ? 0 : 1;
 
       __syncthreads();
 
@@ -1115,11 +1037,11 @@ __global__ void __launch_bounds__(LIMG_MERGE_THREADS) k_merge_banded(MergeArgs a
           diff |= used[i] != snapshot[i];
 
         if (diff)
-          sDirty = 1;
+          sh.dirty = 1;
       }
 
       __syncthreads();
-      const bool dirty = sDirty != 0;
+      const bool dirty = sh.dirty != 0;
 
       if (dirty)
       {
@@ -1129,51 +1051,143 @@ __global__ void __launch_bounds__(LIMG_MERGE_THREADS) k_merge_banded(MergeArgs a
 
       grid_barrier(a.sync, gridDim.x); // every band has read the lists of the previous iteration
 
-      // ---- phase B: dirty bands replay their rows
+      // ---- phase B: dirty bands replay their rows, one chunk of candidate seeds at a time
       if (dirty)
       {
-        if (warp == 0)
+        if (threadIdx.x == 0)
         {
-          MergeScan<CH> scan{ a, used, winBand, extBand, ctrBand, &mail, lane, bandY0, bandY1, a.BY, -1 };
-          const uint32_t count = scan.run_band(stage, myList);
-
-          if (lane == 0)
-          {
-            sCount = count;
-            sRange[0] = scan.readLo;
-            sRange[1] = scan.readHi;
-            mail.kind = 0;
-            dirtyFlags[iter] = 1;
-
-            if (a.stats)
-              atomicAdd(&a.stats[2 + stage], 1u);
-          }
-
-          __syncwarp();
-          named_bar_sync(1, LIMG_MERGE_THREADS); // release the helpers
+          sh.count = 0;
+          sh.rangeLo = bandY0;      // the candidate search reads the in-use bits of every row of the band
+          sh.rangeHi = bandY1 - 1;
         }
-        else
-        {
-          while (true)
-          {
-            named_bar_sync(1, LIMG_MERGE_THREADS);
 
-            if (mail.kind == 0)
+        scan.readLo = a.BY;
+        scan.readHi = -1;
+        __syncthreads();
+
+        for (int y = bandY0; y < bandY1; y++)
+        {
+          int x = 0;
+
+          while (x < a.BX)
+          {
+            // warp 0: the next candidate seeds of this row (unused + the stage's necessary condition on the match word)
+            if (warp == 0)
+            {
+              int n = 0, xx0 = x & ~31;
+
+              for (; xx0 < a.BX && n < a.rowChunk; xx0 += 32)
+              {
+                const int xx = xx0 + lane;
+                bool cand = false;
+
+                if (xx >= x && xx < a.BX && !scan.is_used(xx, y))
+                {
+                  const uint32_t w0 = winBand[(size_t)((y - bandY0) * a.BX + xx) * 2];
+                  cand = stage == 0 ? ((w0 & 0x070707u) == 0x070707u) : ((w0 & 0x0102u) != 0);
+                }
+
+                const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, cand);
+                const int pos = n + __popc(ballot & ((1u << lane) - 1u));
+
+                if (cand && pos < a.rowChunk)
+                  sh.cand[pos] = (short)xx;
+
+                n += __popc(ballot);
+              }
+
+              if (lane == 0)
+              {
+                sh.nCand = min(n, a.rowChunk);
+                // row exhausted and everything taken: done after this chunk; otherwise resume behind the last candidate taken
+                sh.nextX = (xx0 >= a.BX && n <= a.rowChunk) ? a.BX : -1;
+              }
+
+              __syncwarp();
+
+              // Dry run of the scan order on the mask-free growth predicted by the plan kernels: a candidate that lies inside
+              // the rectangle an earlier candidate of this chunk is predicted to emit will most likely be swallowed; it is not
+              // expanded speculatively, commit() expands it on the spot in the rare case it is still free when its turn comes.
+              if (lane == 0)
+              {
+                const int nc = min(n, a.rowChunk);
+                int coverUntil = -1;
+
+                for (int i = 0; i < nc; i++)
+                {
+                  const int xc = sh.cand[i];
+                  const uint32_t u = unmBand[(y - bandY0) * a.BX + xc];
+                  const int prx = u & 0xFF, pry = (u >> 8) & 0x7F;
+
+                  if (xc < coverUntil)
+                  {
+                    // small growths are cheap to expand even if they end up swallowed; only the big ones (which would go on demand) are deferred
+                    sh.res[i].kind = (prx >= 8 || pry >= 8) ? -1 : 0;
+                    continue;
+                  }
+
+                  sh.res[i].kind = 0;
+                  const bool emits = stage == 0 ? (prx >= 3 && pry >= 3) : (prx > 1 || pry > 1);
+
+                  if (emits)
+                    coverUntil = xc + prx;
+                }
+              }
+            }
+
+            __syncthreads();
+            const int nCand = sh.nCand;
+
+            if (nCand == 0)
               break;
 
-            MergeScan<CH>::serve(a, &mail, used, warp);
-            named_bar_sync(2, LIMG_MERGE_THREADS);
+            // every warp: expand its share of the candidates against the current mask (read only)
+            for (int i = warp; i < nCand; i += LIMG_MERGE_WARPS)
+            {
+              // probably swallowed by an earlier candidate's rectangle: only the cheap (bitmap) part is done speculatively
+              const SeedResult r = scan.expand(sh.cand[i], y, stage, sh.res[i].kind < 0);
+
+              if (lane == 0)
+                sh.res[i] = r;
+            }
+
+            __syncthreads();
+
+            if (warp == 0)
+            {
+              uint32_t count = sh.count;
+              scan.commit(y, stage, nCand, myList, count);
+
+              if (lane == 0)
+                sh.count = count;
+            }
+
+            const int lastCand = sh.cand[nCand - 1];
+            const int nextX = sh.nextX;
+            __syncthreads();
+            x = nextX < 0 ? lastCand + 1 : nextX;
           }
+        }
+
+        if (lane == 0 && scan.readHi >= scan.readLo)
+        {
+          atomicMin(&sh.rangeLo, scan.readLo);
+          atomicMax(&sh.rangeHi, scan.readHi);
         }
 
         __syncthreads();
         ran = true;
-        readLo = sRange[0];
-        readHi = sRange[1];
+        readLo = sh.rangeLo;
+        readHi = sh.rangeHi;
 
         if (threadIdx.x == 0)
         {
-          a.counts[k * 2 + stage] = sCount;
+          a.counts[k * 2 + stage] = min(sh.count, (uint32_t)a.listCap);
+          dirtyFlags[iter] = 1;
+
+          if (a.stats)
+            atomicAdd(&a.stats[2 + stage], 1u);
+
           __threadfence();
         }
       }
@@ -1188,6 +1202,14 @@ __global__ void __launch_bounds__(LIMG_MERGE_THREADS) k_merge_banded(MergeArgs a
         break;
       }
     }
+  }
+
+  if (lane == 0 && a.stats)
+  {
+    atomicAdd(&a.stats[4], scan.nSeeds);
+    atomicAdd(&a.stats[5], scan.nOnDemand);
+    atomicAdd(&a.stats[6], scan.nFour);
+    atomicAdd(&a.stats[7], scan.nInline);
   }
 
   // ---- emission order = band order, stage 0 then stage 1; in-use mask for the leftover pass

@@ -41,10 +41,10 @@ struct limgcu_ctx
   uint32_t *dBandSnapshot = nullptr;
   uint32_t *dBandState = nullptr; // [0..8 + 2 * (MAX_BANDS + 2)) barrier + flags, then counts [MAX_BANDS * 2]
   size_t capBandLists = 0, capBandSnapshot = 0;
-  uint32_t *dExtSlot = nullptr, *dExtSeed = nullptr, *dExtBits = nullptr, *dCtrSlot = nullptr, *dCtrBits = nullptr, *dPlanCounters = nullptr;
-  uint4 *dCtrHdr = nullptr;
+  uint32_t *dExtSlot = nullptr, *dExtSeed = nullptr, *dExtBits = nullptr, *dPlanCounters = nullptr;
   uint32_t *dSym = nullptr;
-  uint32_t extCap = 0, ctrCap = 0;
+  uint16_t *dUnmasked = nullptr;
+  uint32_t extCap = 0;
   uint32_t *dScratchPx = nullptr, *dScratchFac = nullptr;
   uint32_t *dCounters = nullptr; // [16]: 0 merged, 1 areaCount, 2 smallCount, 3 largeCount, 4 workSmall, 5 workLarge, 8.. stats
   unsigned long long *dCompare = nullptr;
@@ -55,6 +55,7 @@ struct limgcu_ctx
   uint32_t *dPlaneU32[9] = { nullptr };
   uint8_t *dPlaneU8[7] = { nullptr }; // factors A,B,C, bpp, codes A,B,C
 
+  int mergeExt = 1, mergeChunk = 64; // tunables (LIMGCU_MERGE_EXT, LIMGCU_MERGE_CHUNK)
   bool timing = false;
   cudaEvent_t ev[PHASE_COUNT + 1] = { nullptr };
   float phaseMs[PHASE_COUNT] = { 0 };
@@ -103,14 +104,11 @@ static int ensure_capacity(limgcu_ctx *ctx, size_t W, size_t H)
     CK(regrow(ctx->dLargeList, blocks));
     CK(regrow(ctx->dDemand, blocks));
     ctx->extCap = (uint32_t)(blocks / 2 > 1024 ? blocks / 2 : 1024);
-    ctx->ctrCap = (uint32_t)(blocks / 2 > 1024 ? blocks / 2 : 1024);
     CK(regrow(ctx->dSym, blocks * 8));
+    CK(regrow(ctx->dUnmasked, blocks));
     CK(regrow(ctx->dExtSlot, blocks));
-    CK(regrow(ctx->dCtrSlot, blocks));
     CK(regrow(ctx->dExtSeed, (size_t)ctx->extCap));
     CK(regrow(ctx->dExtBits, (size_t)ctx->extCap * 32));
-    CK(regrow(ctx->dCtrHdr, (size_t)ctx->ctrCap));
-    CK(regrow(ctx->dCtrBits, (size_t)ctx->ctrCap * 32));
     if (ctx->dPlanCounters == nullptr) CK(regrow(ctx->dPlanCounters, (size_t)8));
     ctx->capBlocks = blocks;
   }
@@ -227,6 +225,9 @@ extern "C" int limgcu_create(int device, limgcu_ctx **out)
     ctx->jt.add[j] = ctx->jt.add[j - 1] * (ctx->jt.mul[j - 1] + 1);
   }
 
+  if (const char *v = getenv("LIMGCU_MERGE_EXT")) ctx->mergeExt = atoi(v);
+  if (const char *v = getenv("LIMGCU_MERGE_CHUNK")) ctx->mergeChunk = atoi(v) < 1 ? 1 : (atoi(v) > LIMG_ROW_CHUNK ? LIMG_ROW_CHUNK : atoi(v));
+
   for (auto &e : ctx->ev)
     if (cudaEventCreate(&e) != cudaSuccess) return bail(LIMGCU_ERROR_CUDA);
 
@@ -251,7 +252,7 @@ extern "C" void limgcu_destroy(limgcu_ctx *ctx)
 
   void *ptrs[] = { ctx->dLut, ctx->dTable, ctx->dRec, ctx->dWindow, ctx->dAreas, ctx->dBlockToArea, ctx->dWork, ctx->dSmallList, ctx->dLargeList, ctx->dDemand,
                    ctx->dUsed, ctx->dScratchPx, ctx->dScratchFac, ctx->dCounters, ctx->dCompare, ctx->dSrc, ctx->dBandLists, ctx->dBandSnapshot, ctx->dBandState,
-                   ctx->dExtSlot, ctx->dExtSeed, ctx->dExtBits, ctx->dCtrSlot, ctx->dCtrBits, ctx->dPlanCounters, ctx->dCtrHdr, ctx->dSym };
+                   ctx->dExtSlot, ctx->dExtSeed, ctx->dExtBits, ctx->dPlanCounters, ctx->dSym, ctx->dUnmasked };
 
   for (void *p : ptrs)
     if (p) cudaFree(p);
@@ -361,7 +362,7 @@ static int launch_merge(limgcu_ctx *ctx, const limgcu_decomp *dTable, size_t W, 
     const int bandRows = BY / 128 + 1 > 8 ? BY / 128 + 1 : 8;
     const int numBands = (BY + bandRows - 1) / bandRows;
     const size_t usedBytes = (size_t)BY * wordsPerRow * sizeof(uint32_t);
-    const size_t smemBytes = usedBytes + (size_t)bandRows * BX * 4 * sizeof(uint32_t);
+    const size_t smemBytes = usedBytes + (size_t)bandRows * BX * (3 * sizeof(uint32_t) + sizeof(uint16_t)) + 16;
 
     if (smemBytes > 200 * 1024 || numBands > LIMG_MERGE_MAX_BANDS || numBands > ctx->smCount || BX > 65535 || BY > 65535)
       return fail(ctx, LIMGCU_ERROR_OUT_OF_BOUNDS, "image too large for the shared-memory in-use mask of the banded merge", cudaSuccess);
@@ -388,8 +389,7 @@ static int launch_merge(limgcu_ctx *ctx, const limgcu_decomp *dTable, size_t W, 
     PlanArgs pl;
     pl.rec = ctx->dRec; pl.window = ctx->dWindow; pl.BX = BX; pl.BY = BY;
     pl.extSlot = ctx->dExtSlot; pl.extSeed = ctx->dExtSeed; pl.extBits = ctx->dExtBits;
-    pl.ctrSlot = ctx->dCtrSlot; pl.ctrHdr = ctx->dCtrHdr; pl.ctrBits = ctx->dCtrBits;
-    pl.counters = ctx->dPlanCounters; pl.extCap = ctx->extCap; pl.ctrCap = ctx->ctrCap;
+    pl.counters = ctx->dPlanCounters; pl.extCap = ctx->mergeExt ? ctx->extCap : 0; pl.unmasked = ctx->dUnmasked;
     CK(cudaMemsetAsync(ctx->dPlanCounters, 0, 8 * sizeof(uint32_t), ctx->stream));
     k_plan_seeds<<<(blocks + 255) / 256, 256, 0, ctx->stream>>>(pl);
     CKL("k_plan_seeds");
@@ -412,9 +412,9 @@ static int launch_merge(limgcu_ctx *ctx, const limgcu_decomp *dTable, size_t W, 
 
     MergeArgs m;
     m.rec = ctx->dRec; m.window = ctx->dWindow;
-    m.extSlot = ctx->dExtSlot; m.extBits = ctx->dExtBits; m.ctrSlot = ctx->dCtrSlot; m.ctrBits = ctx->dCtrBits; m.ctrHdr = ctx->dCtrHdr; m.sym = ctx->dSym;
+    m.extSlot = ctx->dExtSlot; m.extBits = ctx->dExtBits; m.sym = ctx->dSym; m.unmasked = ctx->dUnmasked;
     m.BX = BX; m.BY = BY; m.wordsPerRow = wordsPerRow;
-    m.bandRows = bandRows; m.numBands = numBands; m.listCap = bandRows * BX * 2;
+    m.bandRows = bandRows; m.numBands = numBands; m.listCap = bandRows * BX * 2; m.rowChunk = ctx->mergeChunk;
     m.lists = ctx->dBandLists; m.counts = ctx->dBandState + 512; m.snapshot = ctx->dBandSnapshot; m.sync = ctx->dBandState;
     m.areas = dAreas; m.mergedCount = ctx->dCounters + 0; m.usedOut = ctx->dUsed; m.stats = ctx->dCounters + 8;
     void *kargs[] = { &m };

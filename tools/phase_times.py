@@ -18,6 +18,5 @@ for name in ("c1_512_gradient","c5_1080p_frame0","c2_4k_photo","c4_4k_flatui","c
     ph = c.phase_ms()
     tot = sum(ph.values())
     cnt = c.debug_counters()
-    print("   counters: merged %d areas %d small %d large %d | iters %s bandruns %s seeds %d post1 %d post2 %d four %d planned %d | Mcycles search %.1f grow %.1f post %.1f four %.1f" % (cnt[0],cnt[1],cnt[2],cnt[3],cnt[8:10],cnt[10:12],cnt[12],cnt[13],cnt[14],cnt[15],cnt[20],cnt[16]/1024,cnt[17]/1024,cnt[18]/1024,cnt[19]/1024))
-    print("   postInFour %d extSeeds %d planExt %d planCtr %d | postS8 %d postS16 %d postS32 %d bigSeeds %d" % (cnt[21],cnt[22],cnt[24],cnt[25],cnt[23],cnt[9],cnt[8],cnt[11]))
+    print("   merged %d areas %d small %d large %d | iters %s bandruns %s | seedExpansions %d onDemandPredicates %d fourWay %d inlineRecompute %d planExt %d" % (cnt[0],cnt[1],cnt[2],cnt[3],cnt[8:10],cnt[10:12],cnt[12],cnt[13],cnt[14],cnt[15],cnt[24]))
     print(name, "%dx%d"%(w,h), "total %.3f ms (wall %.3f) -> %.1f Mpx/s"%(tot, dt*1e3, w*h/tot/1e3), {k: round(v,3) for k,v in ph.items()})
