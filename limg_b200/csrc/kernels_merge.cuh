@@ -281,6 +281,10 @@ struct PlanArgs
   uint32_t *counters;  // [0] ext slots
   uint32_t extCap;
   uint16_t *unmasked;  // per block: rx | ry << 8 of the mask-free right/down growth inside the best available bitmap
+  uint32_t *candBits;  // [2][BY][wordsPerRow] (zeroed by the host): blocks that can emit in stage 0 (3x3 corner matches) / stage 1 (right or lower neighbour matches)
+  uint32_t *candList;  // [2][blocks] the same as lists, counts in candCount[2]
+  uint32_t *candCount;
+  int wordsPerRow;
 };
 
 // mask-free alternating right/down growth over `rows` (S x S match bitmap of the seed); returns true if it wanted to leave the bitmap
@@ -327,12 +331,38 @@ __device__ __forceinline__ bool expand_unmasked(const uint32_t *rows, int S, int
 __global__ void __launch_bounds__(256) k_plan_seeds(PlanArgs a)
 {
   const int seed = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool inside = seed < a.BX * a.BY;
+  const int y = inside ? seed / a.BX : 0, x = inside ? seed - y * a.BX : 0;
+  const uint32_t w0 = inside ? a.window[(size_t)seed * 2] : 0u, w1 = inside ? a.window[(size_t)seed * 2 + 1] : 0u;
 
-  if (seed >= a.BX * a.BY)
+  if (a.candBits)
+  {
+    // necessary conditions (mask-free) for the seed to emit anything: stage 0 needs a 3x3 rectangle, stage 1 one neighbour
+    const bool c[2] = { inside && (w0 & 0x070707u) == 0x070707u, inside && (w0 & 0x0102u) != 0u };
+    const int lane = threadIdx.x & 31;
+
+#pragma unroll
+    for (int st = 0; st < 2; st++)
+    {
+      const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, c[st]);
+      uint32_t pos = 0;
+
+      if (lane == 0 && ballot)
+        pos = atomicAdd(&a.candCount[st], (uint32_t)__popc(ballot));
+
+      pos = __shfl_sync(0xFFFFFFFFu, pos, 0) + __popc(ballot & ((1u << lane) - 1u));
+
+      if (c[st])
+      {
+        a.candList[(size_t)st * a.BX * a.BY + pos] = (uint32_t)seed;
+        atomicOr(&a.candBits[((size_t)st * a.BY + y) * a.wordsPerRow + (x >> 5)], 1u << (x & 31));
+      }
+    }
+  }
+
+  if (!inside)
     return;
 
-  const int y = seed / a.BX, x = seed - y * a.BX;
-  const uint32_t w0 = a.window[(size_t)seed * 2], w1 = a.window[(size_t)seed * 2 + 1];
   uint32_t rows[8];
 
 #pragma unroll

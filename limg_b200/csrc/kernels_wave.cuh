@@ -1,0 +1,777 @@
+// limg_b200/csrc/kernels_wave.cuh -- the area-expansion scan as a row-pipelined wavefront with an exact verification pass
+// (limg.cpp:1121-1135, 1277-1496, drivers 1814-1858).
+//
+// The reference's merge is a serial greedy raster scan; the only state it carries from seed to seed is the in-use mask, and the
+// predicate "candidate block joins seed" is a pure function of two pass-1 records. Every rectangle the scan emits
+// gets a LOGICAL TIME T = (seed raster index, attempt number); the sequential result is the unique record in which every seed's
+// decision equals what limg_encode_find_block_3d does against the mask { blocks owned by a rectangle with time < T }.
+//
+//   k_merge_wave    one warp per block row (rows handed out by ticket, so a row's predecessor is always running). A row walks
+//                   its candidate seeds left to right against the LIVE mask in global memory (L2). Before a seed's decision
+//                   stands, the row above must have committed every seed left of (right edge of everything the seed probed +
+//                   margin); by induction the rows further up are further ahead. That lag rule is a heuristic: the four-way
+//                   centre-third regrowth can reach arbitrarily far to the left, so
+//   k_merge_verify  replays EVERY candidate seed, fully in parallel, against the mask "owner time < my time" built from the
+//                   per-block owner times the wave wrote, and compares with what the wave recorded. All equal (and no
+//                   rectangle overlap, detected by the atomicOr of the claims)  =>  the record is self-consistent  =>  it is
+//                   the sequential scan's result (induction over T).
+//   fallback        if verification fails, the stage is reset and the same kernel re-runs with rows strictly in sequence
+//                   (row y starts when row y-1 is done): that IS the reference's order, no verification needed.
+//
+// Stage 1 (remaining merges, limg.cpp:1838-1858) repeats the procedure on top of the final stage-0 mask.
+#pragma once
+
+#include "kernels_merge.cuh"
+
+namespace limg
+{
+
+#define LIMG_WAVE_DONE 0x7FFFFFFF
+#define LIMG_TAU_NONE 0xFFFFFFFFu
+#define LIMG_TAU_STAGE1 0x40000000u
+#define LIMG_WAVE_WARPS 4
+#define LIMG_WAVE_MAX_ATTEMPTS 8
+
+struct WaveArgs
+{
+  const PredRec *rec;
+  const uint32_t *window;
+  const uint32_t *extSlot, *extBits, *sym;
+  const uint16_t *unmasked;
+  const uint32_t *candBits;  // [2][BY][wordsPerRow]: mask-free necessary condition for a seed to emit in stage 0 / 1
+  const uint32_t *candList;  // [2][blocks]
+  const uint32_t *candCount; // [2]
+  int BX, BY, wordsPerRow;
+  uint32_t *used;            // [BY][wordsPerRow] live in-use bits
+  uint32_t *tau;             // [blocks] logical time of the rectangle that owns the block
+  int *progress;             // [2][BY] column up to which the row's seeds are committed (LIMG_WAVE_DONE when finished)
+  uint32_t *ticket;          // [2]
+  uint2 *rowLists;           // [2][BY][listCap] (ox | oy << 16, rx | ry << 16) in emission order
+  uint32_t *rowCounts;       // [2][BY]
+  uint32_t *emitInfo;        // [2][blocks] per seed: first entry in its row list << 8 | number of entries
+  uint32_t *flags;           // [0], [1] stage needs the sequential fallback; [2] list overflow (hard error); [3] watchdog (hard error)
+  uint32_t *stats;           // [16] optional counters
+  int listCap, margin;
+};
+
+__device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t *p)
+{
+  uint32_t v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__device__ __forceinline__ int ld_acquire_s32(const int *p)
+{
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__device__ __forceinline__ void st_release_s32(int *p, int v)
+{
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+
+// the live in-use mask (global memory, read at L2)
+struct LiveMask
+{
+  const uint32_t *used;
+  int wordsPerRow, BX, BY;
+
+  // n (<= 32) in-use bits of row y starting at column x (x may be negative); everything outside the grid reads as in use
+  __device__ __forceinline__ uint32_t bits(int x, int y, int n) const
+  {
+    (void)n;
+
+    if (y < 0 || y >= BY)
+      return 0xFFFFFFFFu;
+
+    const uint32_t *row = used + (size_t)y * wordsPerRow;
+
+    if (x < 0)
+    {
+      const int s = -x; // 1..31
+      return (ld_relaxed_u32(row) << s) | ((1u << s) - 1u);
+    }
+
+    const int w0 = x >> 5, s = x & 31;
+    const uint32_t lo = ld_relaxed_u32(row + w0);
+    const uint32_t hi = s ? ld_relaxed_u32(row + w0 + 1) : 0u; // the row has a padding word; columns >= BX are handled by the grid tests of the growth
+    return __funnelshift_r(lo, hi, s);
+  }
+
+  __device__ __forceinline__ bool is_used(int x, int y) const
+  {
+    return (ld_relaxed_u32(used + (size_t)y * wordsPerRow + (x >> 5)) >> (x & 31)) & 1u;
+  }
+};
+
+// the mask the sequential scan shows a seed at logical time T: blocks owned by an earlier rectangle
+struct TimeMask
+{
+  const uint32_t *tau;
+  int BX, BY;
+  uint32_t T;
+
+  __device__ __forceinline__ uint32_t bits(int x, int y, int n) const
+  {
+    if (y < 0 || y >= BY)
+      return 0xFFFFFFFFu;
+
+    const uint32_t *row = tau + (size_t)y * BX;
+    uint32_t b = 0;
+
+    for (int i = 0; i < n; i++)
+    {
+      const int xx = x + i;
+      const bool u = (xx < 0 || xx >= BX) ? true : (__ldg(row + xx) < T);
+      b |= (u ? 1u : 0u) << i;
+    }
+
+    return b;
+  }
+
+  __device__ __forceinline__ bool is_used(int x, int y) const
+  {
+    return __ldg(tau + (size_t)y * BX + x) < T;
+  }
+};
+
+// what one seed does against a given mask
+struct WaveResult
+{
+  int rx, ry;             // right/down rectangle grown from the seed
+  int kind;               // 0 nothing to emit, 1 emit the right/down rectangle, 2 emit the centre-third regrowth (and examine the seed again)
+  int cox, coy, crx, cry; // four-way regrowth (valid when kind == 2)
+  int boxR;               // exclusive right edge of every column whose in-use bits were consulted
+};
+
+// Every method is warp-cooperative: all 32 lanes call it with warp-uniform arguments.
+template <int CH, class Mask>
+struct WaveScan
+{
+  const WaveArgs &a;
+  Mask mask;
+  int lane;
+  uint32_t nOnDemand;
+
+  __device__ bool strip_unused(int x0, int y0, int w, int h)
+  {
+    bool any = false;
+
+    for (int e = lane; e < w * h; e += 32)
+    {
+      const int yy = y0 + e / w, xx = x0 + e % w;
+      any |= mask.is_used(xx, yy);
+    }
+
+    return !__any_sync(0xFFFFFFFFu, any);
+  }
+
+  // every block of the strip matches the seed? short strips one predicate at a time with the 27 samples spread over the lanes,
+  // long strips one predicate per lane.
+  __device__ bool strip_matches(const PredRec &seed, int x0, int y0, int w, int h)
+  {
+    const int count = w * h;
+    nOnDemand += count;
+
+    if (count >= 6)
+    {
+      bool ok = true;
+
+      for (int base = 0; base < count && ok; base += 32)
+      {
+        const int e = base + lane;
+        bool m = true;
+
+        if (e < count)
+        {
+          const int yy = y0 + e / w, xx = x0 + e % w;
+          m = predicate_thread<CH>(seed, a.rec[(size_t)yy * a.BX + xx]);
+        }
+
+        ok = __all_sync(0xFFFFFFFFu, m);
+      }
+
+      return ok;
+    }
+
+    for (int e = 0; e < count; e++)
+    {
+      const int yy = y0 + e / w, xx = x0 + e % w;
+
+      if (!predicate_warp<CH>(seed, a.rec[(size_t)yy * a.BX + xx]))
+        return false;
+    }
+
+    return true;
+  }
+
+  __device__ bool strip_joins(const PredRec &seed, int x0, int y0, int w, int h)
+  {
+    return strip_unused(x0, y0, w, h) && strip_matches(seed, x0, y0, w, h);
+  }
+
+  // right/down growth of a 1x1 seed (limg.cpp:1294-1343). The seed's match bitmap (8x8 word, or the speculative 16x16 / 32x32
+  // extension) lives one row per lane; growth inside it is ballots and shuffles, strips beyond it are evaluated on demand.
+  __device__ void grow_seed(int x, int y, int &rx, int &ry)
+  {
+    const int seed = y * a.BX + x;
+    const uint32_t slot = __ldg(&a.extSlot[seed]);
+    int S = 8;
+    uint32_t rowBits;
+
+    if (slot == LIMG_NO_SLOT)
+    {
+      const uint32_t *wp = a.window + (size_t)seed * 2;
+      rowBits = lane < 8 ? (__ldg(&wp[lane >> 2]) >> (8 * (lane & 3))) & 0xFFu : 0u;
+    }
+    else
+    {
+      S = (slot >> 31) ? 32 : 16;
+      rowBits = lane < S ? __ldg(&a.extBits[(size_t)(slot & 0x7FFFFFFFu) * 32 + lane]) : 0u;
+    }
+
+    const uint32_t avail = lane < S ? (rowBits & ~mask.bits(x, y + lane, S)) : 0u;
+    bool right = true, down = true;
+    bool haveRec = false;
+    PredRec rec;
+    rx = 1;
+    ry = 1;
+
+    while (right || down)
+    {
+      if (right)
+      {
+        bool ok = x + rx + 1 < a.BX;
+
+        if (ok)
+        {
+          const int rows = min(ry, S);
+
+          if (rx < S)
+          {
+            const uint32_t need = rows >= 32 ? 0xFFFFFFFFu : ((1u << rows) - 1u);
+            const uint32_t have = __ballot_sync(0xFFFFFFFFu, (avail >> rx) & 1u);
+            ok = (have & need) == need;
+          }
+
+          if (ok && (rx >= S || ry > S))
+          {
+            if (!haveRec) { rec = a.rec[seed]; haveRec = true; }
+            ok = rx >= S ? strip_joins(rec, x + rx, y, 1, ry) : strip_joins(rec, x + rx, y + S, 1, ry - S);
+          }
+        }
+
+        if (ok) rx++; else right = false;
+      }
+
+      if (down)
+      {
+        bool ok = y + ry + 1 < a.BY;
+
+        if (ok)
+        {
+          const int cols = min(rx, S);
+
+          if (ry < S)
+          {
+            const uint32_t need = cols >= 32 ? 0xFFFFFFFFu : ((1u << cols) - 1u);
+            const uint32_t rowv = __shfl_sync(0xFFFFFFFFu, avail, ry);
+            ok = (rowv & need) == need;
+          }
+
+          if (ok && (ry >= S || rx > S))
+          {
+            if (!haveRec) { rec = a.rec[seed]; haveRec = true; }
+            ok = ry >= S ? strip_joins(rec, x, y + ry, rx, 1) : strip_joins(rec, x + S, y + ry, rx - S, 1);
+          }
+        }
+
+        if (ok) ry++; else down = false;
+      }
+    }
+  }
+
+  // four-way alternating growth from the centre third (limg.cpp:1294-1388, 1426-1433). The centre seed's symmetric 16 x 16 match
+  // window covers [ox - 8, ox + 8) x [oy - 8, oy + 8), one row per lane; strips that leave it are evaluated on demand.
+  __device__ void grow_four_way(int &ox, int &oy, int &rx, int &ry)
+  {
+    const int seed = oy * a.BX + ox;
+    const int rgX = ox - 8, rgY = oy - 8;
+    uint32_t avail = 0;
+
+    if (lane < 16)
+    {
+      const uint32_t w = __ldg(&a.sym[(size_t)seed * 8 + (lane >> 1)]);
+      avail = ((w >> (16 * (lane & 1))) & 0xFFFFu) & ~mask.bits(rgX, rgY + lane, 16);
+    }
+
+    bool haveRec = false;
+    PredRec rec;
+    bool right = true, down = true, up = true, left = true;
+
+    // strip test: inside the window -> bits, otherwise on demand
+    auto joins = [&](int x0, int y0, int w, int h) -> bool {
+      if (x0 >= rgX && y0 >= rgY && x0 + w <= rgX + 16 && y0 + h <= rgY + 16)
+      {
+        const uint32_t m = ((1u << w) - 1u) << (x0 - rgX);
+        const int r0 = y0 - rgY;
+        const bool rowOk = (lane < r0 || lane >= r0 + h) || ((avail & m) == m);
+        return __all_sync(0xFFFFFFFFu, rowOk);
+      }
+
+      if (!haveRec) { rec = a.rec[seed]; haveRec = true; }
+      return strip_joins(rec, x0, y0, w, h);
+    };
+
+    while (right || down || up || left)
+    {
+      if (right)
+      {
+        if (ox + rx + 1 < a.BX && joins(ox + rx, oy, 1, ry)) rx++; else right = false;
+      }
+
+      if (down)
+      {
+        if (oy + ry + 1 < a.BY && joins(ox, oy + ry, rx, 1)) ry++; else down = false;
+      }
+
+      if (up)
+      {
+        if (oy > 0 && joins(ox, oy - 1, rx, 1)) { oy--; ry++; } else up = false;
+      }
+
+      if (left)
+      {
+        if (ox > 0 && joins(ox - 1, oy, 1, ry)) { ox--; rx++; } else left = false;
+      }
+    }
+  }
+
+  // what seed (x, y) does against the mask (limg.cpp:1405-1486)
+  __device__ WaveResult expand(int x, int y, int stage)
+  {
+    WaveResult r;
+    grow_seed(x, y, r.rx, r.ry);
+    r.kind = 0;
+    r.cox = r.coy = r.crx = r.cry = 0;
+    r.boxR = min(x + r.rx + 1, a.BX);
+
+    if (stage == 0)
+    {
+      if (r.rx >= 3 && r.ry >= 3) // Q4
+      {
+        int cox = x + r.rx / 3, coy = y + r.ry / 3, crx = r.rx / 3, cry = r.ry / 3;
+        grow_four_way(cox, coy, crx, cry);
+        r.cox = cox; r.coy = coy; r.crx = crx; r.cry = cry;
+        r.kind = (crx * cry > r.rx * r.ry) ? 2 : 1;
+        r.boxR = max(r.boxR, min(cox + crx + 1, a.BX));
+      }
+    }
+    else
+    {
+      r.kind = (r.rx > 1 || r.ry > 1) ? 1 : 0;
+    }
+
+    return r;
+  }
+};
+
+__device__ __forceinline__ uint2 pack_rect(int ox, int oy, int rx, int ry)
+{
+  return make_uint2((uint32_t)ox | ((uint32_t)oy << 16), (uint32_t)rx | ((uint32_t)ry << 16));
+}
+
+// next column >= x of row y whose candidate bit is set and whose in-use bit (fresh read) is clear; BX if none. Warp-cooperative.
+__device__ __forceinline__ int wave_next_candidate(const uint32_t *candRow, const uint32_t *usedRow, int nWords, int x, int BX, int lane)
+{
+  for (int w0 = x >> 5; w0 < nWords; w0 += 32)
+  {
+    const int w = w0 + lane;
+    uint32_t bits = 0;
+
+    if (w < nWords)
+    {
+      bits = __ldg(candRow + w) & ~ld_relaxed_u32(usedRow + w);
+
+      if (w == (x >> 5))
+        bits &= 0xFFFFFFFFu << (x & 31);
+    }
+
+    const uint32_t any = __ballot_sync(0xFFFFFFFFu, bits != 0);
+
+    if (any)
+    {
+      const int first = __ffs(any) - 1;
+      const uint32_t b = __shfl_sync(0xFFFFFFFFu, bits, first);
+      return min((w0 + first) * 32 + __ffs(b) - 1, BX);
+    }
+  }
+
+  return BX;
+}
+
+// Waits until every one of the 32 rows above row y has committed all seeds left of `need` (LIMG_WAVE_DONE satisfies every need):
+// one acquire load per lane, warp minimum. Rows further up are assumed to be further along (they are whenever the rectangles
+// are less than 32 rows tall; the verification pass covers the rest).
+#define LIMG_WAVE_SPIN_LIMIT (1u << 22) // watchdog: a wait that long (seconds) is a bug; flag it instead of hanging the GPU
+
+__device__ __forceinline__ int wave_wait(const int *progress, int y, int need, uint32_t &polls, uint32_t *flags)
+{
+  const int r = y - 1 - (int)(threadIdx.x & 31);
+  int v;
+
+  for (uint32_t spins = 0;; spins++)
+  {
+    v = r >= 0 ? ld_acquire_s32(progress + r) : LIMG_WAVE_DONE;
+    v = __reduce_min_sync(0xFFFFFFFFu, v);
+
+    if (v >= need)
+      break;
+
+    if (spins > LIMG_WAVE_SPIN_LIMIT)
+    {
+      flags[3] = 1;
+      return LIMG_WAVE_DONE;
+    }
+
+    polls++;
+    __nanosleep(v + 64 < need ? 400 : 40);
+  }
+
+  return v;
+}
+
+template <int CH>
+__global__ void __launch_bounds__(LIMG_WAVE_WARPS * 32) k_merge_wave(WaveArgs a, int stage, int sequential)
+{
+  if (sequential && a.flags[stage] == 0)
+    return; // the fallback only runs when the pipelined pass failed its verification
+
+  const int lane = threadIdx.x & 31;
+  WaveScan<CH, LiveMask> scan{ a, LiveMask{ a.used, a.wordsPerRow, a.BX, a.BY }, lane, 0 };
+  int *progress = a.progress + (size_t)stage * a.BY;
+  const uint32_t *cand = a.candBits + (size_t)stage * a.BY * a.wordsPerRow;
+  uint2 *lists = a.rowLists + (size_t)stage * a.BY * a.listCap;
+  uint32_t *emitInfo = a.emitInfo + (size_t)stage * a.BX * a.BY;
+  const uint32_t base = stage ? LIMG_TAU_STAGE1 : 0u;
+  const int nWords = (a.BX + 31) >> 5;
+  uint32_t nExp = 0, nReexp = 0, nPolls = 0;
+  bool failed = false;
+
+  for (;;)
+  {
+    int y = 0;
+
+    if (lane == 0)
+      y = (int)atomicAdd(&a.ticket[stage], 1u);
+
+    y = __shfl_sync(0xFFFFFFFFu, y, 0);
+
+    if (y >= a.BY)
+      break;
+
+    if (sequential && y > 0)
+    {
+      // strictly one row after the other: the reference's order
+      if (lane == 0)
+      {
+        uint32_t spins = 0;
+
+        while (ld_acquire_s32(progress + y - 1) != LIMG_WAVE_DONE)
+        {
+          if (++spins > (LIMG_WAVE_SPIN_LIMIT << 3)) { a.flags[3] = 1; break; }
+          __nanosleep(100);
+        }
+      }
+
+      __syncwarp();
+    }
+
+    const uint32_t *candRow = cand + (size_t)y * a.wordsPerRow;
+    const uint32_t *usedRow = a.used + (size_t)y * a.wordsPerRow;
+    uint2 *list = lists + (size_t)y * a.listCap;
+    uint32_t count = 0;
+    int x = 0;
+
+    for (;;)
+    {
+      x = wave_next_candidate(candRow, usedRow, nWords, x, a.BX, lane);
+
+      // everything left of x is decided and (after the fence below) visible
+      if (lane == 0)
+        st_release_s32(progress + y, x >= a.BX ? LIMG_WAVE_DONE : x);
+
+      if (x >= a.BX)
+        break;
+
+      const uint32_t first = count;
+      int nextX = x + 1;
+      bool claimed = false;
+
+      for (int k = 0;; k++)
+      {
+        WaveResult r;
+        int p = LIMG_WAVE_DONE;
+        bool taken = false;
+
+        if (y > 0 && !sequential)
+          p = wave_wait(progress, y, min(x + 1 + a.margin, a.BX), nPolls, a.flags);
+
+        for (;;)
+        {
+          if (scan.mask.is_used(x, y)) { taken = true; break; }
+
+          r = scan.expand(x, y, stage);
+          nExp++;
+          const int need = min(r.boxR + a.margin, a.BX);
+
+          if (p >= need)
+            break;
+
+          p = wave_wait(progress, y, need, nPolls, a.flags); // the rows above have to pass everything this seed looked at: look again
+          nReexp++;
+        }
+
+        if (taken || r.kind == 0)
+          break;
+
+        const int eox = r.kind == 2 ? r.cox : x, eoy = r.kind == 2 ? r.coy : y;
+        const int erx = r.kind == 2 ? r.crx : r.rx, ery = r.kind == 2 ? r.cry : r.ry;
+        const uint32_t T = base + ((uint32_t)(y * a.BX + x) << 3) + (uint32_t)min(k, LIMG_WAVE_MAX_ATTEMPTS - 1);
+
+        if (k >= LIMG_WAVE_MAX_ATTEMPTS && !sequential)
+          failed = true; // more regrowths from one seed than the time stamp encodes: let the sequential pass do it
+
+        // claim: in-use bits (an overlap with anybody else's rectangle is a failed speculation) + owner times
+        bool overlap = false;
+
+        for (int rr = lane; rr < ery; rr += 32)
+        {
+          uint32_t *row = a.used + (size_t)(eoy + rr) * a.wordsPerRow;
+
+          for (int xx = eox; xx < eox + erx;)
+          {
+            const int w0 = xx >> 5, b0 = xx & 31;
+            const int cnt = min(32 - b0, eox + erx - xx);
+            const uint32_t m = (cnt == 32 ? 0xFFFFFFFFu : ((1u << cnt) - 1u)) << b0;
+            overlap |= (atomicOr(&row[w0], m) & m) != 0;
+            xx += cnt;
+          }
+        }
+
+        for (int e = lane; e < erx * ery; e += 32)
+          a.tau[(size_t)(eoy + e / erx) * a.BX + eox + e % erx] = T;
+
+        if (__any_sync(0xFFFFFFFFu, overlap))
+          failed = true;
+
+        // the claim is visible to this warp's next look at the mask and to everybody who later reads the progress store
+        __threadfence();
+        __syncwarp();
+
+        if (lane == 0)
+        {
+          if (count < (uint32_t)a.listCap)
+            list[count] = pack_rect(eox, eoy, erx, ery);
+          else
+            a.flags[2] = 1; // reported by the host as LIMGCU_ERROR_OUT_OF_BOUNDS
+        }
+
+        count++;
+        claimed = true;
+
+        if (r.kind == 2)
+        {
+          // limg.cpp:1435-1438: the scan resumes at the same seed (which the regrowth may or may not have covered)
+          if (!(x >= eox && x < eox + erx && y >= eoy && y < eoy + ery))
+            continue;
+
+          break;
+        }
+
+        nextX = x + r.rx;
+        break;
+      }
+
+      if (claimed && lane == 0)
+        emitInfo[(size_t)y * a.BX + x] = (first << 8) | (count - first);
+
+      x = nextX;
+    }
+
+    if (lane == 0)
+      a.rowCounts[(size_t)stage * a.BY + y] = min(count, (uint32_t)a.listCap);
+  }
+
+  if (failed && !sequential && lane == 0)
+    a.flags[stage] = 1;
+
+  if (a.stats && lane == 0)
+  {
+    atomicAdd(&a.stats[0 + stage * 4], nExp);
+    atomicAdd(&a.stats[1 + stage * 4], nReexp);
+    atomicAdd(&a.stats[2 + stage * 4], nPolls);
+    atomicAdd(&a.stats[3 + stage * 4], scan.nOnDemand);
+  }
+}
+
+// Replays every candidate seed of the stage against the mask at its logical time and compares with the wave's record.
+template <int CH>
+__global__ void __launch_bounds__(256) k_merge_verify(WaveArgs a, int stage)
+{
+  if (a.flags[stage] != 0)
+    return; // already failed (overlapping claims)
+
+  const int lane = threadIdx.x & 31;
+  const uint32_t n = a.candCount[stage];
+  const uint32_t *candList = a.candList + (size_t)stage * a.BX * a.BY;
+  const uint2 *lists = a.rowLists + (size_t)stage * a.BY * a.listCap;
+  const uint32_t *emitInfo = a.emitInfo + (size_t)stage * a.BX * a.BY;
+  const uint32_t base = stage ? LIMG_TAU_STAGE1 : 0u;
+  const uint32_t warpsTotal = gridDim.x * (blockDim.x >> 5);
+
+  for (uint32_t i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < n; i += warpsTotal)
+  {
+    const int seed = (int)__ldg(&candList[i]);
+    const int y = seed / a.BX, x = seed - y * a.BX;
+    const uint32_t info = __ldg(&emitInfo[seed]);
+    const uint32_t start = info >> 8, have = info & 0xFFu;
+    const uint2 *rec = lists + (size_t)y * a.listCap + start;
+    uint32_t e = 0;
+    bool ok = true;
+
+    for (int k = 0;; k++)
+    {
+      if (k >= LIMG_WAVE_MAX_ATTEMPTS) { ok = false; break; }
+
+      WaveScan<CH, TimeMask> scan{ a, TimeMask{ a.tau, a.BX, a.BY, base + ((uint32_t)seed << 3) + (uint32_t)k }, lane, 0 };
+
+      if (scan.mask.is_used(x, y)) { ok = e == have; break; }
+
+      const WaveResult r = scan.expand(x, y, stage);
+
+      if (r.kind == 0) { ok = e == have; break; }
+
+      const int eox = r.kind == 2 ? r.cox : x, eoy = r.kind == 2 ? r.coy : y;
+      const int erx = r.kind == 2 ? r.crx : r.rx, ery = r.kind == 2 ? r.cry : r.ry;
+
+      if (e >= have) { ok = false; break; }
+
+      const uint2 want = pack_rect(eox, eoy, erx, ery), got = rec[e];
+      e++;
+
+      if (want.x != got.x || want.y != got.y) { ok = false; break; }
+
+      if (r.kind == 1) { ok = e == have; break; }
+    }
+
+    if (!ok && lane == 0)
+      a.flags[stage] = 1;
+  }
+}
+
+// fallback preparation: undo the stage's claims and counters (only when the stage failed)
+__global__ void __launch_bounds__(256) k_merge_reset(WaveArgs a, int stage)
+{
+  if (a.flags[stage] == 0)
+    return;
+
+  const int blocks = a.BX * a.BY;
+  const uint32_t base = stage ? LIMG_TAU_STAGE1 : 0u;
+
+  for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < blocks; b += gridDim.x * blockDim.x)
+  {
+    const uint32_t t = a.tau[b];
+
+    if (t != LIMG_TAU_NONE && t >= base)
+    {
+      const int y = b / a.BX, x = b - y * a.BX;
+      a.tau[b] = LIMG_TAU_NONE;
+      atomicAnd(&a.used[(size_t)y * a.wordsPerRow + (x >> 5)], ~(1u << (x & 31)));
+    }
+
+    a.emitInfo[(size_t)stage * blocks + b] = 0;
+
+    if (b < a.BY)
+    {
+      a.progress[(size_t)stage * a.BY + b] = 0;
+      a.rowCounts[(size_t)stage * a.BY + b] = 0;
+    }
+
+    if (b == 0)
+      a.ticket[stage] = 0;
+  }
+}
+
+// emission order = stage 0 rows top to bottom, then stage 1 rows; one CTA per block row
+__global__ void __launch_bounds__(128) k_merge_collect(WaveArgs a, limgcu_area *areas, uint32_t *mergedCount)
+{
+  __shared__ uint32_t sRed[3][4];
+  const int y = blockIdx.x;
+  uint32_t before0 = 0, before1 = 0, total0 = 0;
+
+  for (int r = threadIdx.x; r < a.BY; r += blockDim.x)
+  {
+    const uint32_t c0 = a.rowCounts[r], c1 = a.rowCounts[a.BY + r];
+    total0 += c0;
+
+    if (r < y)
+    {
+      before0 += c0;
+      before1 += c1;
+    }
+  }
+
+  uint32_t total1 = 0;
+
+  for (int r = threadIdx.x; r < a.BY; r += blockDim.x)
+    total1 += a.rowCounts[a.BY + r];
+
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+  {
+    before0 += __shfl_xor_sync(0xFFFFFFFFu, before0, o);
+    before1 += __shfl_xor_sync(0xFFFFFFFFu, before1, o);
+    total0 += __shfl_xor_sync(0xFFFFFFFFu, total0, o);
+    total1 += __shfl_xor_sync(0xFFFFFFFFu, total1, o);
+  }
+
+  __shared__ uint32_t sTot1[4];
+
+  if ((threadIdx.x & 31) == 0)
+  {
+    sRed[0][threadIdx.x >> 5] = before0;
+    sRed[1][threadIdx.x >> 5] = before1;
+    sRed[2][threadIdx.x >> 5] = total0;
+    sTot1[threadIdx.x >> 5] = total1;
+  }
+
+  __syncthreads();
+  before0 = sRed[0][0] + sRed[0][1] + sRed[0][2] + sRed[0][3];
+  before1 = sRed[1][0] + sRed[1][1] + sRed[1][2] + sRed[1][3];
+  total0 = sRed[2][0] + sRed[2][1] + sRed[2][2] + sRed[2][3];
+  total1 = sTot1[0] + sTot1[1] + sTot1[2] + sTot1[3];
+
+  for (int stage = 0; stage < 2; stage++)
+  {
+    const uint32_t n = a.rowCounts[(size_t)stage * a.BY + y];
+    const uint2 *l = a.rowLists + ((size_t)stage * a.BY + y) * a.listCap;
+    const uint32_t base = stage == 0 ? before0 : total0 + before1;
+
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x)
+    {
+      const uint2 r = l[i];
+      limgcu_area *out = &areas[base + i];
+      out->ox = r.x & 0xFFFF; out->oy = r.x >> 16; out->rx = r.y & 0xFFFF; out->ry = r.y >> 16;
+      out->stage = stage;
+    }
+  }
+
+  if (y == 0 && threadIdx.x == 0)
+    *mergedCount = total0 + total1;
+}
+
+} // namespace limg

@@ -2,6 +2,7 @@
 // There is no CPU path in this file: every entry point either launches the kernels or fails.
 #include "kernels_fit.cuh"
 #include "kernels_merge.cuh"
+#include "kernels_wave.cuh"
 #include "kernels_stream.cuh"
 #include "rsqrt_lut.h"
 
@@ -55,7 +56,15 @@ struct limgcu_ctx
   uint32_t *dPlaneU32[9] = { nullptr };
   uint8_t *dPlaneU8[7] = { nullptr }; // factors A,B,C, bpp, codes A,B,C
 
+  // wavefront merge (kernels_wave.cuh)
+  uint32_t *dWaveZero = nullptr; // flags[4] ticket[2] candCount[2] | progress[2*BY] | rowCounts[2*BY] | candBits[2*usedWords] | emitInfo[2*blocks]
+  uint32_t *dTau = nullptr, *dCandList = nullptr;
+  uint2 *dRowLists = nullptr;
+  size_t capWaveZero = 0, capRowLists = 0;
+
   int mergeExt = 1, mergeChunk = 64; // tunables (LIMGCU_MERGE_EXT, LIMGCU_MERGE_CHUNK)
+  int mergeMode = 0;                 // LIMGCU_MERGE_MODE: 0 wave (pipelined rows + verification), 1 seq (rows in sequence), 2 banded (round-1a fixed point)
+  int mergeMargin = 8;               // LIMGCU_MERGE_MARGIN: columns a row stays behind the rows above, beyond what its seed probed
   bool timing = false;
   cudaEvent_t ev[PHASE_COUNT + 1] = { nullptr };
   float phaseMs[PHASE_COUNT] = { 0 };
@@ -110,7 +119,25 @@ static int ensure_capacity(limgcu_ctx *ctx, size_t W, size_t H)
     CK(regrow(ctx->dExtSeed, (size_t)ctx->extCap));
     CK(regrow(ctx->dExtBits, (size_t)ctx->extCap * 32));
     if (ctx->dPlanCounters == nullptr) CK(regrow(ctx->dPlanCounters, (size_t)8));
+    CK(regrow(ctx->dTau, blocks));
+    CK(regrow(ctx->dCandList, blocks * 2));
     ctx->capBlocks = blocks;
+  }
+
+  {
+    const size_t waveZero = 8 + 4 * BY + 2 * usedWords + 2 * blocks, rowLists = 2 * BY * (2 * BX);
+
+    if (waveZero > ctx->capWaveZero)
+    {
+      CK(regrow(ctx->dWaveZero, waveZero));
+      ctx->capWaveZero = waveZero;
+    }
+
+    if (rowLists > ctx->capRowLists)
+    {
+      CK(regrow(ctx->dRowLists, rowLists));
+      ctx->capRowLists = rowLists;
+    }
   }
 
   if (usedWords > ctx->capUsedWords)
@@ -228,6 +255,9 @@ extern "C" int limgcu_create(int device, limgcu_ctx **out)
   if (const char *v = getenv("LIMGCU_MERGE_EXT")) ctx->mergeExt = atoi(v);
   if (const char *v = getenv("LIMGCU_MERGE_CHUNK")) ctx->mergeChunk = atoi(v) < 1 ? 1 : (atoi(v) > LIMG_ROW_CHUNK ? LIMG_ROW_CHUNK : atoi(v));
 
+  if (const char *v = getenv("LIMGCU_MERGE_MODE")) ctx->mergeMode = !strcmp(v, "seq") ? 1 : (!strcmp(v, "banded") ? 2 : 0);
+  if (const char *v = getenv("LIMGCU_MERGE_MARGIN")) ctx->mergeMargin = atoi(v) < 0 ? 0 : atoi(v);
+
   for (auto &e : ctx->ev)
     if (cudaEventCreate(&e) != cudaSuccess) return bail(LIMGCU_ERROR_CUDA);
 
@@ -252,7 +282,8 @@ extern "C" void limgcu_destroy(limgcu_ctx *ctx)
 
   void *ptrs[] = { ctx->dLut, ctx->dTable, ctx->dRec, ctx->dWindow, ctx->dAreas, ctx->dBlockToArea, ctx->dWork, ctx->dSmallList, ctx->dLargeList, ctx->dDemand,
                    ctx->dUsed, ctx->dScratchPx, ctx->dScratchFac, ctx->dCounters, ctx->dCompare, ctx->dSrc, ctx->dBandLists, ctx->dBandSnapshot, ctx->dBandState,
-                   ctx->dExtSlot, ctx->dExtSeed, ctx->dExtBits, ctx->dPlanCounters, ctx->dSym, ctx->dUnmasked };
+                   ctx->dExtSlot, ctx->dExtSeed, ctx->dExtBits, ctx->dPlanCounters, ctx->dSym, ctx->dUnmasked,
+                   ctx->dWaveZero, ctx->dTau, ctx->dCandList, ctx->dRowLists };
 
   for (void *p : ptrs)
     if (p) cudaFree(p);
@@ -275,7 +306,7 @@ extern "C" int limgcu_debug_counters(limgcu_ctx *ctx, uint32_t *out32)
 {
   NEED(ctx); NEED(out32);
   CK(cudaMemcpyAsync(out32, ctx->dCounters, 32 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
-  if (ctx->dPlanCounters) CK(cudaMemcpyAsync(out32 + 24, ctx->dPlanCounters, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  if (ctx->dPlanCounters) CK(cudaMemcpyAsync(out32 + 28, ctx->dPlanCounters, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   return LIMGCU_SUCCESS;
 }
@@ -359,14 +390,6 @@ static int launch_merge(limgcu_ctx *ctx, const limgcu_decomp *dTable, size_t W, 
 
   if (!noMerge)
   {
-    const int bandRows = BY / 128 + 1 > 8 ? BY / 128 + 1 : 8;
-    const int numBands = (BY + bandRows - 1) / bandRows;
-    const size_t usedBytes = (size_t)BY * wordsPerRow * sizeof(uint32_t);
-    const size_t smemBytes = usedBytes + (size_t)bandRows * BX * (3 * sizeof(uint32_t) + sizeof(uint16_t)) + 16;
-
-    if (smemBytes > 200 * 1024 || numBands > LIMG_MERGE_MAX_BANDS || numBands > ctx->smCount || BX > 65535 || BY > 65535)
-      return fail(ctx, LIMGCU_ERROR_OUT_OF_BOUNDS, "image too large for the shared-memory in-use mask of the banded merge", cudaSuccess);
-
     if (hasAlpha)
     {
       k_pred_records<4><<<(blocks + 255) / 256, 256, 0, ctx->stream>>>(dTable, blocks, ctx->dRec);
@@ -386,10 +409,21 @@ static int launch_merge(limgcu_ctx *ctx, const limgcu_decomp *dTable, size_t W, 
       CKL("k_pred_symwindow");
     }
 
+    const size_t usedWords = (size_t)BY * wordsPerRow;
+    uint32_t *wz = ctx->dWaveZero;
+    uint32_t *wFlags = wz, *wTicket = wz + 4, *wCandCount = wz + 6;
+    int *wProgress = reinterpret_cast<int *>(wz + 8);
+    uint32_t *wRowCounts = wz + 8 + 2 * BY, *wCandBits = wz + 8 + 4 * BY, *wEmitInfo = wCandBits + 2 * usedWords;
+    const bool banded = ctx->mergeMode == 2;
+
+    if (!banded)
+      CK(cudaMemsetAsync(wz, 0, (8 + 4 * (size_t)BY + 2 * usedWords + 2 * (size_t)blocks) * sizeof(uint32_t), ctx->stream));
+
     PlanArgs pl;
     pl.rec = ctx->dRec; pl.window = ctx->dWindow; pl.BX = BX; pl.BY = BY;
     pl.extSlot = ctx->dExtSlot; pl.extSeed = ctx->dExtSeed; pl.extBits = ctx->dExtBits;
     pl.counters = ctx->dPlanCounters; pl.extCap = ctx->mergeExt ? ctx->extCap : 0; pl.unmasked = ctx->dUnmasked;
+    pl.candBits = banded ? nullptr : wCandBits; pl.candList = ctx->dCandList; pl.candCount = wCandCount; pl.wordsPerRow = wordsPerRow;
     CK(cudaMemsetAsync(ctx->dPlanCounters, 0, 8 * sizeof(uint32_t), ctx->stream));
     k_plan_seeds<<<(blocks + 255) / 256, 256, 0, ctx->stream>>>(pl);
     CKL("k_plan_seeds");
@@ -407,25 +441,95 @@ static int launch_merge(limgcu_ctx *ctx, const limgcu_decomp *dTable, size_t W, 
 
     if (ctx->timing) CK(cudaEventRecord(ctx->ev[PHASE_SCAN], ctx->stream));
 
-    CK(cudaMemsetAsync(ctx->dBandState, 0, 1024 * sizeof(uint32_t), ctx->stream));
+    const size_t usedBytes = usedWords * sizeof(uint32_t);
     CK(cudaMemsetAsync(ctx->dUsed, 0, usedBytes, ctx->stream));
 
-    MergeArgs m;
-    m.rec = ctx->dRec; m.window = ctx->dWindow;
-    m.extSlot = ctx->dExtSlot; m.extBits = ctx->dExtBits; m.sym = ctx->dSym; m.unmasked = ctx->dUnmasked;
-    m.BX = BX; m.BY = BY; m.wordsPerRow = wordsPerRow;
-    m.bandRows = bandRows; m.numBands = numBands; m.listCap = bandRows * BX * 2; m.rowChunk = ctx->mergeChunk;
-    m.lists = ctx->dBandLists; m.counts = ctx->dBandState + 512; m.snapshot = ctx->dBandSnapshot; m.sync = ctx->dBandState;
-    m.areas = dAreas; m.mergedCount = ctx->dCounters + 0; m.usedOut = ctx->dUsed; m.stats = ctx->dCounters + 8;
-    void *kargs[] = { &m };
+    if (!banded)
+    {
+      if (BX > 8190 || BY > 8190)
+        return fail(ctx, LIMGCU_ERROR_OUT_OF_BOUNDS, "image too large for the merge's time stamps", cudaSuccess);
 
-    // cooperative launch: every band CTA must be resident, the bands synchronise through a grid barrier
-    if (hasAlpha)
-      CK(cudaLaunchCooperativeKernel((const void *)k_merge_banded<4>, dim3(numBands), dim3(LIMG_MERGE_THREADS), kargs, smemBytes, ctx->stream));
+      CK(cudaMemsetAsync(ctx->dTau, 0xFF, (size_t)blocks * sizeof(uint32_t), ctx->stream));
+
+      if (ctx->mergeMode == 1)
+        CK(cudaMemsetAsync(wFlags, 1, 2 * sizeof(uint32_t), ctx->stream)); // both stages go straight to the sequential pass
+
+      WaveArgs w;
+      w.rec = ctx->dRec; w.window = ctx->dWindow; w.extSlot = ctx->dExtSlot; w.extBits = ctx->dExtBits; w.sym = ctx->dSym; w.unmasked = ctx->dUnmasked;
+      w.candBits = wCandBits; w.candList = ctx->dCandList; w.candCount = wCandCount;
+      w.BX = BX; w.BY = BY; w.wordsPerRow = wordsPerRow;
+      w.used = ctx->dUsed; w.tau = ctx->dTau; w.progress = wProgress; w.ticket = wTicket;
+      w.rowLists = ctx->dRowLists; w.rowCounts = wRowCounts; w.emitInfo = wEmitInfo; w.flags = wFlags; w.stats = ctx->dCounters + 8;
+      w.listCap = 2 * BX; w.margin = ctx->mergeMargin;
+      const int waveGrid = (BY + LIMG_WAVE_WARPS - 1) / LIMG_WAVE_WARPS < ctx->smCount ? (BY + LIMG_WAVE_WARPS - 1) / LIMG_WAVE_WARPS : ctx->smCount;
+      const int resetGrid = (blocks + 255) / 256 < ctx->smCount * 8 ? (blocks + 255) / 256 : ctx->smCount * 8;
+
+      for (int stage = 0; stage < 2; stage++)
+      {
+        if (hasAlpha)
+        {
+          if (ctx->mergeMode == 0)
+          {
+            k_merge_wave<4><<<waveGrid, LIMG_WAVE_WARPS * 32, 0, ctx->stream>>>(w, stage, 0);
+            CKL("k_merge_wave");
+            k_merge_verify<4><<<ctx->smCount * 8, 256, 0, ctx->stream>>>(w, stage);
+            CKL("k_merge_verify");
+          }
+
+          k_merge_reset<<<resetGrid, 256, 0, ctx->stream>>>(w, stage);
+          CKL("k_merge_reset");
+          k_merge_wave<4><<<1, LIMG_WAVE_WARPS * 32, 0, ctx->stream>>>(w, stage, 1);
+          CKL("k_merge_wave(seq)");
+        }
+        else
+        {
+          if (ctx->mergeMode == 0)
+          {
+            k_merge_wave<3><<<waveGrid, LIMG_WAVE_WARPS * 32, 0, ctx->stream>>>(w, stage, 0);
+            CKL("k_merge_wave");
+            k_merge_verify<3><<<ctx->smCount * 8, 256, 0, ctx->stream>>>(w, stage);
+            CKL("k_merge_verify");
+          }
+
+          k_merge_reset<<<resetGrid, 256, 0, ctx->stream>>>(w, stage);
+          CKL("k_merge_reset");
+          k_merge_wave<3><<<1, LIMG_WAVE_WARPS * 32, 0, ctx->stream>>>(w, stage, 1);
+          CKL("k_merge_wave(seq)");
+        }
+      }
+
+      k_merge_collect<<<BY, 128, 0, ctx->stream>>>(w, dAreas, ctx->dCounters + 0);
+      CKL("k_merge_collect");
+      CK(cudaMemcpyAsync(ctx->dCounters + 24, wFlags, 4 * sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream));
+    }
     else
-      CK(cudaLaunchCooperativeKernel((const void *)k_merge_banded<3>, dim3(numBands), dim3(LIMG_MERGE_THREADS), kargs, smemBytes, ctx->stream));
+    {
+      const int bandRows = BY / 128 + 1 > 8 ? BY / 128 + 1 : 8;
+      const int numBands = (BY + bandRows - 1) / bandRows;
+      const size_t smemBytes = usedBytes + (size_t)bandRows * BX * (3 * sizeof(uint32_t) + sizeof(uint16_t)) + 16;
 
-    CKL("k_merge_banded");
+      if (smemBytes > 200 * 1024 || numBands > LIMG_MERGE_MAX_BANDS || numBands > ctx->smCount || BX > 65535 || BY > 65535)
+        return fail(ctx, LIMGCU_ERROR_OUT_OF_BOUNDS, "image too large for the shared-memory in-use mask of the banded merge", cudaSuccess);
+
+      CK(cudaMemsetAsync(ctx->dBandState, 0, 1024 * sizeof(uint32_t), ctx->stream));
+
+      MergeArgs m;
+      m.rec = ctx->dRec; m.window = ctx->dWindow;
+      m.extSlot = ctx->dExtSlot; m.extBits = ctx->dExtBits; m.sym = ctx->dSym; m.unmasked = ctx->dUnmasked;
+      m.BX = BX; m.BY = BY; m.wordsPerRow = wordsPerRow;
+      m.bandRows = bandRows; m.numBands = numBands; m.listCap = bandRows * BX * 2; m.rowChunk = ctx->mergeChunk;
+      m.lists = ctx->dBandLists; m.counts = ctx->dBandState + 512; m.snapshot = ctx->dBandSnapshot; m.sync = ctx->dBandState;
+      m.areas = dAreas; m.mergedCount = ctx->dCounters + 0; m.usedOut = ctx->dUsed; m.stats = ctx->dCounters + 8;
+      void *kargs[] = { &m };
+
+      // cooperative launch: every band CTA must be resident, the bands synchronise through a grid barrier
+      if (hasAlpha)
+        CK(cudaLaunchCooperativeKernel((const void *)k_merge_banded<4>, dim3(numBands), dim3(LIMG_MERGE_THREADS), kargs, smemBytes, ctx->stream));
+      else
+        CK(cudaLaunchCooperativeKernel((const void *)k_merge_banded<3>, dim3(numBands), dim3(LIMG_MERGE_THREADS), kargs, smemBytes, ctx->stream));
+
+      CKL("k_merge_banded");
+    }
   }
   else if (ctx->timing)
   {
@@ -688,9 +792,16 @@ static int host_encode(limgcu_ctx *ctx, const uint32_t *pIn, size_t W, size_t H,
   if (codesB) CK(cudaMemcpyAsync(codesB, ctx->dPlaneU8[5], n, cudaMemcpyDeviceToHost, ctx->stream));
   if (codesC) CK(cudaMemcpyAsync(codesC, ctx->dPlaneU8[6], n, cudaMemcpyDeviceToHost, ctx->stream));
 
-  uint32_t count = 0;
+  uint32_t count = 0, overflow[2] = { 0, 0 };
   CK(cudaMemcpyAsync(&count, ctx->dCounters + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(overflow, ctx->dCounters + 26, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
+
+  if (overflow[0])
+    return fail(ctx, LIMGCU_ERROR_OUT_OF_BOUNDS, "a block row emitted more rectangles than its list holds", cudaSuccess);
+
+  if (overflow[1])
+    return fail(ctx, LIMGCU_ERROR_GENERIC, "merge watchdog: a block row waited too long for the rows above", cudaSuccess);
 
   if (areas)
   {
@@ -794,9 +905,17 @@ extern "C" int limgcu_host_merge(limgcu_ctx *ctx, const limgcu_decomp *table, si
   CK(cudaMemcpyAsync(ctx->dTable, table, blocks * sizeof(limgcu_decomp), cudaMemcpyHostToDevice, ctx->stream));
   rc = launch_merge(ctx, ctx->dTable, sizeX, sizeY, hasAlpha, ctx->dAreas, ctx->dBlockToArea, false);
   if (rc) return rc;
-  uint32_t count = 0;
+  uint32_t count = 0, overflow[2] = { 0, 0 };
   CK(cudaMemcpyAsync(&count, ctx->dCounters + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(overflow, ctx->dCounters + 26, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
+
+  if (overflow[0])
+    return fail(ctx, LIMGCU_ERROR_OUT_OF_BOUNDS, "a block row emitted more rectangles than its list holds", cudaSuccess);
+
+  if (overflow[1])
+    return fail(ctx, LIMGCU_ERROR_GENERIC, "merge watchdog: a block row waited too long for the rows above", cudaSuccess);
+
   CK(cudaMemcpyAsync(areas, ctx->dAreas, (size_t)count * sizeof(limgcu_area), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   *area_count = count;
