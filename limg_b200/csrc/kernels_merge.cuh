@@ -2,16 +2,20 @@
 //
 // The reference's merge is a serial greedy raster scan whose only inputs are the pass-1 table and the scan order
 // (SURVEY.md Q2): the predicate "candidate block matches seed block" is a pure function of two pass-1 records.
-// B200 design:
+// This file holds everything that is evaluated up front, in parallel on the whole GPU, before the scan (kernels_wave.cuh):
 //   1. k_pred_records : one thread per block derives the predicate-side state of its record once (the divisions).
-//   2. k_pred_window  : for EVERY block as a hypothetical seed, all 63 predicates against the 8x8 window to its lower right are
-//                       evaluated in parallel (one thread per pair) -> one 64-bit match word per block.
-//   3. k_merge_banded : one CTA per band of block rows replays the reference's scan order over its rows (see "banded scan"
-//                       below for why the concurrent bands converge to the sequential result). Inside a band warp 0 walks
-//                       candidate seeds with pure bit arithmetic on (match word & ~in-use window); growth that leaves the
-//                       window and the four-way centre-third regrowth evaluate their predicates on demand, one warp per
-//                       predicate (27 lanes = the 27 samples), across all warps of the CTA.
-//   4. k_area_prepare : leftover blocks (raster order), pixel rectangles, block->area map, size classes, scratch offsets.
+//   2. k_pred_window  : for EVERY block as a hypothetical seed, all 63 predicates against the 8x8 window to its lower right
+//                       (one thread per pair) -> one 64-bit match word per block.
+//   3. k_plan_seeds   : candidate bitmaps / lists of the two merge stages, mask-free growth inside the window, and which stage-0
+//                       candidates can grow out of the window (their run along the seed row or column reaches its edge).
+//   4. k_plan_extend  : for those seeds a 32x32 match bitmap, filled exactly as far as ANY masked growth can reach: a right/down
+//                       rectangle always contains a block of the seed's row and of its column, so it lies inside
+//                       [0, run along the row] x [0, run along the column].
+//   5. k_plan_centres / k_plan_sym : the four-way centre-third regrowth starts at a block that depends on the masked growth;
+//                       the centres the mask-free growth predicts (and up to three to their left, which is where the mask
+//                       moves them) get a match bitmap around the centre, again bounded by the four runs from the centre.
+//   Everything here is a pure accelerator: the scan evaluates on demand whatever a bitmap does not cover.
+//   6. k_area_prepare : leftover blocks (raster order), pixel rectangles, block->area map, size classes, scratch offsets.
 #pragma once
 
 #include "group.cuh"
@@ -232,65 +236,36 @@ __global__ void __launch_bounds__(256) k_pred_window(const PredRec *__restrict__
     window[(size_t)seed * 2 + half] = bits;
 }
 
-// Symmetric match window of every block c: bit (r, col) of its 16 x 16 bitmap = predicate(seed = c, candidate = c + (col - 8, r - 8)),
-// 0 outside the grid. It is what the four-way centre-third regrowth (limg.cpp:1426-1433) asks for: the centre seed sits inside
-// the right/down rectangle it came from, so the regrowth explores a neighbourhood on all four sides. The lower-right quadrant is
-// the 8 x 8 match word. Stored as 8 words per block (two 16-bit rows per word).
-template <int CH>
-__global__ void __launch_bounds__(256) k_pred_symwindow(const PredRec *__restrict__ rec, const uint32_t *__restrict__ window, int BX, int BY, uint32_t *__restrict__ sym)
-{
-  const int c = blockIdx.x;
-  const int cy = c / BX, cx = c - cy * BX;
-  const int r = threadIdx.x >> 4, col = threadIdx.x & 15;
-  const int dx = col - 8, dy = r - 8;
-  bool m = false;
-
-  if (dx >= 0 && dy >= 0)
-  {
-    const uint32_t w = window[(size_t)c * 2 + (dy >> 2)];
-    m = (w >> (8 * (dy & 3) + dx)) & 1u;
-  }
-  else if (cx + dx >= 0 && cx + dx < BX && cy + dy >= 0 && cy + dy < BY)
-  {
-    m = predicate_thread<CH>(rec[c], rec[(size_t)(cy + dy) * BX + cx + dx]);
-  }
-
-  const uint32_t b = __ballot_sync(0xFFFFFFFFu, m);
-
-  if ((threadIdx.x & 31) == 0)
-    sym[(size_t)c * 8 + (threadIdx.x >> 5)] = b;
-}
-
 // ---------------------------------------------------------------------------------------------
-// speculative windows: everything the scan is likely to ask for is evaluated up front, in parallel on the whole GPU.
-//   - seeds whose mask-free right/down growth leaves the 8x8 window get a 16x16 and, if that is left too, a 32x32 match bitmap;
-// The scan uses a bitmap only when its assumptions hold and falls back to on-demand evaluation otherwise, so the bitmaps are a
-// pure accelerator: they never change the result.
+// speculative match bitmaps ("regions"): 32 rows x 32 columns of predicate(seed, block) anchored at (ax, ay), one row per word,
+// with a header that says which part of it is known: hdr = vx0 | vy0 << 8 | vx1 << 16 | vy1 << 24 (relative, half open).
 // ---------------------------------------------------------------------------------------------
 
 #define LIMG_NO_SLOT 0xFFFFFFFFu
+#define LIMG_SYM_BACK 8  // a centre's bitmap is anchored 8 blocks up and to the left of it
 
 struct PlanArgs
 {
   const PredRec *rec;
   const uint32_t *window;
-  int BX, BY;
-  uint32_t *extSlot;   // per block: LIMG_NO_SLOT or slot | (size 32 ? 1u << 31 : 0)
+  int BX, BY, wordsPerRow;
+  uint32_t *extSlot;   // per block: LIMG_NO_SLOT or its slot
   uint32_t *extSeed;   // per slot: block index
-  uint32_t *extBits;   // per slot: 32 row words
-  uint32_t *counters;  // [0] ext slots
-  uint32_t extCap;
-  uint16_t *unmasked;  // per block: rx | ry << 8 of the mask-free right/down growth inside the best available bitmap
+  uint32_t *extBits;   // per slot: 32 row words, anchored at the seed
+  uint32_t *extHdr;    // per slot: known part
+  uint32_t *symSlot, *symSeed, *symBits, *symHdr; // the same around centres, anchored at (cx - 8, cy - 8)
+  uint32_t *counters;  // [0] ext slots, [1] sym slots
+  uint32_t extCap, symCap;
+  uint16_t *unmasked;  // per block: rx | ry << 8 of the mask-free right/down growth
   uint32_t *candBits;  // [2][BY][wordsPerRow] (zeroed by the host): blocks that can emit in stage 0 (3x3 corner matches) / stage 1 (right or lower neighbour matches)
   uint32_t *candList;  // [2][blocks] the same as lists, counts in candCount[2]
   uint32_t *candCount;
-  int wordsPerRow;
 };
 
-// mask-free alternating right/down growth over `rows` (S x S match bitmap of the seed); returns true if it wanted to leave the bitmap
-__device__ __forceinline__ bool expand_unmasked(const uint32_t *rows, int S, int x, int y, int BX, int BY, int &rx, int &ry)
+// mask-free alternating right/down growth over `rows` (S x S match bitmap of the seed)
+__device__ __forceinline__ void expand_unmasked(const uint32_t *rows, int S, int x, int y, int BX, int BY, int &rx, int &ry)
 {
-  bool right = true, down = true, hit = false;
+  bool right = true, down = true;
   rx = 1;
   ry = 1;
 
@@ -298,9 +273,7 @@ __device__ __forceinline__ bool expand_unmasked(const uint32_t *rows, int S, int
   {
     if (right)
     {
-      bool ok = x + rx + 1 < BX;
-
-      if (ok && rx >= S) { hit = true; ok = false; }
+      bool ok = x + rx + 1 < BX && rx < S;
 
       if (ok)
         for (int r = 0; r < ry; r++)
@@ -311,9 +284,7 @@ __device__ __forceinline__ bool expand_unmasked(const uint32_t *rows, int S, int
 
     if (down)
     {
-      bool ok = y + ry + 1 < BY;
-
-      if (ok && ry >= S) { hit = true; ok = false; }
+      bool ok = y + ry + 1 < BY && ry < S;
 
       if (ok)
       {
@@ -324,8 +295,6 @@ __device__ __forceinline__ bool expand_unmasked(const uint32_t *rows, int S, int
       if (ok) ry++; else down = false;
     }
   }
-
-  return hit;
 }
 
 __global__ void __launch_bounds__(256) k_plan_seeds(PlanArgs a)
@@ -334,29 +303,25 @@ __global__ void __launch_bounds__(256) k_plan_seeds(PlanArgs a)
   const bool inside = seed < a.BX * a.BY;
   const int y = inside ? seed / a.BX : 0, x = inside ? seed - y * a.BX : 0;
   const uint32_t w0 = inside ? a.window[(size_t)seed * 2] : 0u, w1 = inside ? a.window[(size_t)seed * 2 + 1] : 0u;
-
-  if (a.candBits)
-  {
-    // necessary conditions (mask-free) for the seed to emit anything: stage 0 needs a 3x3 rectangle, stage 1 one neighbour
-    const bool c[2] = { inside && (w0 & 0x070707u) == 0x070707u, inside && (w0 & 0x0102u) != 0u };
-    const int lane = threadIdx.x & 31;
+  // necessary conditions (mask-free) for the seed to emit anything: stage 0 needs a 3x3 rectangle, stage 1 one neighbour
+  const bool c[2] = { inside && (w0 & 0x070707u) == 0x070707u, inside && (w0 & 0x0102u) != 0u };
+  const int lane = threadIdx.x & 31;
 
 #pragma unroll
-    for (int st = 0; st < 2; st++)
+  for (int st = 0; st < 2; st++)
+  {
+    const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, c[st]);
+    uint32_t pos = 0;
+
+    if (lane == 0 && ballot)
+      pos = atomicAdd(&a.candCount[st], (uint32_t)__popc(ballot));
+
+    pos = __shfl_sync(0xFFFFFFFFu, pos, 0) + __popc(ballot & ((1u << lane) - 1u));
+
+    if (c[st])
     {
-      const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, c[st]);
-      uint32_t pos = 0;
-
-      if (lane == 0 && ballot)
-        pos = atomicAdd(&a.candCount[st], (uint32_t)__popc(ballot));
-
-      pos = __shfl_sync(0xFFFFFFFFu, pos, 0) + __popc(ballot & ((1u << lane) - 1u));
-
-      if (c[st])
-      {
-        a.candList[(size_t)st * a.BX * a.BY + pos] = (uint32_t)seed;
-        atomicOr(&a.candBits[((size_t)st * a.BY + y) * a.wordsPerRow + (x >> 5)], 1u << (x & 31));
-      }
+      a.candList[(size_t)st * a.BX * a.BY + pos] = (uint32_t)seed;
+      atomicOr(&a.candBits[((size_t)st * a.BY + y) * a.wordsPerRow + (x >> 5)], 1u << (x & 31));
     }
   }
 
@@ -373,11 +338,16 @@ __global__ void __launch_bounds__(256) k_plan_seeds(PlanArgs a)
   }
 
   int rx, ry;
-  const bool hit = expand_unmasked(rows, 8, x, y, a.BX, a.BY, rx, ry);
+  expand_unmasked(rows, 8, x, y, a.BX, a.BY, rx, ry);
   a.extSlot[seed] = LIMG_NO_SLOT;
+  a.symSlot[seed] = LIMG_NO_SLOT;
   a.unmasked[seed] = (uint16_t)(rx | (ry << 8));
 
-  if (hit)
+  // a stage-0 candidate whose run along its row or its column reaches the window edge can grow out of the window
+  const bool rowRun = (w0 & 0xFFu) == 0xFFu && x + 8 < a.BX;
+  const bool colRun = (w0 & 0x01010101u) == 0x01010101u && (w1 & 0x01010101u) == 0x01010101u && y + 8 < a.BY;
+
+  if (c[0] && (rowRun || colRun))
   {
     const uint32_t slot = atomicAdd(&a.counters[0], 1u);
 
@@ -389,11 +359,18 @@ __global__ void __launch_bounds__(256) k_plan_seeds(PlanArgs a)
   }
 }
 
+// first zero bit of `known` at or above `from` (32 if none): the run length along one direction
+__device__ __forceinline__ int run_end(uint32_t bits, int from)
+{
+  const uint32_t z = ~bits & (0xFFFFFFFFu << from);
+  return z ? __ffs(z) - 1 : 32;
+}
+
 template <int CH>
 __global__ void __launch_bounds__(256) k_plan_extend(PlanArgs a)
 {
   __shared__ uint32_t rows[32];
-  __shared__ int sHit, sRx, sRy;
+  __shared__ uint32_t sRowRun, sColRun;
   const uint32_t count = min(a.counters[0], a.extCap);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
@@ -405,73 +382,55 @@ __global__ void __launch_bounds__(256) k_plan_extend(PlanArgs a)
     const uint32_t w0 = a.window[(size_t)seed * 2], w1 = a.window[(size_t)seed * 2 + 1];
 
     if (threadIdx.x < 32)
-      rows[threadIdx.x] = 0;
+      rows[threadIdx.x] = threadIdx.x < 8 ? ((threadIdx.x < 4 ? w0 >> (8 * threadIdx.x) : w1 >> (8 * (threadIdx.x - 4))) & 0xFFu) : 0u;
 
     __syncthreads();
 
-    // 16 x 16: thread t -> (dx, dy) = (t & 15, t >> 4); the 8 x 8 corner is known
+    // the two runs: warp 0 the seed's row (dx = lane), warp 1 its column (dy = lane); the first 8 are known
+    if (warp < 2)
     {
-      const int dx = threadIdx.x & 15, dy = threadIdx.x >> 4;
-      bool m = false;
+      const int dx = warp == 0 ? lane : 0, dy = warp == 0 ? 0 : lane;
+      bool m;
 
-      if (dx < 8 && dy < 8)
-        m = ((dy < 4 ? w0 >> (8 * dy) : w1 >> (8 * (dy - 4))) >> dx) & 1u;
-      else if (x + dx < a.BX && y + dy < a.BY)
-        m = predicate_thread<CH>(s, a.rec[(size_t)(y + dy) * a.BX + x + dx]);
+      if (lane < 8)
+        m = (rows[dy] >> dx) & 1u;
+      else
+        m = x + dx < a.BX && y + dy < a.BY && predicate_thread<CH>(s, a.rec[(size_t)(y + dy) * a.BX + x + dx]);
 
       const uint32_t b = __ballot_sync(0xFFFFFFFFu, m);
 
       if (lane == 0)
       {
-        rows[warp * 2] = b & 0xFFFF;
-        rows[warp * 2 + 1] = b >> 16;
+        if (warp == 0) sRowRun = b; else sColRun = b;
       }
     }
 
     __syncthreads();
+    // known part: columns [0, first mismatch along the row], rows [0, first mismatch along the column]
+    const int vx1 = min(run_end(sRowRun, 0) + 1, 32), vy1 = min(run_end(sColRun, 0) + 1, 32);
 
-    if (threadIdx.x == 0)
+    for (int p = 0; p < 4; p++)
     {
-      int rx, ry;
-      sHit = expand_unmasked(rows, 16, x, y, a.BX, a.BY, rx, ry) ? 1 : 0;
-      sRx = rx;
-      sRy = ry;
-    }
+      const int dy = p * 8 + warp, dx = lane;
+      bool m = false;
 
-    __syncthreads();
-    int size = 16;
-
-    if (sHit)
-    {
-      // 32 x 32: four passes of eight rows; the 16 x 16 corner is known
-      size = 32;
-
-      for (int p = 0; p < 4; p++)
+      if (dx < vx1 && dy < vy1)
       {
-        const int dy = p * 8 + warp, dx = lane;
-        bool m = false;
-
-        if (dx < 16 && dy < 16)
+        if (dx < 8 && dy < 8)
           m = (rows[dy] >> dx) & 1u;
+        else if (dy == 0)
+          m = (sRowRun >> dx) & 1u;
+        else if (dx == 0)
+          m = (sColRun >> dy) & 1u;
         else if (x + dx < a.BX && y + dy < a.BY)
           m = predicate_thread<CH>(s, a.rec[(size_t)(y + dy) * a.BX + x + dx]);
-
-        const uint32_t b = __ballot_sync(0xFFFFFFFFu, m);
-        __syncthreads(); // every read of rows[dy] (dy < 16) of this pass happened
-
-        if (lane == 0)
-          rows[dy] = b;
-
-        __syncthreads();
       }
 
-      if (threadIdx.x == 0)
-      {
-        int rx, ry;
-        sHit = expand_unmasked(rows, 32, x, y, a.BX, a.BY, rx, ry) ? 1 : 0;
-        sRx = rx;
-        sRy = ry;
-      }
+      const uint32_t b = __ballot_sync(0xFFFFFFFFu, m);
+      __syncthreads(); // every read of rows[] of this pass happened
+
+      if (lane == 0)
+        rows[dy] = b;
 
       __syncthreads();
     }
@@ -481,802 +440,146 @@ __global__ void __launch_bounds__(256) k_plan_extend(PlanArgs a)
 
     if (threadIdx.x == 0)
     {
-      a.extSlot[seed] = slot | (size == 32 ? 0x80000000u : 0u);
-      a.unmasked[seed] = (uint16_t)(sRx | (sRy << 8));
-
+      int rx, ry;
+      a.extHdr[slot] = (uint32_t)vx1 << 16 | (uint32_t)vy1 << 24;
+      expand_unmasked(rows, 32, x, y, a.BX, a.BY, rx, ry);
+      a.unmasked[seed] = (uint16_t)(min(rx, 255) | (min(ry, 255) << 8));
     }
 
     __syncthreads();
   }
 }
 
-// ---------------------------------------------------------------------------------------------
-// banded scan
-//
-// The reference's scan is sequential only through the in-use mask. The block rows are cut into bands, one CTA per band.
-// Band k replays the reference's scan over ITS rows against an input mask that holds the rectangles emitted by all bands
-// above it. All bands run concurrently from the previous iteration's rectangles; a band re-runs only when the input mask
-// changed inside the row range its last run actually read. Band 0 never depends on anything, so after iteration t bands
-// 0..t are final; in practice influence dies out after a few rows and a handful of iterations suffice. At the fixed point
-// every band saw exactly the mask the sequential scan would have shown it, so the emission lists, concatenated in band
-// order, ARE the reference's emission order. Stage 1 (remaining merges) repeats the procedure on top of the final stage-0 mask.
-// ---------------------------------------------------------------------------------------------
-
-#define LIMG_MERGE_THREADS 512
-#define LIMG_MERGE_WARPS (LIMG_MERGE_THREADS / 32)
-#define LIMG_MERGE_MAX_BANDS 128
-#define LIMG_ROW_CHUNK 128 // candidate seeds of one block row expanded concurrently
-
-struct MergeArgs
+// which blocks will the four-way regrowth probably start from? (limg.cpp:1426-1433 with the mask-free rectangle, and up to three
+// blocks to the left of that: a mask shrinks the rectangle's width far more often than its height)
+__global__ void __launch_bounds__(256) k_plan_centres(PlanArgs a)
 {
-  const PredRec *rec;
-  const uint32_t *window;
-  const uint32_t *extSlot, *extBits, *sym;
-  const uint16_t *unmasked;
-  int BX, BY, wordsPerRow;
-  int bandRows, numBands, listCap;
-  int rowChunk;          // candidate seeds of one block row expanded concurrently (<= LIMG_ROW_CHUNK)
-  uint2 *lists;          // [numBands][2][listCap]: (ox | oy << 16, rx | ry << 16)
-  uint32_t *counts;      // [numBands][2]
-  uint32_t *snapshot;    // [numBands][BY * wordsPerRow]: input mask of the band's last run
-  uint32_t *sync;        // [0] barrier count, [1] barrier generation, [2] error flag, [8 + stage * (MAX_BANDS + 2) + iter] dirty flags
-  limgcu_area *areas;
-  uint32_t *mergedCount; // number of stage 0 + stage 1 areas
-  uint32_t *usedOut;     // BY * wordsPerRow words: in-use mask after both merge stages (zeroed by the host)
-  uint32_t *stats;       // [24] optional counters
-};
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
 
-__device__ __forceinline__ void grid_barrier(uint32_t *sync, uint32_t numBlocks)
-{
-  __syncthreads();
+  if (i >= a.candCount[0])
+    return;
 
-  if (threadIdx.x == 0)
+  const int seed = (int)a.candList[i];
+  const int y = seed / a.BX, x = seed - y * a.BX;
+  const uint32_t u = a.unmasked[seed];
+  const int rx = u & 0xFF, ry = u >> 8;
+
+  if (rx < 3 || ry < 3)
+    return;
+
+  const int cy = y + ry / 3;
+
+  for (int d = 0; d < 4 && rx / 3 - d >= 1; d++)
   {
-    volatile uint32_t *gen = sync + 1;
-    const uint32_t g = *gen;
-    __threadfence();
+    const int c = cy * a.BX + x + rx / 3 - d;
 
-    if (atomicAdd(sync, 1u) == numBlocks - 1)
+    if (atomicCAS(&a.symSlot[c], LIMG_NO_SLOT, LIMG_NO_SLOT - 1u) == LIMG_NO_SLOT) // first one to ask for this centre
     {
-      sync[0] = 0;
-      __threadfence();
-      *gen = g + 1;
-    }
-    else
-    {
-      while (*gen == g) { }
-    }
+      const uint32_t slot = atomicAdd(&a.counters[1], 1u);
 
-    __threadfence();
+      if (slot < a.symCap)
+      {
+        a.symSeed[slot] = (uint32_t)c;
+        a.symSlot[c] = slot;
+      }
+      else
+      {
+        a.symSlot[c] = LIMG_NO_SLOT;
+      }
+    }
   }
-
-  __syncthreads();
 }
 
-// what one seed would do against a given in-use mask
-struct SeedResult
-{
-  short x, rx, ry;       // right/down rectangle grown from the seed
-  short kind;            // 0 nothing to emit, 1 emit the right/down rectangle, 2 emit the centre-third regrowth (and examine the seed again)
-  short cox, coy, crx, cry; // four-way regrowth (valid when attempted)
-  short attempted;
-  short pad;
-};
-
-struct BandShared
-{
-  SeedResult res[LIMG_ROW_CHUNK];
-  short cand[LIMG_ROW_CHUNK];
-  uint2 accepted[LIMG_ROW_CHUNK + 32]; // rectangles committed in the current chunk round
-  int nCand, nextX;
-  int rangeLo, rangeHi;
-  uint32_t count;
-  int dirty;
-};
-
-// A band's scan. Every method is warp-cooperative: all 32 lanes call it with warp-uniform arguments. The in-use mask is only
-// modified by commit() (warp 0, between barriers); expansions read it.
+// Match bitmap around a centre c, anchored at (cx - 8, cy - 8): every four-way rectangle grown from a rectangle that contains c's
+// block row and column segment lies inside the bounding box of the four runs from c (each strip it adds crosses c's row or column).
 template <int CH>
-struct BandScan
+__global__ void __launch_bounds__(256) k_plan_sym(PlanArgs a)
 {
-  const MergeArgs &a;
-  uint32_t *used;          // shared: BY rows of wordsPerRow words
-  const uint32_t *winBand; // shared: match words of the band's rows
-  const uint32_t *extBand; // shared: extension-bitmap slots of the band's seeds
-  BandShared *sh;
-  int lane;
-  int bandY0, bandY1;
-  int readLo, readHi;      // rows whose in-use bits this warp consulted
-  uint32_t nOnDemand, nSeeds, nFour, nInline;
-  bool cheapOnly, aborted; // a speculative expansion of a probably-swallowed candidate gives up instead of evaluating predicates on demand
+  __shared__ uint32_t rows[32];
+  __shared__ uint32_t sRowRun, sColRun;
+  const uint32_t count = min(a.counters[1], a.symCap);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
-  __device__ __forceinline__ void touch_rows(int lo, int hi)
+  for (uint32_t slot = blockIdx.x; slot < count; slot += gridDim.x)
   {
-    readLo = min(readLo, max(lo, 0));
-    readHi = max(readHi, min(hi, a.BY - 1));
-  }
+    const int c = (int)a.symSeed[slot];
+    const int cy = c / a.BX, cx = c - cy * a.BX;
+    const int ax = cx - LIMG_SYM_BACK, ay = cy - LIMG_SYM_BACK;
+    const PredRec s = a.rec[c];
+    const uint32_t w0 = a.window[(size_t)c * 2], w1 = a.window[(size_t)c * 2 + 1];
 
-  __device__ __forceinline__ uint32_t used_bits32(int x, int y) const
-  {
-    // 32 in-use bits of row y starting at column x (x may be negative); everything outside the grid reads as in use
-    if (y < 0 || y >= a.BY)
-      return 0xFFFFFFFFu;
-
-    const uint32_t *row = used + (size_t)y * a.wordsPerRow;
-
-    if (x < 0)
-    {
-      const int s = -x; // 1..31
-      return (row[0] << s) | ((1u << s) - 1u);
-    }
-
-    const int w0 = x >> 5, s = x & 31;
-    return __funnelshift_r(row[w0], row[w0 + 1], s);
-  }
-
-  __device__ __forceinline__ bool is_used(int x, int y) const
-  {
-    return (used[(size_t)y * a.wordsPerRow + (x >> 5)] >> (x & 31)) & 1u;
-  }
-
-  __device__ bool strip_unused(int x0, int y0, int w, int h)
-  {
-    bool any = false;
-    touch_rows(y0, y0 + h - 1);
-
-    for (int e = lane; e < w * h; e += 32)
-    {
-      const int yy = y0 + e / w, xx = x0 + e % w;
-      any |= is_used(xx, yy);
-    }
-
-    return !__any_sync(0xFFFFFFFFu, any);
-  }
-
-  // every block of the strip matches the seed? evaluated by this warp alone: short strips one predicate at a time with the 27
-  // samples spread over the lanes, long strips one predicate per lane.
-  __device__ bool strip_matches(const PredRec &seed, int x0, int y0, int w, int h)
-  {
-    const int count = w * h;
-
-    if (cheapOnly)
-    {
-      aborted = true;
-      return false;
-    }
-
-    nOnDemand += count;
-
-    if (count >= 6)
-    {
-      bool ok = true;
-
-      for (int base = 0; base < count && ok; base += 32)
-      {
-        const int e = base + lane;
-        bool m = true;
-
-        if (e < count)
-        {
-          const int yy = y0 + e / w, xx = x0 + e % w;
-          m = predicate_thread<CH>(seed, a.rec[(size_t)yy * a.BX + xx]);
-        }
-
-        ok = __all_sync(0xFFFFFFFFu, m);
-      }
-
-      return ok;
-    }
-
-    for (int e = 0; e < count; e++)
-    {
-      const int yy = y0 + e / w, xx = x0 + e % w;
-
-      if (!predicate_warp<CH>(seed, a.rec[(size_t)yy * a.BX + xx]))
-        return false;
-    }
-
-    return true;
-  }
-
-  __device__ bool strip_joins(const PredRec &seed, int x0, int y0, int w, int h)
-  {
-    return strip_unused(x0, y0, w, h) && strip_matches(seed, x0, y0, w, h);
-  }
-
-  // right/down growth of a 1x1 seed (limg.cpp:1294-1343). The seed's match bitmap (8x8 word, or the speculative 16x16 / 32x32
-  // extension) lives one row per lane; growth inside it is ballots and shuffles, strips beyond it are evaluated on demand.
-  __device__ void grow_seed(int x, int y, int &rx, int &ry)
-  {
-    const int seed = y * a.BX + x;
-    const uint32_t slot = extBand[(y - bandY0) * a.BX + x];
-    int S = 8;
-    uint32_t rowBits;
-
-    if (slot == LIMG_NO_SLOT)
-    {
-      const uint32_t *wp = winBand + (size_t)((y - bandY0) * a.BX + x) * 2;
-      rowBits = lane < 8 ? (wp[lane >> 2] >> (8 * (lane & 3))) & 0xFFu : 0u;
-    }
-    else
-    {
-      S = (slot >> 31) ? 32 : 16;
-      rowBits = lane < S ? __ldg(&a.extBits[(size_t)(slot & 0x7FFFFFFFu) * 32 + lane]) : 0u;
-    }
-
-    const uint32_t avail = lane < S ? (rowBits & ~used_bits32(x, y + lane)) : 0u;
-    bool right = true, down = true;
-    bool haveRec = false;
-    PredRec rec;
-    rx = 1;
-    ry = 1;
-
-    while (right || down)
-    {
-      if (right)
-      {
-        bool ok = x + rx + 1 < a.BX;
-
-        if (ok)
-        {
-          const int rows = min(ry, S);
-
-          if (rx < S)
-          {
-            const uint32_t need = rows >= 32 ? 0xFFFFFFFFu : ((1u << rows) - 1u);
-            const uint32_t have = __ballot_sync(0xFFFFFFFFu, (avail >> rx) & 1u);
-            ok = (have & need) == need;
-          }
-
-          if (ok && (rx >= S || ry > S))
-          {
-            if (!haveRec) { rec = a.rec[seed]; haveRec = true; }
-            ok = rx >= S ? strip_joins(rec, x + rx, y, 1, ry) : strip_joins(rec, x + rx, y + S, 1, ry - S);
-          }
-        }
-
-        if (ok) rx++; else right = false;
-      }
-
-      if (down)
-      {
-        bool ok = y + ry + 1 < a.BY;
-
-        if (ok)
-        {
-          const int cols = min(rx, S);
-
-          if (ry < S)
-          {
-            const uint32_t need = cols >= 32 ? 0xFFFFFFFFu : ((1u << cols) - 1u);
-            const uint32_t rowv = __shfl_sync(0xFFFFFFFFu, avail, ry);
-            ok = (rowv & need) == need;
-          }
-
-          if (ok && (ry >= S || rx > S))
-          {
-            if (!haveRec) { rec = a.rec[seed]; haveRec = true; }
-            ok = ry >= S ? strip_joins(rec, x, y + ry, rx, 1) : strip_joins(rec, x + S, y + ry, rx - S, 1);
-          }
-        }
-
-        if (ok) ry++; else down = false;
-      }
-    }
-
-    touch_rows(y, y + min(ry, S - 1)); // bitmap rows consulted: up to the failing row (deeper rows go through strip_unused)
-  }
-
-  // four-way alternating growth from the centre third (limg.cpp:1294-1388, 1426-1433). The centre seed's symmetric 16 x 16 match
-  // window covers [ox - 8, ox + 8) x [oy - 8, oy + 8), one row per lane; strips that leave it are evaluated on demand.
-  __device__ void grow_four_way(int &ox, int &oy, int &rx, int &ry)
-  {
-    const int seed = oy * a.BX + ox;
-    const int rgX = ox - 8, rgY = oy - 8;
-    uint32_t avail = 0;
-
-    if (lane < 16)
-    {
-      const uint32_t w = __ldg(&a.sym[(size_t)seed * 8 + (lane >> 1)]);
-      avail = ((w >> (16 * (lane & 1))) & 0xFFFFu) & ~used_bits32(rgX, rgY + lane);
-    }
-
-    touch_rows(rgY, rgY + 15);
-    bool haveRec = false;
-    PredRec rec;
-    bool right = true, down = true, up = true, left = true;
-
-    // strip test: inside the window -> bits, otherwise on demand
-    auto joins = [&](int x0, int y0, int w, int h) -> bool {
-      if (x0 >= rgX && y0 >= rgY && x0 + w <= rgX + 16 && y0 + h <= rgY + 16)
-      {
-        const uint32_t m = ((1u << w) - 1u) << (x0 - rgX);
-        const int r0 = y0 - rgY;
-        const bool rowOk = (lane < r0 || lane >= r0 + h) || ((avail & m) == m);
-        return __all_sync(0xFFFFFFFFu, rowOk);
-      }
-
-      if (!haveRec) { rec = a.rec[seed]; haveRec = true; }
-      return strip_joins(rec, x0, y0, w, h);
+    auto known = [&](int dx, int dy) -> bool { // lower-right 8x8 of c: its match word
+      return ((dy < 4 ? w0 >> (8 * dy) : w1 >> (8 * (dy - 4))) >> dx) & 1u;
     };
 
-    while (right || down || up || left)
+    // runs along c's row (warp 0: column ax + lane) and c's column (warp 1: row ay + lane)
+    if (warp < 2)
     {
-      if (right)
+      const int bx = warp == 0 ? ax + lane : cx, by = warp == 0 ? cy : ay + lane;
+      const int dx = bx - cx, dy = by - cy;
+      bool m = false;
+
+      if (bx >= 0 && bx < a.BX && by >= 0 && by < a.BY)
       {
-        if (ox + rx + 1 < a.BX && joins(ox + rx, oy, 1, ry)) rx++; else right = false;
+        if (dx >= 0 && dx < 8 && dy >= 0 && dy < 8)
+          m = known(dx, dy);
+        else
+          m = predicate_thread<CH>(s, a.rec[(size_t)by * a.BX + bx]);
       }
 
-      if (down)
+      const uint32_t b = __ballot_sync(0xFFFFFFFFu, m);
+
+      if (lane == 0)
       {
-        if (oy + ry + 1 < a.BY && joins(ox, oy + ry, rx, 1)) ry++; else down = false;
-      }
-
-      if (up)
-      {
-        if (oy > 0 && joins(ox, oy - 1, rx, 1)) { oy--; ry++; } else up = false;
-      }
-
-      if (left)
-      {
-        if (ox > 0 && joins(ox - 1, oy, 1, ry)) { ox--; rx++; } else left = false;
-      }
-    }
-  }
-
-  // what seed (x, y) does against the current mask (limg.cpp:1405-1486)
-  __device__ SeedResult expand(int x, int y, int stage, bool cheap = false)
-  {
-    SeedResult r;
-    int rx, ry;
-    nSeeds++;
-    cheapOnly = cheap;
-    aborted = false;
-    grow_seed(x, y, rx, ry);
-    r.x = (short)x; r.rx = (short)rx; r.ry = (short)ry;
-    r.kind = 0; r.attempted = 0; r.pad = 0;
-    r.cox = r.coy = r.crx = r.cry = 0;
-
-    if (stage == 0)
-    {
-      if (rx >= 3 && ry >= 3) // Q4
-      {
-        int cox = x + rx / 3, coy = y + ry / 3, crx = rx / 3, cry = ry / 3;
-        nFour++;
-        grow_four_way(cox, coy, crx, cry);
-        r.cox = (short)cox; r.coy = (short)coy; r.crx = (short)crx; r.cry = (short)cry;
-        r.attempted = 1;
-        r.kind = (crx * cry > rx * ry) ? 2 : 1;
-      }
-    }
-    else
-    {
-      r.kind = (rx > 1 || ry > 1) ? 1 : 0;
-    }
-
-    if (aborted)
-      r.kind = -1; // unknown: commit() expands the seed properly if it is still free when its turn comes
-
-    cheapOnly = false;
-    return r;
-  }
-
-  __device__ void mark_used(int ox, int oy, int rx, int ry)
-  {
-    for (int r = lane; r < ry; r += 32)
-    {
-      uint32_t *row = used + (size_t)(oy + r) * a.wordsPerRow;
-
-      for (int xx = ox; xx < ox + rx;)
-      {
-        const int w0 = xx >> 5, b0 = xx & 31;
-        const int cnt = min(32 - b0, ox + rx - xx);
-        const uint32_t m = (cnt == 32 ? 0xFFFFFFFFu : ((1u << cnt) - 1u)) << b0;
-        row[w0] |= m;
-        xx += cnt;
+        if (warp == 0) sRowRun = b; else sColRun = b;
       }
     }
 
-    __syncwarp();
-  }
+    __syncthreads();
+    // known box: from the first mismatch left of / above c to the first mismatch right of / below c (inclusive), relative to the anchor
+    const uint32_t rowRun = sRowRun, colRun = sColRun;
+    const uint32_t lowRow = ~rowRun & ((1u << LIMG_SYM_BACK) - 1u), lowCol = ~colRun & ((1u << LIMG_SYM_BACK) - 1u);
+    const int vx0 = lowRow ? 31 - __clz(lowRow) : 0, vy0 = lowCol ? 31 - __clz(lowCol) : 0;
+    // the regrowth starts from a rectangle of up to 3 x 3 blocks whose blocks are not tested (limg.cpp:1428-1431): a mismatch
+    // one or two blocks right of / below c does not stop it
+    const int vx1 = min(run_end(rowRun | (3u << (LIMG_SYM_BACK + 1)), LIMG_SYM_BACK) + 1, 32);
+    const int vy1 = min(run_end(colRun | (3u << (LIMG_SYM_BACK + 1)), LIMG_SYM_BACK) + 1, 32);
 
-  // does any rectangle committed in this chunk round touch the inclusive box [x0, x1] x [y0, y1]?
-  __device__ bool touches_accepted(int nAcc, int x0, int y0, int x1, int y1) const
-  {
-    bool hit = false;
-
-    for (int j = lane; j < nAcc; j += 32)
+    for (int p = 0; p < 4; p++)
     {
-      const uint2 r = sh->accepted[j];
-      const int ax = r.x & 0xFFFF, ay = r.x >> 16, aw = r.y & 0xFFFF, ah = r.y >> 16;
-      hit |= ax <= x1 && ax + aw > x0 && ay <= y1 && ay + ah > y0;
+      const int r = p * 8 + warp, col = lane;
+      const int bx = ax + col, by = ay + r;
+      const int dx = bx - cx, dy = by - cy;
+      bool m = false;
+
+      if (col >= vx0 && col < vx1 && r >= vy0 && r < vy1 && bx >= 0 && bx < a.BX && by >= 0 && by < a.BY)
+      {
+        if (dx >= 0 && dx < 8 && dy >= 0 && dy < 8)
+          m = known(dx, dy);
+        else if (dy == 0)
+          m = (rowRun >> col) & 1u;
+        else if (dx == 0)
+          m = (colRun >> r) & 1u;
+        else
+          m = predicate_thread<CH>(s, a.rec[(size_t)by * a.BX + bx]);
+      }
+
+      const uint32_t b = __ballot_sync(0xFFFFFFFFu, m);
+
+      if (lane == 0)
+        rows[r] = b;
     }
 
-    return __any_sync(0xFFFFFFFFu, hit);
+    __syncthreads();
+
+    if (threadIdx.x < 32)
+      a.symBits[(size_t)slot * 32 + threadIdx.x] = rows[threadIdx.x];
+
+    if (threadIdx.x == 0)
+      a.symHdr[slot] = (uint32_t)vx0 | (uint32_t)vy0 << 8 | (uint32_t)vx1 << 16 | (uint32_t)vy1 << 24;
+
+    __syncthreads();
   }
-
-  // warp 0: commit the chunk's expansions in scan order. A result computed against the pre-chunk mask stands unless a rectangle
-  // committed earlier in this chunk touches what it probed; then (and after a centre-third hit, which re-examines the same seed)
-  // the seed is expanded again against the current mask, exactly as the sequential scan would have seen it.
-  __device__ void commit(int y, int stage, int nCand, uint2 *list, uint32_t &count)
-  {
-    int nAcc = 0;
-
-    for (int i = 0; i < nCand; i++)
-    {
-      const int x = sh->cand[i];
-
-      if (is_used(x, y))
-        continue;
-
-      SeedResult r = sh->res[i];
-      bool valid = r.kind >= 0 && !touches_accepted(nAcc, x, y, x + r.rx, y + r.ry);
-
-      if (valid && r.attempted)
-        valid = !touches_accepted(nAcc, r.cox - 1, r.coy - 1, r.cox + r.crx, r.coy + r.cry);
-
-      while (true)
-      {
-        if (!valid)
-        {
-          nInline++;
-          r = expand(x, y, stage);
-          valid = true;
-        }
-
-        if (r.kind == 0)
-          break;
-
-        const int eox = r.kind == 2 ? r.cox : x, eoy = r.kind == 2 ? r.coy : y;
-        const int erx = r.kind == 2 ? r.crx : r.rx, ery = r.kind == 2 ? r.cry : r.ry;
-        mark_used(eox, eoy, erx, ery);
-        const uint2 packed = make_uint2((uint32_t)eox | ((uint32_t)eoy << 16), (uint32_t)erx | ((uint32_t)ery << 16));
-
-        if (lane == 0)
-        {
-          if (count < (uint32_t)a.listCap)
-            list[count] = packed;
-          else
-            a.sync[2] = 1; // list overflow: reported by the host as LIMGCU_ERROR_OUT_OF_BOUNDS
-
-          if (nAcc < LIMG_ROW_CHUNK + 32)
-            sh->accepted[nAcc] = packed;
-        }
-
-        __syncwarp();
-        count++;
-        nAcc++;
-
-        if (nAcc >= LIMG_ROW_CHUNK + 32)
-          nAcc = LIMG_ROW_CHUNK + 32; // list full: every later result of this chunk is re-expanded (still exact)
-
-        if (r.kind == 2 && !is_used(x, y))
-        {
-          valid = false; // limg.cpp:1435-1438: the scan resumes at the same seed
-          continue;
-        }
-
-        break;
-      }
-
-      if (nAcc >= LIMG_ROW_CHUNK + 32)
-      {
-        // cannot track more rectangles: fall back to sequential handling of the rest of the chunk
-        for (int j = i + 1; j < nCand; j++)
-          sh->res[j].attempted = 1, sh->res[j].cox = 0, sh->res[j].coy = 0, sh->res[j].crx = (short)a.BX, sh->res[j].cry = (short)a.BY;
-      }
-    }
-  }
-};
-
-__device__ __forceinline__ void or_rect(uint32_t *mask, int wordsPerRow, uint2 r, bool atomic)
-{
-  const int ox = r.x & 0xFFFF, oy = r.x >> 16, rx = r.y & 0xFFFF, ry = r.y >> 16;
-
-  for (int row = 0; row < ry; row++)
-  {
-    uint32_t *m = mask + (size_t)(oy + row) * wordsPerRow;
-
-    for (int xx = ox; xx < ox + rx;)
-    {
-      const int w0 = xx >> 5, b0 = xx & 31;
-      const int cnt = min(32 - b0, ox + rx - xx);
-      const uint32_t bits = (cnt == 32 ? 0xFFFFFFFFu : ((1u << cnt) - 1u)) << b0;
-      atomicOr(&m[w0], bits);
-      xx += cnt;
-    }
-  }
-
-  (void)atomic;
-}
-
-template <int CH>
-__global__ void __launch_bounds__(LIMG_MERGE_THREADS) k_merge_banded(MergeArgs a)
-{
-  extern __shared__ __align__(16) unsigned char dynSmem[];
-  uint32_t *used = reinterpret_cast<uint32_t *>(dynSmem);
-  const int maskWords = a.BY * a.wordsPerRow;
-  uint32_t *winBand = used + maskWords;
-  uint32_t *extBand = winBand + (size_t)a.bandRows * a.BX * 2;
-  uint16_t *unmBand = reinterpret_cast<uint16_t *>(extBand + (size_t)a.bandRows * a.BX);
-  __shared__ BandShared sh;
-
-  const int k = blockIdx.x;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int bandY0 = k * a.bandRows, bandY1 = min(a.BY, bandY0 + a.bandRows);
-  uint32_t *snapshot = a.snapshot + (size_t)k * maskWords;
-
-  // the band's match words and extension slots never change: shared memory
-  for (int i = threadIdx.x; i < (bandY1 - bandY0) * a.BX * 2; i += blockDim.x)
-    winBand[i] = a.window[(size_t)bandY0 * a.BX * 2 + i];
-
-  for (int i = threadIdx.x; i < (bandY1 - bandY0) * a.BX; i += blockDim.x)
-  {
-    extBand[i] = a.extSlot[(size_t)bandY0 * a.BX + i];
-    unmBand[i] = a.unmasked[(size_t)bandY0 * a.BX + i];
-  }
-
-  BandScan<CH> scan{ a, used, winBand, extBand, &sh, lane, bandY0, bandY1, a.BY, -1, 0, 0, 0, 0, false, false };
-
-  for (int stage = 0; stage < 2; stage++)
-  {
-    bool ran = false;
-    int readLo = a.BY, readHi = -1;
-    uint2 *myList = a.lists + ((size_t)k * 2 + stage) * a.listCap;
-    uint32_t *dirtyFlags = a.sync + 8 + stage * (LIMG_MERGE_MAX_BANDS + 2);
-
-    for (int iter = 0; iter <= a.numBands; iter++)
-    {
-      // ---- phase A: input mask = rectangles of every band above (this stage) [+ all of stage 0 when in stage 1]
-      for (int i = threadIdx.x; i < maskWords; i += blockDim.x)
-        used[i] = 0;
-
-      __syncthreads();
-
-      if (stage == 1)
-      {
-        for (int j = 0; j < a.numBands; j++)
-        {
-          const uint32_t n = a.counts[j * 2 + 0];
-          const uint2 *l = a.lists + ((size_t)j * 2 + 0) * a.listCap;
-
-          for (uint32_t i = threadIdx.x; i < n; i += blockDim.x)
-            or_rect(used, a.wordsPerRow, l[i], true);
-        }
-      }
-
-      for (int j = 0; j < k; j++)
-      {
-        const uint32_t n = a.counts[j * 2 + stage];
-        const uint2 *l = a.lists + ((size_t)j * 2 + stage) * a.listCap;
-
-        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x)
-          or_rect(used, a.wordsPerRow, l[i], true);
-      }
-
-      if (threadIdx.x == 0)
-        sh.dirty = ran ? 0 : 1;
-
-      __syncthreads();
-
-      if (ran && readHi >= readLo)
-      {
-        bool diff = false;
-
-        for (int i = readLo * a.wordsPerRow + threadIdx.x; i < (readHi + 1) * a.wordsPerRow; i += blockDim.x)
-          diff |= used[i] != snapshot[i];
-
-        if (diff)
-          sh.dirty = 1;
-      }
-
-      __syncthreads();
-      const bool dirty = sh.dirty != 0;
-
-      if (dirty)
-      {
-        for (int i = threadIdx.x; i < maskWords; i += blockDim.x)
-          snapshot[i] = used[i];
-      }
-
-      grid_barrier(a.sync, gridDim.x); // every band has read the lists of the previous iteration
-
-      // ---- phase B: dirty bands replay their rows, one chunk of candidate seeds at a time
-      if (dirty)
-      {
-        if (threadIdx.x == 0)
-        {
-          sh.count = 0;
-          sh.rangeLo = bandY0;      // the candidate search reads the in-use bits of every row of the band
-          sh.rangeHi = bandY1 - 1;
-        }
-
-        scan.readLo = a.BY;
-        scan.readHi = -1;
-        __syncthreads();
-
-        for (int y = bandY0; y < bandY1; y++)
-        {
-          int x = 0;
-
-          while (x < a.BX)
-          {
-            // warp 0: the next candidate seeds of this row (unused + the stage's necessary condition on the match word)
-            if (warp == 0)
-            {
-              int n = 0, xx0 = x & ~31;
-
-              for (; xx0 < a.BX && n < a.rowChunk; xx0 += 32)
-              {
-                const int xx = xx0 + lane;
-                bool cand = false;
-
-                if (xx >= x && xx < a.BX && !scan.is_used(xx, y))
-                {
-                  const uint32_t w0 = winBand[(size_t)((y - bandY0) * a.BX + xx) * 2];
-                  cand = stage == 0 ? ((w0 & 0x070707u) == 0x070707u) : ((w0 & 0x0102u) != 0);
-                }
-
-                const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, cand);
-                const int pos = n + __popc(ballot & ((1u << lane) - 1u));
-
-                if (cand && pos < a.rowChunk)
-                  sh.cand[pos] = (short)xx;
-
-                n += __popc(ballot);
-              }
-
-              if (lane == 0)
-              {
-                sh.nCand = min(n, a.rowChunk);
-                // row exhausted and everything taken: done after this chunk; otherwise resume behind the last candidate taken
-                sh.nextX = (xx0 >= a.BX && n <= a.rowChunk) ? a.BX : -1;
-              }
-
-              __syncwarp();
-
-              // Dry run of the scan order on the mask-free growth predicted by the plan kernels: a candidate that lies inside
-              // the rectangle an earlier candidate of this chunk is predicted to emit will most likely be swallowed; it is not
-              // expanded speculatively, commit() expands it on the spot in the rare case it is still free when its turn comes.
-              if (lane == 0)
-              {
-                const int nc = min(n, a.rowChunk);
-                int coverUntil = -1;
-
-                for (int i = 0; i < nc; i++)
-                {
-                  const int xc = sh.cand[i];
-                  const uint32_t u = unmBand[(y - bandY0) * a.BX + xc];
-                  const int prx = u & 0xFF, pry = (u >> 8) & 0x7F;
-
-                  if (xc < coverUntil)
-                  {
-                    // small growths are cheap to expand even if they end up swallowed; only the big ones (which would go on demand) are deferred
-                    sh.res[i].kind = (prx >= 8 || pry >= 8) ? -1 : 0;
-                    continue;
-                  }
-
-                  sh.res[i].kind = 0;
-                  const bool emits = stage == 0 ? (prx >= 3 && pry >= 3) : (prx > 1 || pry > 1);
-
-                  if (emits)
-                    coverUntil = xc + prx;
-                }
-              }
-            }
-
-            __syncthreads();
-            const int nCand = sh.nCand;
-
-            if (nCand == 0)
-              break;
-
-            // every warp: expand its share of the candidates against the current mask (read only)
-            for (int i = warp; i < nCand; i += LIMG_MERGE_WARPS)
-            {
-              // probably swallowed by an earlier candidate's rectangle: only the cheap (bitmap) part is done speculatively
-              const SeedResult r = scan.expand(sh.cand[i], y, stage, sh.res[i].kind < 0);
-
-              if (lane == 0)
-                sh.res[i] = r;
-            }
-
-            __syncthreads();
-
-            if (warp == 0)
-            {
-              uint32_t count = sh.count;
-              scan.commit(y, stage, nCand, myList, count);
-
-              if (lane == 0)
-                sh.count = count;
-            }
-
-            const int lastCand = sh.cand[nCand - 1];
-            const int nextX = sh.nextX;
-            __syncthreads();
-            x = nextX < 0 ? lastCand + 1 : nextX;
-          }
-        }
-
-        if (lane == 0 && scan.readHi >= scan.readLo)
-        {
-          atomicMin(&sh.rangeLo, scan.readLo);
-          atomicMax(&sh.rangeHi, scan.readHi);
-        }
-
-        __syncthreads();
-        ran = true;
-        readLo = sh.rangeLo;
-        readHi = sh.rangeHi;
-
-        if (threadIdx.x == 0)
-        {
-          a.counts[k * 2 + stage] = min(sh.count, (uint32_t)a.listCap);
-          dirtyFlags[iter] = 1;
-
-          if (a.stats)
-            atomicAdd(&a.stats[2 + stage], 1u);
-
-          __threadfence();
-        }
-      }
-
-      grid_barrier(a.sync, gridDim.x); // lists of this iteration are complete
-
-      if (*(volatile uint32_t *)&dirtyFlags[iter] == 0)
-      {
-        if (k == 0 && threadIdx.x == 0 && a.stats)
-          a.stats[stage] = iter;
-
-        break;
-      }
-    }
-  }
-
-  if (lane == 0 && a.stats)
-  {
-    atomicAdd(&a.stats[4], scan.nSeeds);
-    atomicAdd(&a.stats[5], scan.nOnDemand);
-    atomicAdd(&a.stats[6], scan.nFour);
-    atomicAdd(&a.stats[7], scan.nInline);
-  }
-
-  // ---- emission order = band order, stage 0 then stage 1; in-use mask for the leftover pass
-  uint32_t before0 = 0, before1 = 0, total0 = 0, total1 = 0;
-
-  for (int j = 0; j < a.numBands; j++)
-  {
-    const uint32_t c0 = a.counts[j * 2 + 0], c1 = a.counts[j * 2 + 1];
-
-    if (j < k)
-    {
-      before0 += c0;
-      before1 += c1;
-    }
-
-    total0 += c0;
-    total1 += c1;
-  }
-
-  for (int stage = 0; stage < 2; stage++)
-  {
-    const uint32_t n = a.counts[k * 2 + stage];
-    const uint2 *l = a.lists + ((size_t)k * 2 + stage) * a.listCap;
-    const uint32_t base = stage == 0 ? before0 : total0 + before1;
-
-    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x)
-    {
-      const uint2 r = l[i];
-      limgcu_area *out = &a.areas[base + i];
-      out->ox = r.x & 0xFFFF; out->oy = r.x >> 16; out->rx = r.y & 0xFFFF; out->ry = r.y >> 16;
-      out->stage = stage;
-      or_rect(a.usedOut, a.wordsPerRow, r, true);
-    }
-  }
-
-  if (k == 0 && threadIdx.x == 0)
-    *a.mergedCount = total0 + total1;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -36,13 +36,14 @@ struct WaveArgs
 {
   const PredRec *rec;
   const uint32_t *window;
-  const uint32_t *extSlot, *extBits, *sym;
+  const uint32_t *extSlot, *extBits, *extHdr;
+  const uint32_t *symSlot, *symBits, *symHdr;
   const uint16_t *unmasked;
   const uint32_t *candBits;  // [2][BY][wordsPerRow]: mask-free necessary condition for a seed to emit in stage 0 / 1
   const uint32_t *candList;  // [2][blocks]
   const uint32_t *candCount; // [2]
   int BX, BY, wordsPerRow;
-  uint32_t *used;            // [BY][wordsPerRow] live in-use bits
+  uint32_t *used;            // [BY][wordsPerRow] live in-use bits (rows padded by two zero words)
   uint32_t *tau;             // [blocks] logical time of the rectangle that owns the block
   int *progress;             // [2][BY] column up to which the row's seeds are committed (LIMG_WAVE_DONE when finished)
   uint32_t *ticket;          // [2]
@@ -68,10 +69,19 @@ __device__ __forceinline__ int ld_acquire_s32(const int *p)
   return v;
 }
 
-__device__ __forceinline__ void st_release_s32(int *p, int v)
+__device__ __forceinline__ void st_relaxed_s32(int *p, int v)
 {
-  asm volatile("st.release.gpu.global.s32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+  asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
 }
+
+#define LIMG_SNAP_UP 8 // a seed's mask snapshot covers block rows y - 8 .. y + 23, one per lane
+
+// 96 in-use bits per lane: row (r0 + lane), columns [32 * w0, 32 * w0 + 96)
+struct Snapshot
+{
+  uint32_t w[3];
+  int r0, w0;
+};
 
 // the live in-use mask (global memory, read at L2)
 struct LiveMask
@@ -79,11 +89,9 @@ struct LiveMask
   const uint32_t *used;
   int wordsPerRow, BX, BY;
 
-  // n (<= 32) in-use bits of row y starting at column x (x may be negative); everything outside the grid reads as in use
-  __device__ __forceinline__ uint32_t bits(int x, int y, int n) const
+  // 32 in-use bits of row y starting at column x (x may be negative); everything outside the grid rows reads as in use
+  __device__ __forceinline__ uint32_t bits(int x, int y) const
   {
-    (void)n;
-
     if (y < 0 || y >= BY)
       return 0xFFFFFFFFu;
 
@@ -97,8 +105,22 @@ struct LiveMask
 
     const int w0 = x >> 5, s = x & 31;
     const uint32_t lo = ld_relaxed_u32(row + w0);
-    const uint32_t hi = s ? ld_relaxed_u32(row + w0 + 1) : 0u; // the row has a padding word; columns >= BX are handled by the grid tests of the growth
+    const uint32_t hi = s ? ld_relaxed_u32(row + w0 + 1) : 0u; // rows are padded; columns >= BX are never set
     return __funnelshift_r(lo, hi, s);
+  }
+
+  __device__ __forceinline__ void words(int y, int w0, uint32_t out[3]) const
+  {
+    if (y < 0 || y >= BY)
+    {
+      out[0] = out[1] = out[2] = 0xFFFFFFFFu;
+      return;
+    }
+
+    const uint32_t *row = used + (size_t)y * wordsPerRow + w0;
+    out[0] = ld_relaxed_u32(row);
+    out[1] = ld_relaxed_u32(row + 1);
+    out[2] = ld_relaxed_u32(row + 2);
   }
 
   __device__ __forceinline__ bool is_used(int x, int y) const
@@ -114,7 +136,7 @@ struct TimeMask
   int BX, BY;
   uint32_t T;
 
-  __device__ __forceinline__ uint32_t bits(int x, int y, int n) const
+  __device__ __forceinline__ uint32_t bits(int x, int y) const
   {
     if (y < 0 || y >= BY)
       return 0xFFFFFFFFu;
@@ -122,14 +144,21 @@ struct TimeMask
     const uint32_t *row = tau + (size_t)y * BX;
     uint32_t b = 0;
 
-    for (int i = 0; i < n; i++)
+    for (int i = 0; i < 32; i++)
     {
       const int xx = x + i;
-      const bool u = (xx < 0 || xx >= BX) ? true : (__ldg(row + xx) < T);
+      const bool u = xx < 0 ? true : (xx < BX && __ldg(row + xx) < T);
       b |= (u ? 1u : 0u) << i;
     }
 
     return b;
+  }
+
+  __device__ __forceinline__ void words(int y, int w0, uint32_t out[3]) const
+  {
+#pragma unroll
+    for (int j = 0; j < 3; j++)
+      out[j] = bits((w0 + j) * 32, y);
   }
 
   __device__ __forceinline__ bool is_used(int x, int y) const
@@ -147,6 +176,24 @@ struct WaveResult
   int boxR;               // exclusive right edge of every column whose in-use bits were consulted
 };
 
+// everything about a seed that does not depend on the mask: loaded while the row waits for the rows above
+struct SeedPre
+{
+  uint32_t rowBits; // lane: match bits of the seed for block row y + lane, columns x ..
+  int vx1, vy1;     // known part of it: [0, vx1) x [0, vy1)
+  int pcx, pcy;     // centre the mask-free growth predicts (-1: none)
+  uint32_t symRow;  // lane: match bits of that centre for block row pcy - 8 + lane, columns pcx - 8 ..
+  uint32_t symHdr;  // known part (0: no bitmap)
+};
+
+// a match bitmap combined with the mask: bit (row ay + lane, column ax + i) = matches the seed and is free
+struct Region
+{
+  int ax, ay;
+  int vx0, vy0, vx1, vy1; // known part (absolute block coordinates, half open)
+  uint32_t avail;
+};
+
 // Every method is warp-cooperative: all 32 lanes call it with warp-uniform arguments.
 template <int CH, class Mask>
 struct WaveScan
@@ -155,6 +202,7 @@ struct WaveScan
   Mask mask;
   int lane;
   uint32_t nOnDemand;
+  long long tOnDemand = 0, tFour = 0; // profile: clock cycles inside on-demand strips / the four-way regrowth
 
   __device__ bool strip_unused(int x0, int y0, int w, int h)
   {
@@ -210,115 +258,109 @@ struct WaveScan
 
   __device__ bool strip_joins(const PredRec &seed, int x0, int y0, int w, int h)
   {
-    return strip_unused(x0, y0, w, h) && strip_matches(seed, x0, y0, w, h);
+    const long long t0 = clock64();
+    const bool ok = strip_unused(x0, y0, w, h) && strip_matches(seed, x0, y0, w, h);
+    tOnDemand += clock64() - t0;
+    return ok;
   }
 
-  // right/down growth of a 1x1 seed (limg.cpp:1294-1343). The seed's match bitmap (8x8 word, or the speculative 16x16 / 32x32
-  // extension) lives one row per lane; growth inside it is ballots and shuffles, strips beyond it are evaluated on demand.
-  __device__ void grow_seed(int x, int y, int &rx, int &ry)
+  __device__ __forceinline__ Snapshot snapshot(int x, int y) const
   {
+    Snapshot s;
+    s.r0 = y - LIMG_SNAP_UP;
+    s.w0 = max(x - 8, 0) >> 5;
+    mask.words(s.r0 + lane, s.w0, s.w);
+    return s;
+  }
+
+  // is block (x, y) of the snapshot's seed in use? (x - 32 * w0 < 40)
+  __device__ __forceinline__ bool snap_used(const Snapshot &s, int x) const
+  {
+    const int b = x - s.w0 * 32;
+    const uint32_t w = __shfl_sync(0xFFFFFFFFu, b < 32 ? s.w[0] : s.w[1], LIMG_SNAP_UP);
+    return (w >> (b & 31)) & 1u;
+  }
+
+  // in-use bits of row (ay + lane), columns [ax, ax + 32): from the snapshot where it covers them, else read directly
+  __device__ uint32_t region_used(const Snapshot &s, int ax, int ay, int rows) const
+  {
+    const int src = ay + lane - s.r0, sh = ax - s.w0 * 32;
+    const int from = min(max(src, 0), 31);
+    const uint32_t a0 = __shfl_sync(0xFFFFFFFFu, s.w[0], from), a1 = __shfl_sync(0xFFFFFFFFu, s.w[1], from), a2 = __shfl_sync(0xFFFFFFFFu, s.w[2], from);
+
+    if (lane >= rows)
+      return 0xFFFFFFFFu;
+
+    if (src < 0 || src > 31 || sh < 0 || sh > 63)
+      return mask.bits(ax, ay + lane);
+
+    return sh < 32 ? __funnelshift_r(a0, a1, sh) : __funnelshift_r(a1, a2, sh - 32);
+  }
+
+  __device__ __forceinline__ void load_sym(int cx, int cy, uint32_t &row, uint32_t &hdr) const
+  {
+    const uint32_t slot = __ldg(&a.symSlot[(size_t)cy * a.BX + cx]);
+    row = 0;
+    hdr = 0;
+
+    if (slot != LIMG_NO_SLOT)
+    {
+      row = __ldg(&a.symBits[(size_t)slot * 32 + lane]);
+      hdr = __ldg(&a.symHdr[slot]);
+    }
+  }
+
+  __device__ SeedPre prefetch(int x, int y, int stage) const
+  {
+    SeedPre p;
     const int seed = y * a.BX + x;
     const uint32_t slot = __ldg(&a.extSlot[seed]);
-    int S = 8;
-    uint32_t rowBits;
+    const uint32_t u = __ldg(&a.unmasked[seed]);
+    const uint32_t wv = lane < 8 ? __ldg(&a.window[(size_t)seed * 2 + (lane >> 2)]) : 0u;
 
     if (slot == LIMG_NO_SLOT)
     {
-      const uint32_t *wp = a.window + (size_t)seed * 2;
-      rowBits = lane < 8 ? (__ldg(&wp[lane >> 2]) >> (8 * (lane & 3))) & 0xFFu : 0u;
+      p.rowBits = (wv >> (8 * (lane & 3))) & 0xFFu;
+      p.vx1 = 8;
+      p.vy1 = 8;
     }
     else
     {
-      S = (slot >> 31) ? 32 : 16;
-      rowBits = lane < S ? __ldg(&a.extBits[(size_t)(slot & 0x7FFFFFFFu) * 32 + lane]) : 0u;
+      const uint32_t h = __ldg(&a.extHdr[slot]);
+      p.rowBits = __ldg(&a.extBits[(size_t)slot * 32 + lane]);
+      p.vx1 = (h >> 16) & 0xFF;
+      p.vy1 = h >> 24;
     }
 
-    const uint32_t avail = lane < S ? (rowBits & ~mask.bits(x, y + lane, S)) : 0u;
-    bool right = true, down = true;
-    bool haveRec = false;
-    PredRec rec;
-    rx = 1;
-    ry = 1;
+    p.pcx = p.pcy = -1;
+    p.symRow = 0;
+    p.symHdr = 0;
+    const int prx = u & 0xFF, pry = u >> 8;
 
-    while (right || down)
+    if (stage == 0 && prx >= 3 && pry >= 3)
     {
-      if (right)
-      {
-        bool ok = x + rx + 1 < a.BX;
-
-        if (ok)
-        {
-          const int rows = min(ry, S);
-
-          if (rx < S)
-          {
-            const uint32_t need = rows >= 32 ? 0xFFFFFFFFu : ((1u << rows) - 1u);
-            const uint32_t have = __ballot_sync(0xFFFFFFFFu, (avail >> rx) & 1u);
-            ok = (have & need) == need;
-          }
-
-          if (ok && (rx >= S || ry > S))
-          {
-            if (!haveRec) { rec = a.rec[seed]; haveRec = true; }
-            ok = rx >= S ? strip_joins(rec, x + rx, y, 1, ry) : strip_joins(rec, x + rx, y + S, 1, ry - S);
-          }
-        }
-
-        if (ok) rx++; else right = false;
-      }
-
-      if (down)
-      {
-        bool ok = y + ry + 1 < a.BY;
-
-        if (ok)
-        {
-          const int cols = min(rx, S);
-
-          if (ry < S)
-          {
-            const uint32_t need = cols >= 32 ? 0xFFFFFFFFu : ((1u << cols) - 1u);
-            const uint32_t rowv = __shfl_sync(0xFFFFFFFFu, avail, ry);
-            ok = (rowv & need) == need;
-          }
-
-          if (ok && (ry >= S || rx > S))
-          {
-            if (!haveRec) { rec = a.rec[seed]; haveRec = true; }
-            ok = ry >= S ? strip_joins(rec, x, y + ry, rx, 1) : strip_joins(rec, x + S, y + ry, rx - S, 1);
-          }
-        }
-
-        if (ok) ry++; else down = false;
-      }
+      p.pcx = x + prx / 3;
+      p.pcy = y + pry / 3;
+      load_sym(p.pcx, p.pcy, p.symRow, p.symHdr);
     }
+
+    return p;
   }
 
-  // four-way alternating growth from the centre third (limg.cpp:1294-1388, 1426-1433). The centre seed's symmetric 16 x 16 match
-  // window covers [ox - 8, ox + 8) x [oy - 8, oy + 8), one row per lane; strips that leave it are evaluated on demand.
-  __device__ void grow_four_way(int &ox, int &oy, int &rx, int &ry)
+  // alternating growth of the rectangle (ox, oy, rx, ry) of seed block `seed` (limg.cpp:1294-1388): right and down, and also up
+  // and left for the centre-third regrowth. Strips inside the region's known part are bit tests, the others are evaluated on demand.
+  __device__ void grow(int seed, const Region &g, bool fourWay, int &ox, int &oy, int &rx, int &ry)
   {
-    const int seed = oy * a.BX + ox;
-    const int rgX = ox - 8, rgY = oy - 8;
-    uint32_t avail = 0;
-
-    if (lane < 16)
-    {
-      const uint32_t w = __ldg(&a.sym[(size_t)seed * 8 + (lane >> 1)]);
-      avail = ((w >> (16 * (lane & 1))) & 0xFFFFu) & ~mask.bits(rgX, rgY + lane, 16);
-    }
-
     bool haveRec = false;
     PredRec rec;
-    bool right = true, down = true, up = true, left = true;
+    bool right = true, down = true, up = fourWay, left = fourWay;
 
-    // strip test: inside the window -> bits, otherwise on demand
     auto joins = [&](int x0, int y0, int w, int h) -> bool {
-      if (x0 >= rgX && y0 >= rgY && x0 + w <= rgX + 16 && y0 + h <= rgY + 16)
+      if (x0 >= g.vx0 && y0 >= g.vy0 && x0 + w <= g.vx1 && y0 + h <= g.vy1)
       {
-        const uint32_t m = ((1u << w) - 1u) << (x0 - rgX);
-        const int r0 = y0 - rgY;
-        const bool rowOk = (lane < r0 || lane >= r0 + h) || ((avail & m) == m);
+        const uint32_t m = (w >= 32 ? 0xFFFFFFFFu : ((1u << w) - 1u)) << (x0 - g.ax);
+        const int r0 = y0 - g.ay;
+        const bool rowOk = (lane < r0 || lane >= r0 + h) || ((g.avail & m) == m);
         return __all_sync(0xFFFFFFFFu, rowOk);
       }
 
@@ -351,10 +393,16 @@ struct WaveScan
   }
 
   // what seed (x, y) does against the mask (limg.cpp:1405-1486)
-  __device__ WaveResult expand(int x, int y, int stage)
+  __device__ WaveResult expand(int x, int y, int stage, const SeedPre &pre, const Snapshot &sn)
   {
     WaveResult r;
-    grow_seed(x, y, r.rx, r.ry);
+    Region g;
+    g.ax = x; g.ay = y; g.vx0 = x; g.vy0 = y; g.vx1 = x + pre.vx1; g.vy1 = y + pre.vy1;
+    g.avail = pre.rowBits & ~region_used(sn, x, y, pre.vy1);
+    int ox = x, oy = y;
+    r.rx = 1;
+    r.ry = 1;
+    grow(y * a.BX + x, g, false, ox, oy, r.rx, r.ry);
     r.kind = 0;
     r.cox = r.coy = r.crx = r.cry = 0;
     r.boxR = min(x + r.rx + 1, a.BX);
@@ -363,11 +411,24 @@ struct WaveScan
     {
       if (r.rx >= 3 && r.ry >= 3) // Q4
       {
+        const long long t0 = clock64();
         int cox = x + r.rx / 3, coy = y + r.ry / 3, crx = r.rx / 3, cry = r.ry / 3;
-        grow_four_way(cox, coy, crx, cry);
+        uint32_t symRow = pre.symRow, symHdr = pre.symHdr;
+
+        if (cox != pre.pcx || coy != pre.pcy)
+          load_sym(cox, coy, symRow, symHdr);
+
+        Region c;
+        c.ax = cox - LIMG_SYM_BACK; c.ay = coy - LIMG_SYM_BACK;
+        c.vx0 = c.ax + (int)(symHdr & 0xFF); c.vy0 = c.ay + (int)((symHdr >> 8) & 0xFF);
+        c.vx1 = c.ax + (int)((symHdr >> 16) & 0xFF); c.vy1 = c.ay + (int)(symHdr >> 24);
+        c.avail = symHdr ? (symRow & ~region_used(sn, c.ax, c.ay, (int)(symHdr >> 24))) : 0u;
+        const int centre = coy * a.BX + cox;
+        grow(centre, c, true, cox, coy, crx, cry);
         r.cox = cox; r.coy = coy; r.crx = crx; r.cry = cry;
         r.kind = (crx * cry > r.rx * r.ry) ? 2 : 1;
         r.boxR = max(r.boxR, min(cox + crx + 1, a.BX));
+        tFour += clock64() - t0;
       }
     }
     else
@@ -438,7 +499,7 @@ __device__ __forceinline__ int wave_wait(const int *progress, int y, int need, u
     }
 
     polls++;
-    __nanosleep(v + 64 < need ? 400 : 40);
+    __nanosleep(v + 64 < need ? 400 : 20);
   }
 
   return v;
@@ -459,6 +520,7 @@ __global__ void __launch_bounds__(LIMG_WAVE_WARPS * 32) k_merge_wave(WaveArgs a,
   const uint32_t base = stage ? LIMG_TAU_STAGE1 : 0u;
   const int nWords = (a.BX + 31) >> 5;
   uint32_t nExp = 0, nReexp = 0, nPolls = 0;
+  long long tNext = 0, tWait = 0, tExpand = 0, tClaim = 0, tPre = 0, tc;
   bool failed = false;
 
   for (;;)
@@ -494,19 +556,30 @@ __global__ void __launch_bounds__(LIMG_WAVE_WARPS * 32) k_merge_wave(WaveArgs a,
     const uint32_t *usedRow = a.used + (size_t)y * a.wordsPerRow;
     uint2 *list = lists + (size_t)y * a.listCap;
     uint32_t count = 0;
-    int x = 0;
+    int x = 0, published = 0;
 
     for (;;)
     {
+      tc = clock64();
       x = wave_next_candidate(candRow, usedRow, nWords, x, a.BX, lane);
 
-      // everything left of x is decided and (after the fence below) visible
-      if (lane == 0)
-        st_release_s32(progress + y, x >= a.BX ? LIMG_WAVE_DONE : x);
+      // every seed left of x is decided, and its claims were fenced when they were made
+      if (x > published || x >= a.BX)
+      {
+        if (lane == 0)
+          st_relaxed_s32(progress + y, x >= a.BX ? LIMG_WAVE_DONE : x);
+
+        published = x;
+      }
+
+      tNext += clock64() - tc;
 
       if (x >= a.BX)
         break;
 
+      tc = clock64();
+      const SeedPre pre = scan.prefetch(x, y, stage);
+      tPre += clock64() - tc;
       const uint32_t first = count;
       int nextX = x + 1;
       bool claimed = false;
@@ -516,22 +589,31 @@ __global__ void __launch_bounds__(LIMG_WAVE_WARPS * 32) k_merge_wave(WaveArgs a,
         WaveResult r;
         int p = LIMG_WAVE_DONE;
         bool taken = false;
+        tc = clock64();
 
         if (y > 0 && !sequential)
           p = wave_wait(progress, y, min(x + 1 + a.margin, a.BX), nPolls, a.flags);
 
+        tWait += clock64() - tc;
+
         for (;;)
         {
-          if (scan.mask.is_used(x, y)) { taken = true; break; }
+          tc = clock64();
+          const Snapshot sn = scan.snapshot(x, y);
 
-          r = scan.expand(x, y, stage);
+          if (scan.snap_used(sn, x)) { taken = true; break; }
+
+          r = scan.expand(x, y, stage, pre, sn);
           nExp++;
+          tExpand += clock64() - tc;
           const int need = min(r.boxR + a.margin, a.BX);
 
           if (p >= need)
             break;
 
+          tc = clock64();
           p = wave_wait(progress, y, need, nPolls, a.flags); // the rows above have to pass everything this seed looked at: look again
+          tWait += clock64() - tc;
           nReexp++;
         }
 
@@ -545,8 +627,9 @@ __global__ void __launch_bounds__(LIMG_WAVE_WARPS * 32) k_merge_wave(WaveArgs a,
         if (k >= LIMG_WAVE_MAX_ATTEMPTS && !sequential)
           failed = true; // more regrowths from one seed than the time stamp encodes: let the sequential pass do it
 
-        // claim: in-use bits (an overlap with anybody else's rectangle is a failed speculation) + owner times
-        bool overlap = false;
+        // claim: in-use bits and owner times. Two rectangles that overlap (a failed speculation) leave one of them with a foreign
+        // owner time on a block, which the verification pass sees.
+        tc = clock64();
 
         for (int rr = lane; rr < ery; rr += 32)
         {
@@ -557,20 +640,13 @@ __global__ void __launch_bounds__(LIMG_WAVE_WARPS * 32) k_merge_wave(WaveArgs a,
             const int w0 = xx >> 5, b0 = xx & 31;
             const int cnt = min(32 - b0, eox + erx - xx);
             const uint32_t m = (cnt == 32 ? 0xFFFFFFFFu : ((1u << cnt) - 1u)) << b0;
-            overlap |= (atomicOr(&row[w0], m) & m) != 0;
+            atomicOr(&row[w0], m);
             xx += cnt;
           }
         }
 
         for (int e = lane; e < erx * ery; e += 32)
           a.tau[(size_t)(eoy + e / erx) * a.BX + eox + e % erx] = T;
-
-        if (__any_sync(0xFFFFFFFFu, overlap))
-          failed = true;
-
-        // the claim is visible to this warp's next look at the mask and to everybody who later reads the progress store
-        __threadfence();
-        __syncwarp();
 
         if (lane == 0)
         {
@@ -580,8 +656,12 @@ __global__ void __launch_bounds__(LIMG_WAVE_WARPS * 32) k_merge_wave(WaveArgs a,
             a.flags[2] = 1; // reported by the host as LIMGCU_ERROR_OUT_OF_BOUNDS
         }
 
+        // the claim is visible to this warp's next look at the mask and to everybody who later reads the progress store
+        __threadfence();
+        __syncwarp();
         count++;
         claimed = true;
+        tClaim += clock64() - tc;
 
         if (r.kind == 2)
         {
@@ -600,6 +680,15 @@ __global__ void __launch_bounds__(LIMG_WAVE_WARPS * 32) k_merge_wave(WaveArgs a,
         emitInfo[(size_t)y * a.BX + x] = (first << 8) | (count - first);
 
       x = nextX;
+
+      // hand over to the rows below before looking for the next candidate
+      if (x < a.BX)
+      {
+        if (lane == 0)
+          st_relaxed_s32(progress + y, x);
+
+        published = x;
+      }
     }
 
     if (lane == 0)
@@ -615,6 +704,14 @@ __global__ void __launch_bounds__(LIMG_WAVE_WARPS * 32) k_merge_wave(WaveArgs a,
     atomicAdd(&a.stats[1 + stage * 4], nReexp);
     atomicAdd(&a.stats[2 + stage * 4], nPolls);
     atomicAdd(&a.stats[3 + stage * 4], scan.nOnDemand);
+    // profile (kilocycles, summed over warps and both stages): next-candidate + publish, wait, expand (incl. four-way, on-demand), four-way, on-demand, claim, prefetch
+    atomicAdd(&a.stats[8], (uint32_t)(tNext >> 10));
+    atomicAdd(&a.stats[9], (uint32_t)(tWait >> 10));
+    atomicAdd(&a.stats[10], (uint32_t)(tExpand >> 10));
+    atomicAdd(&a.stats[11], (uint32_t)(scan.tFour >> 10));
+    atomicAdd(&a.stats[12], (uint32_t)(scan.tOnDemand >> 10));
+    atomicAdd(&a.stats[13], (uint32_t)(tClaim >> 10));
+    atomicAdd(&a.stats[14], (uint32_t)(tPre >> 10));
   }
 }
 
@@ -623,7 +720,7 @@ template <int CH>
 __global__ void __launch_bounds__(256) k_merge_verify(WaveArgs a, int stage)
 {
   if (a.flags[stage] != 0)
-    return; // already failed (overlapping claims)
+    return; // already failed
 
   const int lane = threadIdx.x & 31;
   const uint32_t n = a.candCount[stage];
@@ -642,16 +739,22 @@ __global__ void __launch_bounds__(256) k_merge_verify(WaveArgs a, int stage)
     const uint2 *rec = lists + (size_t)y * a.listCap + start;
     uint32_t e = 0;
     bool ok = true;
+    bool havePre = false;
+    SeedPre pre;
 
     for (int k = 0;; k++)
     {
       if (k >= LIMG_WAVE_MAX_ATTEMPTS) { ok = false; break; }
 
-      WaveScan<CH, TimeMask> scan{ a, TimeMask{ a.tau, a.BX, a.BY, base + ((uint32_t)seed << 3) + (uint32_t)k }, lane, 0 };
+      const uint32_t T = base + ((uint32_t)seed << 3) + (uint32_t)k;
+      WaveScan<CH, TimeMask> scan{ a, TimeMask{ a.tau, a.BX, a.BY, T }, lane, 0 };
 
       if (scan.mask.is_used(x, y)) { ok = e == have; break; }
 
-      const WaveResult r = scan.expand(x, y, stage);
+      if (!havePre) { pre = scan.prefetch(x, y, stage); havePre = true; }
+
+      const Snapshot sn = scan.snapshot(x, y);
+      const WaveResult r = scan.expand(x, y, stage, pre, sn);
 
       if (r.kind == 0) { ok = e == have; break; }
 
@@ -664,6 +767,14 @@ __global__ void __launch_bounds__(256) k_merge_verify(WaveArgs a, int stage)
       e++;
 
       if (want.x != got.x || want.y != got.y) { ok = false; break; }
+
+      // every block of the rectangle is owned by it (no overlap with another rectangle)
+      bool foreign = false;
+
+      for (int b = lane; b < erx * ery; b += 32)
+        foreign |= __ldg(&a.tau[(size_t)(eoy + b / erx) * a.BX + eox + b % erx]) != T;
+
+      if (__any_sync(0xFFFFFFFFu, foreign)) { ok = false; break; }
 
       if (r.kind == 1) { ok = e == have; break; }
     }

@@ -38,14 +38,10 @@ struct limgcu_ctx
   uint32_t *dSmallList = nullptr, *dLargeList = nullptr;
   uint64_t *dDemand = nullptr;
   uint32_t *dUsed = nullptr;
-  uint2 *dBandLists = nullptr;
-  uint32_t *dBandSnapshot = nullptr;
-  uint32_t *dBandState = nullptr; // [0..8 + 2 * (MAX_BANDS + 2)) barrier + flags, then counts [MAX_BANDS * 2]
-  size_t capBandLists = 0, capBandSnapshot = 0;
-  uint32_t *dExtSlot = nullptr, *dExtSeed = nullptr, *dExtBits = nullptr, *dPlanCounters = nullptr;
-  uint32_t *dSym = nullptr;
+  uint32_t *dExtSlot = nullptr, *dExtSeed = nullptr, *dExtBits = nullptr, *dExtHdr = nullptr, *dPlanCounters = nullptr;
+  uint32_t *dSymSlot = nullptr, *dSymSeed = nullptr, *dSymBits = nullptr, *dSymHdr = nullptr;
   uint16_t *dUnmasked = nullptr;
-  uint32_t extCap = 0;
+  uint32_t extCap = 0, symCap = 0;
   uint32_t *dScratchPx = nullptr, *dScratchFac = nullptr;
   uint32_t *dCounters = nullptr; // [16]: 0 merged, 1 areaCount, 2 smallCount, 3 largeCount, 4 workSmall, 5 workLarge, 8.. stats
   unsigned long long *dCompare = nullptr;
@@ -62,8 +58,8 @@ struct limgcu_ctx
   uint2 *dRowLists = nullptr;
   size_t capWaveZero = 0, capRowLists = 0;
 
-  int mergeExt = 1, mergeChunk = 64; // tunables (LIMGCU_MERGE_EXT, LIMGCU_MERGE_CHUNK)
-  int mergeMode = 0;                 // LIMGCU_MERGE_MODE: 0 wave (pipelined rows + verification), 1 seq (rows in sequence), 2 banded (round-1a fixed point)
+  int mergeExt = 1;                  // LIMGCU_MERGE_EXT=0 disables the speculative match bitmaps (everything beyond the 8x8 window on demand)
+  int mergeMode = 0;                 // LIMGCU_MERGE_MODE: 0 wave (pipelined rows + verification), 1 seq (rows strictly in sequence)
   int mergeMargin = 8;               // LIMGCU_MERGE_MARGIN: columns a row stays behind the rows above, beyond what its seed probed
   bool timing = false;
   cudaEvent_t ev[PHASE_COUNT + 1] = { nullptr };
@@ -99,7 +95,7 @@ static int ensure_capacity(limgcu_ctx *ctx, size_t W, size_t H)
 {
   const size_t BX = (W + 7) / 8, BY = (H + 7) / 8;
   const size_t blocks = BX * BY, pixels = W * H;
-  const size_t usedWords = BY * ((BX + 31) / 32 + 1);
+  const size_t usedWords = BY * ((BX + 31) / 32 + 2);
 
   if (blocks > ctx->capBlocks)
   {
@@ -113,11 +109,16 @@ static int ensure_capacity(limgcu_ctx *ctx, size_t W, size_t H)
     CK(regrow(ctx->dLargeList, blocks));
     CK(regrow(ctx->dDemand, blocks));
     ctx->extCap = (uint32_t)(blocks / 2 > 1024 ? blocks / 2 : 1024);
-    CK(regrow(ctx->dSym, blocks * 8));
+    ctx->symCap = (uint32_t)(blocks > 1024 ? blocks : 1024);
     CK(regrow(ctx->dUnmasked, blocks));
     CK(regrow(ctx->dExtSlot, blocks));
     CK(regrow(ctx->dExtSeed, (size_t)ctx->extCap));
     CK(regrow(ctx->dExtBits, (size_t)ctx->extCap * 32));
+    CK(regrow(ctx->dExtHdr, (size_t)ctx->extCap));
+    CK(regrow(ctx->dSymSlot, blocks));
+    CK(regrow(ctx->dSymSeed, (size_t)ctx->symCap));
+    CK(regrow(ctx->dSymBits, (size_t)ctx->symCap * 32));
+    CK(regrow(ctx->dSymHdr, (size_t)ctx->symCap));
     if (ctx->dPlanCounters == nullptr) CK(regrow(ctx->dPlanCounters, (size_t)8));
     CK(regrow(ctx->dTau, blocks));
     CK(regrow(ctx->dCandList, blocks * 2));
@@ -144,28 +145,6 @@ static int ensure_capacity(limgcu_ctx *ctx, size_t W, size_t H)
   {
     CK(regrow(ctx->dUsed, usedWords));
     ctx->capUsedWords = usedWords;
-  }
-
-  {
-    const size_t bandRows = BY / 128 + 1 > 8 ? BY / 128 + 1 : 8;
-    const size_t numBands = (BY + bandRows - 1) / bandRows;
-    const size_t listCap = bandRows * BX * 2;
-    const size_t lists = numBands * 2 * listCap, snap = numBands * usedWords;
-
-    if (lists > ctx->capBandLists)
-    {
-      CK(regrow(ctx->dBandLists, lists));
-      ctx->capBandLists = lists;
-    }
-
-    if (snap > ctx->capBandSnapshot)
-    {
-      CK(regrow(ctx->dBandSnapshot, snap));
-      ctx->capBandSnapshot = snap;
-    }
-
-    if (ctx->dBandState == nullptr)
-      CK(regrow(ctx->dBandState, (size_t)1024));
   }
 
   if (pixels > ctx->capPixels)
@@ -253,9 +232,8 @@ extern "C" int limgcu_create(int device, limgcu_ctx **out)
   }
 
   if (const char *v = getenv("LIMGCU_MERGE_EXT")) ctx->mergeExt = atoi(v);
-  if (const char *v = getenv("LIMGCU_MERGE_CHUNK")) ctx->mergeChunk = atoi(v) < 1 ? 1 : (atoi(v) > LIMG_ROW_CHUNK ? LIMG_ROW_CHUNK : atoi(v));
 
-  if (const char *v = getenv("LIMGCU_MERGE_MODE")) ctx->mergeMode = !strcmp(v, "seq") ? 1 : (!strcmp(v, "banded") ? 2 : 0);
+  if (const char *v = getenv("LIMGCU_MERGE_MODE")) ctx->mergeMode = !strcmp(v, "seq") ? 1 : 0;
   if (const char *v = getenv("LIMGCU_MERGE_MARGIN")) ctx->mergeMargin = atoi(v) < 0 ? 0 : atoi(v);
 
   for (auto &e : ctx->ev)
@@ -263,8 +241,6 @@ extern "C" int limgcu_create(int device, limgcu_ctx **out)
 
   cudaFuncSetAttribute(k_encode_large<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 + LIMG_CTA_STAGE_PX * 16 + 2 * LIMG_CTA_AREA_CAP * 4);
   cudaFuncSetAttribute(k_encode_large<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 + LIMG_CTA_STAGE_PX * 16 + 2 * LIMG_CTA_AREA_CAP * 4);
-  cudaFuncSetAttribute(k_merge_banded<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-  cudaFuncSetAttribute(k_merge_banded<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
 
   *out = ctx;
   return LIMGCU_SUCCESS;
@@ -281,8 +257,8 @@ extern "C" void limgcu_destroy(limgcu_ctx *ctx)
     cudaStreamSynchronize(ctx->stream);
 
   void *ptrs[] = { ctx->dLut, ctx->dTable, ctx->dRec, ctx->dWindow, ctx->dAreas, ctx->dBlockToArea, ctx->dWork, ctx->dSmallList, ctx->dLargeList, ctx->dDemand,
-                   ctx->dUsed, ctx->dScratchPx, ctx->dScratchFac, ctx->dCounters, ctx->dCompare, ctx->dSrc, ctx->dBandLists, ctx->dBandSnapshot, ctx->dBandState,
-                   ctx->dExtSlot, ctx->dExtSeed, ctx->dExtBits, ctx->dPlanCounters, ctx->dSym, ctx->dUnmasked,
+                   ctx->dUsed, ctx->dScratchPx, ctx->dScratchFac, ctx->dCounters, ctx->dCompare, ctx->dSrc,
+                   ctx->dExtSlot, ctx->dExtSeed, ctx->dExtBits, ctx->dExtHdr, ctx->dPlanCounters, ctx->dSymSlot, ctx->dSymSeed, ctx->dSymBits, ctx->dSymHdr, ctx->dUnmasked,
                    ctx->dWaveZero, ctx->dTau, ctx->dCandList, ctx->dRowLists };
 
   for (void *p : ptrs)
@@ -382,7 +358,7 @@ static int launch_merge(limgcu_ctx *ctx, const limgcu_decomp *dTable, size_t W, 
 {
   const int BX = (int)((W + 7) / 8), BY = (int)((H + 7) / 8);
   const int blocks = BX * BY;
-  const int wordsPerRow = (BX + 31) / 32 + 1;
+  const int wordsPerRow = (BX + 31) / 32 + 2;
 
   CK(cudaMemsetAsync(ctx->dCounters, 0, 32 * sizeof(uint32_t), ctx->stream));
 
@@ -390,14 +366,39 @@ static int launch_merge(limgcu_ctx *ctx, const limgcu_decomp *dTable, size_t W, 
 
   if (!noMerge)
   {
+    if (BX > 8190 || BY > 8190)
+      return fail(ctx, LIMGCU_ERROR_OUT_OF_BOUNDS, "image too large for the merge's time stamps", cudaSuccess);
+
+    const size_t usedWords = (size_t)BY * wordsPerRow;
+    uint32_t *wz = ctx->dWaveZero;
+    uint32_t *wFlags = wz, *wTicket = wz + 4, *wCandCount = wz + 6;
+    int *wProgress = reinterpret_cast<int *>(wz + 8);
+    uint32_t *wRowCounts = wz + 8 + 2 * BY, *wCandBits = wz + 8 + 4 * BY, *wEmitInfo = wCandBits + 2 * usedWords;
+    CK(cudaMemsetAsync(wz, 0, (8 + 4 * (size_t)BY + 2 * usedWords + 2 * (size_t)blocks) * sizeof(uint32_t), ctx->stream));
+    CK(cudaMemsetAsync(ctx->dPlanCounters, 0, 8 * sizeof(uint32_t), ctx->stream));
+
+    PlanArgs pl;
+    pl.rec = ctx->dRec; pl.window = ctx->dWindow; pl.BX = BX; pl.BY = BY; pl.wordsPerRow = wordsPerRow;
+    pl.extSlot = ctx->dExtSlot; pl.extSeed = ctx->dExtSeed; pl.extBits = ctx->dExtBits; pl.extHdr = ctx->dExtHdr;
+    pl.symSlot = ctx->dSymSlot; pl.symSeed = ctx->dSymSeed; pl.symBits = ctx->dSymBits; pl.symHdr = ctx->dSymHdr;
+    pl.counters = ctx->dPlanCounters; pl.extCap = ctx->mergeExt ? ctx->extCap : 0; pl.symCap = ctx->mergeExt ? ctx->symCap : 0; pl.unmasked = ctx->dUnmasked;
+    pl.candBits = wCandBits; pl.candList = ctx->dCandList; pl.candCount = wCandCount;
+    const int planGrid = ctx->smCount * 8;
+
     if (hasAlpha)
     {
       k_pred_records<4><<<(blocks + 255) / 256, 256, 0, ctx->stream>>>(dTable, blocks, ctx->dRec);
       CKL("k_pred_records");
       k_pred_window<4><<<(blocks * 2 + 7) / 8, 256, 0, ctx->stream>>>(ctx->dRec, BX, BY, ctx->dWindow);
       CKL("k_pred_window");
-      k_pred_symwindow<4><<<blocks, 256, 0, ctx->stream>>>(ctx->dRec, ctx->dWindow, BX, BY, ctx->dSym);
-      CKL("k_pred_symwindow");
+      k_plan_seeds<<<(blocks + 255) / 256, 256, 0, ctx->stream>>>(pl);
+      CKL("k_plan_seeds");
+      k_plan_extend<4><<<planGrid, 256, 0, ctx->stream>>>(pl);
+      CKL("k_plan_extend");
+      k_plan_centres<<<(blocks + 255) / 256, 256, 0, ctx->stream>>>(pl);
+      CKL("k_plan_centres");
+      k_plan_sym<4><<<planGrid, 256, 0, ctx->stream>>>(pl);
+      CKL("k_plan_sym");
     }
     else
     {
@@ -405,131 +406,72 @@ static int launch_merge(limgcu_ctx *ctx, const limgcu_decomp *dTable, size_t W, 
       CKL("k_pred_records");
       k_pred_window<3><<<(blocks * 2 + 7) / 8, 256, 0, ctx->stream>>>(ctx->dRec, BX, BY, ctx->dWindow);
       CKL("k_pred_window");
-      k_pred_symwindow<3><<<blocks, 256, 0, ctx->stream>>>(ctx->dRec, ctx->dWindow, BX, BY, ctx->dSym);
-      CKL("k_pred_symwindow");
-    }
-
-    const size_t usedWords = (size_t)BY * wordsPerRow;
-    uint32_t *wz = ctx->dWaveZero;
-    uint32_t *wFlags = wz, *wTicket = wz + 4, *wCandCount = wz + 6;
-    int *wProgress = reinterpret_cast<int *>(wz + 8);
-    uint32_t *wRowCounts = wz + 8 + 2 * BY, *wCandBits = wz + 8 + 4 * BY, *wEmitInfo = wCandBits + 2 * usedWords;
-    const bool banded = ctx->mergeMode == 2;
-
-    if (!banded)
-      CK(cudaMemsetAsync(wz, 0, (8 + 4 * (size_t)BY + 2 * usedWords + 2 * (size_t)blocks) * sizeof(uint32_t), ctx->stream));
-
-    PlanArgs pl;
-    pl.rec = ctx->dRec; pl.window = ctx->dWindow; pl.BX = BX; pl.BY = BY;
-    pl.extSlot = ctx->dExtSlot; pl.extSeed = ctx->dExtSeed; pl.extBits = ctx->dExtBits;
-    pl.counters = ctx->dPlanCounters; pl.extCap = ctx->mergeExt ? ctx->extCap : 0; pl.unmasked = ctx->dUnmasked;
-    pl.candBits = banded ? nullptr : wCandBits; pl.candList = ctx->dCandList; pl.candCount = wCandCount; pl.wordsPerRow = wordsPerRow;
-    CK(cudaMemsetAsync(ctx->dPlanCounters, 0, 8 * sizeof(uint32_t), ctx->stream));
-    k_plan_seeds<<<(blocks + 255) / 256, 256, 0, ctx->stream>>>(pl);
-    CKL("k_plan_seeds");
-
-    if (hasAlpha)
-    {
-      k_plan_extend<4><<<ctx->smCount * 8, 256, 0, ctx->stream>>>(pl);
+      k_plan_seeds<<<(blocks + 255) / 256, 256, 0, ctx->stream>>>(pl);
+      CKL("k_plan_seeds");
+      k_plan_extend<3><<<planGrid, 256, 0, ctx->stream>>>(pl);
       CKL("k_plan_extend");
-    }
-    else
-    {
-      k_plan_extend<3><<<ctx->smCount * 8, 256, 0, ctx->stream>>>(pl);
-      CKL("k_plan_extend");
+      k_plan_centres<<<(blocks + 255) / 256, 256, 0, ctx->stream>>>(pl);
+      CKL("k_plan_centres");
+      k_plan_sym<3><<<planGrid, 256, 0, ctx->stream>>>(pl);
+      CKL("k_plan_sym");
     }
 
     if (ctx->timing) CK(cudaEventRecord(ctx->ev[PHASE_SCAN], ctx->stream));
 
-    const size_t usedBytes = usedWords * sizeof(uint32_t);
-    CK(cudaMemsetAsync(ctx->dUsed, 0, usedBytes, ctx->stream));
+    CK(cudaMemsetAsync(ctx->dUsed, 0, usedWords * sizeof(uint32_t), ctx->stream));
+    CK(cudaMemsetAsync(ctx->dTau, 0xFF, (size_t)blocks * sizeof(uint32_t), ctx->stream));
 
-    if (!banded)
+    if (ctx->mergeMode == 1)
+      CK(cudaMemsetAsync(wFlags, 1, 2 * sizeof(uint32_t), ctx->stream)); // both stages go straight to the sequential pass
+
+    WaveArgs w;
+    w.rec = ctx->dRec; w.window = ctx->dWindow; w.extSlot = ctx->dExtSlot; w.extBits = ctx->dExtBits; w.extHdr = ctx->dExtHdr;
+    w.symSlot = ctx->dSymSlot; w.symBits = ctx->dSymBits; w.symHdr = ctx->dSymHdr; w.unmasked = ctx->dUnmasked;
+    w.candBits = wCandBits; w.candList = ctx->dCandList; w.candCount = wCandCount;
+    w.BX = BX; w.BY = BY; w.wordsPerRow = wordsPerRow;
+    w.used = ctx->dUsed; w.tau = ctx->dTau; w.progress = wProgress; w.ticket = wTicket;
+    w.rowLists = ctx->dRowLists; w.rowCounts = wRowCounts; w.emitInfo = wEmitInfo; w.flags = wFlags; w.stats = ctx->dCounters + 8;
+    w.listCap = 2 * BX; w.margin = ctx->mergeMargin;
+    const int waveGrid = (BY + LIMG_WAVE_WARPS - 1) / LIMG_WAVE_WARPS < ctx->smCount ? (BY + LIMG_WAVE_WARPS - 1) / LIMG_WAVE_WARPS : ctx->smCount;
+    const int resetGrid = (blocks + 255) / 256 < ctx->smCount * 8 ? (blocks + 255) / 256 : ctx->smCount * 8;
+
+    for (int stage = 0; stage < 2; stage++)
     {
-      if (BX > 8190 || BY > 8190)
-        return fail(ctx, LIMGCU_ERROR_OUT_OF_BOUNDS, "image too large for the merge's time stamps", cudaSuccess);
-
-      CK(cudaMemsetAsync(ctx->dTau, 0xFF, (size_t)blocks * sizeof(uint32_t), ctx->stream));
-
-      if (ctx->mergeMode == 1)
-        CK(cudaMemsetAsync(wFlags, 1, 2 * sizeof(uint32_t), ctx->stream)); // both stages go straight to the sequential pass
-
-      WaveArgs w;
-      w.rec = ctx->dRec; w.window = ctx->dWindow; w.extSlot = ctx->dExtSlot; w.extBits = ctx->dExtBits; w.sym = ctx->dSym; w.unmasked = ctx->dUnmasked;
-      w.candBits = wCandBits; w.candList = ctx->dCandList; w.candCount = wCandCount;
-      w.BX = BX; w.BY = BY; w.wordsPerRow = wordsPerRow;
-      w.used = ctx->dUsed; w.tau = ctx->dTau; w.progress = wProgress; w.ticket = wTicket;
-      w.rowLists = ctx->dRowLists; w.rowCounts = wRowCounts; w.emitInfo = wEmitInfo; w.flags = wFlags; w.stats = ctx->dCounters + 8;
-      w.listCap = 2 * BX; w.margin = ctx->mergeMargin;
-      const int waveGrid = (BY + LIMG_WAVE_WARPS - 1) / LIMG_WAVE_WARPS < ctx->smCount ? (BY + LIMG_WAVE_WARPS - 1) / LIMG_WAVE_WARPS : ctx->smCount;
-      const int resetGrid = (blocks + 255) / 256 < ctx->smCount * 8 ? (blocks + 255) / 256 : ctx->smCount * 8;
-
-      for (int stage = 0; stage < 2; stage++)
-      {
-        if (hasAlpha)
-        {
-          if (ctx->mergeMode == 0)
-          {
-            k_merge_wave<4><<<waveGrid, LIMG_WAVE_WARPS * 32, 0, ctx->stream>>>(w, stage, 0);
-            CKL("k_merge_wave");
-            k_merge_verify<4><<<ctx->smCount * 8, 256, 0, ctx->stream>>>(w, stage);
-            CKL("k_merge_verify");
-          }
-
-          k_merge_reset<<<resetGrid, 256, 0, ctx->stream>>>(w, stage);
-          CKL("k_merge_reset");
-          k_merge_wave<4><<<1, LIMG_WAVE_WARPS * 32, 0, ctx->stream>>>(w, stage, 1);
-          CKL("k_merge_wave(seq)");
-        }
-        else
-        {
-          if (ctx->mergeMode == 0)
-          {
-            k_merge_wave<3><<<waveGrid, LIMG_WAVE_WARPS * 32, 0, ctx->stream>>>(w, stage, 0);
-            CKL("k_merge_wave");
-            k_merge_verify<3><<<ctx->smCount * 8, 256, 0, ctx->stream>>>(w, stage);
-            CKL("k_merge_verify");
-          }
-
-          k_merge_reset<<<resetGrid, 256, 0, ctx->stream>>>(w, stage);
-          CKL("k_merge_reset");
-          k_merge_wave<3><<<1, LIMG_WAVE_WARPS * 32, 0, ctx->stream>>>(w, stage, 1);
-          CKL("k_merge_wave(seq)");
-        }
-      }
-
-      k_merge_collect<<<BY, 128, 0, ctx->stream>>>(w, dAreas, ctx->dCounters + 0);
-      CKL("k_merge_collect");
-      CK(cudaMemcpyAsync(ctx->dCounters + 24, wFlags, 4 * sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream));
-    }
-    else
-    {
-      const int bandRows = BY / 128 + 1 > 8 ? BY / 128 + 1 : 8;
-      const int numBands = (BY + bandRows - 1) / bandRows;
-      const size_t smemBytes = usedBytes + (size_t)bandRows * BX * (3 * sizeof(uint32_t) + sizeof(uint16_t)) + 16;
-
-      if (smemBytes > 200 * 1024 || numBands > LIMG_MERGE_MAX_BANDS || numBands > ctx->smCount || BX > 65535 || BY > 65535)
-        return fail(ctx, LIMGCU_ERROR_OUT_OF_BOUNDS, "image too large for the shared-memory in-use mask of the banded merge", cudaSuccess);
-
-      CK(cudaMemsetAsync(ctx->dBandState, 0, 1024 * sizeof(uint32_t), ctx->stream));
-
-      MergeArgs m;
-      m.rec = ctx->dRec; m.window = ctx->dWindow;
-      m.extSlot = ctx->dExtSlot; m.extBits = ctx->dExtBits; m.sym = ctx->dSym; m.unmasked = ctx->dUnmasked;
-      m.BX = BX; m.BY = BY; m.wordsPerRow = wordsPerRow;
-      m.bandRows = bandRows; m.numBands = numBands; m.listCap = bandRows * BX * 2; m.rowChunk = ctx->mergeChunk;
-      m.lists = ctx->dBandLists; m.counts = ctx->dBandState + 512; m.snapshot = ctx->dBandSnapshot; m.sync = ctx->dBandState;
-      m.areas = dAreas; m.mergedCount = ctx->dCounters + 0; m.usedOut = ctx->dUsed; m.stats = ctx->dCounters + 8;
-      void *kargs[] = { &m };
-
-      // cooperative launch: every band CTA must be resident, the bands synchronise through a grid barrier
       if (hasAlpha)
-        CK(cudaLaunchCooperativeKernel((const void *)k_merge_banded<4>, dim3(numBands), dim3(LIMG_MERGE_THREADS), kargs, smemBytes, ctx->stream));
-      else
-        CK(cudaLaunchCooperativeKernel((const void *)k_merge_banded<3>, dim3(numBands), dim3(LIMG_MERGE_THREADS), kargs, smemBytes, ctx->stream));
+      {
+        if (ctx->mergeMode == 0)
+        {
+          k_merge_wave<4><<<waveGrid, LIMG_WAVE_WARPS * 32, 0, ctx->stream>>>(w, stage, 0);
+          CKL("k_merge_wave");
+          k_merge_verify<4><<<ctx->smCount * 8, 256, 0, ctx->stream>>>(w, stage);
+          CKL("k_merge_verify");
+        }
 
-      CKL("k_merge_banded");
+        k_merge_reset<<<resetGrid, 256, 0, ctx->stream>>>(w, stage);
+        CKL("k_merge_reset");
+        k_merge_wave<4><<<1, LIMG_WAVE_WARPS * 32, 0, ctx->stream>>>(w, stage, 1);
+        CKL("k_merge_wave(seq)");
+      }
+      else
+      {
+        if (ctx->mergeMode == 0)
+        {
+          k_merge_wave<3><<<waveGrid, LIMG_WAVE_WARPS * 32, 0, ctx->stream>>>(w, stage, 0);
+          CKL("k_merge_wave");
+          k_merge_verify<3><<<ctx->smCount * 8, 256, 0, ctx->stream>>>(w, stage);
+          CKL("k_merge_verify");
+        }
+
+        k_merge_reset<<<resetGrid, 256, 0, ctx->stream>>>(w, stage);
+        CKL("k_merge_reset");
+        k_merge_wave<3><<<1, LIMG_WAVE_WARPS * 32, 0, ctx->stream>>>(w, stage, 1);
+        CKL("k_merge_wave(seq)");
+      }
     }
+
+    k_merge_collect<<<BY, 128, 0, ctx->stream>>>(w, dAreas, ctx->dCounters + 0);
+    CKL("k_merge_collect");
+    CK(cudaMemcpyAsync(ctx->dCounters + 24, wFlags, 4 * sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream));
   }
   else if (ctx->timing)
   {

@@ -70,12 +70,16 @@ static int strip_ok(Model *m, int seed, int x0, int y0, int w, int h, uint32_t T
   return 1;
 }
 
+static int g_pL, g_pR, g_pU, g_pD; /* probe extents of the last grow() (inclusive block coordinates) */
+
 typedef struct
 {
   int rx, ry, kind;            /* kind 0 nothing, 1 right/down rectangle, 2 centre-third regrowth */
   int cox, coy, crx, cry, attempted;
   int boxR;                    /* exclusive right edge of everything probed */
   int boxL;                    /* inclusive left edge */
+  int c0x, c0y, eL, eR, eU, eD; /* four-way: start centre and probe extents relative to it */
+  int sR, sD;                  /* seed growth probe extents relative to the seed */
 } Result;
 
 /* limg.cpp:1294-1388 */
@@ -84,28 +88,33 @@ static void grow(Model *m, int *pox, int *poy, int *prx, int *pry, int fourWay, 
   int ox = *pox, oy = *poy, rx = *prx, ry = *pry;
   const int seed = oy * m->BX + ox;
   int up = fourWay, down = 1, left = fourWay, right = 1;
+  g_pL = ox; g_pR = ox + rx - 1; g_pU = oy; g_pD = oy + ry - 1;
 
   while (up || down || left || right)
   {
     if (right)
     {
       if (ox + rx + 1 < m->BX) { if (ox + rx + 1 > *boxR) *boxR = ox + rx + 1; }
+      if (ox + rx + 1 < m->BX && ox + rx > g_pR) g_pR = ox + rx;
       if (ox + rx + 1 < m->BX && strip_ok(m, seed, ox + rx, oy, 1, ry, T)) rx++; else right = 0;
     }
 
     if (down)
     {
+      if (oy + ry + 1 < m->BY && oy + ry > g_pD) g_pD = oy + ry;
       if (oy + ry + 1 < m->BY && strip_ok(m, seed, ox, oy + ry, rx, 1, T)) ry++; else down = 0;
     }
 
     if (up)
     {
+      if (oy > 0 && oy - 1 < g_pU) g_pU = oy - 1;
       if (oy > 0 && strip_ok(m, seed, ox, oy - 1, rx, 1, T)) { oy--; ry++; } else up = 0;
     }
 
     if (left)
     {
       if (ox > 0) { if (ox - 1 < *boxL) *boxL = ox - 1; }
+      if (ox > 0 && ox - 1 < g_pL) g_pL = ox - 1;
       if (ox > 0 && strip_ok(m, seed, ox - 1, oy, 1, ry, T)) { ox--; rx++; } else left = 0;
     }
   }
@@ -122,13 +131,16 @@ static Result expand(Model *m, int x, int y, int stage, uint32_t T)
   r.boxL = x; r.boxR = x + 1;
   grow(m, &ox, &oy, &rx, &ry, 0, T, &r.boxL, &r.boxR);
   r.rx = rx; r.ry = ry;
+  r.sR = g_pR - x; r.sD = g_pD - y;
 
   if (stage == 0)
   {
     if (rx >= 3 && ry >= 3)
     {
       int cox = x + rx / 3, coy = y + ry / 3, crx = rx / 3, cry = ry / 3;
+      r.c0x = cox; r.c0y = coy;
       grow(m, &cox, &coy, &crx, &cry, 1, T, &r.boxL, &r.boxR);
+      r.eL = r.c0x - g_pL; r.eR = g_pR - r.c0x; r.eU = r.c0y - g_pU; r.eD = g_pD - r.c0y;
       r.cox = cox; r.coy = coy; r.crx = crx; r.cry = cry; r.attempted = 1;
       r.kind = crx * cry > rx * ry ? 2 : 1;
     }
@@ -164,6 +176,7 @@ typedef struct
   double makespan;
   uint64_t leftExtHist[16]; /* how far left of its seed column a centre-third rectangle reaches */
   uint64_t boxWHist[16];
+  uint64_t fourN, centreMiss, eLH[20], eRH[20], eUH[20], eDH[20], sRH[20], sDH[20];
 } Stats;
 
 static int is_cand(Model *m, int x, int y, int stage)
@@ -306,6 +319,17 @@ size_t model_run(const lo_decomp *table, int BX, int BY, int CH, int workers, in
       case S_COMMIT:
       {
         const Result *r = &k->pend;
+        { int v; v = r->sR > 19 ? 19 : r->sR; st[stage].sRH[v]++; v = r->sD > 19 ? 19 : r->sD; st[stage].sDH[v]++; }
+        if (r->attempted)
+        {
+          int v;
+          st[stage].fourN++;
+          const Result f = expand(&m, k->x, k->y, stage, 0u);
+          if (!f.attempted || f.c0x != r->c0x || f.c0y != r->c0y) st[stage].centreMiss++;
+          { static int nprint = 0; if (nprint < 4000) { nprint++; printf("CM %d %d %d\n", f.attempted, r->c0x - f.c0x, r->c0y - f.c0y); } }
+          v = r->eL > 19 ? 19 : r->eL; st[stage].eLH[v]++; v = r->eR > 19 ? 19 : r->eR; st[stage].eRH[v]++;
+          v = r->eU > 19 ? 19 : r->eU; st[stage].eUH[v]++; v = r->eD > 19 ? 19 : r->eD; st[stage].eDH[v]++;
+        }
 
         if (r->kind != 0)
         {
@@ -398,6 +422,14 @@ size_t model_run(const lo_decomp *table, int BX, int BY, int CH, int workers, in
     for (int i = 0; i < 12; i++) o[20 + i] = (double)st[s].boxWHist[i < 11 ? i : 15];
   }
 
+  for (int s2 = 0; s2 < 2; s2++)
+  {
+    printf("  stage %d: four-way attempts %llu, centre != mask-free centre %llu\n", s2, (unsigned long long)st[s2].fourN, (unsigned long long)st[s2].centreMiss);
+    const char *names[6] = { "4way left ", "4way right", "4way up   ", "4way down ", "seed right", "seed down " };
+    uint64_t *hs[6] = { st[s2].eLH, st[s2].eRH, st[s2].eUH, st[s2].eDH, st[s2].sRH, st[s2].sDH };
+    for (int h = 0; h < 6; h++) { printf("    %s:", names[h]); for (int i = 0; i < 20; i++) printf(" %llu", (unsigned long long)hs[h][i]); printf("\n"); }
+  }
+  fflush(stdout);
   free(m.memoKey); free(m.memoVal); free(m.owner); free(emits); free(cand); free(unmRx); free(progress); free(w);
   return nEmit;
 }

@@ -18,5 +18,6 @@ for name in ("c1_512_gradient","c5_1080p_frame0","c2_4k_photo","c4_4k_flatui","c
     ph = c.phase_ms()
     tot = sum(ph.values())
     cnt = c.debug_counters()
-    print("   merged %d areas %d small %d large %d | stage0 exp %d reexp %d polls %d ondemand %d | stage1 exp %d reexp %d polls %d ondemand %d | fallback flags %s planExt %d" % (cnt[0],cnt[1],cnt[2],cnt[3],cnt[8],cnt[9],cnt[10],cnt[11],cnt[12],cnt[13],cnt[14],cnt[15],cnt[24:27],cnt[28]))
+    print("   merged %d areas %d small %d large %d | stage0 exp %d reexp %d polls %d ondemand %d | stage1 exp %d reexp %d polls %d ondemand %d | fallback flags %s ext slots %d sym slots %d" % (cnt[0],cnt[1],cnt[2],cnt[3],cnt[8],cnt[9],cnt[10],cnt[11],cnt[12],cnt[13],cnt[14],cnt[15],cnt[24:28],cnt[28],cnt[29]))
+    print("   profile kcycles: next %d wait %d expand %d (four-way %d, on-demand %d) claim %d prefetch %d" % tuple(cnt[16:23]))
     print(name, "%dx%d"%(w,h), "total %.3f ms (wall %.3f) -> %.1f Mpx/s"%(tot, dt*1e3, w*h/tot/1e3), {k: round(v,3) for k,v in ph.items()})
