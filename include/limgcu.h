@@ -113,6 +113,11 @@ int limgcu_enable_phase_timing(limgcu_ctx *ctx, int enable);
 float limgcu_phase_ms(limgcu_ctx *ctx, int phase);
 /* 32 internal counters of the last encode / merge (area counts, merge iterations ...), for profiling. Synchronises. */
 int limgcu_debug_counters(limgcu_ctx *ctx, uint32_t *out32);
+/* detailed counters of the last merge scan (kernels_wave.cuh, WaveArgs::dbg): 256 words */
+int limgcu_debug_wave(limgcu_ctx *ctx, uint32_t *out256);
+/* per block row of the last merge scan, both stages: [2][blockY][4] time stamps in ns (ticket, first decision, last decision, done);
+ * recorded only when LIMGCU_MERGE_ROWTIMES=1 is set at limgcu_create time */
+int limgcu_debug_wave_rows(limgcu_ctx *ctx, uint32_t *out, size_t blockY);
 
 /* device-buffer entry points ------------------------------------------------------------------------------------ */
 

@@ -72,6 +72,16 @@ class Codec:
         self._ck(self.lib.limgcu_debug_counters(self.h, _vp(out)), "limgcu_debug_counters")
         return out
 
+    def debug_wave(self) -> np.ndarray:
+        out = np.zeros(256, np.uint32)
+        self._ck(self.lib.limgcu_debug_wave(self.h, _vp(out)), "limgcu_debug_wave")
+        return out
+
+    def debug_wave_rows(self, block_y: int) -> np.ndarray:
+        out = np.zeros((2, block_y, 4), np.uint32)
+        self._ck(self.lib.limgcu_debug_wave_rows(self.h, _vp(out), block_y), "limgcu_debug_wave_rows")
+        return out
+
     # ---- host-buffer operators (reference argument meaning) -------------------------------------------------
 
     @staticmethod

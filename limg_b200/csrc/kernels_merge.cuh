@@ -256,6 +256,8 @@ struct PlanArgs
   uint32_t *symSlot, *symSeed, *symBits, *symHdr; // the same around centres, anchored at (cx - 8, cy - 8)
   uint32_t *counters;  // [0] ext slots, [1] sym slots
   uint32_t extCap, symCap;
+  int extMaxW;         // known part of a seed's bitmap: at most this many columns (rows: 32)
+  int symMaxL, symMaxR, symMaxD; // known part of a centre's bitmap: at most this far left / up, right, down of the centre
   uint16_t *unmasked;  // per block: rx | ry << 8 of the mask-free right/down growth
   uint32_t *candBits;  // [2][BY][wordsPerRow] (zeroed by the host): blocks that can emit in stage 0 (3x3 corner matches) / stage 1 (right or lower neighbour matches)
   uint32_t *candList;  // [2][blocks] the same as lists, counts in candCount[2]
@@ -407,7 +409,7 @@ __global__ void __launch_bounds__(256) k_plan_extend(PlanArgs a)
 
     __syncthreads();
     // known part: columns [0, first mismatch along the row], rows [0, first mismatch along the column]
-    const int vx1 = min(run_end(sRowRun, 0) + 1, 32), vy1 = min(run_end(sColRun, 0) + 1, 32);
+    const int vx1 = min(run_end(sRowRun, 0) + 1, a.extMaxW), vy1 = min(run_end(sColRun, 0) + 1, 32);
 
     for (int p = 0; p < 4; p++)
     {
@@ -539,11 +541,11 @@ __global__ void __launch_bounds__(256) k_plan_sym(PlanArgs a)
     // known box: from the first mismatch left of / above c to the first mismatch right of / below c (inclusive), relative to the anchor
     const uint32_t rowRun = sRowRun, colRun = sColRun;
     const uint32_t lowRow = ~rowRun & ((1u << LIMG_SYM_BACK) - 1u), lowCol = ~colRun & ((1u << LIMG_SYM_BACK) - 1u);
-    const int vx0 = lowRow ? 31 - __clz(lowRow) : 0, vy0 = lowCol ? 31 - __clz(lowCol) : 0;
+    const int vx0 = max(lowRow ? 31 - __clz(lowRow) : 0, LIMG_SYM_BACK - a.symMaxL), vy0 = max(lowCol ? 31 - __clz(lowCol) : 0, LIMG_SYM_BACK - a.symMaxL);
     // the regrowth starts from a rectangle of up to 3 x 3 blocks whose blocks are not tested (limg.cpp:1428-1431): a mismatch
     // one or two blocks right of / below c does not stop it
-    const int vx1 = min(run_end(rowRun | (3u << (LIMG_SYM_BACK + 1)), LIMG_SYM_BACK) + 1, 32);
-    const int vy1 = min(run_end(colRun | (3u << (LIMG_SYM_BACK + 1)), LIMG_SYM_BACK) + 1, 32);
+    const int vx1 = min(run_end(rowRun | (3u << (LIMG_SYM_BACK + 1)), LIMG_SYM_BACK) + 1, LIMG_SYM_BACK + a.symMaxR);
+    const int vy1 = min(run_end(colRun | (3u << (LIMG_SYM_BACK + 1)), LIMG_SYM_BACK) + 1, LIMG_SYM_BACK + a.symMaxD);
 
     for (int p = 0; p < 4; p++)
     {

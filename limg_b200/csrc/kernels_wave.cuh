@@ -46,13 +46,17 @@ struct WaveArgs
   uint32_t *used;            // [BY][wordsPerRow] live in-use bits (rows padded by two zero words)
   uint32_t *tau;             // [blocks] logical time of the rectangle that owns the block
   int *progress;             // [2][BY] column up to which the row's seeds are committed (LIMG_WAVE_DONE when finished)
-  uint32_t *ticket;          // [2]
+  uint32_t *ticket;          // [0] row tickets of both stages, [1] number of finished stage-0 rows
   uint2 *rowLists;           // [2][BY][listCap] (ox | oy << 16, rx | ry << 16) in emission order
   uint32_t *rowCounts;       // [2][BY]
   uint32_t *emitInfo;        // [2][blocks] per seed: first entry in its row list << 8 | number of entries
-  uint32_t *flags;           // [0], [1] stage needs the sequential fallback; [2] list overflow (hard error); [3] watchdog (hard error)
+  uint32_t *flags;           // [0] number of failed tries, [1], [2] a stage failed the verification of the current try, [3] watchdog (hard error), [4] list overflow (hard error)
   uint32_t *stats;           // [16] optional counters
+  uint32_t *dbg;             // [256] detailed counters (see tools/phase_times.py)
+  uint32_t *dbgRows;         // [2][BY][4] optional per-row time stamps (globaltimer ns, low 32 bits): ticket, first decision, last decision, done
   int listCap, margin;
+  int stageGap;              // block rows stage 1 stays behind stage 0
+  int specAhead;             // a seed is expanded speculatively once the rows above are within this many columns of where they have to be
 };
 
 __device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t *p)
@@ -172,7 +176,8 @@ struct WaveResult
 {
   int rx, ry;             // right/down rectangle grown from the seed
   int kind;               // 0 nothing to emit, 1 emit the right/down rectangle, 2 emit the centre-third regrowth (and examine the seed again)
-  int cox, coy, crx, cry; // four-way regrowth (valid when kind == 2)
+  int cox, coy, crx, cry; // four-way regrowth (valid when attempted)
+  int attempted;          // the centre-third regrowth ran
   int boxR;               // exclusive right edge of every column whose in-use bits were consulted
 };
 
@@ -203,10 +208,38 @@ struct WaveScan
   int lane;
   uint32_t nOnDemand;
   long long tOnDemand = 0, tFour = 0; // profile: clock cycles inside on-demand strips / the four-way regrowth
+  const Snapshot *cur = nullptr;      // the mask snapshot the running expansion is based on
+  bool volatileReads = false;         // the running expansion read in-use bits that the snapshot does not hold
+  int cause = 0;                      // who asks for on-demand strips: 0 seed growth, 1 four-way with a bitmap, 2 four-way without
+  uint32_t nStrips[3] = { 0, 0, 0 };
+  long long tStrips[3] = { 0, 0, 0 };
+  uint32_t nFour = 0, nFourMiss = 0, nFourNoSym = 0;
 
   __device__ bool strip_unused(int x0, int y0, int w, int h)
   {
     bool any = false;
+
+    if (cur && y0 >= cur->r0 && y0 + h <= cur->r0 + 32 && x0 >= cur->w0 * 32 && x0 + w <= cur->w0 * 32 + 96)
+    {
+      // inside the snapshot: lane = row, test the columns of the strip
+      const int row = cur->r0 + lane, b0 = x0 - cur->w0 * 32;
+
+      if (row >= y0 && row < y0 + h)
+      {
+        for (int j = 0; j < 3; j++)
+        {
+          const int lo = max(b0 - 32 * j, 0), hi = min(b0 + w - 32 * j, 32);
+
+          if (hi > lo)
+          {
+            const uint32_t m = (hi - lo >= 32 ? 0xFFFFFFFFu : ((1u << (hi - lo)) - 1u)) << lo;
+            any |= (cur->w[j] & m) != 0;
+          }
+        }
+      }
+
+      return !__any_sync(0xFFFFFFFFu, any);
+    }
 
     for (int e = lane; e < w * h; e += 32)
     {
@@ -260,7 +293,10 @@ struct WaveScan
   {
     const long long t0 = clock64();
     const bool ok = strip_unused(x0, y0, w, h) && strip_matches(seed, x0, y0, w, h);
-    tOnDemand += clock64() - t0;
+    const long long dt = clock64() - t0;
+    tOnDemand += dt;
+    nStrips[cause]++;
+    tStrips[cause] += dt;
     return ok;
   }
 
@@ -292,9 +328,39 @@ struct WaveScan
       return 0xFFFFFFFFu;
 
     if (src < 0 || src > 31 || sh < 0 || sh > 63)
-      return mask.bits(ax, ay + lane);
+      return mask.bits(ax, ay + lane); // outside the snapshot (expand() notes whether the growth consulted such bits)
 
     return sh < 32 ? __funnelshift_r(a0, a1, sh) : __funnelshift_r(a1, a2, sh - 32);
+  }
+
+  // do two snapshots of the same seed agree on every in-use bit the expansion `r` of seed (x, y) consulted? (the strips it tested
+  // lie inside the seed rectangle's box and, if the regrowth ran, the regrowth rectangle's box, one block wider on each side)
+  __device__ bool same_where_probed(const Snapshot &p, const Snapshot &q, const WaveResult &r, int x, int y) const
+  {
+    const int row = p.r0 + lane, c0 = p.w0 * 32;
+    uint32_t m[3] = { 0, 0, 0 };
+
+    auto add = [&](int bx0, int by0, int bx1, int by1) {
+      if (row < by0 || row >= by1)
+        return;
+
+#pragma unroll
+      for (int j = 0; j < 3; j++)
+      {
+        const int lo = max(bx0 - c0 - 32 * j, 0), hi = min(bx1 - c0 - 32 * j, 32);
+
+        if (hi > lo)
+          m[j] |= (hi - lo >= 32 ? 0xFFFFFFFFu : ((1u << (hi - lo)) - 1u)) << lo;
+      }
+    };
+
+    add(x, y, x + r.rx + 1, y + r.ry + 1);
+
+    if (r.attempted)
+      add(r.cox - 1, r.coy - 1, r.cox + r.crx + 1, r.coy + r.cry + 1);
+
+    const bool same = ((p.w[0] ^ q.w[0]) & m[0]) == 0 && ((p.w[1] ^ q.w[1]) & m[1]) == 0 && ((p.w[2] ^ q.w[2]) & m[2]) == 0;
+    return __all_sync(0xFFFFFFFFu, same);
   }
 
   __device__ __forceinline__ void load_sym(int cx, int cy, uint32_t &row, uint32_t &hdr) const
@@ -349,7 +415,7 @@ struct WaveScan
 
   // alternating growth of the rectangle (ox, oy, rx, ry) of seed block `seed` (limg.cpp:1294-1388): right and down, and also up
   // and left for the centre-third regrowth. Strips inside the region's known part are bit tests, the others are evaluated on demand.
-  __device__ void grow(int seed, const Region &g, bool fourWay, int &ox, int &oy, int &rx, int &ry)
+  __device__ void grow(int seed, const Region &g, bool fourWay, int minSide, int &ox, int &oy, int &rx, int &ry)
   {
     bool haveRec = false;
     PredRec rec;
@@ -362,6 +428,16 @@ struct WaveScan
         const int r0 = y0 - g.ay;
         const bool rowOk = (lane < r0 || lane >= r0 + h) || ((g.avail & m) == m);
         return __all_sync(0xFFFFFFFFu, rowOk);
+      }
+
+      if (a.dbg && lane == 0)
+      {
+        // which side of the known part did the strip leave? (per cause: left, up, right, down)
+        const int side = x0 < g.vx0 ? 0 : (y0 < g.vy0 ? 1 : (x0 + w > g.vx1 ? 2 : 3));
+        atomicAdd(&a.dbg[64 + cause * 4 + side], 1u);
+
+        if (cause == 1 && side >= 2)
+          atomicAdd(&a.dbg[80 + min(15, side == 2 ? g.vx1 - g.ax - LIMG_SYM_BACK : g.vy1 - g.ay - LIMG_SYM_BACK)], 1u); // how far the known part reached
       }
 
       if (!haveRec) { rec = a.rec[seed]; haveRec = true; }
@@ -389,6 +465,11 @@ struct WaveScan
       {
         if (ox > 0 && joins(ox - 1, oy, 1, ry)) { ox--; rx++; } else left = false;
       }
+
+      // stage 0 only keeps rectangles of at least 3 x 3 blocks (limg.cpp:1424): once a side that can no longer grow is shorter,
+      // the rest of the growth cannot change the outcome
+      if (minSide && ((!right && rx < minSide) || (!down && ry < minSide)))
+        break;
     }
   }
 
@@ -397,14 +478,17 @@ struct WaveScan
   {
     WaveResult r;
     Region g;
+    cur = &sn;
+    volatileReads = false;
     g.ax = x; g.ay = y; g.vx0 = x; g.vy0 = y; g.vx1 = x + pre.vx1; g.vy1 = y + pre.vy1;
     g.avail = pre.rowBits & ~region_used(sn, x, y, pre.vy1);
     int ox = x, oy = y;
     r.rx = 1;
     r.ry = 1;
-    grow(y * a.BX + x, g, false, ox, oy, r.rx, r.ry);
+    grow(y * a.BX + x, g, false, stage == 0 ? 3 : 0, ox, oy, r.rx, r.ry);
     r.kind = 0;
     r.cox = r.coy = r.crx = r.cry = 0;
+    r.attempted = 0;
     r.boxR = min(x + r.rx + 1, a.BX);
 
     if (stage == 0)
@@ -415,8 +499,16 @@ struct WaveScan
         int cox = x + r.rx / 3, coy = y + r.ry / 3, crx = r.rx / 3, cry = r.ry / 3;
         uint32_t symRow = pre.symRow, symHdr = pre.symHdr;
 
+        nFour++;
+
         if (cox != pre.pcx || coy != pre.pcy)
+        {
           load_sym(cox, coy, symRow, symHdr);
+          nFourMiss++;
+        }
+
+        if (!symHdr) nFourNoSym++;
+        cause = symHdr ? 1 : 2;
 
         Region c;
         c.ax = cox - LIMG_SYM_BACK; c.ay = coy - LIMG_SYM_BACK;
@@ -424,11 +516,13 @@ struct WaveScan
         c.vx1 = c.ax + (int)((symHdr >> 16) & 0xFF); c.vy1 = c.ay + (int)(symHdr >> 24);
         c.avail = symHdr ? (symRow & ~region_used(sn, c.ax, c.ay, (int)(symHdr >> 24))) : 0u;
         const int centre = coy * a.BX + cox;
-        grow(centre, c, true, cox, coy, crx, cry);
+        grow(centre, c, true, 0, cox, coy, crx, cry);
         r.cox = cox; r.coy = coy; r.crx = crx; r.cry = cry;
+        r.attempted = 1;
         r.kind = (crx * cry > r.rx * r.ry) ? 2 : 1;
         r.boxR = max(r.boxR, min(cox + crx + 1, a.BX));
         tFour += clock64() - t0;
+        cause = 0;
       }
     }
     else
@@ -436,17 +530,32 @@ struct WaveScan
       r.kind = (r.rx > 1 || r.ry > 1) ? 1 : 0;
     }
 
+    // every in-use bit the growth consulted lies inside the two boxes of same_where_probed(); were they all inside the snapshot?
+    auto inside = [&](int bx0, int by0, int bx1, int by1) -> bool {
+      return max(by0, 0) >= sn.r0 && min(by1, a.BY) <= sn.r0 + 32 && max(bx0, 0) >= sn.w0 * 32 && min(bx1, a.BX) <= sn.w0 * 32 + 96;
+    };
+
+    volatileReads = !inside(x, y, x + r.rx + 1, y + r.ry + 1) || (r.attempted && !inside(r.cox - 1, r.coy - 1, r.cox + r.crx + 1, r.coy + r.cry + 1));
     return r;
   }
 };
+
+__device__ __forceinline__ uint32_t global_ns()
+{
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return (uint32_t)t;
+}
 
 __device__ __forceinline__ uint2 pack_rect(int ox, int oy, int rx, int ry)
 {
   return make_uint2((uint32_t)ox | ((uint32_t)oy << 16), (uint32_t)rx | ((uint32_t)ry << 16));
 }
 
-// next column >= x of row y whose candidate bit is set and whose in-use bit (fresh read) is clear; BX if none. Warp-cooperative.
-__device__ __forceinline__ int wave_next_candidate(const uint32_t *candRow, const uint32_t *usedRow, int nWords, int x, int BX, int lane)
+// next column >= x of row y whose candidate bit is set and which can still emit given a fresh read of the in-use bits: in stage 0
+// its whole 3 x 3 corner must be free (limg.cpp:1424 keeps nothing smaller), in stage 1 the block and its right or lower neighbour.
+// In-use bits at columns >= x of these rows only ever come from logically earlier rectangles, so skipping is exact. BX if none.
+__device__ __forceinline__ int wave_next_candidate(const uint32_t *candRow, const uint32_t *usedRow, int wordsPerRow, int nWords, int x, int BX, int stage, int lane)
 {
   for (int w0 = x >> 5; w0 < nWords; w0 += 32)
   {
@@ -455,7 +564,22 @@ __device__ __forceinline__ int wave_next_candidate(const uint32_t *candRow, cons
 
     if (w < nWords)
     {
-      bits = __ldg(candRow + w) & ~ld_relaxed_u32(usedRow + w);
+      // rows are padded with zero words, and candidates never sit in the last block rows (their 3 x 3 corner / lower neighbour is inside the grid)
+      const unsigned long long u0 = ld_relaxed_u32(usedRow + w) | ((unsigned long long)ld_relaxed_u32(usedRow + w + 1) << 32);
+      bits = __ldg(candRow + w);
+
+      if (stage == 0 && bits) // a candidate bit in this word: block rows y + 1 and y + 2 exist
+      {
+        const unsigned long long u1 = ld_relaxed_u32(usedRow + wordsPerRow + w) | ((unsigned long long)ld_relaxed_u32(usedRow + wordsPerRow + w + 1) << 32);
+        const unsigned long long u2 = ld_relaxed_u32(usedRow + 2 * wordsPerRow + w) | ((unsigned long long)ld_relaxed_u32(usedRow + 2 * wordsPerRow + w + 1) << 32);
+        const unsigned long long u = u0 | u1 | u2;
+        bits &= (uint32_t)~(u | (u >> 1) | (u >> 2));
+      }
+      else
+      {
+        // the lower neighbour may be outside the grid in the last row: then only the right neighbour counts (its bit is clear in the padding)
+        bits &= (uint32_t)~u0;
+      }
 
       if (w == (x >> 5))
         bits &= 0xFFFFFFFFu << (x & 31);
@@ -505,21 +629,20 @@ __device__ __forceinline__ int wave_wait(const int *progress, int y, int need, u
   return v;
 }
 
+// Both merge stages in one launch: tickets 0 .. BY-1 are the block rows of stage 0, tickets BY .. 2BY-1 the rows of stage 1. A
+// stage-1 row starts once stage 0 is done with every row down to `stageGap` rows below it (the centre-third regrowth of a stage-0
+// seed further down would have to reach that far up to matter, which the verification pass would notice).
+// `attempt` numbers the tries of the host: the kernel runs only if flags[0] == attempt, i.e. every earlier try failed.
 template <int CH>
-__global__ void __launch_bounds__(LIMG_WAVE_WARPS * 32) k_merge_wave(WaveArgs a, int stage, int sequential)
+__global__ void __launch_bounds__(LIMG_WAVE_WARPS * 32) k_merge_wave(WaveArgs a, int attempt, int sequential)
 {
-  if (sequential && a.flags[stage] == 0)
-    return; // the fallback only runs when the pipelined pass failed its verification
+  if (a.flags[0] != (uint32_t)attempt)
+    return;
 
   const int lane = threadIdx.x & 31;
   WaveScan<CH, LiveMask> scan{ a, LiveMask{ a.used, a.wordsPerRow, a.BX, a.BY }, lane, 0 };
-  int *progress = a.progress + (size_t)stage * a.BY;
-  const uint32_t *cand = a.candBits + (size_t)stage * a.BY * a.wordsPerRow;
-  uint2 *lists = a.rowLists + (size_t)stage * a.BY * a.listCap;
-  uint32_t *emitInfo = a.emitInfo + (size_t)stage * a.BX * a.BY;
-  const uint32_t base = stage ? LIMG_TAU_STAGE1 : 0u;
   const int nWords = (a.BX + 31) >> 5;
-  uint32_t nExp = 0, nReexp = 0, nPolls = 0;
+  uint32_t nExp[2] = { 0, 0 }, nReexp[2] = { 0, 0 }, nPolls[2] = { 0, 0 }, nOnDemand[2] = { 0, 0 };
   long long tNext = 0, tWait = 0, tExpand = 0, tClaim = 0, tPre = 0, tc;
   bool failed = false;
 
@@ -528,12 +651,42 @@ __global__ void __launch_bounds__(LIMG_WAVE_WARPS * 32) k_merge_wave(WaveArgs a,
     int y = 0;
 
     if (lane == 0)
-      y = (int)atomicAdd(&a.ticket[stage], 1u);
+      y = (int)atomicAdd(&a.ticket[0], 1u);
 
     y = __shfl_sync(0xFFFFFFFFu, y, 0);
 
-    if (y >= a.BY)
+    if (y >= 2 * a.BY)
       break;
+
+    const int stage = y >= a.BY ? 1 : 0;
+    y -= stage * a.BY;
+    int *progress = a.progress + (size_t)stage * a.BY;
+    const uint32_t *cand = a.candBits + (size_t)stage * a.BY * a.wordsPerRow;
+    uint2 *lists = a.rowLists + (size_t)stage * a.BY * a.listCap;
+    uint32_t *emitInfo = a.emitInfo + (size_t)stage * a.BX * a.BY;
+    const uint32_t base = stage ? LIMG_TAU_STAGE1 : 0u;
+    const uint32_t onDemandBefore = scan.nOnDemand;
+
+    if (stage == 1)
+    {
+      // wait for stage 0 (rows are done in order, so a count of finished rows is enough)
+      const uint32_t need = sequential ? (uint32_t)a.BY : (uint32_t)min(y + a.stageGap + 1, a.BY);
+
+      if (lane == 0)
+      {
+        uint32_t spins = 0;
+
+        while (ld_relaxed_u32(&a.ticket[1]) < need)
+        {
+          if (++spins > (LIMG_WAVE_SPIN_LIMIT << 3)) { a.flags[3] = 1; break; }
+          __nanosleep(200);
+        }
+
+        __threadfence();
+      }
+
+      __syncwarp();
+    }
 
     if (sequential && y > 0)
     {
@@ -552,26 +705,39 @@ __global__ void __launch_bounds__(LIMG_WAVE_WARPS * 32) k_merge_wave(WaveArgs a,
       __syncwarp();
     }
 
+    uint32_t *rowT = a.dbgRows ? a.dbgRows + ((size_t)stage * a.BY + y) * 4 : nullptr;
+
+    if (rowT && lane == 0)
+      rowT[0] = global_ns();
+
     const uint32_t *candRow = cand + (size_t)y * a.wordsPerRow;
     const uint32_t *usedRow = a.used + (size_t)y * a.wordsPerRow;
     uint2 *list = lists + (size_t)y * a.listCap;
     uint32_t count = 0;
     int x = 0, published = 0;
+    int pAbove = (y == 0 || sequential) ? LIMG_WAVE_DONE : 0; // last observed minimum over the rows above
+
+    // a row never claims to be further than the rows above it: the published values fall monotonically from row to row, so
+    // looking at the 32 rows above is as good as looking at all of them
+    auto publish = [&](int own) {
+      const int v = min(own, pAbove);
+
+      if (v > published)
+      {
+        if (lane == 0)
+          st_relaxed_s32(progress + y, v);
+
+        published = v;
+      }
+    };
 
     for (;;)
     {
       tc = clock64();
-      x = wave_next_candidate(candRow, usedRow, nWords, x, a.BX, lane);
+      x = wave_next_candidate(candRow, usedRow, a.wordsPerRow, nWords, x, a.BX, stage, lane);
 
       // every seed left of x is decided, and its claims were fenced when they were made
-      if (x > published || x >= a.BX)
-      {
-        if (lane == 0)
-          st_relaxed_s32(progress + y, x >= a.BX ? LIMG_WAVE_DONE : x);
-
-        published = x;
-      }
-
+      publish(x >= a.BX ? LIMG_WAVE_DONE : x);
       tNext += clock64() - tc;
 
       if (x >= a.BX)
@@ -586,35 +752,68 @@ __global__ void __launch_bounds__(LIMG_WAVE_WARPS * 32) k_merge_wave(WaveArgs a,
 
       for (int k = 0;; k++)
       {
+        // Speculate while the rows above are not far enough: the seed is expanded against the mask as it is NOW and expanded again
+        // only when a bit it consulted changes. Once the rows above have passed everything it consulted (+ margin), a snapshot
+        // taken after that observation which agrees with the one the expansion used makes the expansion final.
         WaveResult r;
-        int p = LIMG_WAVE_DONE;
-        bool taken = false;
-        tc = clock64();
+        Snapshot used;
+        bool have = false, taken = false, unstable = false;
 
-        if (y > 0 && !sequential)
-          p = wave_wait(progress, y, min(x + 1 + a.margin, a.BX), nPolls, a.flags);
-
-        tWait += clock64() - tc;
-
-        for (;;)
+        for (uint32_t spins = 0;; spins++)
         {
           tc = clock64();
-          const Snapshot sn = scan.snapshot(x, y);
+          int p = LIMG_WAVE_DONE;
+
+          if (y > 0 && !sequential)
+          {
+            const int row = y - 1 - lane;
+            p = __reduce_min_sync(0xFFFFFFFFu, row >= 0 ? ld_acquire_s32(progress + row) : LIMG_WAVE_DONE);
+            pAbove = p;
+            publish(x);
+          }
+
+          if (p < min(x + 1 + a.margin - a.specAhead, a.BX))
+          {
+            // the rows above are still far away: whatever the mask shows now is not worth expanding against
+            tWait += clock64() - tc;
+
+            if (spins > LIMG_WAVE_SPIN_LIMIT) { a.flags[3] = 1; taken = true; break; }
+
+            nPolls[stage]++;
+            __nanosleep(p + 64 < x ? 400 : 20);
+            continue;
+          }
+
+          const Snapshot sn = scan.snapshot(x, y); // after the progress read
+          tWait += clock64() - tc;
 
           if (scan.snap_used(sn, x)) { taken = true; break; }
 
-          r = scan.expand(x, y, stage, pre, sn);
-          nExp++;
-          tExpand += clock64() - tc;
-          const int need = min(r.boxR + a.margin, a.BX);
+          if (!have || unstable || !scan.same_where_probed(sn, used, r, x, y))
+          {
+            tc = clock64();
 
-          if (p >= need)
+            if (have) nReexp[stage]++;
+
+            r = scan.expand(x, y, stage, pre, sn);
+            unstable = scan.volatileReads; // it read in-use bits outside the snapshot: only good if the rows above had already passed
+            used = sn;
+            have = true;
+            nExp[stage]++;
+            const long long dt = clock64() - tc;
+            tExpand += dt;
+
+            if (a.dbg && lane == 0)
+              atomicAdd(&a.dbg[stage * 16 + min(15, 63 - __clzll((dt >> 8) | 1))], 1u);
+          }
+
+          if (p >= min(r.boxR + a.margin, a.BX))
             break;
 
-          tc = clock64();
-          p = wave_wait(progress, y, need, nPolls, a.flags); // the rows above have to pass everything this seed looked at: look again
-          tWait += clock64() - tc;
-          nReexp++;
+          if (spins > LIMG_WAVE_SPIN_LIMIT) { a.flags[3] = 1; break; }
+
+          nPolls[stage]++;
+          __nanosleep(p + 64 < x ? 400 : 20);
         }
 
         if (taken || r.kind == 0)
@@ -653,7 +852,7 @@ __global__ void __launch_bounds__(LIMG_WAVE_WARPS * 32) k_merge_wave(WaveArgs a,
           if (count < (uint32_t)a.listCap)
             list[count] = pack_rect(eox, eoy, erx, ery);
           else
-            a.flags[2] = 1; // reported by the host as LIMGCU_ERROR_OUT_OF_BOUNDS
+            a.flags[4] = 1; // reported by the host as LIMGCU_ERROR_OUT_OF_BOUNDS
         }
 
         // the claim is visible to this warp's next look at the mask and to everybody who later reads the progress store
@@ -681,29 +880,62 @@ __global__ void __launch_bounds__(LIMG_WAVE_WARPS * 32) k_merge_wave(WaveArgs a,
 
       x = nextX;
 
+      if (rowT && lane == 0)
+      {
+        const uint32_t t = global_ns();
+        if (rowT[1] == 0) rowT[1] = t;
+        rowT[2] = t;
+      }
+
       // hand over to the rows below before looking for the next candidate
       if (x < a.BX)
-      {
-        if (lane == 0)
-          st_relaxed_s32(progress + y, x);
-
-        published = x;
-      }
+        publish(x);
     }
 
     if (lane == 0)
       a.rowCounts[(size_t)stage * a.BY + y] = min(count, (uint32_t)a.listCap);
+
+    if (rowT && lane == 0)
+      rowT[3] = global_ns();
+
+    // the row is done, but it keeps relaying the progress of the rows above until they are done too
+    for (uint32_t spins = 0; published != LIMG_WAVE_DONE; spins++)
+    {
+      const int row = y - 1 - lane;
+      pAbove = __reduce_min_sync(0xFFFFFFFFu, row >= 0 ? ld_acquire_s32(progress + row) : LIMG_WAVE_DONE);
+      publish(LIMG_WAVE_DONE);
+
+      if (published == LIMG_WAVE_DONE)
+        break;
+
+      if (spins > LIMG_WAVE_SPIN_LIMIT) { a.flags[3] = 1; if (lane == 0) st_relaxed_s32(progress + y, LIMG_WAVE_DONE); break; }
+
+      __nanosleep(100);
+    }
+
+    // rows finish in order (a row publishes DONE only after every row above it did): the count of finished stage-0 rows
+    if (stage == 0 && lane == 0)
+    {
+      __threadfence();
+      atomicMax(&a.ticket[1], (uint32_t)(y + 1));
+    }
+
+    nOnDemand[stage] += scan.nOnDemand - onDemandBefore;
   }
 
   if (failed && !sequential && lane == 0)
-    a.flags[stage] = 1;
+    a.flags[0] = (uint32_t)attempt + 1;
 
   if (a.stats && lane == 0)
   {
-    atomicAdd(&a.stats[0 + stage * 4], nExp);
-    atomicAdd(&a.stats[1 + stage * 4], nReexp);
-    atomicAdd(&a.stats[2 + stage * 4], nPolls);
-    atomicAdd(&a.stats[3 + stage * 4], scan.nOnDemand);
+    for (int st = 0; st < 2; st++)
+    {
+      atomicAdd(&a.stats[0 + st * 4], nExp[st]);
+      atomicAdd(&a.stats[1 + st * 4], nReexp[st]);
+      atomicAdd(&a.stats[2 + st * 4], nPolls[st]);
+      atomicAdd(&a.stats[3 + st * 4], nOnDemand[st]);
+    }
+
     // profile (kilocycles, summed over warps and both stages): next-candidate + publish, wait, expand (incl. four-way, on-demand), four-way, on-demand, claim, prefetch
     atomicAdd(&a.stats[8], (uint32_t)(tNext >> 10));
     atomicAdd(&a.stats[9], (uint32_t)(tWait >> 10));
@@ -712,15 +944,28 @@ __global__ void __launch_bounds__(LIMG_WAVE_WARPS * 32) k_merge_wave(WaveArgs a,
     atomicAdd(&a.stats[12], (uint32_t)(scan.tOnDemand >> 10));
     atomicAdd(&a.stats[13], (uint32_t)(tClaim >> 10));
     atomicAdd(&a.stats[14], (uint32_t)(tPre >> 10));
+
+    if (a.dbg)
+    {
+      for (int c = 0; c < 3; c++)
+      {
+        atomicAdd(&a.dbg[32 + c], scan.nStrips[c]);
+        atomicAdd(&a.dbg[32 + 4 + c], (uint32_t)(scan.tStrips[c] >> 10));
+      }
+
+      atomicAdd(&a.dbg[48], scan.nFour);
+      atomicAdd(&a.dbg[49], scan.nFourMiss);
+      atomicAdd(&a.dbg[50], scan.nFourNoSym);
+    }
   }
 }
 
 // Replays every candidate seed of the stage against the mask at its logical time and compares with the wave's record.
 template <int CH>
-__global__ void __launch_bounds__(256) k_merge_verify(WaveArgs a, int stage)
+__global__ void __launch_bounds__(256) k_merge_verify(WaveArgs a, int stage, int attempt)
 {
-  if (a.flags[stage] != 0)
-    return; // already failed
+  if (a.flags[0] != (uint32_t)attempt)
+    return; // this try did not run, or already failed
 
   const int lane = threadIdx.x & 31;
   const uint32_t n = a.candCount[stage];
@@ -780,40 +1025,55 @@ __global__ void __launch_bounds__(256) k_merge_verify(WaveArgs a, int stage)
     }
 
     if (!ok && lane == 0)
-      a.flags[stage] = 1;
+      a.flags[1 + stage] = 1;
   }
 }
 
-// fallback preparation: undo the stage's claims and counters (only when the stage failed)
-__global__ void __launch_bounds__(256) k_merge_reset(WaveArgs a, int stage)
+__global__ void k_merge_set_tries(WaveArgs a, int tries)
 {
-  if (a.flags[stage] == 0)
+  a.flags[0] = (uint32_t)tries;
+}
+
+// after both verification kernels of a try: a failed stage fails the try
+__global__ void k_merge_judge(WaveArgs a, int attempt)
+{
+  if (a.flags[0] == (uint32_t)attempt && (a.flags[1] | a.flags[2]))
+  {
+    a.flags[0] = (uint32_t)attempt + 1;
+    a.flags[1] = 0;
+    a.flags[2] = 0;
+  }
+}
+
+// preparation of try `attempt` > 0 (runs only when every earlier try failed): undo all claims and counters
+__global__ void __launch_bounds__(256) k_merge_reset(WaveArgs a, int attempt)
+{
+  if (a.flags[0] != (uint32_t)attempt)
     return;
 
   const int blocks = a.BX * a.BY;
-  const uint32_t base = stage ? LIMG_TAU_STAGE1 : 0u;
+  const int n = max(blocks, max(a.BY * a.wordsPerRow, 2 * a.BY));
 
-  for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < blocks; b += gridDim.x * blockDim.x)
+  for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < n; b += gridDim.x * blockDim.x)
   {
-    const uint32_t t = a.tau[b];
-
-    if (t != LIMG_TAU_NONE && t >= base)
+    if (b < blocks)
     {
-      const int y = b / a.BX, x = b - y * a.BX;
       a.tau[b] = LIMG_TAU_NONE;
-      atomicAnd(&a.used[(size_t)y * a.wordsPerRow + (x >> 5)], ~(1u << (x & 31)));
+      a.emitInfo[b] = 0;
+      a.emitInfo[blocks + b] = 0;
     }
 
-    a.emitInfo[(size_t)stage * blocks + b] = 0;
+    if (b < a.BY * a.wordsPerRow)
+      a.used[b] = 0;
 
-    if (b < a.BY)
+    if (b < 2 * a.BY)
     {
-      a.progress[(size_t)stage * a.BY + b] = 0;
-      a.rowCounts[(size_t)stage * a.BY + b] = 0;
+      a.progress[b] = 0;
+      a.rowCounts[b] = 0;
     }
 
-    if (b == 0)
-      a.ticket[stage] = 0;
+    if (b < 2)
+      a.ticket[b] = 0;
   }
 }
 

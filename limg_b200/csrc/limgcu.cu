@@ -53,13 +53,19 @@ struct limgcu_ctx
   uint8_t *dPlaneU8[7] = { nullptr }; // factors A,B,C, bpp, codes A,B,C
 
   // wavefront merge (kernels_wave.cuh)
-  uint32_t *dWaveZero = nullptr; // flags[4] ticket[2] candCount[2] | progress[2*BY] | rowCounts[2*BY] | candBits[2*usedWords] | emitInfo[2*blocks]
-  uint32_t *dTau = nullptr, *dCandList = nullptr;
+  uint32_t *dWaveZero = nullptr; // flags[8] ticket[2] candCount[2] pad[4] | progress[2*BY] | rowCounts[2*BY] | candBits[2*usedWords] | emitInfo[2*blocks]
+  uint32_t *dTau = nullptr, *dCandList = nullptr, *dWaveDbg = nullptr, *dWaveRows = nullptr;
+  size_t capWaveRows = 0;
+  int waveRowTimes = 0;              // LIMGCU_MERGE_ROWTIMES=1: per-row time stamps of the scan (limgcu_debug_wave_rows)
   uint2 *dRowLists = nullptr;
   size_t capWaveZero = 0, capRowLists = 0;
 
   int mergeExt = 1;                  // LIMGCU_MERGE_EXT=0 disables the speculative match bitmaps (everything beyond the 8x8 window on demand)
   int mergeMode = 0;                 // LIMGCU_MERGE_MODE: 0 wave (pipelined rows + verification), 1 seq (rows strictly in sequence)
+  int planExtW = 16, planSymL = 6, planSymR = 12, planSymD = 16; // LIMGCU_PLAN_EXTW / SYML / SYMR / SYMD: size caps of the speculative bitmaps
+  int mergeGap = 16;                 // LIMGCU_MERGE_GAP: block rows stage 1 stays behind stage 0
+  int mergeWideMargin = 64;          // margin (and stage gap) of the second try
+  int mergeSpec = 8;                 // LIMGCU_MERGE_SPEC: columns of lookahead for the speculative expansion
   int mergeMargin = 8;               // LIMGCU_MERGE_MARGIN: columns a row stays behind the rows above, beyond what its seed probed
   bool timing = false;
   cudaEvent_t ev[PHASE_COUNT + 1] = { nullptr };
@@ -126,7 +132,7 @@ static int ensure_capacity(limgcu_ctx *ctx, size_t W, size_t H)
   }
 
   {
-    const size_t waveZero = 8 + 4 * BY + 2 * usedWords + 2 * blocks, rowLists = 2 * BY * (2 * BX);
+    const size_t waveZero = 16 + 4 * BY + 2 * usedWords + 2 * blocks, rowLists = 2 * BY * (2 * BX);
 
     if (waveZero > ctx->capWaveZero)
     {
@@ -220,6 +226,7 @@ extern "C" int limgcu_create(int device, limgcu_ctx **out)
   if (cudaMemcpy(ctx->dLut, LIMG_RSQRT_LUT, 2048 * sizeof(uint16_t), cudaMemcpyHostToDevice) != cudaSuccess) return bail(LIMGCU_ERROR_CUDA);
   if (cudaMalloc(&ctx->dCounters, 32 * sizeof(uint32_t)) != cudaSuccess) return bail(LIMGCU_ERROR_MEMORY_ALLOCATION_FAILURE);
   if (cudaMalloc(&ctx->dCompare, sizeof(unsigned long long)) != cudaSuccess) return bail(LIMGCU_ERROR_MEMORY_ALLOCATION_FAILURE);
+  if (cudaMalloc(&ctx->dWaveDbg, 256 * sizeof(uint32_t)) != cudaSuccess) return bail(LIMGCU_ERROR_MEMORY_ALLOCATION_FAILURE);
 
   // LCG jump table: f^(2^j)(h) = mul[j] * h + add[j]
   ctx->jt.mul[0] = LIMG_LCG_MUL;
@@ -235,6 +242,13 @@ extern "C" int limgcu_create(int device, limgcu_ctx **out)
 
   if (const char *v = getenv("LIMGCU_MERGE_MODE")) ctx->mergeMode = !strcmp(v, "seq") ? 1 : 0;
   if (const char *v = getenv("LIMGCU_MERGE_MARGIN")) ctx->mergeMargin = atoi(v) < 0 ? 0 : atoi(v);
+  if (const char *v = getenv("LIMGCU_PLAN_EXTW")) ctx->planExtW = atoi(v) < 8 ? 8 : (atoi(v) > 32 ? 32 : atoi(v));
+  if (const char *v = getenv("LIMGCU_PLAN_SYML")) ctx->planSymL = atoi(v) < 1 ? 1 : (atoi(v) > 8 ? 8 : atoi(v));
+  if (const char *v = getenv("LIMGCU_PLAN_SYMR")) ctx->planSymR = atoi(v) < 8 ? 8 : (atoi(v) > 24 ? 24 : atoi(v));
+  if (const char *v = getenv("LIMGCU_PLAN_SYMD")) ctx->planSymD = atoi(v) < 8 ? 8 : (atoi(v) > 24 ? 24 : atoi(v));
+  if (const char *v = getenv("LIMGCU_MERGE_ROWTIMES")) ctx->waveRowTimes = atoi(v);
+  if (const char *v = getenv("LIMGCU_MERGE_GAP")) ctx->mergeGap = atoi(v) < 0 ? 0 : atoi(v);
+  if (const char *v = getenv("LIMGCU_MERGE_SPEC")) ctx->mergeSpec = atoi(v) < 0 ? 0 : atoi(v);
 
   for (auto &e : ctx->ev)
     if (cudaEventCreate(&e) != cudaSuccess) return bail(LIMGCU_ERROR_CUDA);
@@ -259,7 +273,7 @@ extern "C" void limgcu_destroy(limgcu_ctx *ctx)
   void *ptrs[] = { ctx->dLut, ctx->dTable, ctx->dRec, ctx->dWindow, ctx->dAreas, ctx->dBlockToArea, ctx->dWork, ctx->dSmallList, ctx->dLargeList, ctx->dDemand,
                    ctx->dUsed, ctx->dScratchPx, ctx->dScratchFac, ctx->dCounters, ctx->dCompare, ctx->dSrc,
                    ctx->dExtSlot, ctx->dExtSeed, ctx->dExtBits, ctx->dExtHdr, ctx->dPlanCounters, ctx->dSymSlot, ctx->dSymSeed, ctx->dSymBits, ctx->dSymHdr, ctx->dUnmasked,
-                   ctx->dWaveZero, ctx->dTau, ctx->dCandList, ctx->dRowLists };
+                   ctx->dWaveZero, ctx->dTau, ctx->dCandList, ctx->dRowLists, ctx->dWaveDbg, ctx->dWaveRows };
 
   for (void *p : ptrs)
     if (p) cudaFree(p);
@@ -282,7 +296,27 @@ extern "C" int limgcu_debug_counters(limgcu_ctx *ctx, uint32_t *out32)
 {
   NEED(ctx); NEED(out32);
   CK(cudaMemcpyAsync(out32, ctx->dCounters, 32 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
-  if (ctx->dPlanCounters) CK(cudaMemcpyAsync(out32 + 28, ctx->dPlanCounters, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  if (ctx->dPlanCounters) CK(cudaMemcpyAsync(out32 + 29, ctx->dPlanCounters, 3 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return LIMGCU_SUCCESS;
+}
+
+extern "C" int limgcu_debug_wave(limgcu_ctx *ctx, uint32_t *out256)
+{
+  NEED(ctx); NEED(out256);
+  CK(cudaMemcpyAsync(out256, ctx->dWaveDbg, 256 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return LIMGCU_SUCCESS;
+}
+
+extern "C" int limgcu_debug_wave_rows(limgcu_ctx *ctx, uint32_t *out, size_t blockY)
+{
+  NEED(ctx); NEED(out);
+
+  if (ctx->dWaveRows == nullptr || blockY * 8 > ctx->capWaveRows)
+    return fail(ctx, LIMGCU_ERROR_INVALID_PARAMETER, "no row time stamps were recorded (LIMGCU_MERGE_ROWTIMES=1)", cudaSuccess);
+
+  CK(cudaMemcpyAsync(out, ctx->dWaveRows, blockY * 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   return LIMGCU_SUCCESS;
 }
@@ -371,10 +405,10 @@ static int launch_merge(limgcu_ctx *ctx, const limgcu_decomp *dTable, size_t W, 
 
     const size_t usedWords = (size_t)BY * wordsPerRow;
     uint32_t *wz = ctx->dWaveZero;
-    uint32_t *wFlags = wz, *wTicket = wz + 4, *wCandCount = wz + 6;
-    int *wProgress = reinterpret_cast<int *>(wz + 8);
-    uint32_t *wRowCounts = wz + 8 + 2 * BY, *wCandBits = wz + 8 + 4 * BY, *wEmitInfo = wCandBits + 2 * usedWords;
-    CK(cudaMemsetAsync(wz, 0, (8 + 4 * (size_t)BY + 2 * usedWords + 2 * (size_t)blocks) * sizeof(uint32_t), ctx->stream));
+    uint32_t *wFlags = wz, *wTicket = wz + 8, *wCandCount = wz + 10;
+    int *wProgress = reinterpret_cast<int *>(wz + 16);
+    uint32_t *wRowCounts = wz + 16 + 2 * BY, *wCandBits = wz + 16 + 4 * BY, *wEmitInfo = wCandBits + 2 * usedWords;
+    CK(cudaMemsetAsync(wz, 0, (16 + 4 * (size_t)BY + 2 * usedWords + 2 * (size_t)blocks) * sizeof(uint32_t), ctx->stream));
     CK(cudaMemsetAsync(ctx->dPlanCounters, 0, 8 * sizeof(uint32_t), ctx->stream));
 
     PlanArgs pl;
@@ -383,6 +417,7 @@ static int launch_merge(limgcu_ctx *ctx, const limgcu_decomp *dTable, size_t W, 
     pl.symSlot = ctx->dSymSlot; pl.symSeed = ctx->dSymSeed; pl.symBits = ctx->dSymBits; pl.symHdr = ctx->dSymHdr;
     pl.counters = ctx->dPlanCounters; pl.extCap = ctx->mergeExt ? ctx->extCap : 0; pl.symCap = ctx->mergeExt ? ctx->symCap : 0; pl.unmasked = ctx->dUnmasked;
     pl.candBits = wCandBits; pl.candList = ctx->dCandList; pl.candCount = wCandCount;
+    pl.extMaxW = ctx->planExtW; pl.symMaxL = ctx->planSymL; pl.symMaxR = ctx->planSymR; pl.symMaxD = ctx->planSymD;
     const int planGrid = ctx->smCount * 8;
 
     if (hasAlpha)
@@ -421,9 +456,6 @@ static int launch_merge(limgcu_ctx *ctx, const limgcu_decomp *dTable, size_t W, 
     CK(cudaMemsetAsync(ctx->dUsed, 0, usedWords * sizeof(uint32_t), ctx->stream));
     CK(cudaMemsetAsync(ctx->dTau, 0xFF, (size_t)blocks * sizeof(uint32_t), ctx->stream));
 
-    if (ctx->mergeMode == 1)
-      CK(cudaMemsetAsync(wFlags, 1, 2 * sizeof(uint32_t), ctx->stream)); // both stages go straight to the sequential pass
-
     WaveArgs w;
     w.rec = ctx->dRec; w.window = ctx->dWindow; w.extSlot = ctx->dExtSlot; w.extBits = ctx->dExtBits; w.extHdr = ctx->dExtHdr;
     w.symSlot = ctx->dSymSlot; w.symBits = ctx->dSymBits; w.symHdr = ctx->dSymHdr; w.unmasked = ctx->dUnmasked;
@@ -431,47 +463,79 @@ static int launch_merge(limgcu_ctx *ctx, const limgcu_decomp *dTable, size_t W, 
     w.BX = BX; w.BY = BY; w.wordsPerRow = wordsPerRow;
     w.used = ctx->dUsed; w.tau = ctx->dTau; w.progress = wProgress; w.ticket = wTicket;
     w.rowLists = ctx->dRowLists; w.rowCounts = wRowCounts; w.emitInfo = wEmitInfo; w.flags = wFlags; w.stats = ctx->dCounters + 8;
-    w.listCap = 2 * BX; w.margin = ctx->mergeMargin;
-    const int waveGrid = (BY + LIMG_WAVE_WARPS - 1) / LIMG_WAVE_WARPS < ctx->smCount ? (BY + LIMG_WAVE_WARPS - 1) / LIMG_WAVE_WARPS : ctx->smCount;
+    w.listCap = 2 * BX; w.margin = ctx->mergeMargin; w.stageGap = ctx->mergeGap; w.specAhead = ctx->mergeSpec; w.dbg = ctx->dWaveDbg;
+    CK(cudaMemsetAsync(ctx->dWaveDbg, 0, 256 * sizeof(uint32_t), ctx->stream));
+    w.dbgRows = nullptr;
+
+    if (ctx->waveRowTimes)
+    {
+      if ((size_t)BY * 8 > ctx->capWaveRows)
+      {
+        CK(regrow(ctx->dWaveRows, (size_t)BY * 8));
+        ctx->capWaveRows = (size_t)BY * 8;
+      }
+
+      CK(cudaMemsetAsync(ctx->dWaveRows, 0, (size_t)BY * 8 * sizeof(uint32_t), ctx->stream));
+      w.dbgRows = ctx->dWaveRows;
+    }
+
+    // Tries: 0 pipelined rows with the normal margin, 1 pipelined with a wide margin (flat content, where a regrowth can reach far
+    // to the left), 2 rows strictly in sequence (the reference's order, always exact). A try runs only if the one before failed its
+    // verification; on ordinary content only try 0 does any work.
+    const int rowsTotal = 2 * BY;
+    const int waveGrid = (rowsTotal + LIMG_WAVE_WARPS - 1) / LIMG_WAVE_WARPS < ctx->smCount ? (rowsTotal + LIMG_WAVE_WARPS - 1) / LIMG_WAVE_WARPS : ctx->smCount;
     const int resetGrid = (blocks + 255) / 256 < ctx->smCount * 8 ? (blocks + 255) / 256 : ctx->smCount * 8;
 
-    for (int stage = 0; stage < 2; stage++)
+    if (ctx->mergeMode == 1)
     {
-      if (hasAlpha)
-      {
-        if (ctx->mergeMode == 0)
-        {
-          k_merge_wave<4><<<waveGrid, LIMG_WAVE_WARPS * 32, 0, ctx->stream>>>(w, stage, 0);
-          CKL("k_merge_wave");
-          k_merge_verify<4><<<ctx->smCount * 8, 256, 0, ctx->stream>>>(w, stage);
-          CKL("k_merge_verify");
-        }
+      k_merge_set_tries<<<1, 1, 0, ctx->stream>>>(w, 2);
+      CKL("k_merge_set_tries");
+    }
 
-        k_merge_reset<<<resetGrid, 256, 0, ctx->stream>>>(w, stage);
-        CKL("k_merge_reset");
-        k_merge_wave<4><<<1, LIMG_WAVE_WARPS * 32, 0, ctx->stream>>>(w, stage, 1);
-        CKL("k_merge_wave(seq)");
+    for (int attempt = 0; attempt < 3; attempt++)
+    {
+      WaveArgs wa = w;
+      const int sequential = attempt == 2 ? 1 : 0;
+
+      if (attempt == 1)
+      {
+        wa.margin = ctx->mergeWideMargin;
+        wa.stageGap = ctx->mergeWideMargin;
       }
-      else
+
+      if (attempt > 0)
       {
-        if (ctx->mergeMode == 0)
+        k_merge_reset<<<resetGrid, 256, 0, ctx->stream>>>(wa, attempt);
+        CKL("k_merge_reset");
+      }
+
+      if (hasAlpha)
+        k_merge_wave<4><<<sequential ? 1 : waveGrid, LIMG_WAVE_WARPS * 32, 0, ctx->stream>>>(wa, attempt, sequential);
+      else
+        k_merge_wave<3><<<sequential ? 1 : waveGrid, LIMG_WAVE_WARPS * 32, 0, ctx->stream>>>(wa, attempt, sequential);
+
+      CKL("k_merge_wave");
+
+      if (!sequential)
+      {
+        for (int stage = 0; stage < 2; stage++)
         {
-          k_merge_wave<3><<<waveGrid, LIMG_WAVE_WARPS * 32, 0, ctx->stream>>>(w, stage, 0);
-          CKL("k_merge_wave");
-          k_merge_verify<3><<<ctx->smCount * 8, 256, 0, ctx->stream>>>(w, stage);
+          if (hasAlpha)
+            k_merge_verify<4><<<ctx->smCount * 8, 256, 0, ctx->stream>>>(wa, stage, attempt);
+          else
+            k_merge_verify<3><<<ctx->smCount * 8, 256, 0, ctx->stream>>>(wa, stage, attempt);
+
           CKL("k_merge_verify");
         }
 
-        k_merge_reset<<<resetGrid, 256, 0, ctx->stream>>>(w, stage);
-        CKL("k_merge_reset");
-        k_merge_wave<3><<<1, LIMG_WAVE_WARPS * 32, 0, ctx->stream>>>(w, stage, 1);
-        CKL("k_merge_wave(seq)");
+        k_merge_judge<<<1, 1, 0, ctx->stream>>>(wa, attempt);
+        CKL("k_merge_judge");
       }
     }
 
     k_merge_collect<<<BY, 128, 0, ctx->stream>>>(w, dAreas, ctx->dCounters + 0);
     CKL("k_merge_collect");
-    CK(cudaMemcpyAsync(ctx->dCounters + 24, wFlags, 4 * sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->dCounters + 24, wFlags, 5 * sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream));
   }
   else if (ctx->timing)
   {
@@ -736,13 +800,13 @@ static int host_encode(limgcu_ctx *ctx, const uint32_t *pIn, size_t W, size_t H,
 
   uint32_t count = 0, overflow[2] = { 0, 0 };
   CK(cudaMemcpyAsync(&count, ctx->dCounters + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaMemcpyAsync(overflow, ctx->dCounters + 26, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(overflow, ctx->dCounters + 27, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
 
-  if (overflow[0])
+  if (overflow[1])
     return fail(ctx, LIMGCU_ERROR_OUT_OF_BOUNDS, "a block row emitted more rectangles than its list holds", cudaSuccess);
 
-  if (overflow[1])
+  if (overflow[0])
     return fail(ctx, LIMGCU_ERROR_GENERIC, "merge watchdog: a block row waited too long for the rows above", cudaSuccess);
 
   if (areas)
@@ -849,13 +913,13 @@ extern "C" int limgcu_host_merge(limgcu_ctx *ctx, const limgcu_decomp *table, si
   if (rc) return rc;
   uint32_t count = 0, overflow[2] = { 0, 0 };
   CK(cudaMemcpyAsync(&count, ctx->dCounters + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaMemcpyAsync(overflow, ctx->dCounters + 26, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(overflow, ctx->dCounters + 27, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
 
-  if (overflow[0])
+  if (overflow[1])
     return fail(ctx, LIMGCU_ERROR_OUT_OF_BOUNDS, "a block row emitted more rectangles than its list holds", cudaSuccess);
 
-  if (overflow[1])
+  if (overflow[0])
     return fail(ctx, LIMGCU_ERROR_GENERIC, "merge watchdog: a block row waited too long for the rows above", cudaSuccess);
 
   CK(cudaMemcpyAsync(areas, ctx->dAreas, (size_t)count * sizeof(limgcu_area), cudaMemcpyDeviceToHost, ctx->stream));

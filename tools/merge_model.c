@@ -176,6 +176,7 @@ typedef struct
   double makespan;
   uint64_t leftExtHist[16]; /* how far left of its seed column a centre-third rectangle reaches */
   uint64_t boxWHist[16];
+  uint64_t nDecide, nBlocked;
   uint64_t fourN, centreMiss, eLH[20], eRH[20], eUH[20], eDH[20], sRH[20], sDH[20];
 } Stats;
 
@@ -286,7 +287,8 @@ size_t model_run(const lo_decomp *table, int BX, int BY, int CH, int workers, in
 
       case S_TRY:
       {
-        const int p = k->y == 0 ? DONE : progress[k->y - 1];
+        int p = DONE;
+        for (int rr = 0; rr < k->y; rr++) if (progress[rr] < p) p = progress[rr]; /* monotone relay */
 
         if (sequential ? (p != DONE) : (p != DONE && p < k->x + (int)unmRx[k->y * BX + k->x] + margin))
         {
@@ -299,8 +301,33 @@ size_t model_run(const lo_decomp *table, int BX, int BY, int CH, int workers, in
         const uint32_t T = base + (((uint32_t)(k->y * BX + k->x)) << 3) + (uint32_t)k->k;
         k->pend = expand(&m, k->x, k->y, stage, NONE);
         st[stage].expansions++;
-        k->t += c.exp + (k->pend.attempted ? c.four : 0);
-        const int need = k->pend.boxR + margin;
+        { static uint32_t lcg = 12345u; lcg = lcg * 1664525u + 1013904223u; const double j = 1.0 + costs7[10] * (((lcg >> 8) & 0xFFFF) / 32768.0 - 1.0); k->t += j * (c.exp + (k->pend.attempted ? c.four : 0)); }
+        int need = k->pend.boxR + margin;
+        {
+          /* proven safe: every row of the probed boxes (one more above and below) has an in-use block just right of them */
+          const Result *r = &k->pend;
+          int top = k->y, bottom = k->y + r->ry;
+          if (r->attempted) { if (r->coy - 1 < top) top = r->coy - 1; if (r->coy + r->cry > bottom) bottom = r->coy + r->cry; }
+          int blocked = 1;
+          if (costs7[9] > 0 && bottom + 1 > k->y + (int)costs7[9]) bottom = k->y + (int)costs7[9] - 1;
+          for (int rr = top - 1; rr <= bottom + 1 && blocked; rr++)
+          {
+            if (rr < 0 || rr >= BY) continue;
+            int any = r->boxR >= BX;
+            for (int cc = r->boxR; cc < r->boxR + margin && cc < BX && !any; cc++) any = used_at(&m, cc, rr, NONE);
+            if (!any && costs7[11] > 0)
+            {
+              /* no in-use block: only dangerous if the blocks there form a run of matches (a flat region) */
+              int run = 1;
+              const int b0 = rr * BX + r->boxR;
+              while (run < 8 && r->boxR + run < BX && match(&m, b0, b0 + run)) run++;
+              if (run < 8) any = 1;
+            }
+            blocked = any;
+          }
+          st[stage].nDecide++; st[stage].nBlocked += blocked;
+          if (!blocked) need = k->pend.boxR + (int)costs7[8];
+        }
 
         if (p != DONE && p < need)
         {
@@ -324,9 +351,8 @@ size_t model_run(const lo_decomp *table, int BX, int BY, int CH, int workers, in
         {
           int v;
           st[stage].fourN++;
-          const Result f = expand(&m, k->x, k->y, stage, 0u);
-          if (!f.attempted || f.c0x != r->c0x || f.c0y != r->c0y) st[stage].centreMiss++;
-          { static int nprint = 0; if (nprint < 4000) { nprint++; printf("CM %d %d %d\n", f.attempted, r->c0x - f.c0x, r->c0y - f.c0y); } }
+          Result f; f.attempted = 1; f.c0x = r->c0x; f.c0y = r->c0y;
+
           v = r->eL > 19 ? 19 : r->eL; st[stage].eLH[v]++; v = r->eR > 19 ? 19 : r->eR; st[stage].eRH[v]++;
           v = r->eU > 19 ? 19 : r->eU; st[stage].eUH[v]++; v = r->eD > 19 ? 19 : r->eD; st[stage].eDH[v]++;
         }
@@ -424,7 +450,7 @@ size_t model_run(const lo_decomp *table, int BX, int BY, int CH, int workers, in
 
   for (int s2 = 0; s2 < 2; s2++)
   {
-    printf("  stage %d: four-way attempts %llu, centre != mask-free centre %llu\n", s2, (unsigned long long)st[s2].fourN, (unsigned long long)st[s2].centreMiss);
+    printf("  stage %d: four-way attempts %llu, centre != mask-free centre %llu; decisions %llu of which proven safe %llu\n", s2, (unsigned long long)st[s2].fourN, (unsigned long long)st[s2].centreMiss, (unsigned long long)st[s2].nDecide, (unsigned long long)st[s2].nBlocked);
     const char *names[6] = { "4way left ", "4way right", "4way up   ", "4way down ", "seed right", "seed down " };
     uint64_t *hs[6] = { st[s2].eLH, st[s2].eRH, st[s2].eUH, st[s2].eDH, st[s2].sRH, st[s2].sDH };
     for (int h = 0; h < 6; h++) { printf("    %s:", names[h]); for (int i = 0; i < 20; i++) printf(" %llu", (unsigned long long)hs[h][i]); printf("\n"); }

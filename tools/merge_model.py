@@ -21,7 +21,11 @@ def main():
     ap.add_argument("--workers", type=int, default=128)
     ap.add_argument("--margin", type=int, nargs="*", default=[4, 8])
     ap.add_argument("--sequential", type=int, default=0)
-    ap.add_argument("--predict", type=float, default=1.0)
+    ap.add_argument("--predict", type=float, default=0.0)
+    ap.add_argument("--wide", type=float, default=8.0)
+    ap.add_argument("--depth", type=float, default=0.0)
+    ap.add_argument("--jitter", type=float, default=0.0)
+    ap.add_argument("--runrule", type=float, default=0.0)
     ap.add_argument("--poll", type=float, default=0.4)
     ap.add_argument("--exp", type=float, default=1.0)
     a = ap.parse_args()
@@ -29,7 +33,7 @@ def main():
     lo.lib()
     m = C.CDLL(SO)
     m.model_run.restype = C.c_size_t
-    costs = (C.c_double * 8)(1.0, a.poll, 0.1, a.exp, 0.8, 0.3, 0.1, a.predict)
+    costs = (C.c_double * 12)(1.0, a.poll, 0.1, a.exp, 0.8, 0.3, 0.1, a.predict, a.wide, a.depth, a.jitter, a.runrule)
     for name in a.configs:
         img, alpha = synth.CONFIGS[name]()
         h, w = img.shape

@@ -18,6 +18,10 @@ for name in ("c1_512_gradient","c5_1080p_frame0","c2_4k_photo","c4_4k_flatui","c
     ph = c.phase_ms()
     tot = sum(ph.values())
     cnt = c.debug_counters()
-    print("   merged %d areas %d small %d large %d | stage0 exp %d reexp %d polls %d ondemand %d | stage1 exp %d reexp %d polls %d ondemand %d | fallback flags %s ext slots %d sym slots %d" % (cnt[0],cnt[1],cnt[2],cnt[3],cnt[8],cnt[9],cnt[10],cnt[11],cnt[12],cnt[13],cnt[14],cnt[15],cnt[24:28],cnt[28],cnt[29]))
+    print("   merged %d areas %d small %d large %d | stage0 exp %d reexp %d polls %d ondemand %d | stage1 exp %d reexp %d polls %d ondemand %d | failed tries / flags %s ext slots %d sym slots %d" % (cnt[0],cnt[1],cnt[2],cnt[3],cnt[8],cnt[9],cnt[10],cnt[11],cnt[12],cnt[13],cnt[14],cnt[15],cnt[24:29],cnt[29],cnt[30]))
     print("   profile kcycles: next %d wait %d expand %d (four-way %d, on-demand %d) claim %d prefetch %d" % tuple(cnt[16:23]))
+    dbg = c.debug_wave()
+    print("   expansion duration histogram (log2 of cycles/256) stage0 %s stage1 %s" % (dbg[0:16].tolist(), dbg[16:32].tolist()))
+    print("   on-demand strips [seed, 4way+bitmap, 4way no bitmap]: n %s kcyc %s | - %s %s | four-way attempts %d, centre mispredicted %d, no bitmap %d" % (dbg[32:35].tolist(), dbg[36:39].tolist(), dbg[40:43].tolist(), dbg[44:47].tolist(), dbg[48], dbg[49], dbg[50]))
+    print("   strips outside the known part [left, up, right, down]: seed %s 4way+bitmap %s 4way-no-bitmap %s ; known reach (blocks from centre) when right/down left it: %s" % (dbg[64:68].tolist(), dbg[68:72].tolist(), dbg[72:76].tolist(), dbg[80:96].tolist()))
     print(name, "%dx%d"%(w,h), "total %.3f ms (wall %.3f) -> %.1f Mpx/s"%(tot, dt*1e3, w*h/tot/1e3), {k: round(v,3) for k,v in ph.items()})
