@@ -242,6 +242,7 @@ __global__ void __launch_bounds__(256) k_pred_window(const PredRec *__restrict__
 // ---------------------------------------------------------------------------------------------
 
 #define LIMG_NO_SLOT 0xFFFFFFFFu
+#define LIMG_SLOT_PENDING 0xFFFFFFFEu // asked for, bitmap not written (yet)
 #define LIMG_SYM_BACK 8  // a centre's bitmap is anchored 8 blocks up and to the left of it
 
 struct PlanArgs
@@ -354,10 +355,7 @@ __global__ void __launch_bounds__(256) k_plan_seeds(PlanArgs a)
     const uint32_t slot = atomicAdd(&a.counters[0], 1u);
 
     if (slot < a.extCap)
-    {
-      a.extSeed[slot] = seed;
-      a.extSlot[seed] = slot;
-    }
+      a.extSeed[slot] = seed; // k_plan_extend publishes extSlot[seed] once the bitmap exists (the scan may already be running)
   }
 }
 
@@ -368,87 +366,80 @@ __device__ __forceinline__ int run_end(uint32_t bits, int from)
   return z ? __ffs(z) - 1 : 32;
 }
 
+// One WARP per slot: the cells of the known part that are not already known are evaluated 32 at a time (one predicate per lane),
+// so no lane idles while others work and no block-wide barrier is needed.
+#define LIMG_PLAN_WARPS 8
+
 template <int CH>
-__global__ void __launch_bounds__(256) k_plan_extend(PlanArgs a)
+__global__ void __launch_bounds__(LIMG_PLAN_WARPS * 32) k_plan_extend(PlanArgs a)
 {
-  __shared__ uint32_t rows[32];
-  __shared__ uint32_t sRowRun, sColRun;
+  __shared__ uint32_t sRows[LIMG_PLAN_WARPS][32];
   const uint32_t count = min(a.counters[0], a.extCap);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t *rows = sRows[warp];
+  const uint32_t warpsTotal = gridDim.x * LIMG_PLAN_WARPS;
 
-  for (uint32_t slot = blockIdx.x; slot < count; slot += gridDim.x)
+  for (uint32_t slot = blockIdx.x * LIMG_PLAN_WARPS + warp; slot < count; slot += warpsTotal)
   {
     const int seed = (int)a.extSeed[slot];
     const int y = seed / a.BX, x = seed - y * a.BX;
     const PredRec s = a.rec[seed];
     const uint32_t w0 = a.window[(size_t)seed * 2], w1 = a.window[(size_t)seed * 2 + 1];
+    const uint32_t win = lane < 8 ? ((lane < 4 ? w0 >> (8 * lane) : w1 >> (8 * (lane - 4))) & 0xFFu) : 0u; // lane = row of the 8x8 window
 
-    if (threadIdx.x < 32)
-      rows[threadIdx.x] = threadIdx.x < 8 ? ((threadIdx.x < 4 ? w0 >> (8 * threadIdx.x) : w1 >> (8 * (threadIdx.x - 4))) & 0xFFu) : 0u;
+    // the two runs: along the seed's row (dx = lane) and along its column (dy = lane); the first 8 are known
+    bool mr, mc;
 
-    __syncthreads();
-
-    // the two runs: warp 0 the seed's row (dx = lane), warp 1 its column (dy = lane); the first 8 are known
-    if (warp < 2)
+    if (lane < 8)
     {
-      const int dx = warp == 0 ? lane : 0, dy = warp == 0 ? 0 : lane;
-      bool m;
-
-      if (lane < 8)
-        m = (rows[dy] >> dx) & 1u;
-      else
-        m = x + dx < a.BX && y + dy < a.BY && predicate_thread<CH>(s, a.rec[(size_t)(y + dy) * a.BX + x + dx]);
-
-      const uint32_t b = __ballot_sync(0xFFFFFFFFu, m);
-
-      if (lane == 0)
-      {
-        if (warp == 0) sRowRun = b; else sColRun = b;
-      }
+      mr = (w0 >> lane) & 1u;
+      mc = win & 1u;
+    }
+    else
+    {
+      mr = x + lane < a.BX && predicate_thread<CH>(s, a.rec[(size_t)y * a.BX + x + lane]);
+      mc = y + lane < a.BY && predicate_thread<CH>(s, a.rec[(size_t)(y + lane) * a.BX + x]);
     }
 
-    __syncthreads();
+    const uint32_t rowRun = __ballot_sync(0xFFFFFFFFu, mr), colRun = __ballot_sync(0xFFFFFFFFu, mc);
     // known part: columns [0, first mismatch along the row], rows [0, first mismatch along the column]
-    const int vx1 = min(run_end(sRowRun, 0) + 1, a.extMaxW), vy1 = min(run_end(sColRun, 0) + 1, 32);
+    const int vx1 = min(run_end(rowRun, 0) + 1, a.extMaxW), vy1 = min(run_end(colRun, 0) + 1, 32);
 
-    for (int p = 0; p < 4; p++)
+    // row words start with what is known: the window, the row run (row 0), the column run (column 0)
+    rows[lane] = lane >= vy1 ? 0u : ((lane == 0 ? rowRun : win) | ((colRun >> lane) & 1u)) & (vx1 >= 32 ? 0xFFFFFFFFu : ((1u << vx1) - 1u));
+    __syncwarp();
+
+    for (int base = 0; base < vx1 * vy1; base += 32)
     {
-      const int dy = p * 8 + warp, dx = lane;
-      bool m = false;
+      const int cell = base + lane;
+      const int dy = cell / vx1, dx = cell - dy * vx1;
 
-      if (dx < vx1 && dy < vy1)
+      if (cell < vx1 * vy1 && dx > 0 && dy > 0 && (dx >= 8 || dy >= 8) && x + dx < a.BX && y + dy < a.BY)
       {
-        if (dx < 8 && dy < 8)
-          m = (rows[dy] >> dx) & 1u;
-        else if (dy == 0)
-          m = (sRowRun >> dx) & 1u;
-        else if (dx == 0)
-          m = (sColRun >> dy) & 1u;
-        else if (x + dx < a.BX && y + dy < a.BY)
-          m = predicate_thread<CH>(s, a.rec[(size_t)(y + dy) * a.BX + x + dx]);
+        if (predicate_thread<CH>(s, a.rec[(size_t)(y + dy) * a.BX + x + dx]))
+          atomicOr(&rows[dy], 1u << dx);
       }
-
-      const uint32_t b = __ballot_sync(0xFFFFFFFFu, m);
-      __syncthreads(); // every read of rows[] of this pass happened
-
-      if (lane == 0)
-        rows[dy] = b;
-
-      __syncthreads();
     }
 
-    if (threadIdx.x < 32)
-      a.extBits[(size_t)slot * 32 + threadIdx.x] = rows[threadIdx.x];
+    __syncwarp();
+    a.extBits[(size_t)slot * 32 + lane] = rows[lane];
 
-    if (threadIdx.x == 0)
+    if (lane == 0)
     {
       int rx, ry;
       a.extHdr[slot] = (uint32_t)vx1 << 16 | (uint32_t)vy1 << 24;
       expand_unmasked(rows, 32, x, y, a.BX, a.BY, rx, ry);
-      a.unmasked[seed] = (uint16_t)(min(rx, 255) | (min(ry, 255) << 8));
+      *(volatile uint16_t *)&a.unmasked[seed] = (uint16_t)(min(rx, 255) | (min(ry, 255) << 8));
     }
 
-    __syncthreads();
+    // publish: the bitmap is complete before anybody can find it
+    __threadfence();
+    __syncwarp();
+
+    if (lane == 0)
+      *(volatile uint32_t *)&a.extSlot[seed] = slot;
+
+    __syncwarp();
   }
 }
 
@@ -475,19 +466,12 @@ __global__ void __launch_bounds__(256) k_plan_centres(PlanArgs a)
   {
     const int c = cy * a.BX + x + rx / 3 - d;
 
-    if (atomicCAS(&a.symSlot[c], LIMG_NO_SLOT, LIMG_NO_SLOT - 1u) == LIMG_NO_SLOT) // first one to ask for this centre
+    if (atomicCAS(&a.symSlot[c], LIMG_NO_SLOT, LIMG_SLOT_PENDING) == LIMG_NO_SLOT) // first one to ask for this centre
     {
       const uint32_t slot = atomicAdd(&a.counters[1], 1u);
 
       if (slot < a.symCap)
-      {
-        a.symSeed[slot] = (uint32_t)c;
-        a.symSlot[c] = slot;
-      }
-      else
-      {
-        a.symSlot[c] = LIMG_NO_SLOT;
-      }
+        a.symSeed[slot] = (uint32_t)c; // symSlot[c] stays "pending" until k_plan_sym has written the bitmap
     }
   }
 }
@@ -495,14 +479,15 @@ __global__ void __launch_bounds__(256) k_plan_centres(PlanArgs a)
 // Match bitmap around a centre c, anchored at (cx - 8, cy - 8): every four-way rectangle grown from a rectangle that contains c's
 // block row and column segment lies inside the bounding box of the four runs from c (each strip it adds crosses c's row or column).
 template <int CH>
-__global__ void __launch_bounds__(256) k_plan_sym(PlanArgs a)
+__global__ void __launch_bounds__(LIMG_PLAN_WARPS * 32) k_plan_sym(PlanArgs a)
 {
-  __shared__ uint32_t rows[32];
-  __shared__ uint32_t sRowRun, sColRun;
+  __shared__ uint32_t sRows[LIMG_PLAN_WARPS][32];
   const uint32_t count = min(a.counters[1], a.symCap);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t *rows = sRows[warp];
+  const uint32_t warpsTotal = gridDim.x * LIMG_PLAN_WARPS;
 
-  for (uint32_t slot = blockIdx.x; slot < count; slot += gridDim.x)
+  for (uint32_t slot = blockIdx.x * LIMG_PLAN_WARPS + warp; slot < count; slot += warpsTotal)
   {
     const int c = (int)a.symSeed[slot];
     const int cy = c / a.BX, cx = c - cy * a.BX;
@@ -514,73 +499,83 @@ __global__ void __launch_bounds__(256) k_plan_sym(PlanArgs a)
       return ((dy < 4 ? w0 >> (8 * dy) : w1 >> (8 * (dy - 4))) >> dx) & 1u;
     };
 
-    // runs along c's row (warp 0: column ax + lane) and c's column (warp 1: row ay + lane)
-    if (warp < 2)
+    // runs along c's row (column ax + lane) and c's column (row ay + lane), limited to the part the caps allow
+    const int d = lane - LIMG_SYM_BACK;
+    bool mr = false, mc = false;
+
+    if (d >= 0 && d < 8)
     {
-      const int bx = warp == 0 ? ax + lane : cx, by = warp == 0 ? cy : ay + lane;
-      const int dx = bx - cx, dy = by - cy;
-      bool m = false;
+      mr = known(d, 0);
+      mc = known(0, d);
+    }
+    else
+    {
+      if (d >= -a.symMaxL && d < a.symMaxR && cx + d >= 0 && cx + d < a.BX)
+        mr = predicate_thread<CH>(s, a.rec[(size_t)cy * a.BX + cx + d]);
 
-      if (bx >= 0 && bx < a.BX && by >= 0 && by < a.BY)
-      {
-        if (dx >= 0 && dx < 8 && dy >= 0 && dy < 8)
-          m = known(dx, dy);
-        else
-          m = predicate_thread<CH>(s, a.rec[(size_t)by * a.BX + bx]);
-      }
-
-      const uint32_t b = __ballot_sync(0xFFFFFFFFu, m);
-
-      if (lane == 0)
-      {
-        if (warp == 0) sRowRun = b; else sColRun = b;
-      }
+      if (d >= -a.symMaxL && d < a.symMaxD && cy + d >= 0 && cy + d < a.BY)
+        mc = predicate_thread<CH>(s, a.rec[(size_t)(cy + d) * a.BX + cx]);
     }
 
-    __syncthreads();
+    const uint32_t rowRun = __ballot_sync(0xFFFFFFFFu, mr), colRun = __ballot_sync(0xFFFFFFFFu, mc);
     // known box: from the first mismatch left of / above c to the first mismatch right of / below c (inclusive), relative to the anchor
-    const uint32_t rowRun = sRowRun, colRun = sColRun;
     const uint32_t lowRow = ~rowRun & ((1u << LIMG_SYM_BACK) - 1u), lowCol = ~colRun & ((1u << LIMG_SYM_BACK) - 1u);
     const int vx0 = max(lowRow ? 31 - __clz(lowRow) : 0, LIMG_SYM_BACK - a.symMaxL), vy0 = max(lowCol ? 31 - __clz(lowCol) : 0, LIMG_SYM_BACK - a.symMaxL);
     // the regrowth starts from a rectangle of up to 3 x 3 blocks whose blocks are not tested (limg.cpp:1428-1431): a mismatch
     // one or two blocks right of / below c does not stop it
     const int vx1 = min(run_end(rowRun | (3u << (LIMG_SYM_BACK + 1)), LIMG_SYM_BACK) + 1, LIMG_SYM_BACK + a.symMaxR);
     const int vy1 = min(run_end(colRun | (3u << (LIMG_SYM_BACK + 1)), LIMG_SYM_BACK) + 1, LIMG_SYM_BACK + a.symMaxD);
+    const int bw = vx1 - vx0, bh = vy1 - vy0;
 
-    for (int p = 0; p < 4; p++)
+    // what is known without further predicates: c's match word (lower-right quadrant), c's row, c's column
     {
-      const int r = p * 8 + warp, col = lane;
-      const int bx = ax + col, by = ay + r;
-      const int dx = bx - cx, dy = by - cy;
-      bool m = false;
+      uint32_t r = 0;
+      const int dy = lane - LIMG_SYM_BACK;
 
-      if (col >= vx0 && col < vx1 && r >= vy0 && r < vy1 && bx >= 0 && bx < a.BX && by >= 0 && by < a.BY)
+      if (lane >= vy0 && lane < vy1)
       {
-        if (dx >= 0 && dx < 8 && dy >= 0 && dy < 8)
-          m = known(dx, dy);
-        else if (dy == 0)
-          m = (rowRun >> col) & 1u;
-        else if (dx == 0)
-          m = (colRun >> r) & 1u;
-        else
-          m = predicate_thread<CH>(s, a.rec[(size_t)by * a.BX + bx]);
+        if (dy >= 0 && dy < 8)
+          r = ((dy < 4 ? w0 >> (8 * dy) : w1 >> (8 * (dy - 4))) & 0xFFu) << LIMG_SYM_BACK;
+
+        if (dy == 0)
+          r |= rowRun;
+
+        r |= ((colRun >> lane) & 1u) << LIMG_SYM_BACK;
+        r &= (vx1 >= 32 ? 0xFFFFFFFFu : ((1u << vx1) - 1u)) & (0xFFFFFFFFu << vx0);
       }
 
-      const uint32_t b = __ballot_sync(0xFFFFFFFFu, m);
-
-      if (lane == 0)
-        rows[r] = b;
+      rows[lane] = r;
     }
 
-    __syncthreads();
+    __syncwarp();
 
-    if (threadIdx.x < 32)
-      a.symBits[(size_t)slot * 32 + threadIdx.x] = rows[threadIdx.x];
+    for (int base = 0; base < bw * bh; base += 32)
+    {
+      const int cell = base + lane;
+      const int r = vy0 + cell / bw, col = vx0 + cell % bw;
+      const int dx = col - LIMG_SYM_BACK, dy = r - LIMG_SYM_BACK;
+      const int bx = ax + col, by = ay + r;
 
-    if (threadIdx.x == 0)
+      if (cell < bw * bh && dx != 0 && dy != 0 && !(dx > 0 && dx < 8 && dy > 0 && dy < 8) && bx >= 0 && bx < a.BX && by >= 0 && by < a.BY)
+      {
+        if (predicate_thread<CH>(s, a.rec[(size_t)by * a.BX + bx]))
+          atomicOr(&rows[r], 1u << col);
+      }
+    }
+
+    __syncwarp();
+    a.symBits[(size_t)slot * 32 + lane] = rows[lane];
+
+    if (lane == 0)
       a.symHdr[slot] = (uint32_t)vx0 | (uint32_t)vy0 << 8 | (uint32_t)vx1 << 16 | (uint32_t)vy1 << 24;
 
-    __syncthreads();
+    __threadfence();
+    __syncwarp();
+
+    if (lane == 0)
+      *(volatile uint32_t *)&a.symSlot[c] = slot;
+
+    __syncwarp();
   }
 }
 

@@ -365,14 +365,15 @@ struct WaveScan
 
   __device__ __forceinline__ void load_sym(int cx, int cy, uint32_t &row, uint32_t &hdr) const
   {
-    const uint32_t slot = __ldg(&a.symSlot[(size_t)cy * a.BX + cx]);
+    // the plan kernels may still be running on the other stream: slots appear while the scan runs
+    const uint32_t slot = ld_relaxed_u32(&a.symSlot[(size_t)cy * a.BX + cx]);
     row = 0;
     hdr = 0;
 
-    if (slot != LIMG_NO_SLOT)
+    if (slot < LIMG_SLOT_PENDING)
     {
-      row = __ldg(&a.symBits[(size_t)slot * 32 + lane]);
-      hdr = __ldg(&a.symHdr[slot]);
+      row = ld_relaxed_u32(&a.symBits[(size_t)slot * 32 + lane]);
+      hdr = ld_relaxed_u32(&a.symHdr[slot]);
     }
   }
 
@@ -380,11 +381,11 @@ struct WaveScan
   {
     SeedPre p;
     const int seed = y * a.BX + x;
-    const uint32_t slot = __ldg(&a.extSlot[seed]);
-    const uint32_t u = __ldg(&a.unmasked[seed]);
+    const uint32_t slot = ld_relaxed_u32(&a.extSlot[seed]);
+    const uint32_t u = *(const volatile uint16_t *)&a.unmasked[seed];
     const uint32_t wv = lane < 8 ? __ldg(&a.window[(size_t)seed * 2 + (lane >> 2)]) : 0u;
 
-    if (slot == LIMG_NO_SLOT)
+    if (slot >= LIMG_SLOT_PENDING)
     {
       p.rowBits = (wv >> (8 * (lane & 3))) & 0xFFu;
       p.vx1 = 8;
@@ -392,8 +393,8 @@ struct WaveScan
     }
     else
     {
-      const uint32_t h = __ldg(&a.extHdr[slot]);
-      p.rowBits = __ldg(&a.extBits[(size_t)slot * 32 + lane]);
+      const uint32_t h = ld_relaxed_u32(&a.extHdr[slot]);
+      p.rowBits = ld_relaxed_u32(&a.extBits[(size_t)slot * 32 + lane]);
       p.vx1 = (h >> 16) & 0xFF;
       p.vy1 = h >> 24;
     }
@@ -924,7 +925,10 @@ __global__ void __launch_bounds__(LIMG_WAVE_WARPS * 32) k_merge_wave(WaveArgs a,
   }
 
   if (failed && !sequential && lane == 0)
+  {
+    a.flags[5] |= 4u << (4 * attempt);
     a.flags[0] = (uint32_t)attempt + 1;
+  }
 
   if (a.stats && lane == 0)
   {
@@ -1025,7 +1029,22 @@ __global__ void __launch_bounds__(256) k_merge_verify(WaveArgs a, int stage, int
     }
 
     if (!ok && lane == 0)
+    {
       a.flags[1 + stage] = 1;
+
+      // diagnostics: the first few failing seeds (stage, x, y, recorded count, replayed count so far)
+      if (a.dbg)
+      {
+        const uint32_t slot = atomicAdd(&a.dbg[100], 1u);
+
+        if (slot < 8)
+        {
+          uint32_t *o = a.dbg + 104 + slot * 8;
+          o[0] = (uint32_t)stage | ((uint32_t)attempt << 8); o[1] = (uint32_t)x; o[2] = (uint32_t)y; o[3] = have; o[4] = e;
+          o[5] = have ? rec[0].x : 0u; o[6] = have ? rec[0].y : 0u;
+        }
+      }
+    }
   }
 }
 
@@ -1039,6 +1058,7 @@ __global__ void k_merge_judge(WaveArgs a, int attempt)
 {
   if (a.flags[0] == (uint32_t)attempt && (a.flags[1] | a.flags[2]))
   {
+    a.flags[5] |= ((a.flags[1] ? 1u : 0u) | (a.flags[2] ? 2u : 0u)) << (4 * attempt); // which stage failed in which try (diagnostics)
     a.flags[0] = (uint32_t)attempt + 1;
     a.flags[1] = 0;
     a.flags[2] = 0;

@@ -20,6 +20,9 @@ struct limgcu_ctx
 {
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t streamAux = nullptr; // the speculative match bitmaps are computed here while the scan already runs on `stream`
+  cudaEvent_t evFork = nullptr, evJoin = nullptr;
+  int planAsync = 1;                // LIMGCU_PLAN_ASYNC=0: everything on one stream
   char err[512] = { 0 };
   uint64_t launches = 0;
   int smCount = 148;
@@ -219,7 +222,14 @@ extern "C" int limgcu_create(int device, limgcu_ctx **out)
   };
 
   if (cudaSetDevice(device) != cudaSuccess) return bail(LIMGCU_ERROR_CUDA);
-  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(LIMGCU_ERROR_CUDA);
+  {
+    int prLow = 0, prHigh = 0;
+    cudaDeviceGetStreamPriorityRange(&prLow, &prHigh);
+    if (cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prHigh) != cudaSuccess) return bail(LIMGCU_ERROR_CUDA);
+    if (cudaStreamCreateWithPriority(&ctx->streamAux, cudaStreamNonBlocking, prLow) != cudaSuccess) return bail(LIMGCU_ERROR_CUDA);
+    if (cudaEventCreateWithFlags(&ctx->evFork, cudaEventDisableTiming) != cudaSuccess) return bail(LIMGCU_ERROR_CUDA);
+    if (cudaEventCreateWithFlags(&ctx->evJoin, cudaEventDisableTiming) != cudaSuccess) return bail(LIMGCU_ERROR_CUDA);
+  }
   cudaDeviceGetAttribute(&ctx->smCount, cudaDevAttrMultiProcessorCount, device);
 
   if (cudaMalloc(&ctx->dLut, 2048 * sizeof(uint16_t)) != cudaSuccess) return bail(LIMGCU_ERROR_MEMORY_ALLOCATION_FAILURE);
@@ -247,6 +257,7 @@ extern "C" int limgcu_create(int device, limgcu_ctx **out)
   if (const char *v = getenv("LIMGCU_PLAN_SYMR")) ctx->planSymR = atoi(v) < 8 ? 8 : (atoi(v) > 24 ? 24 : atoi(v));
   if (const char *v = getenv("LIMGCU_PLAN_SYMD")) ctx->planSymD = atoi(v) < 8 ? 8 : (atoi(v) > 24 ? 24 : atoi(v));
   if (const char *v = getenv("LIMGCU_MERGE_ROWTIMES")) ctx->waveRowTimes = atoi(v);
+  if (const char *v = getenv("LIMGCU_PLAN_ASYNC")) ctx->planAsync = atoi(v);
   if (const char *v = getenv("LIMGCU_MERGE_GAP")) ctx->mergeGap = atoi(v) < 0 ? 0 : atoi(v);
   if (const char *v = getenv("LIMGCU_MERGE_SPEC")) ctx->mergeSpec = atoi(v) < 0 ? 0 : atoi(v);
 
@@ -285,6 +296,15 @@ extern "C" void limgcu_destroy(limgcu_ctx *ctx)
   if (ctx->stream)
     cudaStreamDestroy(ctx->stream);
 
+  if (ctx->streamAux)
+  {
+    cudaStreamSynchronize(ctx->streamAux);
+    cudaStreamDestroy(ctx->streamAux);
+  }
+
+  if (ctx->evFork) cudaEventDestroy(ctx->evFork);
+  if (ctx->evJoin) cudaEventDestroy(ctx->evJoin);
+
   delete ctx;
 }
 
@@ -296,7 +316,7 @@ extern "C" int limgcu_debug_counters(limgcu_ctx *ctx, uint32_t *out32)
 {
   NEED(ctx); NEED(out32);
   CK(cudaMemcpyAsync(out32, ctx->dCounters, 32 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
-  if (ctx->dPlanCounters) CK(cudaMemcpyAsync(out32 + 29, ctx->dPlanCounters, 3 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  if (ctx->dPlanCounters) CK(cudaMemcpyAsync(out32 + 29, ctx->dPlanCounters, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   return LIMGCU_SUCCESS;
 }
@@ -418,7 +438,12 @@ static int launch_merge(limgcu_ctx *ctx, const limgcu_decomp *dTable, size_t W, 
     pl.counters = ctx->dPlanCounters; pl.extCap = ctx->mergeExt ? ctx->extCap : 0; pl.symCap = ctx->mergeExt ? ctx->symCap : 0; pl.unmasked = ctx->dUnmasked;
     pl.candBits = wCandBits; pl.candList = ctx->dCandList; pl.candCount = wCandCount;
     pl.extMaxW = ctx->planExtW; pl.symMaxL = ctx->planSymL; pl.symMaxR = ctx->planSymR; pl.symMaxD = ctx->planSymD;
-    const int planGrid = ctx->smCount * 8;
+    // The bitmaps beyond the 8x8 windows are pure accelerators of the scan and appear slot by slot, so their kernels run on a second,
+    // low-priority stream WHILE the scan already walks the image top-down on the main stream; a seed whose bitmap is not there yet
+    // is grown with on-demand predicates. Two plan CTAs per SM leave room for a scan CTA.
+    const bool async = ctx->planAsync != 0;
+    const int planGrid = ctx->smCount * (async ? 2 : 6);
+    cudaStream_t planStream = async ? ctx->streamAux : ctx->stream;
 
     if (hasAlpha)
     {
@@ -426,14 +451,6 @@ static int launch_merge(limgcu_ctx *ctx, const limgcu_decomp *dTable, size_t W, 
       CKL("k_pred_records");
       k_pred_window<4><<<(blocks * 2 + 7) / 8, 256, 0, ctx->stream>>>(ctx->dRec, BX, BY, ctx->dWindow);
       CKL("k_pred_window");
-      k_plan_seeds<<<(blocks + 255) / 256, 256, 0, ctx->stream>>>(pl);
-      CKL("k_plan_seeds");
-      k_plan_extend<4><<<planGrid, 256, 0, ctx->stream>>>(pl);
-      CKL("k_plan_extend");
-      k_plan_centres<<<(blocks + 255) / 256, 256, 0, ctx->stream>>>(pl);
-      CKL("k_plan_centres");
-      k_plan_sym<4><<<planGrid, 256, 0, ctx->stream>>>(pl);
-      CKL("k_plan_sym");
     }
     else
     {
@@ -441,15 +458,38 @@ static int launch_merge(limgcu_ctx *ctx, const limgcu_decomp *dTable, size_t W, 
       CKL("k_pred_records");
       k_pred_window<3><<<(blocks * 2 + 7) / 8, 256, 0, ctx->stream>>>(ctx->dRec, BX, BY, ctx->dWindow);
       CKL("k_pred_window");
-      k_plan_seeds<<<(blocks + 255) / 256, 256, 0, ctx->stream>>>(pl);
-      CKL("k_plan_seeds");
-      k_plan_extend<3><<<planGrid, 256, 0, ctx->stream>>>(pl);
+    }
+
+    k_plan_seeds<<<(blocks + 255) / 256, 256, 0, ctx->stream>>>(pl);
+    CKL("k_plan_seeds");
+
+    if (async)
+    {
+      CK(cudaEventRecord(ctx->evFork, ctx->stream));
+      CK(cudaStreamWaitEvent(ctx->streamAux, ctx->evFork, 0));
+    }
+
+    if (hasAlpha)
+    {
+      k_plan_extend<4><<<planGrid, LIMG_PLAN_WARPS * 32, 0, planStream>>>(pl);
       CKL("k_plan_extend");
-      k_plan_centres<<<(blocks + 255) / 256, 256, 0, ctx->stream>>>(pl);
+      k_plan_centres<<<(blocks + 255) / 256, 256, 0, planStream>>>(pl);
       CKL("k_plan_centres");
-      k_plan_sym<3><<<planGrid, 256, 0, ctx->stream>>>(pl);
+      k_plan_sym<4><<<planGrid, LIMG_PLAN_WARPS * 32, 0, planStream>>>(pl);
       CKL("k_plan_sym");
     }
+    else
+    {
+      k_plan_extend<3><<<planGrid, LIMG_PLAN_WARPS * 32, 0, planStream>>>(pl);
+      CKL("k_plan_extend");
+      k_plan_centres<<<(blocks + 255) / 256, 256, 0, planStream>>>(pl);
+      CKL("k_plan_centres");
+      k_plan_sym<3><<<planGrid, LIMG_PLAN_WARPS * 32, 0, planStream>>>(pl);
+      CKL("k_plan_sym");
+    }
+
+    if (async)
+      CK(cudaEventRecord(ctx->evJoin, ctx->streamAux));
 
     if (ctx->timing) CK(cudaEventRecord(ctx->ev[PHASE_SCAN], ctx->stream));
 
@@ -516,6 +556,9 @@ static int launch_merge(limgcu_ctx *ctx, const limgcu_decomp *dTable, size_t W, 
 
       CKL("k_merge_wave");
 
+      if (async && attempt == 0)
+        CK(cudaStreamWaitEvent(ctx->stream, ctx->evJoin, 0)); // everything after the first scan sees the complete bitmaps
+
       if (!sequential)
       {
         for (int stage = 0; stage < 2; stage++)
@@ -536,6 +579,7 @@ static int launch_merge(limgcu_ctx *ctx, const limgcu_decomp *dTable, size_t W, 
     k_merge_collect<<<BY, 128, 0, ctx->stream>>>(w, dAreas, ctx->dCounters + 0);
     CKL("k_merge_collect");
     CK(cudaMemcpyAsync(ctx->dCounters + 24, wFlags, 5 * sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->dCounters + 31, wFlags + 5, sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream));
   }
   else if (ctx->timing)
   {

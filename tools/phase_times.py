@@ -18,7 +18,7 @@ for name in ("c1_512_gradient","c5_1080p_frame0","c2_4k_photo","c4_4k_flatui","c
     ph = c.phase_ms()
     tot = sum(ph.values())
     cnt = c.debug_counters()
-    print("   merged %d areas %d small %d large %d | stage0 exp %d reexp %d polls %d ondemand %d | stage1 exp %d reexp %d polls %d ondemand %d | failed tries / flags %s ext slots %d sym slots %d" % (cnt[0],cnt[1],cnt[2],cnt[3],cnt[8],cnt[9],cnt[10],cnt[11],cnt[12],cnt[13],cnt[14],cnt[15],cnt[24:29],cnt[29],cnt[30]))
+    print("   merged %d areas %d small %d large %d | stage0 exp %d reexp %d polls %d ondemand %d | stage1 exp %d reexp %d polls %d ondemand %d | failed tries / flags %s which 0x%x ext slots %d sym slots %d" % (cnt[0],cnt[1],cnt[2],cnt[3],cnt[8],cnt[9],cnt[10],cnt[11],cnt[12],cnt[13],cnt[14],cnt[15],cnt[24:29],cnt[31],cnt[29],cnt[30]))
     print("   profile kcycles: next %d wait %d expand %d (four-way %d, on-demand %d) claim %d prefetch %d" % tuple(cnt[16:23]))
     dbg = c.debug_wave()
     print("   expansion duration histogram (log2 of cycles/256) stage0 %s stage1 %s" % (dbg[0:16].tolist(), dbg[16:32].tolist()))
