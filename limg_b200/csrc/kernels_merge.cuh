@@ -255,6 +255,7 @@ struct PlanArgs
   uint32_t *extBits;   // per slot: 32 row words, anchored at the seed
   uint32_t *extHdr;    // per slot: known part
   uint32_t *symSlot, *symSeed, *symBits, *symHdr; // the same around centres, anchored at (cx - 8, cy - 8)
+  uint32_t *symStart;  // per block: largest start rectangle (crx | cry << 8) a seed will regrow from this centre with
   uint32_t *counters;  // [0] ext slots, [1] sym slots
   uint32_t extCap, symCap;
   int extMaxW;         // known part of a seed's bitmap: at most this many columns (rows: 32)
@@ -344,6 +345,7 @@ __global__ void __launch_bounds__(256) k_plan_seeds(PlanArgs a)
   expand_unmasked(rows, 8, x, y, a.BX, a.BY, rx, ry);
   a.extSlot[seed] = LIMG_NO_SLOT;
   a.symSlot[seed] = LIMG_NO_SLOT;
+  a.symStart[seed] = 0;
   a.unmasked[seed] = (uint16_t)(rx | (ry << 8));
 
   // a stage-0 candidate whose run along its row or its column reaches the window edge can grow out of the window
@@ -465,6 +467,8 @@ __global__ void __launch_bounds__(256) k_plan_centres(PlanArgs a)
   for (int d = 0; d < 4 && rx / 3 - d >= 1; d++)
   {
     const int c = cy * a.BX + x + rx / 3 - d;
+    // the regrowth starts from an untested rectangle of (rx / 3) x (ry / 3) blocks: remember the largest one asked for
+    atomicMax(&a.symStart[c], (uint32_t)min(rx / 3, 15) | ((uint32_t)min(ry / 3, 15) << 8));
 
     if (atomicCAS(&a.symSlot[c], LIMG_NO_SLOT, LIMG_SLOT_PENDING) == LIMG_NO_SLOT) // first one to ask for this centre
     {
@@ -521,10 +525,12 @@ __global__ void __launch_bounds__(LIMG_PLAN_WARPS * 32) k_plan_sym(PlanArgs a)
     // known box: from the first mismatch left of / above c to the first mismatch right of / below c (inclusive), relative to the anchor
     const uint32_t lowRow = ~rowRun & ((1u << LIMG_SYM_BACK) - 1u), lowCol = ~colRun & ((1u << LIMG_SYM_BACK) - 1u);
     const int vx0 = max(lowRow ? 31 - __clz(lowRow) : 0, LIMG_SYM_BACK - a.symMaxL), vy0 = max(lowCol ? 31 - __clz(lowCol) : 0, LIMG_SYM_BACK - a.symMaxL);
-    // the regrowth starts from a rectangle of up to 3 x 3 blocks whose blocks are not tested (limg.cpp:1428-1431): a mismatch
-    // one or two blocks right of / below c does not stop it
-    const int vx1 = min(run_end(rowRun | (3u << (LIMG_SYM_BACK + 1)), LIMG_SYM_BACK) + 1, LIMG_SYM_BACK + a.symMaxR);
-    const int vy1 = min(run_end(colRun | (3u << (LIMG_SYM_BACK + 1)), LIMG_SYM_BACK) + 1, LIMG_SYM_BACK + a.symMaxD);
+    // the regrowth starts from a rectangle of crx x cry blocks that are not tested (limg.cpp:1428-1431): a mismatch less than crx
+    // blocks right of c / cry blocks below it does not stop the growth
+    const uint32_t start = a.symStart[c];
+    const int crx = max((int)(start & 0xFF), 3), cry = max((int)(start >> 8), 3);
+    const int vx1 = min(run_end(rowRun | (((1u << (crx - 1)) - 1u) << (LIMG_SYM_BACK + 1)), LIMG_SYM_BACK) + 1, LIMG_SYM_BACK + a.symMaxR);
+    const int vy1 = min(run_end(colRun | (((1u << (cry - 1)) - 1u) << (LIMG_SYM_BACK + 1)), LIMG_SYM_BACK) + 1, LIMG_SYM_BACK + a.symMaxD);
     const int bw = vx1 - vx0, bh = vy1 - vy0;
 
     // what is known without further predicates: c's match word (lower-right quadrant), c's row, c's column
@@ -580,163 +586,210 @@ __global__ void __launch_bounds__(LIMG_PLAN_WARPS * 32) k_plan_sym(PlanArgs a)
 }
 
 // ---------------------------------------------------------------------------------------------
-// after the scan: leftovers, geometry, block map, size classes (single CTA, 1024 threads)
+// after the scan: leftovers, geometry, block map, size classes (all grid-wide; the area order is stage 0, stage 1, leftovers in
+// raster order, limg.cpp:1814-1878)
 // ---------------------------------------------------------------------------------------------
 
 struct PrepareArgs
 {
-  int W, H, BX, BY, wordsPerRow;
+  int W, H, BX, BY, wordsPerRow, listCap;
   limgcu_area *areas;
-  const uint32_t *mergedCount;
-  const uint32_t *used;
-  uint32_t *areaCount;
+  const uint32_t *used;      // [BY][wordsPerRow] in-use mask after both merge stages (all zero: every block is its own area)
+  const uint32_t *rowCounts; // [2][BY] rectangles emitted per block row and stage
+  const uint2 *rowLists;     // [2][BY][listCap]
+  const uint32_t *tau;       // [blocks] owner time of merged blocks (nullptr: nothing merged)
+  const uint32_t *emitInfo;  // [2][blocks]
+  uint32_t *rowLeft;         // [BY] leftover blocks per row
+  uint32_t *rowBase;         // [3][BY] index of the first area of the row's stage-0 / stage-1 rectangles / leftovers
+  uint32_t *mergedCount, *areaCount;
   uint32_t *blockToArea;
   AreaWork *work;
   uint32_t *smallList, *largeList;
-  uint32_t *smallCount, *largeCount;
-  int noMerge; // every block is its own area (limg_encode3d_test): mergedCount is ignored
+  uint32_t *smallCount, *largeCount, *scratchTop;
 };
 
-__device__ __forceinline__ uint32_t block_exclusive_scan_1024(uint32_t v, uint32_t *warpSums /* [33] */, uint32_t &total)
+// one warp per block row: number of blocks no rectangle covers
+__global__ void __launch_bounds__(32) k_prepare_rowleft(PrepareArgs a)
 {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  uint32_t incl = v;
+  const int y = blockIdx.x, lane = threadIdx.x;
+  const int nWords = (a.BX + 31) >> 5;
+  uint32_t n = 0;
 
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1)
+  for (int w = lane; w < nWords; w += 32)
   {
-    const uint32_t n = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-    if (lane >= o) incl += n;
+    const int cols = min(32, a.BX - w * 32);
+    const uint32_t valid = cols == 32 ? 0xFFFFFFFFu : ((1u << cols) - 1u);
+    n += __popc(~a.used[(size_t)y * a.wordsPerRow + w] & valid);
   }
 
-  if (lane == 31)
-    warpSums[warp] = incl;
+  n = __reduce_add_sync(0xFFFFFFFFu, n);
 
-  __syncthreads();
-
-  if (warp == 0)
-  {
-    uint32_t s = warpSums[lane];
-    uint32_t si = s;
-
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1)
-    {
-      const uint32_t n = __shfl_up_sync(0xFFFFFFFFu, si, o);
-      if (lane >= o) si += n;
-    }
-
-    warpSums[lane] = si - s;
-
-    if (lane == 31)
-      warpSums[32] = si;
-  }
-
-  __syncthreads();
-  const uint32_t r = warpSums[warp] + incl - v;
-  total = warpSums[32];
-  __syncthreads();
-  return r;
+  if (lane == 0)
+    a.rowLeft[y] = n;
 }
 
-__global__ void __launch_bounds__(1024) k_area_prepare(PrepareArgs a)
+// one CTA per block row: where the row's areas go in the emission order, then the rectangles and leftovers themselves
+__global__ void __launch_bounds__(128) k_prepare_collect(PrepareArgs a)
 {
-  __shared__ uint32_t warpSums[33];
-  __shared__ uint32_t sSmall, sLarge;
-  const int nBlocks = a.BX * a.BY;
-  const uint32_t merged = a.noMerge ? 0u : *a.mergedCount;
+  __shared__ uint32_t sRed[6][4];
+  const int y = blockIdx.x;
+  uint32_t v[6] = { 0, 0, 0, 0, 0, 0 }; // before0, before1, beforeLeft, total0, total1, totalLeft
 
-  if (threadIdx.x == 0)
+  for (int r = threadIdx.x; r < a.BY; r += blockDim.x)
   {
-    sSmall = 0;
-    sLarge = 0;
+    const uint32_t c0 = a.rowCounts[r], c1 = a.rowCounts[a.BY + r], cl = a.rowLeft[r];
+    v[3] += c0; v[4] += c1; v[5] += cl;
+
+    if (r < y)
+    {
+      v[0] += c0; v[1] += c1; v[2] += cl;
+    }
   }
 
-  // 1. leftovers in raster order (limg.cpp:1860-1878)
-  uint32_t carry = merged;
-
-  for (int base = 0; base < nBlocks; base += 1024)
+#pragma unroll
+  for (int i = 0; i < 6; i++)
   {
-    const int b = base + threadIdx.x;
-    uint32_t isLeft = 0;
-    int by = 0, bx = 0;
+    v[i] = __reduce_add_sync(0xFFFFFFFFu, v[i]);
 
-    if (b < nBlocks)
-    {
-      by = b / a.BX;
-      bx = b - by * a.BX;
-      isLeft = a.noMerge ? 1u : (((a.used[(size_t)by * a.wordsPerRow + (bx >> 5)] >> (bx & 31)) & 1u) ^ 1u);
-    }
-
-    uint32_t total;
-    const uint32_t pos = block_exclusive_scan_1024(isLeft, warpSums, total);
-
-    if (isLeft)
-    {
-      limgcu_area *out = &a.areas[carry + pos];
-      out->ox = bx; out->oy = by; out->rx = 1; out->ry = 1;
-      out->stage = 2;
-    }
-
-    carry += total;
-  }
-
-  const uint32_t count = carry;
-
-  if (threadIdx.x == 0)
-    *a.areaCount = count;
-
-  __syncthreads();
-
-  // 2. geometry, block map, size class, scratch offsets
-  uint32_t offCarry = 0;
-
-  for (uint32_t base = 0; base < count; base += 1024)
-  {
-    const uint32_t k = base + threadIdx.x;
-    uint32_t n = 0;
-
-    if (k < count)
-    {
-      limgcu_area *ar = &a.areas[k];
-      const uint32_t ox = ar->ox, oy = ar->oy, rx = ar->rx, ry = ar->ry;
-      uint32_t pw = rx * LIMG_BLOCK, ph = ry * LIMG_BLOCK;
-
-      if (ox + rx == (uint32_t)a.BX && (a.W % LIMG_BLOCK)) pw = pw - LIMG_BLOCK + a.W % LIMG_BLOCK; // limg.cpp:1725-1739
-      if (oy + ry == (uint32_t)a.BY && (a.H % LIMG_BLOCK)) ph = ph - LIMG_BLOCK + a.H % LIMG_BLOCK;
-
-      ar->px_x = ox * LIMG_BLOCK; ar->px_y = oy * LIMG_BLOCK; ar->px_w = pw; ar->px_h = ph;
-      n = pw * ph;
-
-      for (uint32_t yy = oy; yy < oy + ry; yy++)
-        for (uint32_t xx = ox; xx < ox + rx; xx++)
-          a.blockToArea[(size_t)yy * a.BX + xx] = k;
-
-      if (n <= LIMG_SMALL_AREA_PX)
-        a.smallList[atomicAdd(&sSmall, 1u)] = k;
-      else
-        a.largeList[atomicAdd(&sLarge, 1u)] = k;
-    }
-
-    uint32_t total;
-    const uint32_t off = block_exclusive_scan_1024(n, warpSums, total);
-
-    if (k < count)
-    {
-      a.work[k].n = n;
-      a.work[k].scratchOff = offCarry + off;
-    }
-
-    offCarry += total;
+    if ((threadIdx.x & 31) == 0)
+      sRed[i][threadIdx.x >> 5] = v[i];
   }
 
   __syncthreads();
 
-  if (threadIdx.x == 0)
+#pragma unroll
+  for (int i = 0; i < 6; i++)
+    v[i] = sRed[i][0] + sRed[i][1] + sRed[i][2] + sRed[i][3];
+
+  const uint32_t base[3] = { v[0], v[3] + v[1], v[3] + v[4] + v[2] };
+
+  if (threadIdx.x < 3)
+    a.rowBase[threadIdx.x * a.BY + y] = base[threadIdx.x];
+
+  for (int stage = 0; stage < 2; stage++)
   {
-    *a.smallCount = sSmall;
-    *a.largeCount = sLarge;
+    const uint32_t n = a.rowCounts[(size_t)stage * a.BY + y];
+    const uint2 *l = a.rowLists + ((size_t)stage * a.BY + y) * a.listCap;
+
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x)
+    {
+      const uint2 r = l[i];
+      limgcu_area *out = &a.areas[base[stage] + i];
+      out->ox = r.x & 0xFFFF; out->oy = r.x >> 16; out->rx = r.y & 0xFFFF; out->ry = r.y >> 16;
+      out->stage = stage;
+    }
   }
+
+  // leftovers of this row, left to right (warp 0)
+  if (threadIdx.x < 32)
+  {
+    const int nWords = (a.BX + 31) >> 5;
+    uint32_t at = base[2];
+
+    for (int w0 = 0; w0 < nWords; w0 += 32)
+    {
+      const int w = w0 + threadIdx.x;
+      uint32_t free = 0;
+
+      if (w < nWords)
+      {
+        const int cols = min(32, a.BX - w * 32);
+        free = ~a.used[(size_t)y * a.wordsPerRow + w] & (cols == 32 ? 0xFFFFFFFFu : ((1u << cols) - 1u));
+      }
+
+      // exclusive prefix of the word counts over the lanes
+      const uint32_t cnt = __popc(free);
+      uint32_t incl = cnt;
+
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1)
+      {
+        const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+        if ((int)threadIdx.x >= o) incl += t;
+      }
+
+      uint32_t k = at + incl - cnt;
+
+      while (free)
+      {
+        const int b = __ffs(free) - 1;
+        free &= free - 1;
+        limgcu_area *out = &a.areas[k++];
+        out->ox = w * 32 + b; out->oy = y; out->rx = 1; out->ry = 1;
+        out->stage = 2;
+      }
+
+      at += __shfl_sync(0xFFFFFFFFu, incl, 31);
+    }
+  }
+
+  if (y == 0 && threadIdx.x == 0)
+  {
+    *a.mergedCount = v[3] + v[4];
+    *a.areaCount = v[3] + v[4] + v[5];
+  }
+}
+
+// one thread per area: pixel rectangle (edge fit, limg.cpp:1725-1739), size class, scratch
+__global__ void __launch_bounds__(256) k_prepare_geometry(PrepareArgs a)
+{
+  const uint32_t count = *a.areaCount;
+
+  for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < count; k += gridDim.x * blockDim.x)
+  {
+    limgcu_area *ar = &a.areas[k];
+    const uint32_t ox = ar->ox, oy = ar->oy, rx = ar->rx, ry = ar->ry;
+    uint32_t pw = rx * LIMG_BLOCK, ph = ry * LIMG_BLOCK;
+
+    if (ox + rx == (uint32_t)a.BX && (a.W % LIMG_BLOCK)) pw = pw - LIMG_BLOCK + a.W % LIMG_BLOCK;
+    if (oy + ry == (uint32_t)a.BY && (a.H % LIMG_BLOCK)) ph = ph - LIMG_BLOCK + a.H % LIMG_BLOCK;
+
+    ar->px_x = ox * LIMG_BLOCK; ar->px_y = oy * LIMG_BLOCK; ar->px_w = pw; ar->px_h = ph;
+    const uint32_t n = pw * ph;
+    a.work[k].n = n;
+    // area-contiguous scratch: any disjoint ranges do (the areas tile the image, so they fit into one image-sized buffer)
+    a.work[k].scratchOff = n > LIMG_SMALL_AREA_PX ? atomicAdd(a.scratchTop, n) : 0u;
+
+    if (n <= LIMG_SMALL_AREA_PX)
+      a.smallList[atomicAdd(a.smallCount, 1u)] = k;
+    else
+      a.largeList[atomicAdd(a.largeCount, 1u)] = k;
+  }
+}
+
+// one thread per block: which area owns it (from the owner times the scan wrote; leftovers by position)
+__global__ void __launch_bounds__(256) k_prepare_blockmap(PrepareArgs a)
+{
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+
+  if (b >= a.BX * a.BY)
+    return;
+
+  const int y = b / a.BX, x = b - y * a.BX;
+  const uint32_t t = a.tau ? a.tau[b] : 0xFFFFFFFFu;
+  uint32_t k;
+
+  if (t == 0xFFFFFFFFu)
+  {
+    // leftover: blocks of the row that are free and left of this one
+    const uint32_t *row = a.used + (size_t)y * a.wordsPerRow;
+    uint32_t before = 0;
+
+    for (int w = 0; w < (x >> 5); w++)
+      before += __popc(~row[w]);
+
+    before += __popc(~row[x >> 5] & ((1u << (x & 31)) - 1u));
+    k = a.rowBase[2 * a.BY + y] + before;
+  }
+  else
+  {
+    const int stage = t >= 0x40000000u ? 1 : 0;
+    const uint32_t seed = (t & 0x3FFFFFFFu) >> 3, attempt = t & 7u;
+    const uint32_t sy = seed / a.BX;
+    k = a.rowBase[stage * a.BY + sy] + (a.emitInfo[(size_t)stage * a.BX * a.BY + seed] >> 8) + attempt;
+  }
+
+  a.blockToArea[b] = k;
 }
 
 } // namespace limg

@@ -1097,72 +1097,4 @@ __global__ void __launch_bounds__(256) k_merge_reset(WaveArgs a, int attempt)
   }
 }
 
-// emission order = stage 0 rows top to bottom, then stage 1 rows; one CTA per block row
-__global__ void __launch_bounds__(128) k_merge_collect(WaveArgs a, limgcu_area *areas, uint32_t *mergedCount)
-{
-  __shared__ uint32_t sRed[3][4];
-  const int y = blockIdx.x;
-  uint32_t before0 = 0, before1 = 0, total0 = 0;
-
-  for (int r = threadIdx.x; r < a.BY; r += blockDim.x)
-  {
-    const uint32_t c0 = a.rowCounts[r], c1 = a.rowCounts[a.BY + r];
-    total0 += c0;
-
-    if (r < y)
-    {
-      before0 += c0;
-      before1 += c1;
-    }
-  }
-
-  uint32_t total1 = 0;
-
-  for (int r = threadIdx.x; r < a.BY; r += blockDim.x)
-    total1 += a.rowCounts[a.BY + r];
-
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1)
-  {
-    before0 += __shfl_xor_sync(0xFFFFFFFFu, before0, o);
-    before1 += __shfl_xor_sync(0xFFFFFFFFu, before1, o);
-    total0 += __shfl_xor_sync(0xFFFFFFFFu, total0, o);
-    total1 += __shfl_xor_sync(0xFFFFFFFFu, total1, o);
-  }
-
-  __shared__ uint32_t sTot1[4];
-
-  if ((threadIdx.x & 31) == 0)
-  {
-    sRed[0][threadIdx.x >> 5] = before0;
-    sRed[1][threadIdx.x >> 5] = before1;
-    sRed[2][threadIdx.x >> 5] = total0;
-    sTot1[threadIdx.x >> 5] = total1;
-  }
-
-  __syncthreads();
-  before0 = sRed[0][0] + sRed[0][1] + sRed[0][2] + sRed[0][3];
-  before1 = sRed[1][0] + sRed[1][1] + sRed[1][2] + sRed[1][3];
-  total0 = sRed[2][0] + sRed[2][1] + sRed[2][2] + sRed[2][3];
-  total1 = sTot1[0] + sTot1[1] + sTot1[2] + sTot1[3];
-
-  for (int stage = 0; stage < 2; stage++)
-  {
-    const uint32_t n = a.rowCounts[(size_t)stage * a.BY + y];
-    const uint2 *l = a.rowLists + ((size_t)stage * a.BY + y) * a.listCap;
-    const uint32_t base = stage == 0 ? before0 : total0 + before1;
-
-    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x)
-    {
-      const uint2 r = l[i];
-      limgcu_area *out = &areas[base + i];
-      out->ox = r.x & 0xFFFF; out->oy = r.x >> 16; out->rx = r.y & 0xFFFF; out->ry = r.y >> 16;
-      out->stage = stage;
-    }
-  }
-
-  if (y == 0 && threadIdx.x == 0)
-    *mergedCount = total0 + total1;
-}
-
 } // namespace limg

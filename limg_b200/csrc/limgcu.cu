@@ -42,7 +42,7 @@ struct limgcu_ctx
   uint64_t *dDemand = nullptr;
   uint32_t *dUsed = nullptr;
   uint32_t *dExtSlot = nullptr, *dExtSeed = nullptr, *dExtBits = nullptr, *dExtHdr = nullptr, *dPlanCounters = nullptr;
-  uint32_t *dSymSlot = nullptr, *dSymSeed = nullptr, *dSymBits = nullptr, *dSymHdr = nullptr;
+  uint32_t *dSymSlot = nullptr, *dSymSeed = nullptr, *dSymBits = nullptr, *dSymHdr = nullptr, *dSymStart = nullptr;
   uint16_t *dUnmasked = nullptr;
   uint32_t extCap = 0, symCap = 0;
   uint32_t *dScratchPx = nullptr, *dScratchFac = nullptr;
@@ -61,6 +61,8 @@ struct limgcu_ctx
   size_t capWaveRows = 0;
   int waveRowTimes = 0;              // LIMGCU_MERGE_ROWTIMES=1: per-row time stamps of the scan (limgcu_debug_wave_rows)
   uint2 *dRowLists = nullptr;
+  uint32_t *dRowMeta = nullptr; // rowLeft[BY], rowBase[3][BY]
+  size_t capRowMeta = 0;
   size_t capWaveZero = 0, capRowLists = 0;
 
   int mergeExt = 1;                  // LIMGCU_MERGE_EXT=0 disables the speculative match bitmaps (everything beyond the 8x8 window on demand)
@@ -125,6 +127,7 @@ static int ensure_capacity(limgcu_ctx *ctx, size_t W, size_t H)
     CK(regrow(ctx->dExtBits, (size_t)ctx->extCap * 32));
     CK(regrow(ctx->dExtHdr, (size_t)ctx->extCap));
     CK(regrow(ctx->dSymSlot, blocks));
+    CK(regrow(ctx->dSymStart, blocks));
     CK(regrow(ctx->dSymSeed, (size_t)ctx->symCap));
     CK(regrow(ctx->dSymBits, (size_t)ctx->symCap * 32));
     CK(regrow(ctx->dSymHdr, (size_t)ctx->symCap));
@@ -141,6 +144,12 @@ static int ensure_capacity(limgcu_ctx *ctx, size_t W, size_t H)
     {
       CK(regrow(ctx->dWaveZero, waveZero));
       ctx->capWaveZero = waveZero;
+    }
+
+    if (4 * BY > ctx->capRowMeta)
+    {
+      CK(regrow(ctx->dRowMeta, 4 * BY));
+      ctx->capRowMeta = 4 * BY;
     }
 
     if (rowLists > ctx->capRowLists)
@@ -283,8 +292,8 @@ extern "C" void limgcu_destroy(limgcu_ctx *ctx)
 
   void *ptrs[] = { ctx->dLut, ctx->dTable, ctx->dRec, ctx->dWindow, ctx->dAreas, ctx->dBlockToArea, ctx->dWork, ctx->dSmallList, ctx->dLargeList, ctx->dDemand,
                    ctx->dUsed, ctx->dScratchPx, ctx->dScratchFac, ctx->dCounters, ctx->dCompare, ctx->dSrc,
-                   ctx->dExtSlot, ctx->dExtSeed, ctx->dExtBits, ctx->dExtHdr, ctx->dPlanCounters, ctx->dSymSlot, ctx->dSymSeed, ctx->dSymBits, ctx->dSymHdr, ctx->dUnmasked,
-                   ctx->dWaveZero, ctx->dTau, ctx->dCandList, ctx->dRowLists, ctx->dWaveDbg, ctx->dWaveRows };
+                   ctx->dExtSlot, ctx->dExtSeed, ctx->dExtBits, ctx->dExtHdr, ctx->dPlanCounters, ctx->dSymSlot, ctx->dSymSeed, ctx->dSymBits, ctx->dSymHdr, ctx->dSymStart, ctx->dUnmasked,
+                   ctx->dWaveZero, ctx->dTau, ctx->dCandList, ctx->dRowLists, ctx->dWaveDbg, ctx->dWaveRows, ctx->dRowMeta };
 
   for (void *p : ptrs)
     if (p) cudaFree(p);
@@ -434,7 +443,7 @@ static int launch_merge(limgcu_ctx *ctx, const limgcu_decomp *dTable, size_t W, 
     PlanArgs pl;
     pl.rec = ctx->dRec; pl.window = ctx->dWindow; pl.BX = BX; pl.BY = BY; pl.wordsPerRow = wordsPerRow;
     pl.extSlot = ctx->dExtSlot; pl.extSeed = ctx->dExtSeed; pl.extBits = ctx->dExtBits; pl.extHdr = ctx->dExtHdr;
-    pl.symSlot = ctx->dSymSlot; pl.symSeed = ctx->dSymSeed; pl.symBits = ctx->dSymBits; pl.symHdr = ctx->dSymHdr;
+    pl.symSlot = ctx->dSymSlot; pl.symSeed = ctx->dSymSeed; pl.symBits = ctx->dSymBits; pl.symHdr = ctx->dSymHdr; pl.symStart = ctx->dSymStart;
     pl.counters = ctx->dPlanCounters; pl.extCap = ctx->mergeExt ? ctx->extCap : 0; pl.symCap = ctx->mergeExt ? ctx->symCap : 0; pl.unmasked = ctx->dUnmasked;
     pl.candBits = wCandBits; pl.candList = ctx->dCandList; pl.candCount = wCandCount;
     pl.extMaxW = ctx->planExtW; pl.symMaxL = ctx->planSymL; pl.symMaxR = ctx->planSymR; pl.symMaxD = ctx->planSymD;
@@ -576,23 +585,36 @@ static int launch_merge(limgcu_ctx *ctx, const limgcu_decomp *dTable, size_t W, 
       }
     }
 
-    k_merge_collect<<<BY, 128, 0, ctx->stream>>>(w, dAreas, ctx->dCounters + 0);
-    CKL("k_merge_collect");
     CK(cudaMemcpyAsync(ctx->dCounters + 24, wFlags, 5 * sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->dCounters + 31, wFlags + 5, sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream));
   }
-  else if (ctx->timing)
+  else
   {
-    CK(cudaEventRecord(ctx->ev[PHASE_SCAN], ctx->stream));
+    // every block is its own area: nothing in use, nothing emitted
+    const size_t usedWords = (size_t)BY * wordsPerRow;
+    CK(cudaMemsetAsync(ctx->dUsed, 0, usedWords * sizeof(uint32_t), ctx->stream));
+    CK(cudaMemsetAsync(ctx->dWaveZero + 16 + 2 * BY, 0, 2 * (size_t)BY * sizeof(uint32_t), ctx->stream));
+
+    if (ctx->timing) CK(cudaEventRecord(ctx->ev[PHASE_SCAN], ctx->stream));
   }
 
   PrepareArgs p;
-  p.W = (int)W; p.H = (int)H; p.BX = BX; p.BY = BY; p.wordsPerRow = wordsPerRow;
-  p.areas = dAreas; p.mergedCount = ctx->dCounters + 0; p.used = ctx->dUsed; p.areaCount = ctx->dCounters + 1;
+  p.W = (int)W; p.H = (int)H; p.BX = BX; p.BY = BY; p.wordsPerRow = wordsPerRow; p.listCap = 2 * BX;
+  p.areas = dAreas; p.used = ctx->dUsed;
+  p.rowCounts = ctx->dWaveZero + 16 + 2 * BY; p.rowLists = ctx->dRowLists;
+  p.tau = noMerge ? nullptr : ctx->dTau; p.emitInfo = ctx->dWaveZero + 16 + 4 * BY + 2 * (size_t)BY * wordsPerRow;
+  p.rowLeft = ctx->dRowMeta; p.rowBase = ctx->dRowMeta + BY;
+  p.mergedCount = ctx->dCounters + 0; p.areaCount = ctx->dCounters + 1;
   p.blockToArea = dBlockToArea; p.work = ctx->dWork; p.smallList = ctx->dSmallList; p.largeList = ctx->dLargeList;
-  p.smallCount = ctx->dCounters + 2; p.largeCount = ctx->dCounters + 3; p.noMerge = noMerge ? 1 : 0;
-  k_area_prepare<<<1, 1024, 0, ctx->stream>>>(p);
-  CKL("k_area_prepare");
+  p.smallCount = ctx->dCounters + 2; p.largeCount = ctx->dCounters + 3; p.scratchTop = ctx->dCounters + 6;
+  k_prepare_rowleft<<<BY, 32, 0, ctx->stream>>>(p);
+  CKL("k_prepare_rowleft");
+  k_prepare_collect<<<BY, 128, 0, ctx->stream>>>(p);
+  CKL("k_prepare_collect");
+  k_prepare_geometry<<<ctx->smCount * 4, 256, 0, ctx->stream>>>(p);
+  CKL("k_prepare_geometry");
+  k_prepare_blockmap<<<(blocks + 255) / 256, 256, 0, ctx->stream>>>(p);
+  CKL("k_prepare_blockmap");
   return LIMGCU_SUCCESS;
 }
 
