@@ -253,6 +253,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         for k, v in codec.phase_ms().items():
             phase_acc[k] = phase_acc.get(k, 0.0) + v / reps
     codec.enable_phase_timing(False)
+    counters = codec.debug_counters()
 
     # ---- end to end through the host-buffer C ABI, pinned host memory ----------------------------------------------
     h_src = torch.from_numpy(frame.view(np.int32)).pin_memory()
@@ -315,7 +316,10 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             "roofline": {"bound": "hbm", "achieved": enc_gbs, "peak": peak, "unit": "GB/s", "frac": enc_gbs / peak, "traffic": None,
                          "kernel": "encode path (all kernels of limgcu_blocked_encode3d), 7 algorithmic B/px", "peak_source": peak_src,
                          "dominant_kernel": dominant, "dominant_share": phase_acc[dominant] / max(sum(phase_acc.values()), 1e-9),
-                         "phase_ms": {k: round(v, 4) for k, v in phase_acc.items()}},
+                         "phase_ms": {k: round(v, 4) for k, v in phase_acc.items()},
+                         "note": "merge_scan = the row-pipelined greedy area scan (latency bound, not HBM bound); predicate_windows = the main-stream part of the "
+                                 "predicate precompute (the speculative match bitmaps run on a second stream concurrently with the scan)"},
+            "merge": {"failed_first_tries": int(counters[24]), "areas": int(counters[1]), "merged_rectangles": int(counters[0])},
             "roofline_decode": {"bound": "hbm", "achieved": dec_gbs, "peak": peak, "unit": "GB/s", "frac": dec_gbs / peak, "traffic": None,
                                 "kernel": "k_decode, 7 algorithmic B/px"},
         }

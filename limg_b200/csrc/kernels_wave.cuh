@@ -1000,6 +1000,27 @@ __global__ void __launch_bounds__(256) k_merge_verify(WaveArgs a, int stage, int
 
       if (scan.mask.is_used(x, y)) { ok = e == have; break; }
 
+      // the same necessary conditions wave_next_candidate() uses, before anything expensive: stage 0 needs its whole 3 x 3 corner
+      // free (the candidate bit says it is inside the grid), stage 1 the right or the lower neighbour
+      {
+        bool busy = false;
+
+        if (stage == 0)
+        {
+          if (lane < 9)
+            busy = scan.mask.is_used(x + lane % 3, y + lane / 3);
+
+          busy = __any_sync(0xFFFFFFFFu, busy);
+        }
+        else
+        {
+          const bool rightFree = x + 1 < a.BX && !scan.mask.is_used(x + 1, y), downFree = y + 1 < a.BY && !scan.mask.is_used(x, y + 1);
+          busy = !rightFree && !downFree;
+        }
+
+        if (busy) { ok = e == have; break; }
+      }
+
       if (!havePre) { pre = scan.prefetch(x, y, stage); havePre = true; }
 
       const Snapshot sn = scan.snapshot(x, y);
