@@ -241,3 +241,63 @@ def test_compare_matches_oracle(codec, lo):
     for alpha in (False, True):
         got, want = codec.compare(a, b, alpha), lo.compare(a, b, alpha)
         assert abs(got[0] - want[0]) < 1e-12 and abs(got[1] - want[1]) < 1e-6 and got[2] == want[2]
+
+
+# ---- (d) the merge scan: pipelined rows + verification vs the sequential order ------------------------------------------
+
+@pytest.mark.parametrize("cfg", ["c2_4k_photo", "c4_4k_flatui"])
+def test_full_size_area_map_vs_oracle(codec, lo, cfg):
+    """BASELINE.json's 4K configs: the whole area map (rectangles, stages, emission order) equals the C oracle's greedy scan."""
+    img, alpha = synth.CONFIGS[cfg]()
+    h, w = img.shape
+    table = codec.pass1(img, alpha)
+    areas = codec.merge(table, w, h, alpha)
+    want, _ = lo.merge(table, (w + 7) // 8, (h + 7) // 8, alpha)
+    assert len(areas) == len(want)
+    for k in ("ox", "oy", "rx", "ry", "stage"):
+        assert np.array_equal(areas[k], want[k]), k
+
+
+def _codec_with_env(monkeypatch, **env):
+    from limg_b200 import Codec
+    for k, v in env.items():
+        monkeypatch.setenv(k, str(v))
+    return Codec(0)  # the tunables are read when the context is created
+
+
+@pytest.mark.parametrize("cfg", ["c5_1080p_frame0", "c3_8k_rgba"])
+def test_merge_pipelined_equals_sequential(codec, monkeypatch, cfg):
+    """Rows strictly in sequence (the reference's order by construction) and the pipelined scan give the same area table."""
+    img, alpha = synth.CONFIGS[cfg]()
+    h, w = img.shape
+    table = codec.pass1(img, alpha)
+    seq = _codec_with_env(monkeypatch, LIMGCU_MERGE_MODE="seq")
+    try:
+        a = codec.merge(table, w, h, alpha)
+        b = seq.merge(table, w, h, alpha)
+        assert seq.debug_counters()[24] == 2  # went straight to the sequential pass
+    finally:
+        seq.close()
+    assert a.tobytes() == b.tobytes()
+
+
+@pytest.mark.parametrize("name", ["frame_1080p", "flatui_1080p", "odd_rgba_301x203"])
+def test_failed_speculation_is_repaired(monkeypatch, lo, name):
+    """With no safety margin at all the pipelined scan mis-speculates; the verification pass must notice and the retry must
+    deliver the exact result anyway."""
+    factory, alpha = SEEDED[name]
+    img = factory()
+    h, w = img.shape
+    c = _codec_with_env(monkeypatch, LIMGCU_MERGE_MARGIN=0, LIMGCU_MERGE_GAP=0, LIMGCU_MERGE_SPEC=64)
+    try:
+        table = c.pass1(img, alpha)
+        tries = []
+        for _ in range(3):
+            areas = c.merge(table, w, h, alpha)
+            tries.append(int(c.debug_counters()[24]))
+            want, _ = lo.merge(table, (w + 7) // 8, (h + 7) // 8, alpha)
+            for k in ("ox", "oy", "rx", "ry", "stage"):
+                assert np.array_equal(areas[k], want[k]), (k, tries)
+        print(name, "failed first tries per run:", tries)
+    finally:
+        c.close()
