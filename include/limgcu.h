@@ -115,8 +115,13 @@ float limgcu_phase_ms(limgcu_ctx *ctx, int phase);
 int limgcu_debug_counters(limgcu_ctx *ctx, uint32_t *out32);
 /* detailed counters of the last merge scan (kernels_wave.cuh, WaveArgs::dbg): 256 words */
 int limgcu_debug_wave(limgcu_ctx *ctx, uint32_t *out256);
+/* self check of the merge predicate's guard-banded shortcut (kernels_merge.cuh, predicate_shortcut) against the reference-order
+ * evaluation on a pass-1 table (host memory): out4 = { pairs that needed the 27-sample score, pairs the shortcut decided,
+ * disagreements (must be 0), reserved } */
+int limgcu_debug_predicate_check(limgcu_ctx *ctx, const limgcu_decomp *table, size_t sizeX, size_t sizeY, int hasAlpha, uint64_t *out4);
 /* per block row of the last merge scan, both stages: [2][blockY][4] time stamps in ns (ticket, first decision, last decision, done);
- * recorded only when LIMGCU_MERGE_ROWTIMES=1 is set at limgcu_create time */
+ * followed by 512 words of per-decision events of four rows; recorded only when LIMGCU_MERGE_ROWTIMES is set at limgcu_create
+ * time (1: row stamps, n > 1: also the decisions of stage-0 rows n .. n+3). `out` needs 8 * blockY + 512 words. */
 int limgcu_debug_wave_rows(limgcu_ctx *ctx, uint32_t *out, size_t blockY);
 
 /* device-buffer entry points ------------------------------------------------------------------------------------ */

@@ -40,7 +40,7 @@ FLAG_NO_MERGE = 2
 SYMBOLS = (
     "limgcu_create", "limgcu_destroy", "limgcu_last_error", "limgcu_device_count", "limgcu_set_rsqrt_lut",
     "limgcu_stream_handle", "limgcu_sync", "limgcu_launch_count", "limgcu_enable_phase_timing", "limgcu_phase_ms",
-    "limgcu_debug_counters", "limgcu_debug_wave", "limgcu_debug_wave_rows", "limgcu_pass1", "limgcu_merge", "limgcu_blocked_encode3d", "limgcu_decode", "limgcu_build_block_map", "limgcu_compare",
+    "limgcu_debug_counters", "limgcu_debug_wave", "limgcu_debug_predicate_check", "limgcu_debug_wave_rows", "limgcu_pass1", "limgcu_merge", "limgcu_blocked_encode3d", "limgcu_decode", "limgcu_build_block_map", "limgcu_compare",
     "limgcu_host_blocked_encode3d", "limgcu_host_encode3d", "limgcu_host_encode_stream", "limgcu_host_decode",
     "limgcu_host_pass1", "limgcu_host_merge", "limgcu_host_compare",
 )
@@ -88,6 +88,7 @@ def load():
     lib.limgcu_phase_ms.restype = C.c_float
     lib.limgcu_debug_counters.argtypes = [vp, vp]
     lib.limgcu_debug_wave.argtypes = [vp, vp]
+    lib.limgcu_debug_predicate_check.argtypes = [vp, vp, sz, sz, i32, vp]
     lib.limgcu_debug_wave_rows.argtypes = [vp, vp, C.c_size_t]
     lib.limgcu_pass1.argtypes = [vp, vp, sz, sz, i32, vp]
     lib.limgcu_merge.argtypes = [vp, vp, sz, sz, i32, vp, vp, vp]

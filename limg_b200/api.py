@@ -77,10 +77,18 @@ class Codec:
         self._ck(self.lib.limgcu_debug_wave(self.h, _vp(out)), "limgcu_debug_wave")
         return out
 
-    def debug_wave_rows(self, block_y: int) -> np.ndarray:
-        out = np.zeros((2, block_y, 4), np.uint32)
-        self._ck(self.lib.limgcu_debug_wave_rows(self.h, _vp(out), block_y), "limgcu_debug_wave_rows")
+    def predicate_check(self, table, w: int, h: int, has_alpha: bool) -> np.ndarray:
+        """(scored pairs, decided by the shortcut, disagreements, reserved) -- see limgcu_debug_predicate_check."""
+        table = np.ascontiguousarray(table, dtype=DECOMP_DTYPE)
+        out = np.zeros(4, np.uint64)
+        self._ck(self.lib.limgcu_debug_predicate_check(self.h, _vp(table), w, h, int(has_alpha), _vp(out)), "limgcu_debug_predicate_check")
         return out
+
+    def debug_wave_rows(self, block_y: int) -> np.ndarray:
+        out = np.zeros(block_y * 8 + 512, np.uint32)
+        self._ck(self.lib.limgcu_debug_wave_rows(self.h, _vp(out), block_y), "limgcu_debug_wave_rows")
+        self.wave_events = out[block_y * 8:].reshape(4, 64, 2)
+        return out[: block_y * 8].reshape(2, block_y, 4)
 
     # ---- host-buffer operators (reference argument meaning) -------------------------------------------------
 

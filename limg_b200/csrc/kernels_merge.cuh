@@ -163,15 +163,10 @@ __device__ __forceinline__ float sample_term(const PredRec &a, const PredRec &b,
   return factor_term<CH>(color, a, a.invLen);
 }
 
-// one thread evaluates the whole predicate (limg.cpp:1137-1269). a = seed, b = candidate.
+// the 27-sample score of limg.cpp:1214-1267, every operation in the reference's order
 template <int CH>
-__device__ bool predicate_thread(const PredRec &a, const PredRec &b)
+__device__ __forceinline__ float predicate_score(const PredRec &a, const PredRec &b)
 {
-  const int q = predicate_quick<CH>(a, b);
-
-  if (q >= 0)
-    return q != 0;
-
   // Q1: the second term of every iteration projects avg(a) into b: loop invariant, but part of the ordered sum.
   const float constTerm = factor_term<CH>(a.avg, b, b.invLen);
   float sum = 0.0f;
@@ -182,7 +177,161 @@ __device__ bool predicate_thread(const PredRec &a, const PredRec &b)
     sum = fadd(sum, constTerm);
   }
 
-  return fmul(sum, 1.f / (3 * 3 * 3)) < 3.0f;
+  return fmul(sum, 1.f / (3 * 3 * 3));
+}
+
+// The three factors are an affine function of the colour (limg_factorization.h:9-41 without its roundings): f(c) = g + M c.
+// `lin` evaluates the linear part only (no offsets). Contracted arithmetic is fine here: this feeds the guard-banded shortcut below.
+template <int CH>
+__device__ __forceinline__ void factors_affine(const float c[4], const PredRec &s, bool lin, float f[3])
+{
+  float t[4], est[4];
+  float dA = 0.0f, dB = 0.0f, dC = 0.0f;
+
+#pragma unroll
+  for (int i = 0; i < CH; i++)
+  {
+    t[i] = lin ? c[i] : c[i] - s.minA[i];
+    dA = fmaf(t[i], s.nA[i], dA);
+  }
+
+  f[0] = dA * s.inv[0];
+
+#pragma unroll
+  for (int i = 0; i < CH; i++)
+  {
+    est[i] = fmaf(f[0], s.nA[i], lin ? 0.0f : s.minA[i]);
+    t[i] = (c[i] - est[i]) - (lin ? 0.0f : s.offB[i]);
+    dB = fmaf(t[i], s.nB[i], dB);
+  }
+
+  f[1] = dB * s.inv[1];
+
+#pragma unroll
+  for (int i = 0; i < CH; i++)
+  {
+    est[i] = fmaf(f[1], s.nB[i], est[i]);
+    t[i] = (c[i] - est[i]) - (lin ? 0.0f : s.offC[i]);
+    dC = fmaf(t[i], s.nC[i], dC);
+  }
+
+  f[2] = dC * s.inv[2];
+}
+
+// Guard-banded shortcut for the 27-sample score. The sample colours are b.nA x/2 + b.nB y/2 + b.nC z/2, so the factors at the 27
+// samples are g + x u + y v + z w with four evaluations of the affine map instead of 27: the same real-valued score with ~4x fewer
+// operations and different rounding. The decision is taken from it only when the score is further from the threshold than a
+// guard that is ~500 units in the last place of the largest intermediate magnitude (the two evaluations differ by a few); inside
+// the guard the reference-order evaluation decides, so the predicate is still the reference's bit for bit.
+// returns 1 / 0, or -1 when the exact evaluation has to decide
+template <int CH>
+__device__ __forceinline__ int predicate_shortcut(const PredRec &a, const PredRec &b)
+{
+  float zero[4] = { 0, 0, 0, 0 }, cA[4], cB[4], cC[4], g[3], u[3], v[3], w[3];
+
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+  {
+    cA[i] = b.nA[i] * 0.5f;
+    cB[i] = b.nB[i] * 0.5f;
+    cC[i] = b.nC[i] * 0.5f;
+  }
+
+  factors_affine<CH>(zero, a, false, g);
+  factors_affine<CH>(cA, a, true, u);
+  factors_affine<CH>(cB, a, true, v);
+  factors_affine<CH>(cC, a, true, w);
+  const float il0 = a.invLen[0], il1 = a.invLen[1], il2 = a.invLen[2];
+  float sum = 0.0f;
+
+#pragma unroll
+  for (int z = 0; z < 3; z++)
+  {
+#pragma unroll
+    for (int y = 0; y < 3; y++)
+    {
+      const float b0 = fmaf((float)z, w[0], fmaf((float)y, v[0], g[0]));
+      const float b1 = 0.5f - fmaf((float)z, w[1], fmaf((float)y, v[1], g[1]));
+      const float b2 = 0.5f - fmaf((float)z, w[2], fmaf((float)y, v[2], g[2]));
+
+#pragma unroll
+      for (int x = 0; x < 3; x++)
+        sum += fabsf(fmaf((float)x, u[0], b0)) * il0 + fabsf(fmaf(-(float)x, u[1], b1)) * il1 + fabsf(fmaf(-(float)x, u[2], b2)) * il2;
+    }
+  }
+
+  const float constTerm = factor_term<CH>(a.avg, b, b.invLen);
+  const float mean = fmaf(sum, 1.f / 27.f, constTerm);
+  // magnitude the roundings scale with: the largest intermediate of every term (not the possibly cancelled result)
+  const float mag = il0 * (fabsf(g[0]) + 2.0f * (fabsf(u[0]) + fabsf(v[0]) + fabsf(w[0]))) + il1 * (0.5f + fabsf(g[1]) + 2.0f * (fabsf(u[1]) + fabsf(v[1]) + fabsf(w[1]))) +
+                    il2 * (0.5f + fabsf(g[2]) + 2.0f * (fabsf(u[2]) + fabsf(v[2]) + fabsf(w[2]))) + fabsf(constTerm);
+  const float guard = fmaf(3e-5f, mag, 1e-3f);
+
+  if (!(guard < 0.5f)) // also catches NaN / Inf
+    return -1;
+
+  if (mean < 3.0f - guard)
+    return 1;
+
+  if (mean > 3.0f + guard)
+    return 0;
+
+  return -1;
+}
+
+// one thread evaluates the whole predicate (limg.cpp:1137-1269). a = seed, b = candidate.
+template <int CH>
+__device__ bool predicate_thread(const PredRec &a, const PredRec &b)
+{
+  const int q = predicate_quick<CH>(a, b);
+
+  if (q >= 0)
+    return q != 0;
+
+#ifndef LIMG_EXACT_PREDICATE_ONLY
+  const int s = predicate_shortcut<CH>(a, b);
+
+  if (s >= 0)
+    return s != 0;
+#endif
+
+  return predicate_score<CH>(a, b) < 3.0f;
+}
+
+// check mode (limgcu_debug_predicate_check): the reference-order evaluation and the shortcut side by side
+template <int CH>
+__global__ void __launch_bounds__(256) k_pred_check(const PredRec *__restrict__ rec, int BX, int BY, unsigned long long *__restrict__ out /* [4]: scored pairs, shortcut decided, disagreements, max |gap| in 1e-9 */)
+{
+  const int pair = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int seed = pair >> 1, half = pair & 1;
+
+  if (seed >= BX * BY)
+    return;
+
+  const int o = half * 32 + (threadIdx.x & 31);
+  const int dx = (o & 7) * 2 - 7, dy = (o >> 3) * 2 - 7; // a 15 x 15 neighbourhood sampled every other block, both directions
+  const int sy = seed / BX, sx = seed - sy * BX;
+  const int cx = sx + dx, cy = sy + dy;
+
+  if (cx < 0 || cy < 0 || cx >= BX || cy >= BY)
+    return;
+
+  const PredRec a = rec[seed], b = rec[(size_t)cy * BX + cx];
+
+  if (predicate_quick<CH>(a, b) >= 0)
+    return;
+
+  const float exact = predicate_score<CH>(a, b);
+  const int s = predicate_shortcut<CH>(a, b);
+  atomicAdd(&out[0], 1ull);
+
+  if (s >= 0)
+  {
+    atomicAdd(&out[1], 1ull);
+
+    if ((s != 0) != (exact < 3.0f))
+      atomicAdd(&out[2], 1ull);
+  }
 }
 
 // one warp evaluates one predicate: lane k < 27 computes sample k, the ordered sum is replayed by every lane.

@@ -53,6 +53,7 @@ struct WaveArgs
   uint32_t *flags;           // [0] number of failed tries, [1], [2] a stage failed the verification of the current try, [3] watchdog (hard error), [4] list overflow (hard error)
   uint32_t *stats;           // [16] optional counters
   uint32_t *dbg;             // [256] detailed counters (see tools/phase_times.py)
+  int eventRow;              // diagnostics: decisions of stage-0 rows eventRow .. eventRow + 3 go to dbgRows + 8 * BY as [4][64](x | kind << 16 | waited << 20, ns)
   uint32_t *dbgRows;         // [2][BY][4] optional per-row time stamps (globaltimer ns, low 32 bits): ticket, first decision, last decision, done
   int listCap, margin;
   int stageGap;              // block rows stage 1 stays behind stage 0
@@ -715,7 +716,7 @@ __global__ void __launch_bounds__(LIMG_WAVE_WARPS * 32) k_merge_wave(WaveArgs a,
     const uint32_t *usedRow = a.used + (size_t)y * a.wordsPerRow;
     uint2 *list = lists + (size_t)y * a.listCap;
     uint32_t count = 0;
-    int x = 0, published = 0;
+    int x = 0, published = 0, nEvents = 0, xEvent = 0;
     int pAbove = (y == 0 || sequential) ? LIMG_WAVE_DONE : 0; // last observed minimum over the rows above
 
     // a row never claims to be further than the rows above it: the published values fall monotonically from row to row, so
@@ -750,6 +751,7 @@ __global__ void __launch_bounds__(LIMG_WAVE_WARPS * 32) k_merge_wave(WaveArgs a,
       const uint32_t first = count;
       int nextX = x + 1;
       bool claimed = false;
+      xEvent = x;
 
       for (int k = 0;; k++)
       {
@@ -809,7 +811,18 @@ __global__ void __launch_bounds__(LIMG_WAVE_WARPS * 32) k_merge_wave(WaveArgs a,
           }
 
           if (p >= min(r.boxR + a.margin, a.BX))
+          {
+            if (a.dbg && lane == 0 && stage == 0)
+            {
+              // diagnostics: how far ahead the rows above are when the seed's decision stands, how wide its probe box was, and
+              // whether it had to wait at all
+              atomicAdd(&a.dbg[128 + min(31, (min(p, a.BX) - x) >> 2)], 1u);
+              atomicAdd(&a.dbg[160 + min(31, (r.boxR - x) >> 1)], 1u);
+              atomicAdd(&a.dbg[192 + (spins == 0 ? 0 : 1)], 1u);
+            }
+
             break;
+          }
 
           if (spins > LIMG_WAVE_SPIN_LIMIT) { a.flags[3] = 1; break; }
 
@@ -886,6 +899,14 @@ __global__ void __launch_bounds__(LIMG_WAVE_WARPS * 32) k_merge_wave(WaveArgs a,
         const uint32_t t = global_ns();
         if (rowT[1] == 0) rowT[1] = t;
         rowT[2] = t;
+
+        if (stage == 0 && y >= a.eventRow && y < a.eventRow + 4 && nEvents < 64)
+        {
+          uint32_t *ev = a.dbgRows + (size_t)8 * a.BY + ((size_t)(y - a.eventRow) * 64 + nEvents) * 2;
+          ev[0] = (uint32_t)xEvent | ((uint32_t)(claimed ? 1 : 0) << 16);
+          ev[1] = t;
+          nEvents++;
+        }
       }
 
       // hand over to the rows below before looking for the next candidate

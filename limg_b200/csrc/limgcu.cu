@@ -342,10 +342,10 @@ extern "C" int limgcu_debug_wave_rows(limgcu_ctx *ctx, uint32_t *out, size_t blo
 {
   NEED(ctx); NEED(out);
 
-  if (ctx->dWaveRows == nullptr || blockY * 8 > ctx->capWaveRows)
+  if (ctx->dWaveRows == nullptr || blockY * 8 + 512 > ctx->capWaveRows)
     return fail(ctx, LIMGCU_ERROR_INVALID_PARAMETER, "no row time stamps were recorded (LIMGCU_MERGE_ROWTIMES=1)", cudaSuccess);
 
-  CK(cudaMemcpyAsync(out, ctx->dWaveRows, blockY * 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(out, ctx->dWaveRows, (blockY * 8 + 512) * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   return LIMGCU_SUCCESS;
 }
@@ -515,16 +515,17 @@ static int launch_merge(limgcu_ctx *ctx, const limgcu_decomp *dTable, size_t W, 
     w.listCap = 2 * BX; w.margin = ctx->mergeMargin; w.stageGap = ctx->mergeGap; w.specAhead = ctx->mergeSpec; w.dbg = ctx->dWaveDbg;
     CK(cudaMemsetAsync(ctx->dWaveDbg, 0, 256 * sizeof(uint32_t), ctx->stream));
     w.dbgRows = nullptr;
+    w.eventRow = ctx->waveRowTimes > 1 ? ctx->waveRowTimes : 0;
 
     if (ctx->waveRowTimes)
     {
-      if ((size_t)BY * 8 > ctx->capWaveRows)
+      if ((size_t)BY * 8 + 512 > ctx->capWaveRows)
       {
-        CK(regrow(ctx->dWaveRows, (size_t)BY * 8));
-        ctx->capWaveRows = (size_t)BY * 8;
+        CK(regrow(ctx->dWaveRows, (size_t)BY * 8 + 512));
+        ctx->capWaveRows = (size_t)BY * 8 + 512;
       }
 
-      CK(cudaMemsetAsync(ctx->dWaveRows, 0, (size_t)BY * 8 * sizeof(uint32_t), ctx->stream));
+      CK(cudaMemsetAsync(ctx->dWaveRows, 0, ((size_t)BY * 8 + 512) * sizeof(uint32_t), ctx->stream));
       w.dbgRows = ctx->dWaveRows;
     }
 
@@ -991,6 +992,39 @@ extern "C" int limgcu_host_merge(limgcu_ctx *ctx, const limgcu_decomp *table, si
   CK(cudaMemcpyAsync(areas, ctx->dAreas, (size_t)count * sizeof(limgcu_area), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   *area_count = count;
+  return LIMGCU_SUCCESS;
+}
+
+extern "C" int limgcu_debug_predicate_check(limgcu_ctx *ctx, const limgcu_decomp *table, size_t sizeX, size_t sizeY, int hasAlpha, uint64_t *out4)
+{
+  NEED(ctx); NEED(table); NEED(out4);
+  int rc = check_image(ctx, sizeX, sizeY);
+  if (rc) return rc;
+  CK(cudaSetDevice(ctx->device));
+  rc = ensure_capacity(ctx, sizeX, sizeY);
+  if (rc) return rc;
+  const int BX = (int)((sizeX + 7) / 8), BY = (int)((sizeY + 7) / 8), blocks = BX * BY;
+  unsigned long long *dOut = nullptr;
+  CK(cudaMalloc(&dOut, 4 * sizeof(unsigned long long)));
+  CK(cudaMemsetAsync(dOut, 0, 4 * sizeof(unsigned long long), ctx->stream));
+  CK(cudaMemcpyAsync(ctx->dTable, table, (size_t)blocks * sizeof(limgcu_decomp), cudaMemcpyHostToDevice, ctx->stream));
+
+  if (hasAlpha)
+  {
+    k_pred_records<4><<<(blocks + 255) / 256, 256, 0, ctx->stream>>>(ctx->dTable, blocks, ctx->dRec);
+    k_pred_check<4><<<(blocks * 2 + 7) / 8, 256, 0, ctx->stream>>>(ctx->dRec, BX, BY, dOut);
+  }
+  else
+  {
+    k_pred_records<3><<<(blocks + 255) / 256, 256, 0, ctx->stream>>>(ctx->dTable, blocks, ctx->dRec);
+    k_pred_check<3><<<(blocks * 2 + 7) / 8, 256, 0, ctx->stream>>>(ctx->dRec, BX, BY, dOut);
+  }
+
+  CKL("k_pred_check");
+  cudaError_t e = cudaMemcpyAsync(out4, dOut, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  cudaFree(dOut);
+  if (e != cudaSuccess) return fail(ctx, LIMGCU_ERROR_CUDA, "limgcu_debug_predicate_check", e);
   return LIMGCU_SUCCESS;
 }
 

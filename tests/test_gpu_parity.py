@@ -278,7 +278,9 @@ def test_merge_pipelined_equals_sequential(codec, monkeypatch, cfg):
         assert seq.debug_counters()[24] == 2  # went straight to the sequential pass
     finally:
         seq.close()
-    assert a.tobytes() == b.tobytes()
+    assert len(a) == len(b)
+    for k in ("ox", "oy", "rx", "ry", "stage", "px_x", "px_y", "px_w", "px_h"):  # limgcu_merge fills nothing else
+        assert np.array_equal(a[k], b[k]), k
 
 
 @pytest.mark.parametrize("name", ["frame_1080p", "flatui_1080p", "odd_rgba_301x203"])
@@ -301,3 +303,32 @@ def test_failed_speculation_is_repaired(monkeypatch, lo, name):
         print(name, "failed first tries per run:", tries)
     finally:
         c.close()
+
+
+@pytest.mark.parametrize("cfg", ["c1_512_gradient", "c5_1080p_frame0", "c2_4k_photo", "c4_4k_flatui", "c3_8k_rgba"])
+def test_predicate_shortcut_never_disagrees(codec, cfg):
+    """The guard-banded shortcut of the merge predicate decides only where the reference-order 27-sample score decides the same."""
+    img, alpha = synth.CONFIGS[cfg]()
+    h, w = img.shape
+    scored, decided, wrong, _ = [int(v) for v in codec.predicate_check(codec.pass1(img, alpha), w, h, alpha)]
+    print(cfg, "pairs scored", scored, "decided by the shortcut %.3f %%" % (100.0 * decided / max(scored, 1)), "disagreements", wrong)
+    assert wrong == 0
+    assert scored == 0 or decided > 0.9 * scored
+
+
+def test_predicate_shortcut_on_adversarial_records(codec):
+    """Random decompositions (endpoints all over the int16 range the fit can produce, tiny and huge normals)."""
+    from limg_b200 import DECOMP_DTYPE
+    rng = np.random.default_rng(11)
+    w, h = 1024, 1024
+    t = np.zeros((h // 8) * (w // 8), dtype=DECOMP_DTYPE)
+    n = t.size
+    t["avg"][:, :3] = rng.uniform(0, 255, (n, 3)).astype(np.float32)
+    scale = rng.choice([1, 2, 6, 20, 80, 255], (n, 1))
+    for lo_name, hi_name in (("dirA_min", "dirA_max"), ("dirB_offset", "dirB_mag"), ("dirC_offset", "dirC_mag")):
+        lo_v = rng.integers(-255, 256, (n, 3))
+        t[lo_name][:, :3] = lo_v
+        t[hi_name][:, :3] = lo_v + rng.integers(-1, 2, (n, 3)) * rng.integers(0, scale + 1, (n, 3))
+    scored, decided, wrong, _ = [int(v) for v in codec.predicate_check(t, w, h, False)]
+    print("adversarial: pairs scored", scored, "decided", decided, "disagreements", wrong)
+    assert scored > 10000 and wrong == 0

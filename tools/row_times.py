@@ -1,6 +1,7 @@
 """Per-row time stamps of the merge scan (LIMGCU_MERGE_ROWTIMES=1): prints the wavefront's slope and where rows spend time."""
 import os, sys
-os.environ["LIMGCU_MERGE_ROWTIMES"] = "1"
+os.environ["LIMGCU_MERGE_ROWTIMES"] = os.environ.get("ROW", "120")
+os.environ.setdefault("LIMGCU_PLAN_ASYNC", "0")
 sys.path.insert(0, ".")
 import numpy as np, torch
 from limg_b200 import Codec, synth
@@ -28,3 +29,11 @@ for st in range(2):
         print("   row %4d: ticket %8.1f first %8.1f last %8.1f done %8.1f  (row busy %.1f us)" % (y, r[y, 0], first[y], last[y], done[y], last[y] - first[y]))
     if len(ys) > 2:
         print("   slope of 'last decision' vs row: %.2f us/row ; mean row busy time %.1f us" % (np.polyfit(ys, last[ys], 1)[0], (last[ys] - first[ys]).mean()))
+
+ev = c.wave_events.astype(np.int64)
+t0 = t[0][:, 0].min()
+print("decisions of four consecutive stage-0 rows (column, time us, c = claimed):")
+for r in range(4):
+    e = ev[r]
+    n = int((e[:, 1] != 0).sum())
+    print("  row +%d: " % r + " ".join("%d%s@%.0f" % (e[i, 0] & 0xFFFF, "c" if (e[i, 0] >> 16) & 1 else "", (e[i, 1] - t0) / 1e3) for i in range(n)))
