@@ -74,6 +74,16 @@ __device__ __forceinline__ int ld_acquire_s32(const int *p)
   return v;
 }
 
+// Polling uses relaxed (strong, L2-coherent) loads: an acquire load costs an L1 invalidation (CCTL.IVALL) plus a fence on every
+// poll. Everything read after a satisfied poll is itself a relaxed gpu-scope load issued behind the branch on the polled value,
+// and the producer fences between its claims and its progress store.
+__device__ __forceinline__ int ld_relaxed_s32(const int *p)
+{
+  int v;
+  asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
 __device__ __forceinline__ void st_relaxed_s32(int *p, int v)
 {
   asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
@@ -770,7 +780,7 @@ __global__ void __launch_bounds__(LIMG_WAVE_WARPS * 32) k_merge_wave(WaveArgs a,
           if (y > 0 && !sequential)
           {
             const int row = y - 1 - lane;
-            p = __reduce_min_sync(0xFFFFFFFFu, row >= 0 ? ld_acquire_s32(progress + row) : LIMG_WAVE_DONE);
+            p = __reduce_min_sync(0xFFFFFFFFu, row >= 0 ? ld_relaxed_s32(progress + row) : LIMG_WAVE_DONE);
             pAbove = p;
             publish(x);
           }
@@ -858,6 +868,15 @@ __global__ void __launch_bounds__(LIMG_WAVE_WARPS * 32) k_merge_wave(WaveArgs a,
           }
         }
 
+        // the claim is visible to this warp's next look at the mask and to everybody who later reads the progress store
+        __threadfence();
+        __syncwarp();
+
+        // hand over to the rows below as early as possible: a right/down rectangle decides every seed up to its right edge
+        if (r.kind == 1 && x + r.rx < a.BX)
+          publish(x + r.rx);
+
+        // bookkeeping nobody waits for (read after the kernel): owner times, the row's list
         for (int e = lane; e < erx * ery; e += 32)
           a.tau[(size_t)(eoy + e / erx) * a.BX + eox + e % erx] = T;
 
@@ -869,17 +888,15 @@ __global__ void __launch_bounds__(LIMG_WAVE_WARPS * 32) k_merge_wave(WaveArgs a,
             a.flags[4] = 1; // reported by the host as LIMGCU_ERROR_OUT_OF_BOUNDS
         }
 
-        // the claim is visible to this warp's next look at the mask and to everybody who later reads the progress store
-        __threadfence();
-        __syncwarp();
         count++;
         claimed = true;
         tClaim += clock64() - tc;
 
         if (r.kind == 2)
         {
-          // limg.cpp:1435-1438: the scan resumes at the same seed (which the regrowth may or may not have covered)
-          if (!(x >= eox && x < eox + erx && y >= eoy && y < eoy + ery))
+          // limg.cpp:1435-1438: the scan resumes at the same seed (which the regrowth may or may not have covered). In stage 0 the
+          // seed can only emit again if its whole 3 x 3 corner is still free, i.e. if the regrowth rectangle stays clear of it.
+          if (!(x < eox + erx && x + 3 > eox && y < eoy + ery && y + 3 > eoy))
             continue;
 
           break;
@@ -924,7 +941,7 @@ __global__ void __launch_bounds__(LIMG_WAVE_WARPS * 32) k_merge_wave(WaveArgs a,
     for (uint32_t spins = 0; published != LIMG_WAVE_DONE; spins++)
     {
       const int row = y - 1 - lane;
-      pAbove = __reduce_min_sync(0xFFFFFFFFu, row >= 0 ? ld_acquire_s32(progress + row) : LIMG_WAVE_DONE);
+      pAbove = __reduce_min_sync(0xFFFFFFFFu, row >= 0 ? ld_relaxed_s32(progress + row) : LIMG_WAVE_DONE);
       publish(LIMG_WAVE_DONE);
 
       if (published == LIMG_WAVE_DONE)

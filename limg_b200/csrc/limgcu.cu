@@ -22,7 +22,7 @@ struct limgcu_ctx
   cudaStream_t stream = nullptr;
   cudaStream_t streamAux = nullptr; // the speculative match bitmaps are computed here while the scan already runs on `stream`
   cudaEvent_t evFork = nullptr, evJoin = nullptr;
-  int planAsync = 1;                // LIMGCU_PLAN_ASYNC=0: everything on one stream
+  int planAsync = 0;                // LIMGCU_PLAN_ASYNC=1: the plan kernels on the second stream, concurrently with the scan
   char err[512] = { 0 };
   uint64_t launches = 0;
   int smCount = 148;
