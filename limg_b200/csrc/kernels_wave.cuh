@@ -300,6 +300,44 @@ struct WaveScan
     return true;
   }
 
+  // in-use bit of one block for THIS lane's own cell (lanes ask for different blocks): the current snapshot is indexed by lane = row,
+  // so a lane cannot take another row's word from its registers; cells read the live mask (monotone: never clears)
+  __device__ __forceinline__ bool cell_used(int xx, int yy) const
+  {
+    return mask.is_used(xx, yy);
+  }
+
+  // When only ONE direction of a growth is still alive the strips that follow are known in advance (same length, next row /
+  // column): evaluate as many of them as fit into the 32 lanes at once instead of one after the other. Returns how many
+  // consecutive strips join (0 .. n). dirX, dirY = step from strip to strip; (x0, y0, w, h) = the first strip.
+  __device__ int strips_run(const PredRec &seed, int x0, int y0, int w, int h, int dirX, int dirY, int n)
+  {
+    const long long t0 = clock64();
+    const int cells = w * h;
+    const int j = lane / cells, e = lane - j * cells; // strip index, cell inside the strip
+    bool ok = true;
+
+    if (j < n)
+    {
+      const int xx = x0 + j * dirX + e % w, yy = y0 + j * dirY + e / w;
+      ok = !cell_used(xx, yy) && predicate_thread<CH>(seed, a.rec[(size_t)yy * a.BX + xx]);
+    }
+
+    nOnDemand += (uint32_t)(n * cells);
+    // first strip with a failing cell
+    const uint32_t bad = __ballot_sync(0xFFFFFFFFu, !ok);
+    int good = n;
+
+    if (bad)
+      good = min(n, (__ffs(bad) - 1) / cells);
+
+    const long long dt = clock64() - t0;
+    tOnDemand += dt;
+    nStrips[cause]++;
+    tStrips[cause] += dt;
+    return good;
+  }
+
   __device__ bool strip_joins(const PredRec &seed, int x0, int y0, int w, int h)
   {
     const long long t0 = clock64();
@@ -456,8 +494,48 @@ struct WaveScan
       return strip_joins(rec, x0, y0, w, h);
     };
 
+    // is the strip outside the known part (so that it would be evaluated on demand)?
+    auto outside = [&](int x0, int y0, int w, int h) -> bool {
+      return !(x0 >= g.vx0 && y0 >= g.vy0 && x0 + w <= g.vx1 && y0 + h <= g.vy1);
+    };
+
     while (right || down || up || left)
     {
+      // one direction left and its strips are evaluated on demand: take them in batches (same result, far fewer round trips)
+      if (right + down + up + left == 1)
+      {
+        const int cells = right || left ? ry : rx;
+
+        if (cells <= 16)
+        {
+          const int x0 = right ? ox + rx : (left ? ox - 1 : ox), y0 = down ? oy + ry : (up ? oy - 1 : oy);
+          const int w = right || left ? 1 : rx, h = right || left ? ry : 1;
+
+          if (outside(x0, y0, w, h))
+          {
+            // how many more strips the grid allows (limg.cpp:1321, 1335: the last block column / row is never entered)
+            const int room = right ? a.BX - 1 - (ox + rx) : (down ? a.BY - 1 - (oy + ry) : (up ? oy : ox));
+            const int n = min(32 / cells, room);
+
+            if (n <= 0)
+              break;
+
+            if (!haveRec) { rec = a.rec[seed]; haveRec = true; }
+            const int good = strips_run(rec, x0, y0, w, h, right ? 1 : (left ? -1 : 0), down ? 1 : (up ? -1 : 0), n);
+
+            if (right) rx += good;
+            else if (down) ry += good;
+            else if (up) { oy -= good; ry += good; }
+            else { ox -= good; rx += good; }
+
+            if (good < n)
+              break; // the direction is exhausted, and it was the last one
+
+            continue;
+          }
+        }
+      }
+
       if (right)
       {
         if (ox + rx + 1 < a.BX && joins(ox + rx, oy, 1, ry)) rx++; else right = false;
@@ -1002,16 +1080,77 @@ __global__ void __launch_bounds__(LIMG_WAVE_WARPS * 32) k_merge_wave(WaveArgs a,
   }
 }
 
-// Replays every candidate seed of the stage against the mask at its logical time and compares with the wave's record.
+// Verification, part 1 (one THREAD per candidate seed): most candidates were in use before their turn came, or could not emit
+// any more (stage 0: a block of the 3 x 3 corner taken, stage 1: both neighbours taken). Those must not have emitted anything;
+// the others go on the replay list.
+__global__ void __launch_bounds__(256) k_merge_verify_filter(WaveArgs a, int stage, int attempt, uint32_t *replayList, uint32_t *replayCount)
+{
+  if (a.flags[0] != (uint32_t)attempt)
+    return;
+
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t blocks = (uint32_t)(a.BX * a.BY);
+  bool replay = false;
+  uint32_t seed = 0;
+
+  if (i < a.candCount[stage])
+  {
+    seed = __ldg(&a.candList[(size_t)stage * blocks + i]);
+    const int y = (int)(seed / (uint32_t)a.BX), x = (int)(seed - (uint32_t)y * (uint32_t)a.BX);
+    const uint32_t T = (stage ? LIMG_TAU_STAGE1 : 0u) + (seed << 3);
+    const uint32_t *t = a.tau + seed;
+    bool dead;
+
+    if (stage == 0) // the candidate bit says the corner is inside the grid
+    {
+      dead = false;
+
+#pragma unroll
+      for (int dy = 0; dy < 3; dy++)
+#pragma unroll
+        for (int dx = 0; dx < 3; dx++)
+          dead |= __ldg(t + (size_t)dy * a.BX + dx) < T;
+    }
+    else
+    {
+      const bool rightFree = x + 1 < a.BX && !(__ldg(t + 1) < T), downFree = y + 1 < a.BY && !(__ldg(t + a.BX) < T);
+      dead = __ldg(t) < T || (!rightFree && !downFree);
+    }
+
+    if (dead)
+    {
+      if (__ldg(&a.emitInfo[(size_t)stage * blocks + seed]) & 0xFFu)
+        a.flags[1 + stage] = 1; // recorded an emission it cannot have made
+    }
+    else
+    {
+      replay = true;
+    }
+  }
+
+  const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, replay);
+  uint32_t pos = 0;
+
+  if ((threadIdx.x & 31) == 0 && ballot)
+    pos = atomicAdd(&replayCount[stage], (uint32_t)__popc(ballot));
+
+  pos = __shfl_sync(0xFFFFFFFFu, pos, 0) + __popc(ballot & ((1u << (threadIdx.x & 31)) - 1u));
+
+  if (replay)
+    replayList[(size_t)stage * blocks + pos] = seed;
+}
+
+// Verification, part 2 (one WARP per remaining seed): replays the seed against the mask at its logical time and compares with the
+// wave's record.
 template <int CH>
-__global__ void __launch_bounds__(256) k_merge_verify(WaveArgs a, int stage, int attempt)
+__global__ void __launch_bounds__(256) k_merge_verify(WaveArgs a, int stage, int attempt, const uint32_t *replayList, const uint32_t *replayCount)
 {
   if (a.flags[0] != (uint32_t)attempt)
     return; // this try did not run, or already failed
 
   const int lane = threadIdx.x & 31;
-  const uint32_t n = a.candCount[stage];
-  const uint32_t *candList = a.candList + (size_t)stage * a.BX * a.BY;
+  const uint32_t n = replayCount[stage];
+  const uint32_t *candList = replayList + (size_t)stage * a.BX * a.BY;
   const uint2 *lists = a.rowLists + (size_t)stage * a.BY * a.listCap;
   const uint32_t *emitInfo = a.emitInfo + (size_t)stage * a.BX * a.BY;
   const uint32_t base = stage ? LIMG_TAU_STAGE1 : 0u;

@@ -57,6 +57,7 @@ struct limgcu_ctx
 
   // wavefront merge (kernels_wave.cuh)
   uint32_t *dWaveZero = nullptr; // flags[8] ticket[2] candCount[2] pad[4] | progress[2*BY] | rowCounts[2*BY] | candBits[2*usedWords] | emitInfo[2*blocks]
+  uint32_t *dReplayList = nullptr, *dReplayCount = nullptr;
   uint32_t *dTau = nullptr, *dCandList = nullptr, *dWaveDbg = nullptr, *dWaveRows = nullptr;
   size_t capWaveRows = 0;
   int waveRowTimes = 0;              // LIMGCU_MERGE_ROWTIMES=1: per-row time stamps of the scan (limgcu_debug_wave_rows)
@@ -134,6 +135,8 @@ static int ensure_capacity(limgcu_ctx *ctx, size_t W, size_t H)
     if (ctx->dPlanCounters == nullptr) CK(regrow(ctx->dPlanCounters, (size_t)8));
     CK(regrow(ctx->dTau, blocks));
     CK(regrow(ctx->dCandList, blocks * 2));
+    CK(regrow(ctx->dReplayList, blocks * 2));
+    if (ctx->dReplayCount == nullptr) CK(regrow(ctx->dReplayCount, (size_t)2));
     ctx->capBlocks = blocks;
   }
 
@@ -293,7 +296,7 @@ extern "C" void limgcu_destroy(limgcu_ctx *ctx)
   void *ptrs[] = { ctx->dLut, ctx->dTable, ctx->dRec, ctx->dWindow, ctx->dAreas, ctx->dBlockToArea, ctx->dWork, ctx->dSmallList, ctx->dLargeList, ctx->dDemand,
                    ctx->dUsed, ctx->dScratchPx, ctx->dScratchFac, ctx->dCounters, ctx->dCompare, ctx->dSrc,
                    ctx->dExtSlot, ctx->dExtSeed, ctx->dExtBits, ctx->dExtHdr, ctx->dPlanCounters, ctx->dSymSlot, ctx->dSymSeed, ctx->dSymBits, ctx->dSymHdr, ctx->dSymStart, ctx->dUnmasked,
-                   ctx->dWaveZero, ctx->dTau, ctx->dCandList, ctx->dRowLists, ctx->dWaveDbg, ctx->dWaveRows, ctx->dRowMeta };
+                   ctx->dWaveZero, ctx->dTau, ctx->dCandList, ctx->dRowLists, ctx->dWaveDbg, ctx->dWaveRows, ctx->dRowMeta, ctx->dReplayList, ctx->dReplayCount };
 
   for (void *p : ptrs)
     if (p) cudaFree(p);
@@ -571,12 +574,20 @@ static int launch_merge(limgcu_ctx *ctx, const limgcu_decomp *dTable, size_t W, 
 
       if (!sequential)
       {
+        CK(cudaMemsetAsync(ctx->dReplayCount, 0, 2 * sizeof(uint32_t), ctx->stream));
+
+        for (int stage = 0; stage < 2; stage++)
+        {
+          k_merge_verify_filter<<<(blocks + 255) / 256, 256, 0, ctx->stream>>>(wa, stage, attempt, ctx->dReplayList, ctx->dReplayCount);
+          CKL("k_merge_verify_filter");
+        }
+
         for (int stage = 0; stage < 2; stage++)
         {
           if (hasAlpha)
-            k_merge_verify<4><<<ctx->smCount * 8, 256, 0, ctx->stream>>>(wa, stage, attempt);
+            k_merge_verify<4><<<ctx->smCount * 4, 256, 0, ctx->stream>>>(wa, stage, attempt, ctx->dReplayList, ctx->dReplayCount);
           else
-            k_merge_verify<3><<<ctx->smCount * 8, 256, 0, ctx->stream>>>(wa, stage, attempt);
+            k_merge_verify<3><<<ctx->smCount * 4, 256, 0, ctx->stream>>>(wa, stage, attempt, ctx->dReplayList, ctx->dReplayCount);
 
           CKL("k_merge_verify");
         }
