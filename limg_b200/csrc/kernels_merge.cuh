@@ -631,98 +631,112 @@ __global__ void __launch_bounds__(256) k_plan_centres(PlanArgs a)
 
 // Match bitmap around a centre c, anchored at (cx - 8, cy - 8): every four-way rectangle grown from a rectangle that contains c's
 // block row and column segment lies inside the bounding box of the four runs from c (each strip it adds crosses c's row or column).
+// Warp-cooperative; `rows` are 32 words of shared memory private to the warp. The regrowth starts from an untested rectangle of
+// crx x cry blocks (limg.cpp:1428-1431): a mismatch less than crx blocks right of c / cry blocks below it does not stop the growth.
+// Returns this lane's row word and the header (known part) in hdr.
+template <int CH>
+__device__ uint32_t build_centre_bitmap(const PredRec *__restrict__ rec, const uint32_t *__restrict__ window, int BX, int BY, int c, int crx, int cry, int maxL, int maxR, int maxD,
+                                        uint32_t *rows, uint32_t &hdr)
+{
+  const int lane = threadIdx.x & 31;
+  const int cy = c / BX, cx = c - cy * BX;
+  const int ax = cx - LIMG_SYM_BACK, ay = cy - LIMG_SYM_BACK;
+  const PredRec s = rec[c];
+  const uint32_t w0 = window[(size_t)c * 2], w1 = window[(size_t)c * 2 + 1];
+
+  auto known = [&](int dx, int dy) -> bool { // lower-right 8x8 of c: its match word
+    return ((dy < 4 ? w0 >> (8 * dy) : w1 >> (8 * (dy - 4))) >> dx) & 1u;
+  };
+
+  // runs along c's row (column ax + lane) and c's column (row ay + lane), limited to the part the caps allow
+  const int d = lane - LIMG_SYM_BACK;
+  bool mr = false, mc = false;
+
+  if (d >= 0 && d < 8)
+  {
+    mr = known(d, 0);
+    mc = known(0, d);
+  }
+  else
+  {
+    if (d >= -maxL && d < maxR && cx + d >= 0 && cx + d < BX)
+      mr = predicate_thread<CH>(s, rec[(size_t)cy * BX + cx + d]);
+
+    if (d >= -maxL && d < maxD && cy + d >= 0 && cy + d < BY)
+      mc = predicate_thread<CH>(s, rec[(size_t)(cy + d) * BX + cx]);
+  }
+
+  const uint32_t rowRun = __ballot_sync(0xFFFFFFFFu, mr), colRun = __ballot_sync(0xFFFFFFFFu, mc);
+  // known box: from the first mismatch left of / above c to the first mismatch right of / below c (inclusive), relative to the anchor
+  const uint32_t lowRow = ~rowRun & ((1u << LIMG_SYM_BACK) - 1u), lowCol = ~colRun & ((1u << LIMG_SYM_BACK) - 1u);
+  const int vx0 = max(lowRow ? 31 - __clz(lowRow) : 0, LIMG_SYM_BACK - maxL), vy0 = max(lowCol ? 31 - __clz(lowCol) : 0, LIMG_SYM_BACK - maxL);
+  crx = max(min(crx, 15), 3);
+  cry = max(min(cry, 15), 3);
+  const int vx1 = min(run_end(rowRun | (((1u << (crx - 1)) - 1u) << (LIMG_SYM_BACK + 1)), LIMG_SYM_BACK) + 1, LIMG_SYM_BACK + maxR);
+  const int vy1 = min(run_end(colRun | (((1u << (cry - 1)) - 1u) << (LIMG_SYM_BACK + 1)), LIMG_SYM_BACK) + 1, LIMG_SYM_BACK + maxD);
+  const int bw = vx1 - vx0, bh = vy1 - vy0;
+
+  // what is known without further predicates: c's match word (lower-right quadrant), c's row, c's column
+  {
+    uint32_t r = 0;
+    const int dy = lane - LIMG_SYM_BACK;
+
+    if (lane >= vy0 && lane < vy1)
+    {
+      if (dy >= 0 && dy < 8)
+        r = ((dy < 4 ? w0 >> (8 * dy) : w1 >> (8 * (dy - 4))) & 0xFFu) << LIMG_SYM_BACK;
+
+      if (dy == 0)
+        r |= rowRun;
+
+      r |= ((colRun >> lane) & 1u) << LIMG_SYM_BACK;
+      r &= (vx1 >= 32 ? 0xFFFFFFFFu : ((1u << vx1) - 1u)) & (0xFFFFFFFFu << vx0);
+    }
+
+    rows[lane] = r;
+  }
+
+  __syncwarp();
+
+  for (int base = 0; base < bw * bh; base += 32)
+  {
+    const int cell = base + lane;
+    const int r = vy0 + cell / bw, col = vx0 + cell % bw;
+    const int dx = col - LIMG_SYM_BACK, dy = r - LIMG_SYM_BACK;
+    const int bx = ax + col, by = ay + r;
+
+    if (cell < bw * bh && dx != 0 && dy != 0 && !(dx > 0 && dx < 8 && dy > 0 && dy < 8) && bx >= 0 && bx < BX && by >= 0 && by < BY)
+    {
+      if (predicate_thread<CH>(s, rec[(size_t)by * BX + bx]))
+        atomicOr(&rows[r], 1u << col);
+    }
+  }
+
+  __syncwarp();
+  hdr = (uint32_t)vx0 | (uint32_t)vy0 << 8 | (uint32_t)vx1 << 16 | (uint32_t)vy1 << 24;
+  const uint32_t mine = rows[lane];
+  __syncwarp();
+  return mine;
+}
+
 template <int CH>
 __global__ void __launch_bounds__(LIMG_PLAN_WARPS * 32) k_plan_sym(PlanArgs a)
 {
   __shared__ uint32_t sRows[LIMG_PLAN_WARPS][32];
   const uint32_t count = min(a.counters[1], a.symCap);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  uint32_t *rows = sRows[warp];
   const uint32_t warpsTotal = gridDim.x * LIMG_PLAN_WARPS;
 
   for (uint32_t slot = blockIdx.x * LIMG_PLAN_WARPS + warp; slot < count; slot += warpsTotal)
   {
     const int c = (int)a.symSeed[slot];
-    const int cy = c / a.BX, cx = c - cy * a.BX;
-    const int ax = cx - LIMG_SYM_BACK, ay = cy - LIMG_SYM_BACK;
-    const PredRec s = a.rec[c];
-    const uint32_t w0 = a.window[(size_t)c * 2], w1 = a.window[(size_t)c * 2 + 1];
-
-    auto known = [&](int dx, int dy) -> bool { // lower-right 8x8 of c: its match word
-      return ((dy < 4 ? w0 >> (8 * dy) : w1 >> (8 * (dy - 4))) >> dx) & 1u;
-    };
-
-    // runs along c's row (column ax + lane) and c's column (row ay + lane), limited to the part the caps allow
-    const int d = lane - LIMG_SYM_BACK;
-    bool mr = false, mc = false;
-
-    if (d >= 0 && d < 8)
-    {
-      mr = known(d, 0);
-      mc = known(0, d);
-    }
-    else
-    {
-      if (d >= -a.symMaxL && d < a.symMaxR && cx + d >= 0 && cx + d < a.BX)
-        mr = predicate_thread<CH>(s, a.rec[(size_t)cy * a.BX + cx + d]);
-
-      if (d >= -a.symMaxL && d < a.symMaxD && cy + d >= 0 && cy + d < a.BY)
-        mc = predicate_thread<CH>(s, a.rec[(size_t)(cy + d) * a.BX + cx]);
-    }
-
-    const uint32_t rowRun = __ballot_sync(0xFFFFFFFFu, mr), colRun = __ballot_sync(0xFFFFFFFFu, mc);
-    // known box: from the first mismatch left of / above c to the first mismatch right of / below c (inclusive), relative to the anchor
-    const uint32_t lowRow = ~rowRun & ((1u << LIMG_SYM_BACK) - 1u), lowCol = ~colRun & ((1u << LIMG_SYM_BACK) - 1u);
-    const int vx0 = max(lowRow ? 31 - __clz(lowRow) : 0, LIMG_SYM_BACK - a.symMaxL), vy0 = max(lowCol ? 31 - __clz(lowCol) : 0, LIMG_SYM_BACK - a.symMaxL);
-    // the regrowth starts from a rectangle of crx x cry blocks that are not tested (limg.cpp:1428-1431): a mismatch less than crx
-    // blocks right of c / cry blocks below it does not stop the growth
     const uint32_t start = a.symStart[c];
-    const int crx = max((int)(start & 0xFF), 3), cry = max((int)(start >> 8), 3);
-    const int vx1 = min(run_end(rowRun | (((1u << (crx - 1)) - 1u) << (LIMG_SYM_BACK + 1)), LIMG_SYM_BACK) + 1, LIMG_SYM_BACK + a.symMaxR);
-    const int vy1 = min(run_end(colRun | (((1u << (cry - 1)) - 1u) << (LIMG_SYM_BACK + 1)), LIMG_SYM_BACK) + 1, LIMG_SYM_BACK + a.symMaxD);
-    const int bw = vx1 - vx0, bh = vy1 - vy0;
-
-    // what is known without further predicates: c's match word (lower-right quadrant), c's row, c's column
-    {
-      uint32_t r = 0;
-      const int dy = lane - LIMG_SYM_BACK;
-
-      if (lane >= vy0 && lane < vy1)
-      {
-        if (dy >= 0 && dy < 8)
-          r = ((dy < 4 ? w0 >> (8 * dy) : w1 >> (8 * (dy - 4))) & 0xFFu) << LIMG_SYM_BACK;
-
-        if (dy == 0)
-          r |= rowRun;
-
-        r |= ((colRun >> lane) & 1u) << LIMG_SYM_BACK;
-        r &= (vx1 >= 32 ? 0xFFFFFFFFu : ((1u << vx1) - 1u)) & (0xFFFFFFFFu << vx0);
-      }
-
-      rows[lane] = r;
-    }
-
-    __syncwarp();
-
-    for (int base = 0; base < bw * bh; base += 32)
-    {
-      const int cell = base + lane;
-      const int r = vy0 + cell / bw, col = vx0 + cell % bw;
-      const int dx = col - LIMG_SYM_BACK, dy = r - LIMG_SYM_BACK;
-      const int bx = ax + col, by = ay + r;
-
-      if (cell < bw * bh && dx != 0 && dy != 0 && !(dx > 0 && dx < 8 && dy > 0 && dy < 8) && bx >= 0 && bx < a.BX && by >= 0 && by < a.BY)
-      {
-        if (predicate_thread<CH>(s, a.rec[(size_t)by * a.BX + bx]))
-          atomicOr(&rows[r], 1u << col);
-      }
-    }
-
-    __syncwarp();
-    a.symBits[(size_t)slot * 32 + lane] = rows[lane];
+    uint32_t hdr;
+    const uint32_t row = build_centre_bitmap<CH>(a.rec, a.window, a.BX, a.BY, c, (int)(start & 0xFF), (int)(start >> 8), a.symMaxL, a.symMaxR, a.symMaxD, sRows[warp], hdr);
+    a.symBits[(size_t)slot * 32 + lane] = row;
 
     if (lane == 0)
-      a.symHdr[slot] = (uint32_t)vx0 | (uint32_t)vy0 << 8 | (uint32_t)vx1 << 16 | (uint32_t)vy1 << 24;
+      a.symHdr[slot] = hdr;
 
     __threadfence();
     __syncwarp();

@@ -56,6 +56,7 @@ struct WaveArgs
   int eventRow;              // diagnostics: decisions of stage-0 rows eventRow .. eventRow + 3 go to dbgRows + 8 * BY as [4][64](x | kind << 16 | waited << 20, ns)
   uint32_t *dbgRows;         // [2][BY][4] optional per-row time stamps (globaltimer ns, low 32 bits): ticket, first decision, last decision, done
   int listCap, margin;
+  int symMaxL, symMaxR, symMaxD; // size caps of a centre bitmap built on the fly (same as the plan's)
   int stageGap;              // block rows stage 1 stays behind stage 0
   int specAhead;             // a seed is expanded speculatively once the rows above are within this many columns of where they have to be
 };
@@ -200,6 +201,9 @@ struct SeedPre
   int pcx, pcy;     // centre the mask-free growth predicts (-1: none)
   uint32_t symRow;  // lane: match bits of that centre for block row pcy - 8 + lane, columns pcx - 8 ..
   uint32_t symHdr;  // known part (0: no bitmap)
+  // a bitmap built on the fly for a centre that had none (kept for the seed's next expansions)
+  int ccx, ccy;
+  uint32_t cRow, cHdr;
 };
 
 // a match bitmap combined with the mask: bit (row ay + lane, column ax + i) = matches the seed and is free
@@ -219,12 +223,13 @@ struct WaveScan
   int lane;
   uint32_t nOnDemand;
   long long tOnDemand = 0, tFour = 0; // profile: clock cycles inside on-demand strips / the four-way regrowth
+  uint32_t *scratch = nullptr;        // 32 words of shared memory private to the warp
   const Snapshot *cur = nullptr;      // the mask snapshot the running expansion is based on
   bool volatileReads = false;         // the running expansion read in-use bits that the snapshot does not hold
   int cause = 0;                      // who asks for on-demand strips: 0 seed growth, 1 four-way with a bitmap, 2 four-way without
   uint32_t nStrips[3] = { 0, 0, 0 };
   long long tStrips[3] = { 0, 0, 0 };
-  uint32_t nFour = 0, nFourMiss = 0, nFourNoSym = 0;
+  uint32_t nFour = 0, nFourMiss = 0, nFourNoSym = 0, nBuilt = 0;
 
   __device__ bool strip_unused(int x0, int y0, int w, int h)
   {
@@ -451,6 +456,9 @@ struct WaveScan
     p.pcx = p.pcy = -1;
     p.symRow = 0;
     p.symHdr = 0;
+    p.ccx = p.ccy = -1;
+    p.cRow = 0;
+    p.cHdr = 0;
     const int prx = u & 0xFF, pry = u >> 8;
 
     if (stage == 0 && prx >= 3 && pry >= 3)
@@ -564,7 +572,7 @@ struct WaveScan
   }
 
   // what seed (x, y) does against the mask (limg.cpp:1405-1486)
-  __device__ WaveResult expand(int x, int y, int stage, const SeedPre &pre, const Snapshot &sn)
+  __device__ WaveResult expand(int x, int y, int stage, SeedPre &pre, const Snapshot &sn)
   {
     WaveResult r;
     Region g;
@@ -593,8 +601,43 @@ struct WaveScan
 
         if (cox != pre.pcx || coy != pre.pcy)
         {
-          load_sym(cox, coy, symRow, symHdr);
           nFourMiss++;
+
+          if (cox == pre.ccx && coy == pre.ccy)
+          {
+            symRow = pre.cRow;
+            symHdr = pre.cHdr;
+          }
+          else
+          {
+            load_sym(cox, coy, symRow, symHdr);
+
+            if (!symHdr && scratch)
+            {
+              // no bitmap for this centre: build one now, once, instead of evaluating strip after strip on every expansion
+              const long long tb = clock64();
+              symRow = build_centre_bitmap<CH>(a.rec, a.window, a.BX, a.BY, coy * a.BX + cox, crx, cry, a.symMaxL, a.symMaxR, a.symMaxD, scratch, symHdr);
+              pre.ccx = cox; pre.ccy = coy; pre.cRow = symRow; pre.cHdr = symHdr;
+              nBuilt++;
+              tOnDemand += clock64() - tb;
+            }
+          }
+        }
+        else if (!symHdr && scratch && pre.pcx >= 0)
+        {
+          if (pre.ccx == cox && pre.ccy == coy)
+          {
+            symRow = pre.cRow;
+            symHdr = pre.cHdr;
+          }
+          else
+          {
+            const long long tb = clock64();
+            symRow = build_centre_bitmap<CH>(a.rec, a.window, a.BX, a.BY, coy * a.BX + cox, crx, cry, a.symMaxL, a.symMaxR, a.symMaxD, scratch, symHdr);
+            pre.ccx = cox; pre.ccy = coy; pre.cRow = symRow; pre.cHdr = symHdr;
+            nBuilt++;
+            tOnDemand += clock64() - tb;
+          }
         }
 
         if (!symHdr) nFourNoSym++;
@@ -729,8 +772,10 @@ __global__ void __launch_bounds__(LIMG_WAVE_WARPS * 32) k_merge_wave(WaveArgs a,
   if (a.flags[0] != (uint32_t)attempt)
     return;
 
+  __shared__ uint32_t sScratch[LIMG_WAVE_WARPS][32];
   const int lane = threadIdx.x & 31;
   WaveScan<CH, LiveMask> scan{ a, LiveMask{ a.used, a.wordsPerRow, a.BX, a.BY }, lane, 0 };
+  scan.scratch = sScratch[threadIdx.x >> 5];
   const int nWords = (a.BX + 31) >> 5;
   uint32_t nExp[2] = { 0, 0 }, nReexp[2] = { 0, 0 }, nPolls[2] = { 0, 0 }, nOnDemand[2] = { 0, 0 };
   long long tNext = 0, tWait = 0, tExpand = 0, tClaim = 0, tPre = 0, tc;
@@ -834,7 +879,7 @@ __global__ void __launch_bounds__(LIMG_WAVE_WARPS * 32) k_merge_wave(WaveArgs a,
         break;
 
       tc = clock64();
-      const SeedPre pre = scan.prefetch(x, y, stage);
+      SeedPre pre = scan.prefetch(x, y, stage);
       tPre += clock64() - tc;
       const uint32_t first = count;
       int nextX = x + 1;
@@ -1073,6 +1118,7 @@ __global__ void __launch_bounds__(LIMG_WAVE_WARPS * 32) k_merge_wave(WaveArgs a,
         atomicAdd(&a.dbg[32 + 4 + c], (uint32_t)(scan.tStrips[c] >> 10));
       }
 
+      atomicAdd(&a.dbg[53], scan.nBuilt);
       atomicAdd(&a.dbg[48], scan.nFour);
       atomicAdd(&a.dbg[49], scan.nFourMiss);
       atomicAdd(&a.dbg[50], scan.nFourNoSym);
@@ -1148,6 +1194,7 @@ __global__ void __launch_bounds__(256) k_merge_verify(WaveArgs a, int stage, int
   if (a.flags[0] != (uint32_t)attempt)
     return; // this try did not run, or already failed
 
+  __shared__ uint32_t sScratchV[8][32];
   const int lane = threadIdx.x & 31;
   const uint32_t n = replayCount[stage];
   const uint32_t *candList = replayList + (size_t)stage * a.BX * a.BY;
@@ -1174,6 +1221,7 @@ __global__ void __launch_bounds__(256) k_merge_verify(WaveArgs a, int stage, int
 
       const uint32_t T = base + ((uint32_t)seed << 3) + (uint32_t)k;
       WaveScan<CH, TimeMask> scan{ a, TimeMask{ a.tau, a.BX, a.BY, T }, lane, 0 };
+      scan.scratch = sScratchV[threadIdx.x >> 5];
 
       if (scan.mask.is_used(x, y)) { ok = e == have; break; }
 

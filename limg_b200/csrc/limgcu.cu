@@ -515,7 +515,7 @@ static int launch_merge(limgcu_ctx *ctx, const limgcu_decomp *dTable, size_t W, 
     w.BX = BX; w.BY = BY; w.wordsPerRow = wordsPerRow;
     w.used = ctx->dUsed; w.tau = ctx->dTau; w.progress = wProgress; w.ticket = wTicket;
     w.rowLists = ctx->dRowLists; w.rowCounts = wRowCounts; w.emitInfo = wEmitInfo; w.flags = wFlags; w.stats = ctx->dCounters + 8;
-    w.listCap = 2 * BX; w.margin = ctx->mergeMargin; w.stageGap = ctx->mergeGap; w.specAhead = ctx->mergeSpec; w.dbg = ctx->dWaveDbg;
+    w.listCap = 2 * BX; w.margin = ctx->mergeMargin; w.stageGap = ctx->mergeGap; w.symMaxL = ctx->planSymL; w.symMaxR = ctx->planSymR; w.symMaxD = ctx->planSymD; w.specAhead = ctx->mergeSpec; w.dbg = ctx->dWaveDbg;
     CK(cudaMemsetAsync(ctx->dWaveDbg, 0, 256 * sizeof(uint32_t), ctx->stream));
     w.dbgRows = nullptr;
     w.eventRow = ctx->waveRowTimes > 1 ? ctx->waveRowTimes : 0;
