@@ -26,6 +26,21 @@
 namespace limg
 {
 
+// LIMG_WAVE_PROFILE=1 compiles the cycle counters and detailed diagnostics of the scan in (tools/phase_times.py, tools/row_times.py
+// print them); they cost ~30 registers per thread in a kernel that is already at the limit, so the default build leaves them out.
+#ifndef LIMG_WAVE_PROFILE
+#define LIMG_WAVE_PROFILE 0
+#endif
+
+__device__ __forceinline__ long long wave_clock()
+{
+#if LIMG_WAVE_PROFILE
+  return clock64();
+#else
+  return 0;
+#endif
+}
+
 #define LIMG_WAVE_DONE 0x7FFFFFFF
 #define LIMG_TAU_NONE 0xFFFFFFFFu
 #define LIMG_TAU_STAGE1 0x40000000u
@@ -317,7 +332,7 @@ struct WaveScan
   // consecutive strips join (0 .. n). dirX, dirY = step from strip to strip; (x0, y0, w, h) = the first strip.
   __device__ int strips_run(const PredRec &seed, int x0, int y0, int w, int h, int dirX, int dirY, int n)
   {
-    const long long t0 = clock64();
+    const long long t0 = wave_clock();
     const int cells = w * h;
     const int j = lane / cells, e = lane - j * cells; // strip index, cell inside the strip
     bool ok = true;
@@ -336,7 +351,7 @@ struct WaveScan
     if (bad)
       good = min(n, (__ffs(bad) - 1) / cells);
 
-    const long long dt = clock64() - t0;
+    const long long dt = wave_clock() - t0;
     tOnDemand += dt;
     nStrips[cause]++;
     tStrips[cause] += dt;
@@ -345,9 +360,9 @@ struct WaveScan
 
   __device__ bool strip_joins(const PredRec &seed, int x0, int y0, int w, int h)
   {
-    const long long t0 = clock64();
+    const long long t0 = wave_clock();
     const bool ok = strip_unused(x0, y0, w, h) && strip_matches(seed, x0, y0, w, h);
-    const long long dt = clock64() - t0;
+    const long long dt = wave_clock() - t0;
     tOnDemand += dt;
     nStrips[cause]++;
     tStrips[cause] += dt;
@@ -488,7 +503,7 @@ struct WaveScan
         return __all_sync(0xFFFFFFFFu, rowOk);
       }
 
-      if (a.dbg && lane == 0)
+      if (LIMG_WAVE_PROFILE && a.dbg && lane == 0)
       {
         // which side of the known part did the strip leave? (per cause: left, up, right, down)
         const int side = x0 < g.vx0 ? 0 : (y0 < g.vy0 ? 1 : (x0 + w > g.vx1 ? 2 : 3));
@@ -593,7 +608,7 @@ struct WaveScan
     {
       if (r.rx >= 3 && r.ry >= 3) // Q4
       {
-        const long long t0 = clock64();
+        const long long t0 = wave_clock();
         int cox = x + r.rx / 3, coy = y + r.ry / 3, crx = r.rx / 3, cry = r.ry / 3;
         uint32_t symRow = pre.symRow, symHdr = pre.symHdr;
 
@@ -615,11 +630,11 @@ struct WaveScan
             if (!symHdr && scratch)
             {
               // no bitmap for this centre: build one now, once, instead of evaluating strip after strip on every expansion
-              const long long tb = clock64();
+              const long long tb = wave_clock();
               symRow = build_centre_bitmap<CH>(a.rec, a.window, a.BX, a.BY, coy * a.BX + cox, crx, cry, a.symMaxL, a.symMaxR, a.symMaxD, scratch, symHdr);
               pre.ccx = cox; pre.ccy = coy; pre.cRow = symRow; pre.cHdr = symHdr;
               nBuilt++;
-              tOnDemand += clock64() - tb;
+              tOnDemand += wave_clock() - tb;
             }
           }
         }
@@ -632,11 +647,11 @@ struct WaveScan
           }
           else
           {
-            const long long tb = clock64();
+            const long long tb = wave_clock();
             symRow = build_centre_bitmap<CH>(a.rec, a.window, a.BX, a.BY, coy * a.BX + cox, crx, cry, a.symMaxL, a.symMaxR, a.symMaxD, scratch, symHdr);
             pre.ccx = cox; pre.ccy = coy; pre.cRow = symRow; pre.cHdr = symHdr;
             nBuilt++;
-            tOnDemand += clock64() - tb;
+            tOnDemand += wave_clock() - tb;
           }
         }
 
@@ -654,7 +669,7 @@ struct WaveScan
         r.attempted = 1;
         r.kind = (crx * cry > r.rx * r.ry) ? 2 : 1;
         r.boxR = max(r.boxR, min(cox + crx + 1, a.BX));
-        tFour += clock64() - t0;
+        tFour += wave_clock() - t0;
         cause = 0;
       }
     }
@@ -840,7 +855,7 @@ __global__ void __launch_bounds__(LIMG_WAVE_WARPS * 32) k_merge_wave(WaveArgs a,
       __syncwarp();
     }
 
-    uint32_t *rowT = a.dbgRows ? a.dbgRows + ((size_t)stage * a.BY + y) * 4 : nullptr;
+    uint32_t *rowT = (LIMG_WAVE_PROFILE && a.dbgRows) ? a.dbgRows + ((size_t)stage * a.BY + y) * 4 : nullptr;
 
     if (rowT && lane == 0)
       rowT[0] = global_ns();
@@ -868,19 +883,19 @@ __global__ void __launch_bounds__(LIMG_WAVE_WARPS * 32) k_merge_wave(WaveArgs a,
 
     for (;;)
     {
-      tc = clock64();
+      tc = wave_clock();
       x = wave_next_candidate(candRow, usedRow, a.wordsPerRow, nWords, x, a.BX, stage, lane);
 
       // every seed left of x is decided, and its claims were fenced when they were made
       publish(x >= a.BX ? LIMG_WAVE_DONE : x);
-      tNext += clock64() - tc;
+      tNext += wave_clock() - tc;
 
       if (x >= a.BX)
         break;
 
-      tc = clock64();
+      tc = wave_clock();
       SeedPre pre = scan.prefetch(x, y, stage);
-      tPre += clock64() - tc;
+      tPre += wave_clock() - tc;
       const uint32_t first = count;
       int nextX = x + 1;
       bool claimed = false;
@@ -897,7 +912,7 @@ __global__ void __launch_bounds__(LIMG_WAVE_WARPS * 32) k_merge_wave(WaveArgs a,
 
         for (uint32_t spins = 0;; spins++)
         {
-          tc = clock64();
+          tc = wave_clock();
           int p = LIMG_WAVE_DONE;
 
           if (y > 0 && !sequential)
@@ -911,7 +926,7 @@ __global__ void __launch_bounds__(LIMG_WAVE_WARPS * 32) k_merge_wave(WaveArgs a,
           if (p < min(x + 1 + a.margin - a.specAhead, a.BX))
           {
             // the rows above are still far away: whatever the mask shows now is not worth expanding against
-            tWait += clock64() - tc;
+            tWait += wave_clock() - tc;
 
             if (spins > LIMG_WAVE_SPIN_LIMIT) { a.flags[3] = 1; taken = true; break; }
 
@@ -921,13 +936,13 @@ __global__ void __launch_bounds__(LIMG_WAVE_WARPS * 32) k_merge_wave(WaveArgs a,
           }
 
           const Snapshot sn = scan.snapshot(x, y); // after the progress read
-          tWait += clock64() - tc;
+          tWait += wave_clock() - tc;
 
           if (scan.snap_used(sn, x)) { taken = true; break; }
 
           if (!have || unstable || !scan.same_where_probed(sn, used, r, x, y))
           {
-            tc = clock64();
+            tc = wave_clock();
 
             if (have) nReexp[stage]++;
 
@@ -936,16 +951,16 @@ __global__ void __launch_bounds__(LIMG_WAVE_WARPS * 32) k_merge_wave(WaveArgs a,
             used = sn;
             have = true;
             nExp[stage]++;
-            const long long dt = clock64() - tc;
+            const long long dt = wave_clock() - tc;
             tExpand += dt;
 
-            if (a.dbg && lane == 0)
+            if (LIMG_WAVE_PROFILE && a.dbg && lane == 0)
               atomicAdd(&a.dbg[stage * 16 + min(15, 63 - __clzll((dt >> 8) | 1))], 1u);
           }
 
           if (p >= min(r.boxR + a.margin, a.BX))
           {
-            if (a.dbg && lane == 0 && stage == 0)
+            if (LIMG_WAVE_PROFILE && a.dbg && lane == 0 && stage == 0)
             {
               // diagnostics: how far ahead the rows above are when the seed's decision stands, how wide its probe box was, and
               // whether it had to wait at all
@@ -975,7 +990,7 @@ __global__ void __launch_bounds__(LIMG_WAVE_WARPS * 32) k_merge_wave(WaveArgs a,
 
         // claim: in-use bits and owner times. Two rectangles that overlap (a failed speculation) leave one of them with a foreign
         // owner time on a block, which the verification pass sees.
-        tc = clock64();
+        tc = wave_clock();
 
         for (int rr = lane; rr < ery; rr += 32)
         {
@@ -1013,7 +1028,7 @@ __global__ void __launch_bounds__(LIMG_WAVE_WARPS * 32) k_merge_wave(WaveArgs a,
 
         count++;
         claimed = true;
-        tClaim += clock64() - tc;
+        tClaim += wave_clock() - tc;
 
         if (r.kind == 2)
         {
