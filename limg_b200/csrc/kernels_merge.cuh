@@ -629,6 +629,32 @@ __global__ void __launch_bounds__(256) k_plan_centres(PlanArgs a)
   }
 }
 
+// After the bitmaps exist: every stage-0 candidate remembers the slots of the four centres k_plan_centres asked for on its behalf,
+// so the scan finds them with the seed's first load instead of a dependent lookup per centre.
+__global__ void __launch_bounds__(256) k_plan_link(PlanArgs a, uint4 *__restrict__ seedSym)
+{
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+
+  if (i >= a.candCount[0])
+    return;
+
+  const int seed = (int)a.candList[i];
+  const int y = seed / a.BX, x = seed - y * a.BX;
+  const uint32_t u = a.unmasked[seed];
+  const int rx = u & 0xFF, ry = u >> 8;
+  uint32_t s[4] = { LIMG_NO_SLOT, LIMG_NO_SLOT, LIMG_NO_SLOT, LIMG_NO_SLOT };
+
+  if (rx >= 3 && ry >= 3)
+  {
+    const int cy = y + ry / 3;
+
+    for (int d = 0; d < 4 && rx / 3 - d >= 1; d++)
+      s[d] = a.symSlot[cy * a.BX + x + rx / 3 - d];
+  }
+
+  seedSym[seed] = make_uint4(s[0], s[1], s[2], s[3]);
+}
+
 // Match bitmap around a centre c, anchored at (cx - 8, cy - 8): every four-way rectangle grown from a rectangle that contains c's
 // block row and column segment lies inside the bounding box of the four runs from c (each strip it adds crosses c's row or column).
 // Warp-cooperative; `rows` are 32 words of shared memory private to the warp. The regrowth starts from an untested rectangle of

@@ -54,6 +54,7 @@ struct WaveArgs
   const uint32_t *extSlot, *extBits, *extHdr;
   const uint32_t *symSlot, *symBits, *symHdr;
   const uint16_t *unmasked;
+  const uint4 *seedSym;      // per stage-0 candidate: bitmap slots of its predicted centre and the three to its left (nullptr: look them up)
   const uint32_t *candBits;  // [2][BY][wordsPerRow]: mask-free necessary condition for a seed to emit in stage 0 / 1
   const uint32_t *candList;  // [2][blocks]
   const uint32_t *candCount; // [2]
@@ -216,6 +217,7 @@ struct SeedPre
   int pcx, pcy;     // centre the mask-free growth predicts (-1: none)
   uint32_t symRow;  // lane: match bits of that centre for block row pcy - 8 + lane, columns pcx - 8 ..
   uint32_t symHdr;  // known part (0: no bitmap)
+  uint32_t alt[3];  // bitmap slots of the centres one, two and three blocks left of the predicted one
   // a bitmap built on the fly for a centre that had none (kept for the seed's next expansions)
   int ccx, ccy;
   uint32_t cRow, cHdr;
@@ -432,6 +434,18 @@ struct WaveScan
     return __all_sync(0xFFFFFFFFu, same);
   }
 
+  __device__ __forceinline__ void load_sym_slot(uint32_t slot, uint32_t &row, uint32_t &hdr) const
+  {
+    row = 0;
+    hdr = 0;
+
+    if (slot < LIMG_SLOT_PENDING)
+    {
+      row = ld_relaxed_u32(&a.symBits[(size_t)slot * 32 + lane]);
+      hdr = ld_relaxed_u32(&a.symHdr[slot]);
+    }
+  }
+
   __device__ __forceinline__ void load_sym(int cx, int cy, uint32_t &row, uint32_t &hdr) const
   {
     // the plan kernels may still be running on the other stream: slots appear while the scan runs
@@ -453,6 +467,7 @@ struct WaveScan
     const uint32_t slot = ld_relaxed_u32(&a.extSlot[seed]);
     const uint32_t u = *(const volatile uint16_t *)&a.unmasked[seed];
     const uint32_t wv = lane < 8 ? __ldg(&a.window[(size_t)seed * 2 + (lane >> 2)]) : 0u;
+    const uint4 links = (a.seedSym && stage == 0) ? __ldg(&a.seedSym[seed]) : make_uint4(LIMG_NO_SLOT, LIMG_NO_SLOT, LIMG_NO_SLOT, LIMG_NO_SLOT);
 
     if (slot >= LIMG_SLOT_PENDING)
     {
@@ -476,11 +491,22 @@ struct WaveScan
     p.cHdr = 0;
     const int prx = u & 0xFF, pry = u >> 8;
 
+    p.alt[0] = p.alt[1] = p.alt[2] = LIMG_NO_SLOT;
+
     if (stage == 0 && prx >= 3 && pry >= 3)
     {
       p.pcx = x + prx / 3;
       p.pcy = y + pry / 3;
-      load_sym(p.pcx, p.pcy, p.symRow, p.symHdr);
+
+      if (a.seedSym)
+      {
+        p.alt[0] = links.y; p.alt[1] = links.z; p.alt[2] = links.w;
+        load_sym_slot(links.x, p.symRow, p.symHdr);
+      }
+      else
+      {
+        load_sym(p.pcx, p.pcy, p.symRow, p.symHdr);
+      }
     }
 
     return p;
@@ -625,7 +651,12 @@ struct WaveScan
           }
           else
           {
-            load_sym(cox, coy, symRow, symHdr);
+            const int dLeft = pre.pcx - cox;
+
+            if (a.seedSym && coy == pre.pcy && dLeft >= 1 && dLeft <= 3)
+              load_sym_slot(pre.alt[dLeft - 1], symRow, symHdr); // one of the centres the plan linked to this seed
+            else
+              load_sym(cox, coy, symRow, symHdr);
 
             if (!symHdr && scratch)
             {

@@ -42,6 +42,7 @@ struct limgcu_ctx
   uint64_t *dDemand = nullptr;
   uint32_t *dUsed = nullptr;
   uint32_t *dExtSlot = nullptr, *dExtSeed = nullptr, *dExtBits = nullptr, *dExtHdr = nullptr, *dPlanCounters = nullptr;
+  uint4 *dSeedSym = nullptr;
   uint32_t *dSymSlot = nullptr, *dSymSeed = nullptr, *dSymBits = nullptr, *dSymHdr = nullptr, *dSymStart = nullptr;
   uint16_t *dUnmasked = nullptr;
   uint32_t extCap = 0, symCap = 0;
@@ -129,6 +130,7 @@ static int ensure_capacity(limgcu_ctx *ctx, size_t W, size_t H)
     CK(regrow(ctx->dExtHdr, (size_t)ctx->extCap));
     CK(regrow(ctx->dSymSlot, blocks));
     CK(regrow(ctx->dSymStart, blocks));
+    CK(regrow(ctx->dSeedSym, blocks));
     CK(regrow(ctx->dSymSeed, (size_t)ctx->symCap));
     CK(regrow(ctx->dSymBits, (size_t)ctx->symCap * 32));
     CK(regrow(ctx->dSymHdr, (size_t)ctx->symCap));
@@ -295,7 +297,7 @@ extern "C" void limgcu_destroy(limgcu_ctx *ctx)
 
   void *ptrs[] = { ctx->dLut, ctx->dTable, ctx->dRec, ctx->dWindow, ctx->dAreas, ctx->dBlockToArea, ctx->dWork, ctx->dSmallList, ctx->dLargeList, ctx->dDemand,
                    ctx->dUsed, ctx->dScratchPx, ctx->dScratchFac, ctx->dCounters, ctx->dCompare, ctx->dSrc,
-                   ctx->dExtSlot, ctx->dExtSeed, ctx->dExtBits, ctx->dExtHdr, ctx->dPlanCounters, ctx->dSymSlot, ctx->dSymSeed, ctx->dSymBits, ctx->dSymHdr, ctx->dSymStart, ctx->dUnmasked,
+                   ctx->dExtSlot, ctx->dExtSeed, ctx->dExtBits, ctx->dExtHdr, ctx->dPlanCounters, ctx->dSymSlot, ctx->dSymSeed, ctx->dSymBits, ctx->dSymHdr, ctx->dSymStart, ctx->dSeedSym, ctx->dUnmasked,
                    ctx->dWaveZero, ctx->dTau, ctx->dCandList, ctx->dRowLists, ctx->dWaveDbg, ctx->dWaveRows, ctx->dRowMeta, ctx->dReplayList, ctx->dReplayCount };
 
   for (void *p : ptrs)
@@ -501,7 +503,14 @@ static int launch_merge(limgcu_ctx *ctx, const limgcu_decomp *dTable, size_t W, 
     }
 
     if (async)
+    {
       CK(cudaEventRecord(ctx->evJoin, ctx->streamAux));
+    }
+    else
+    {
+      k_plan_link<<<(blocks + 255) / 256, 256, 0, ctx->stream>>>(pl, ctx->dSeedSym);
+      CKL("k_plan_link");
+    }
 
     if (ctx->timing) CK(cudaEventRecord(ctx->ev[PHASE_SCAN], ctx->stream));
 
@@ -510,7 +519,7 @@ static int launch_merge(limgcu_ctx *ctx, const limgcu_decomp *dTable, size_t W, 
 
     WaveArgs w;
     w.rec = ctx->dRec; w.window = ctx->dWindow; w.extSlot = ctx->dExtSlot; w.extBits = ctx->dExtBits; w.extHdr = ctx->dExtHdr;
-    w.symSlot = ctx->dSymSlot; w.symBits = ctx->dSymBits; w.symHdr = ctx->dSymHdr; w.unmasked = ctx->dUnmasked;
+    w.symSlot = ctx->dSymSlot; w.symBits = ctx->dSymBits; w.symHdr = ctx->dSymHdr; w.unmasked = ctx->dUnmasked; w.seedSym = async ? nullptr : ctx->dSeedSym;
     w.candBits = wCandBits; w.candList = ctx->dCandList; w.candCount = wCandCount;
     w.BX = BX; w.BY = BY; w.wordsPerRow = wordsPerRow;
     w.used = ctx->dUsed; w.tau = ctx->dTau; w.progress = wProgress; w.ticket = wTicket;
