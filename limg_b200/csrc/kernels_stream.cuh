@@ -309,64 +309,92 @@ __global__ void __launch_bounds__(256) k_finalize(FinalizeArgs a)
 // decode: streaming reconstruction from the compact stream (limg_decode.h:326-340 per area)
 // ---------------------------------------------------------------------------------------------
 
+// One thread reconstructs four rows of one 8x8 block: the area's reconstruction state is set up once per 32 pixels, the twelve
+// 8-byte code loads and eight 16-byte stores of a thread are independent (memory-level parallelism instead of occupancy), and
+// neighbouring threads cover neighbouring blocks of the same rows, so a warp touches 256 contiguous bytes of every code row and 1 KB
+// of every output row. For RGB the alpha byte is the constant 0xFF the reference's 0xFFFF "min" trick produces (limg_decode.h:95-97).
 template <int CH>
-__global__ void __launch_bounds__(256) k_decode(const limgcu_area *__restrict__ areas, const uint32_t *__restrict__ blockToArea, const uint8_t *__restrict__ codesA,
+__global__ void __launch_bounds__(256, 4) k_decode(const limgcu_area *__restrict__ areas, const uint32_t *__restrict__ blockToArea, const uint8_t *__restrict__ codesA,
                                                 const uint8_t *__restrict__ codesB, const uint8_t *__restrict__ codesC, int W, int H, int BX, uint32_t *__restrict__ dst, int vec)
 {
-  const int segsPerRow = (W + 7) >> 3;
-  const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int BY = (H + 7) >> 3;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
 
-  if (s >= (long long)segsPerRow * H)
+  if (t >= (long long)BX * BY * 2)
     return;
 
-  const int y = (int)(s / segsPerRow);
-  const int bx = (int)(s - (long long)y * segsPerRow);
-  const int x0 = bx * 8;
-  const int npx = min(8, W - x0);
-  const size_t rowOff = (size_t)y * W + x0;
-  const bool aligned = vec != 0;
+  // consecutive threads = consecutive blocks of one half-row of blocks
+  const int bx = (int)(t % BX);
+  const int rest = (int)(t / BX);
+  const int by = rest >> 1, half = rest & 1;
+  const int x0 = bx * 8, y0 = by * 8 + half * 4;
 
-  const uint32_t k = blockToArea[(size_t)(y >> 3) * BX + bx];
+  if (y0 >= H)
+    return;
+
+  const int npx = min(8, W - x0), nrows = min(4, H - y0);
+  const bool fast = vec != 0 && npx == 8;
+  const uint32_t k = blockToArea[(size_t)by * BX + bx];
   const limgcu_area *ar = &areas[k];
   Recon r;
   init_recon<CH>(ar->decomp, ar->shift[0], ar->shift[1], ar->shift[2], 0xFFFF, r);
 
-  uint32_t a[8], b[8], c[8], out[8];
+  uint2 va[4], vb[4], vc[4];
 
-  if (npx == 8 && aligned)
+  if (fast)
   {
-    const uint2 va = *reinterpret_cast<const uint2 *>(codesA + rowOff);
-    const uint2 vb = *reinterpret_cast<const uint2 *>(codesB + rowOff);
-    const uint2 vc = *reinterpret_cast<const uint2 *>(codesC + rowOff);
-
 #pragma unroll
     for (int j = 0; j < 4; j++)
     {
-      a[j] = (va.x >> (8 * j)) & 0xFF; a[j + 4] = (va.y >> (8 * j)) & 0xFF;
-      b[j] = (vb.x >> (8 * j)) & 0xFF; b[j + 4] = (vb.y >> (8 * j)) & 0xFF;
-      c[j] = (vc.x >> (8 * j)) & 0xFF; c[j + 4] = (vc.y >> (8 * j)) & 0xFF;
+      if (j < nrows)
+      {
+        const size_t off = (size_t)(y0 + j) * W + x0;
+        va[j] = __ldg(reinterpret_cast<const uint2 *>(codesA + off));
+        vb[j] = __ldg(reinterpret_cast<const uint2 *>(codesB + off));
+        vc[j] = __ldg(reinterpret_cast<const uint2 *>(codesC + off));
+      }
     }
   }
-  else
-  {
+
 #pragma unroll
-    for (int j = 0; j < 8; j++)
+  for (int j = 0; j < 4; j++)
+  {
+    if (j >= nrows)
+      break;
+
+    const size_t off = (size_t)(y0 + j) * W + x0;
+    uint32_t out[8];
+
+#pragma unroll
+    for (int i = 0; i < 8; i++)
     {
-      a[j] = j < npx ? codesA[rowOff + j] : 0;
-      b[j] = j < npx ? codesB[rowOff + j] : 0;
-      c[j] = j < npx ? codesC[rowOff + j] : 0;
+      int32_t eA, eB, eC;
+
+      if (fast)
+      {
+        eA = (int32_t)(((i < 4 ? va[j].x : va[j].y) >> (8 * (i & 3))) & 0xFF);
+        eB = (int32_t)(((i < 4 ? vb[j].x : vb[j].y) >> (8 * (i & 3))) & 0xFF);
+        eC = (int32_t)(((i < 4 ? vc[j].x : vc[j].y) >> (8 * (i & 3))) & 0xFF);
+      }
+      else
+      {
+        eA = i < npx ? codesA[off + i] : 0;
+        eB = i < npx ? codesB[off + i] : 0;
+        eC = i < npx ? codesC[off + i] : 0;
+      }
+
+      uint32_t px = (uint32_t)recon_channel(r, 0, eA, eB, eC) | ((uint32_t)recon_channel(r, 1, eA, eB, eC) << 8) | ((uint32_t)recon_channel(r, 2, eA, eB, eC) << 16);
+
+      if (CH == 4)
+        px |= (uint32_t)recon_channel(r, 3, eA, eB, eC) << 24;
+      else
+        px |= 0xFF000000u;
+
+      out[i] = px;
     }
-  }
 
-#pragma unroll
-  for (int j = 0; j < 8; j++)
-  {
-    const int32_t eA = (int32_t)a[j], eB = (int32_t)b[j], eC = (int32_t)c[j];
-    out[j] = (uint32_t)recon_channel(r, 0, eA, eB, eC) | ((uint32_t)recon_channel(r, 1, eA, eB, eC) << 8) |
-             ((uint32_t)recon_channel(r, 2, eA, eB, eC) << 16) | ((uint32_t)recon_channel(r, 3, eA, eB, eC) << 24);
+    store8_u32(dst + off, out, npx, fast);
   }
-
-  store8_u32(dst + rowOff, out, npx, aligned);
 }
 
 // block map from an area table produced elsewhere

@@ -790,7 +790,7 @@ extern "C" int limgcu_decode(limgcu_ctx *ctx, const limgcu_area *d_areas, const 
   CK(cudaSetDevice(ctx->device));
 
   const int W = (int)sizeX, H = (int)sizeY, BX = (W + 7) / 8;
-  const long long segs = (long long)BX * H;
+  const long long segs = (long long)BX * ((H + 7) / 8) * 2; // one thread per half block (8 x 4 pixels)
   const int grid = (int)((segs + 255) / 256);
   const int vec = (W % 8 == 0) && aligned32(d_codesA) && aligned32(d_codesB) && aligned32(d_codesC) && aligned32(d_dst);
 
