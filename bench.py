@@ -313,7 +313,9 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": npx * world * args.steps / 1e6 / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "path": "limgcu_host_encode_stream + limgcu_host_decode, pinned host buffers"},
-            "roofline": {"bound": "hbm", "achieved": enc_gbs, "peak": peak, "unit": "GB/s", "frac": enc_gbs / peak, "traffic": None,
+            "roofline": {"bound": "hbm", "achieved": enc_gbs, "peak": peak, "unit": "GB/s", "frac": enc_gbs / peak,
+                         # DRAM bytes of the dominant kernel (k_merge_wave) per launch from profiles/r1_d_ncu_wave_details.txt (4K photo only)
+                         "traffic": 7.19e6 if args.workload == "c2_4k_photo" else None,
                          "kernel": "encode path (all kernels of limgcu_blocked_encode3d), 7 algorithmic B/px", "peak_source": peak_src,
                          "dominant_kernel": dominant, "dominant_share": phase_acc[dominant] / max(sum(phase_acc.values()), 1e-9),
                          "phase_ms": {k: round(v, 4) for k, v in phase_acc.items()},
