@@ -543,6 +543,76 @@ struct WaveScan
       return strip_joins(rec, x0, y0, w, h);
     };
 
+    // Fast path: while the rectangle and every strip the next iteration can ask for lie inside the known part, an iteration is four
+    // bit tests (one ballot / shuffle each) on `avail`, no predicates and no lambdas. The order of the tests inside an iteration is
+    // the reference's: right, down, up, left (limg.cpp:1315-1383).
+    if (ox >= g.vx0 && oy >= g.vy0 && ox + rx <= g.vx1 && oy + ry <= g.vy1)
+    {
+      const uint32_t av = g.avail;
+
+      while (right || down || up || left)
+      {
+        // containment of the strips does not depend on what the earlier directions of the same iteration do
+        if ((right && ox + rx >= g.vx1) || (down && oy + ry >= g.vy1) || (up && oy - 1 < g.vy0) || (left && ox - 1 < g.vx0))
+          break; // continue with the general loop below (same state)
+
+        if (right)
+        {
+          bool ok = ox + rx + 1 < a.BX;
+
+          if (ok)
+          {
+            const uint32_t rows = (ry >= 32 ? 0xFFFFFFFFu : ((1u << ry) - 1u)) << (oy - g.ay);
+            ok = (__ballot_sync(0xFFFFFFFFu, (av >> (ox + rx - g.ax)) & 1u) & rows) == rows;
+          }
+
+          if (ok) rx++; else right = false;
+        }
+
+        if (down)
+        {
+          bool ok = oy + ry + 1 < a.BY;
+
+          if (ok)
+          {
+            const uint32_t cols = (rx >= 32 ? 0xFFFFFFFFu : ((1u << rx) - 1u)) << (ox - g.ax);
+            ok = (__shfl_sync(0xFFFFFFFFu, av, oy + ry - g.ay) & cols) == cols;
+          }
+
+          if (ok) ry++; else down = false;
+        }
+
+        if (up)
+        {
+          bool ok = oy > 0;
+
+          if (ok)
+          {
+            const uint32_t cols = (rx >= 32 ? 0xFFFFFFFFu : ((1u << rx) - 1u)) << (ox - g.ax);
+            ok = (__shfl_sync(0xFFFFFFFFu, av, oy - 1 - g.ay) & cols) == cols;
+          }
+
+          if (ok) { oy--; ry++; } else up = false;
+        }
+
+        if (left)
+        {
+          bool ok = ox > 0;
+
+          if (ok)
+          {
+            const uint32_t rows = (ry >= 32 ? 0xFFFFFFFFu : ((1u << ry) - 1u)) << (oy - g.ay);
+            ok = (__ballot_sync(0xFFFFFFFFu, (av >> (ox - 1 - g.ax)) & 1u) & rows) == rows;
+          }
+
+          if (ok) { ox--; rx++; } else left = false;
+        }
+
+        if (minSide && ((!right && rx < minSide) || (!down && ry < minSide)))
+          return;
+      }
+    }
+
     // is the strip outside the known part (so that it would be evaluated on demand)?
     auto outside = [&](int x0, int y0, int w, int h) -> bool {
       return !(x0 >= g.vx0 && y0 >= g.vy0 && x0 + w <= g.vx1 && y0 + h <= g.vy1);
@@ -825,6 +895,8 @@ __global__ void __launch_bounds__(LIMG_WAVE_WARPS * 32) k_merge_wave(WaveArgs a,
   const int nWords = (a.BX + 31) >> 5;
   uint32_t nExp[2] = { 0, 0 }, nReexp[2] = { 0, 0 }, nPolls[2] = { 0, 0 }, nOnDemand[2] = { 0, 0 };
   long long tNext = 0, tWait = 0, tExpand = 0, tClaim = 0, tPre = 0, tc;
+  long long cSeedStart = 0, cPre = 0, cWait = 0, cExp = 0, cClaim = 0, cTotal[2] = { 0, 0 }, cParts[2][4] = { { 0, 0, 0, 0 }, { 0, 0, 0, 0 } };
+  uint32_t cIters = 0, cCount[2] = { 0, 0 }, cItersSum[2] = { 0, 0 };
   bool failed = false;
 
   for (;;)
@@ -925,8 +997,10 @@ __global__ void __launch_bounds__(LIMG_WAVE_WARPS * 32) k_merge_wave(WaveArgs a,
         break;
 
       tc = wave_clock();
+      cSeedStart = tc;
       SeedPre pre = scan.prefetch(x, y, stage);
       tPre += wave_clock() - tc;
+      cPre = wave_clock() - tc; cWait = 0; cExp = 0; cClaim = 0; cIters = 0;
       const uint32_t first = count;
       int nextX = x + 1;
       bool claimed = false;
@@ -968,6 +1042,7 @@ __global__ void __launch_bounds__(LIMG_WAVE_WARPS * 32) k_merge_wave(WaveArgs a,
 
           const Snapshot sn = scan.snapshot(x, y); // after the progress read
           tWait += wave_clock() - tc;
+          cWait += wave_clock() - tc; cIters++;
 
           if (scan.snap_used(sn, x)) { taken = true; break; }
 
@@ -984,6 +1059,7 @@ __global__ void __launch_bounds__(LIMG_WAVE_WARPS * 32) k_merge_wave(WaveArgs a,
             nExp[stage]++;
             const long long dt = wave_clock() - tc;
             tExpand += dt;
+            cExp += dt;
 
             if (LIMG_WAVE_PROFILE && a.dbg && lane == 0)
               atomicAdd(&a.dbg[stage * 16 + min(15, 63 - __clzll((dt >> 8) | 1))], 1u);
@@ -1060,6 +1136,7 @@ __global__ void __launch_bounds__(LIMG_WAVE_WARPS * 32) k_merge_wave(WaveArgs a,
         count++;
         claimed = true;
         tClaim += wave_clock() - tc;
+        cClaim += wave_clock() - tc;
 
         if (r.kind == 2)
         {
@@ -1077,6 +1154,14 @@ __global__ void __launch_bounds__(LIMG_WAVE_WARPS * 32) k_merge_wave(WaveArgs a,
 
       if (claimed && lane == 0)
         emitInfo[(size_t)y * a.BX + x] = (first << 8) | (count - first);
+
+      if (LIMG_WAVE_PROFILE && claimed)
+      {
+        cTotal[stage] += wave_clock() - cSeedStart;
+        cParts[stage][0] += cPre; cParts[stage][1] += cWait; cParts[stage][2] += cExp; cParts[stage][3] += cClaim;
+        cCount[stage]++;
+        cItersSum[stage] += cIters;
+      }
 
       x = nextX;
 
@@ -1162,6 +1247,17 @@ __global__ void __launch_bounds__(LIMG_WAVE_WARPS * 32) k_merge_wave(WaveArgs a,
       {
         atomicAdd(&a.dbg[32 + c], scan.nStrips[c]);
         atomicAdd(&a.dbg[32 + 4 + c], (uint32_t)(scan.tStrips[c] >> 10));
+      }
+
+      for (int st = 0; st < 2; st++)
+      {
+        atomicAdd(&a.dbg[200 + st * 8 + 0], cCount[st]);
+        atomicAdd(&a.dbg[200 + st * 8 + 1], (uint32_t)(cTotal[st] >> 10));
+        atomicAdd(&a.dbg[200 + st * 8 + 2], (uint32_t)(cParts[st][0] >> 10));
+        atomicAdd(&a.dbg[200 + st * 8 + 3], (uint32_t)(cParts[st][1] >> 10));
+        atomicAdd(&a.dbg[200 + st * 8 + 4], (uint32_t)(cParts[st][2] >> 10));
+        atomicAdd(&a.dbg[200 + st * 8 + 5], (uint32_t)(cParts[st][3] >> 10));
+        atomicAdd(&a.dbg[200 + st * 8 + 6], cItersSum[st]);
       }
 
       atomicAdd(&a.dbg[53], scan.nBuilt);

@@ -25,4 +25,8 @@ for name in ("c1_512_gradient","c5_1080p_frame0","c2_4k_photo","c4_4k_flatui","c
     print("   on-demand strips [seed, 4way+bitmap, 4way no bitmap]: n %s kcyc %s | - %s %s | four-way attempts %d, centre mispredicted %d, no bitmap %d, built on the fly %d" % (dbg[32:35].tolist(), dbg[36:39].tolist(), dbg[40:43].tolist(), dbg[44:47].tolist(), dbg[48], dbg[49], dbg[50], dbg[53]))
     print("   strips outside the known part [left, up, right, down]: seed %s 4way+bitmap %s 4way-no-bitmap %s ; known reach (blocks from centre) when right/down left it: %s" % (dbg[64:68].tolist(), dbg[68:72].tolist(), dbg[72:76].tolist(), dbg[80:96].tolist()))
     print("   stage 0 at commit: rows above ahead by (x4 columns) %s ; probe box width (x2) %s ; immediate %d waited %d" % (dbg[128:160].tolist(), dbg[160:192].tolist(), dbg[192], dbg[193]))
+    for st in range(2):
+        o = dbg[200 + st * 8: 208 + st * 8].astype(float)
+        if o[0] > 0:
+            print("   stage %d emitting seeds: %d, per seed (cycles): total %.0f = prefetch %.0f + poll/snapshot %.0f (%.1f iterations) + expand %.0f + claim %.0f + rest" % (st, o[0], 1024 * o[1] / o[0], 1024 * o[2] / o[0], 1024 * o[3] / o[0], o[6] / o[0], 1024 * o[4] / o[0], 1024 * o[5] / o[0]))
     print(name, "%dx%d"%(w,h), "total %.3f ms (wall %.3f) -> %.1f Mpx/s"%(tot, dt*1e3, w*h/tot/1e3), {k: round(v,3) for k,v in ph.items()})
