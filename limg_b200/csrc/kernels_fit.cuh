@@ -46,30 +46,32 @@ __global__ void __launch_bounds__(256) k_pass1(const uint32_t *__restrict__ src,
   __syncthreads();
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int b = blockIdx.x * 8 + warp;
-
-  if (b >= BX * BY)
-    return;
-
-  const int by = b / BX, bx = b - by * BX;
-  const int x0 = bx * LIMG_BLOCK, y0 = by * LIMG_BLOCK;
-  const int w = min(LIMG_BLOCK, W - x0), h = min(LIMG_BLOCK, H - y0);
-  const uint32_t n = (uint32_t)(w * h);
-
-  for (uint32_t i = lane; i < n; i += 32)
-  {
-    const int row = i / w, col = i - row * w;
-    sPx[warp][i] = src[(size_t)(y0 + row) * W + x0 + col];
-  }
-
-  __syncwarp();
-
-  limgcu_decomp d;
   uint32_t parity = 0;
-  group_fit<CH, 1>(sPx[warp], n, sLut, sStage[warp], 64, &sGs[warp], parity, d);
 
-  if (lane == 0)
-    store_decomp(&table[b], d);
+  // persistent warps: the 4 KB rsqrt table is staged once per CTA, not once per eight blocks
+  for (int b = blockIdx.x * 8 + warp; b < BX * BY; b += gridDim.x * 8)
+  {
+    const int by = b / BX, bx = b - by * BX;
+    const int x0 = bx * LIMG_BLOCK, y0 = by * LIMG_BLOCK;
+    const int w = min(LIMG_BLOCK, W - x0), h = min(LIMG_BLOCK, H - y0);
+    const uint32_t n = (uint32_t)(w * h);
+
+    for (uint32_t i = lane; i < n; i += 32)
+    {
+      const int row = i / w, col = i - row * w;
+      sPx[warp][i] = src[(size_t)(y0 + row) * W + x0 + col];
+    }
+
+    __syncwarp();
+
+    limgcu_decomp d;
+    group_fit<CH, 1>(sPx[warp], n, sLut, sStage[warp], 64, &sGs[warp], parity, d);
+
+    if (lane == 0)
+      store_decomp(&table[b], d);
+
+    __syncwarp();
+  }
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -401,7 +401,7 @@ static int check_image(limgcu_ctx *ctx, size_t W, size_t H)
 static int launch_pass1(limgcu_ctx *ctx, const uint32_t *dSrc, size_t W, size_t H, int hasAlpha, limgcu_decomp *dTable)
 {
   const int BX = (int)((W + 7) / 8), BY = (int)((H + 7) / 8);
-  const int grid = (BX * BY + 7) / 8;
+  const int grid = (BX * BY + 7) / 8 < ctx->smCount * 8 ? (BX * BY + 7) / 8 : ctx->smCount * 8;
 
   if (hasAlpha)
     k_pass1<4><<<grid, 256, 0, ctx->stream>>>(dSrc, (int)W, (int)H, BX, BY, ctx->dLut, dTable);
