@@ -66,19 +66,61 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock + throttle reasons during the timed region (B200_PROFILING.md's clocks line), sampled in-process through NVML
+    every few ms (the timed region of a short run is shorter than nvidia-smi's start-up); nvidia-smi -lms is the fallback."""
 
     FIELDS = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
     def __init__(self, gpu_index: int):
         self.gpu_index = gpu_index
         self.proc = None
         self.lines = []
+        self.sm, self.mx, self.reasons = [], [], set()
+        self.stop_flag = threading.Event()
+        self.thread = None
+        self.source = None
+
+    def _nvml_handle(self):
+        import pynvml
+        pynvml.nvmlInit()
+        visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+        index = self.gpu_index
+        if visible:
+            entry = visible.split(",")[self.gpu_index].strip()
+            if entry.isdigit():
+                index = int(entry)
+            else:
+                return pynvml, pynvml.nvmlDeviceGetHandleByUUID(entry)
+        return pynvml, pynvml.nvmlDeviceGetHandleByIndex(index)
+
+    def _poll_nvml(self, pynvml, handle):
+        while True:
+            try:
+                self.sm.append(float(pynvml.nvmlDeviceGetClockInfo(handle, pynvml.NVML_CLOCK_SM)))
+                mask = int(pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(handle))
+                for name, bit in self.REASONS:
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            if self.stop_flag.wait(0.004):
+                break
 
     def start(self):
         try:
+            pynvml, handle = self._nvml_handle()
+            self.mx.append(float(pynvml.nvmlDeviceGetMaxClockInfo(handle, pynvml.NVML_CLOCK_SM)))
+            self.source = "nvml"
+            self.thread = threading.Thread(target=self._poll_nvml, args=(pynvml, handle), daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.source = None
+        try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.source = "nvidia-smi"
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except Exception:
@@ -89,26 +131,30 @@ class ClockSampler:
             self.lines.append(line.strip())
 
     def stop(self) -> dict:
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        for line in self.lines:
-            p = [x.strip() for x in line.split(",")]
-            if len(p) < 9:
-                continue
+        if self.source is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml and nvidia-smi unavailable"], "samples": 0}
+        if self.source == "nvml":
+            self.stop_flag.set()
+            self.thread.join(timeout=2)
+        else:
+            self.proc.terminate()
             try:
-                sm.append(float(p[1])); mx.append(float(p[2]))
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+            for line in self.lines:
+                p = [x.strip() for x in line.split(",")]
+                if len(p) < 9:
+                    continue
+                try:
+                    self.sm.append(float(p[1])); self.mx.append(float(p[2]))
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[5:9]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(name)
+        sm, mx = self.sm, self.mx
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(self.reasons), "samples": len(sm), "source": self.source}
 
 
 def host_cores() -> int:

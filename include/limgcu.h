@@ -124,6 +124,11 @@ int limgcu_debug_predicate_check(limgcu_ctx *ctx, const limgcu_decomp *table, si
  * time (1: row stamps, n > 1: also the decisions of stage-0 rows n .. n+3). `out` needs 8 * blockY + 512 words. */
 int limgcu_debug_wave_rows(limgcu_ctx *ctx, uint32_t *out, size_t blockY);
 
+/* selects the reconstruction kernel of limgcu_decode (tuning / A-B timing, tools/decode_time.py): 0 = generic k_decode,
+ * 2 / 4 / 8 = rows of an 8x8 block one thread of k_decode_tile reconstructs (kernels_decode.cuh; needs sizeX % 8 == 0, otherwise the
+ * generic kernel runs). Results are identical for every value. */
+int limgcu_debug_set_decode_variant(limgcu_ctx *ctx, int variant);
+
 /* device-buffer entry points ------------------------------------------------------------------------------------ */
 
 /* pass 1: three-factor fit of every 8x8 block -> blockX*blockY records (limg.cpp:1088-1119). */

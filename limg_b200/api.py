@@ -55,6 +55,9 @@ class Codec:
     def launch_count(self) -> int:
         return int(self.lib.limgcu_launch_count(self.h))
 
+    def set_decode_variant(self, variant: int):
+        self._ck(self.lib.limgcu_debug_set_decode_variant(self.h, int(variant)), "limgcu_debug_set_decode_variant")
+
     def set_rsqrt_lut(self, lut=None):
         if lut is not None:
             lut = np.ascontiguousarray(lut, dtype=np.uint16)

@@ -4,6 +4,7 @@
 #include "kernels_merge.cuh"
 #include "kernels_wave.cuh"
 #include "kernels_stream.cuh"
+#include "kernels_decode.cuh"
 #include "rsqrt_lut.h"
 
 #include <stdio.h>
@@ -73,6 +74,7 @@ struct limgcu_ctx
   int mergeGap = 16;                 // LIMGCU_MERGE_GAP: block rows stage 1 stays behind stage 0
   int mergeWideMargin = 64;          // margin (and stage gap) of the second try
   int mergeSpec = 8;                 // LIMGCU_MERGE_SPEC: columns of lookahead for the speculative expansion
+  int decodeVariant = 4;             // LIMGCU_DECODE_VARIANT: 0 generic k_decode; 2 / 4 / 8 = rows per thread of k_decode_tile (width % 8 == 0)
   int mergeMargin = 8;               // LIMGCU_MERGE_MARGIN: columns a row stays behind the rows above, beyond what its seed probed
   bool timing = false;
   cudaEvent_t ev[PHASE_COUNT + 1] = { nullptr };
@@ -273,6 +275,7 @@ extern "C" int limgcu_create(int device, limgcu_ctx **out)
   if (const char *v = getenv("LIMGCU_MERGE_ROWTIMES")) ctx->waveRowTimes = atoi(v);
   if (const char *v = getenv("LIMGCU_PLAN_ASYNC")) ctx->planAsync = atoi(v);
   if (const char *v = getenv("LIMGCU_MERGE_GAP")) ctx->mergeGap = atoi(v) < 0 ? 0 : atoi(v);
+  if (const char *v = getenv("LIMGCU_DECODE_VARIANT")) ctx->decodeVariant = atoi(v);
   if (const char *v = getenv("LIMGCU_MERGE_SPEC")) ctx->mergeSpec = atoi(v) < 0 ? 0 : atoi(v);
 
   for (auto &e : ctx->ev)
@@ -794,12 +797,35 @@ extern "C" int limgcu_decode(limgcu_ctx *ctx, const limgcu_area *d_areas, const 
   const int grid = (int)((segs + 255) / 256);
   const int vec = (W % 8 == 0) && aligned32(d_codesA) && aligned32(d_codesB) && aligned32(d_codesC) && aligned32(d_dst);
 
-  if (hasAlpha)
+  if (vec && ctx->decodeVariant > 0)
+  {
+    const int rows = ctx->decodeVariant;
+    const long long threads = (long long)BX * ((H + 7) / 8) * (8 / rows);
+    const int g = (int)((threads + 255) / 256);
+#define LIMG_DECODE_CASE(R) \
+    if (rows == R) \
+    { \
+      if (hasAlpha) k_decode_tile<4, R><<<g, 256, 0, ctx->stream>>>(d_areas, d_block_to_area, d_codesA, d_codesB, d_codesC, W, H, BX, (uint32_t)threads, d_dst); \
+      else k_decode_tile<3, R><<<g, 256, 0, ctx->stream>>>(d_areas, d_block_to_area, d_codesA, d_codesB, d_codesC, W, H, BX, (uint32_t)threads, d_dst); \
+    }
+    LIMG_DECODE_CASE(2) LIMG_DECODE_CASE(4) LIMG_DECODE_CASE(8)
+#undef LIMG_DECODE_CASE
+  }
+  else if (hasAlpha)
     k_decode<4><<<grid, 256, 0, ctx->stream>>>(d_areas, d_block_to_area, d_codesA, d_codesB, d_codesC, W, H, BX, d_dst, vec);
   else
     k_decode<3><<<grid, 256, 0, ctx->stream>>>(d_areas, d_block_to_area, d_codesA, d_codesB, d_codesC, W, H, BX, d_dst, vec);
 
   CKL("k_decode");
+  return LIMGCU_SUCCESS;
+}
+
+extern "C" int limgcu_debug_set_decode_variant(limgcu_ctx *ctx, int variant)
+{
+  if (!ctx) return LIMGCU_ERROR_ARGUMENT_NULL;
+  if (variant != 0 && variant != 2 && variant != 4 && variant != 8)
+    return fail(ctx, LIMGCU_ERROR_INVALID_PARAMETER, "decode variant: 0, 2, 4 or 8", cudaSuccess);
+  ctx->decodeVariant = variant;
   return LIMGCU_SUCCESS;
 }
 
