@@ -74,7 +74,7 @@ struct limgcu_ctx
   int mergeGap = 16;                 // LIMGCU_MERGE_GAP: block rows stage 1 stays behind stage 0
   int mergeWideMargin = 64;          // margin (and stage gap) of the second try
   int mergeSpec = 8;                 // LIMGCU_MERGE_SPEC: columns of lookahead for the speculative expansion
-  int decodeVariant = 4;             // LIMGCU_DECODE_VARIANT: 0 generic k_decode; 2 / 4 / 8 = rows per thread of k_decode_tile (width % 8 == 0)
+  int decodeVariant = 20;            // LIMGCU_DECODE_VARIANT: 0 generic k_decode; 2 / 4 / 8 = rows per thread of k_decode_tile (width % 8 == 0)
   int mergeMargin = 8;               // LIMGCU_MERGE_MARGIN: columns a row stays behind the rows above, beyond what its seed probed
   bool timing = false;
   cudaEvent_t ev[PHASE_COUNT + 1] = { nullptr };
@@ -797,18 +797,46 @@ extern "C" int limgcu_decode(limgcu_ctx *ctx, const limgcu_area *d_areas, const 
   const int grid = (int)((segs + 255) / 256);
   const int vec = (W % 8 == 0) && aligned32(d_codesA) && aligned32(d_codesB) && aligned32(d_codesC) && aligned32(d_dst);
 
-  if (vec && ctx->decodeVariant > 0)
+  const bool bulkOk = (W % 16 == 0) && (((uintptr_t)d_codesA | (uintptr_t)d_codesB | (uintptr_t)d_codesC | (uintptr_t)d_dst) & 15) == 0;
+
+  if (vec && bulkOk && (ctx->decodeVariant & 64))
   {
-    const int rows = ctx->decodeVariant;
-    const long long threads = (long long)BX * ((H + 7) / 8) * (8 / rows);
-    const int g = (int)((threads + 255) / 256);
-#define LIMG_DECODE_CASE(R) \
-    if (rows == R) \
+    const int warps = ctx->decodeVariant & 15;
+    const int tilesX = (BX + kDecodeTileBlocks - 1) / kDecodeTileBlocks, tiles = tilesX * ((H + 7) / 8);
+    const size_t smem = (size_t)warps * (2 * kDecodeStageBytes + 16);
+    const int perSM = (int)((227 * 1024) / (smem + 1024)) < 2048 / (warps * 32) ? (int)((227 * 1024) / (smem + 1024)) : 2048 / (warps * 32);
+    const int g = (tiles + warps - 1) / warps < ctx->smCount * perSM ? (tiles + warps - 1) / warps : ctx->smCount * perSM;
+#define LIMG_DECODE_CASE(WP) \
+    if (warps == WP) \
     { \
-      if (hasAlpha) k_decode_tile<4, R><<<g, 256, 0, ctx->stream>>>(d_areas, d_block_to_area, d_codesA, d_codesB, d_codesC, W, H, BX, (uint32_t)threads, d_dst); \
-      else k_decode_tile<3, R><<<g, 256, 0, ctx->stream>>>(d_areas, d_block_to_area, d_codesA, d_codesB, d_codesC, W, H, BX, (uint32_t)threads, d_dst); \
+      if (hasAlpha) \
+      { \
+        CK(cudaFuncSetAttribute(k_decode_stream<4, WP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        k_decode_stream<4, WP><<<g, WP * 32, smem, ctx->stream>>>(d_areas, d_block_to_area, d_codesA, d_codesB, d_codesC, W, H, BX, tilesX, tiles, d_dst); \
+      } \
+      else \
+      { \
+        CK(cudaFuncSetAttribute(k_decode_stream<3, WP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        k_decode_stream<3, WP><<<g, WP * 32, smem, ctx->stream>>>(d_areas, d_block_to_area, d_codesA, d_codesB, d_codesC, W, H, BX, tilesX, tiles, d_dst); \
+      } \
     }
-    LIMG_DECODE_CASE(2) LIMG_DECODE_CASE(4) LIMG_DECODE_CASE(8)
+    LIMG_DECODE_CASE(1) LIMG_DECODE_CASE(2) LIMG_DECODE_CASE(4) LIMG_DECODE_CASE(8)
+#undef LIMG_DECODE_CASE
+  }
+  else if (vec && (ctx->decodeVariant & 15) > 0)
+  {
+    const int rows = ctx->decodeVariant & 15, cta = (ctx->decodeVariant & 16) ? 128 : 256, cs = (ctx->decodeVariant & 32) ? 1 : 0;
+    const long long threads = (long long)BX * ((H + 7) / 8) * (8 / rows);
+    const int g = (int)((threads + cta - 1) / cta);
+#define LIMG_DECODE_CASE(R, T, S) \
+    if (rows == R && cta == T && cs == S) \
+    { \
+      if (hasAlpha) k_decode_tile<4, R, T, S != 0><<<g, T, 0, ctx->stream>>>(d_areas, d_block_to_area, d_codesA, d_codesB, d_codesC, W, H, BX, (uint32_t)threads, d_dst); \
+      else k_decode_tile<3, R, T, S != 0><<<g, T, 0, ctx->stream>>>(d_areas, d_block_to_area, d_codesA, d_codesB, d_codesC, W, H, BX, (uint32_t)threads, d_dst); \
+    }
+    LIMG_DECODE_CASE(2, 256, 0) LIMG_DECODE_CASE(4, 256, 0) LIMG_DECODE_CASE(8, 256, 0)
+    LIMG_DECODE_CASE(2, 128, 0) LIMG_DECODE_CASE(4, 128, 0)
+    LIMG_DECODE_CASE(4, 256, 1) LIMG_DECODE_CASE(4, 128, 1)
 #undef LIMG_DECODE_CASE
   }
   else if (hasAlpha)
@@ -823,8 +851,11 @@ extern "C" int limgcu_decode(limgcu_ctx *ctx, const limgcu_area *d_areas, const 
 extern "C" int limgcu_debug_set_decode_variant(limgcu_ctx *ctx, int variant)
 {
   if (!ctx) return LIMGCU_ERROR_ARGUMENT_NULL;
-  if (variant != 0 && variant != 2 && variant != 4 && variant != 8)
-    return fail(ctx, LIMGCU_ERROR_INVALID_PARAMETER, "decode variant: 0, 2, 4 or 8", cudaSuccess);
+  static const int known[] = {0, 2, 4, 8, 18, 20, 36, 52, 65, 66, 68, 72};
+  bool ok = false;
+  for (int v : known) ok |= v == variant;
+  if (!ok)
+    return fail(ctx, LIMGCU_ERROR_INVALID_PARAMETER, "decode variant: 0, 2, 4, 8, 18, 20, 36, 52, 65, 66, 68, 72", cudaSuccess);
   ctx->decodeVariant = variant;
   return LIMGCU_SUCCESS;
 }

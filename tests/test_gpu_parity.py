@@ -332,3 +332,66 @@ def test_predicate_shortcut_on_adversarial_records(codec):
     scored, decided, wrong, _ = [int(v) for v in codec.predicate_check(t, w, h, False)]
     print("adversarial: pairs scored", scored, "decided", decided, "disagreements", wrong)
     assert scored > 10000 and wrong == 0
+
+
+# ---- decode kernel variants (kernels_decode.cuh) against the oracle on adversarial streams -----------------------------------
+
+DECODE_VARIANTS = (0, 2, 4, 8, 18, 20, 36, 52, 65, 66, 68, 72)
+
+
+def random_stream(rng, w, h, alpha, extreme):
+    """A syntactically valid stream that no encoder would produce: random rectangles (one block row high), random int16 decompositions
+    (the full int16 range when `extreme`), random shifts 0..8 and random code bytes (not even masked to 8 - shift bits)."""
+    from limg_b200 import AREA_DTYPE
+    bx, by = (w + 7) // 8, (h + 7) // 8
+    rects = []
+    for y in range(by):
+        x = 0
+        while x < bx:
+            rx = int(min(bx - x, rng.integers(1, 4)))
+            rects.append((x, y, rx, 1))
+            x += rx
+    a = np.zeros(len(rects), dtype=AREA_DTYPE)
+    r = np.array(rects, dtype=np.uint32)
+    a["ox"], a["oy"], a["rx"], a["ry"] = r[:, 0], r[:, 1], r[:, 2], r[:, 3]
+    a["stage"] = 2
+    a["px_x"], a["px_y"] = r[:, 0] * 8, r[:, 1] * 8
+    a["px_w"] = np.minimum(r[:, 2] * 8, w - r[:, 0] * 8)
+    a["px_h"] = np.minimum(8, h - r[:, 1] * 8)
+    a["shift"] = rng.integers(0, 9, (len(rects), 3), dtype=np.uint8)
+    lim = 32767 if extreme else 300
+    for name in a["decomp"].dtype.names:
+        if name != "avg":
+            a["decomp"][name] = rng.integers(-lim - 1 if extreme else -lim, lim + 1, (len(rects), 4)).astype(np.int16)
+    if not alpha:
+        for name in a["decomp"].dtype.names:
+            if name != "avg":
+                a["decomp"][name][:, 3] = 0
+    codes = [rng.integers(0, 256, (h, w), dtype=np.uint8) for _ in range(3)]
+    return a, codes
+
+
+def gather_streams(areas, codes):
+    """image-layout code planes -> the area-contiguous streams the oracle's decoder reads"""
+    out = []
+    for plane in codes:
+        out.append(np.concatenate([plane[y:y + ph, x:x + pw].ravel() for x, y, pw, ph in zip(areas["px_x"], areas["px_y"], areas["px_w"], areas["px_h"])]))
+    return out
+
+
+@pytest.mark.parametrize("shape", [(64, 40, False, False), (128, 68, True, True), (72, 32, False, True), (61, 37, True, False), (784, 264, False, True), (1040, 72, True, True)])
+def test_decode_variants_on_adversarial_streams(codec, lo, shape):
+    """Every reconstruction kernel (generic, register tiles, bulk-copy pipeline) == the oracle's decoder, including 32-bit wrap-around,
+    dropped factors (shift 8, Q7), widths that are not a multiple of 8 / 16 and heights that are not a multiple of 8."""
+    w, h, alpha, extreme = shape
+    rng = np.random.default_rng(w * 1000 + h)
+    areas, codes = random_stream(rng, w, h, alpha, extreme)
+    fa, fb, fc = gather_streams(areas, codes)
+    want = lo.decode_areas(alpha, areas, fa, fb, fc, h, w)
+    try:
+        for v in DECODE_VARIANTS:
+            codec.set_decode_variant(v)
+            got = codec.decode(areas, codes[0], codes[1], codes[2], alpha)
+            assert np.array_equal(got, want), "decode variant %d" % v
+    finally:
+        codec.set_decode_variant(20)
