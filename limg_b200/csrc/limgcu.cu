@@ -23,7 +23,8 @@ struct limgcu_ctx
   cudaStream_t stream = nullptr;
   cudaStream_t streamAux = nullptr; // the speculative match bitmaps are computed here while the scan already runs on `stream`
   cudaEvent_t evFork = nullptr, evJoin = nullptr;
-  int planAsync = 0;                // LIMGCU_PLAN_ASYNC=1: the plan kernels on the second stream, concurrently with the scan
+  int planAsync = 1;                // LIMGCU_PLAN_ASYNC: 0 plan kernels on the main stream, 1 both on the second stream concurrently with the scan, 2 only k_plan_sym
+  int planAsyncCtas = 2;            // LIMGCU_PLAN_CTAS: CTAs per SM of an asynchronous plan kernel (the scan needs room next to them)
   char err[512] = { 0 };
   uint64_t launches = 0;
   int smCount = 148;
@@ -274,6 +275,7 @@ extern "C" int limgcu_create(int device, limgcu_ctx **out)
   if (const char *v = getenv("LIMGCU_PLAN_SYMD")) ctx->planSymD = atoi(v) < 8 ? 8 : (atoi(v) > 24 ? 24 : atoi(v));
   if (const char *v = getenv("LIMGCU_MERGE_ROWTIMES")) ctx->waveRowTimes = atoi(v);
   if (const char *v = getenv("LIMGCU_PLAN_ASYNC")) ctx->planAsync = atoi(v);
+  if (const char *v = getenv("LIMGCU_PLAN_CTAS")) ctx->planAsyncCtas = atoi(v) < 1 ? 1 : (atoi(v) > 8 ? 8 : atoi(v));
   if (const char *v = getenv("LIMGCU_MERGE_GAP")) ctx->mergeGap = atoi(v) < 0 ? 0 : atoi(v);
   if (const char *v = getenv("LIMGCU_DECODE_VARIANT")) ctx->decodeVariant = atoi(v);
   if (const char *v = getenv("LIMGCU_MERGE_SPEC")) ctx->mergeSpec = atoi(v) < 0 ? 0 : atoi(v);
@@ -458,9 +460,14 @@ static int launch_merge(limgcu_ctx *ctx, const limgcu_decomp *dTable, size_t W, 
     // The bitmaps beyond the 8x8 windows are pure accelerators of the scan and appear slot by slot, so their kernels run on a second,
     // low-priority stream WHILE the scan already walks the image top-down on the main stream; a seed whose bitmap is not there yet
     // is grown with on-demand predicates. Two plan CTAs per SM leave room for a scan CTA.
+    // planAsync: 0 everything on the main stream, 1 both bitmap kernels on the second stream, 2 the stage-0 extension bitmaps on the main
+    // stream (the first rows of the scan need them at once) and only the regrowth-centre bitmaps on the second stream.
     const bool async = ctx->planAsync != 0;
-    const int planGrid = ctx->smCount * (async ? 2 : 6);
+    const bool extendAsync = ctx->planAsync == 1;
+    const int planGrid = ctx->smCount * (async ? ctx->planAsyncCtas : 6);
+    const int extendGrid = ctx->smCount * (extendAsync ? ctx->planAsyncCtas : 6);
     cudaStream_t planStream = async ? ctx->streamAux : ctx->stream;
+    cudaStream_t extendStream = extendAsync ? ctx->streamAux : ctx->stream;
 
     if (hasAlpha)
     {
@@ -480,30 +487,34 @@ static int launch_merge(limgcu_ctx *ctx, const limgcu_decomp *dTable, size_t W, 
     k_plan_seeds<<<(blocks + 255) / 256, 256, 0, ctx->stream>>>(pl);
     CKL("k_plan_seeds");
 
-    if (async)
+    if (extendAsync)
     {
       CK(cudaEventRecord(ctx->evFork, ctx->stream));
       CK(cudaStreamWaitEvent(ctx->streamAux, ctx->evFork, 0));
     }
 
     if (hasAlpha)
-    {
-      k_plan_extend<4><<<planGrid, LIMG_PLAN_WARPS * 32, 0, planStream>>>(pl);
-      CKL("k_plan_extend");
-      k_plan_centres<<<(blocks + 255) / 256, 256, 0, planStream>>>(pl);
-      CKL("k_plan_centres");
-      k_plan_sym<4><<<planGrid, LIMG_PLAN_WARPS * 32, 0, planStream>>>(pl);
-      CKL("k_plan_sym");
-    }
+      k_plan_extend<4><<<extendGrid, LIMG_PLAN_WARPS * 32, 0, extendStream>>>(pl);
     else
+      k_plan_extend<3><<<extendGrid, LIMG_PLAN_WARPS * 32, 0, extendStream>>>(pl);
+
+    CKL("k_plan_extend");
+
+    if (async && !extendAsync)
     {
-      k_plan_extend<3><<<planGrid, LIMG_PLAN_WARPS * 32, 0, planStream>>>(pl);
-      CKL("k_plan_extend");
-      k_plan_centres<<<(blocks + 255) / 256, 256, 0, planStream>>>(pl);
-      CKL("k_plan_centres");
-      k_plan_sym<3><<<planGrid, LIMG_PLAN_WARPS * 32, 0, planStream>>>(pl);
-      CKL("k_plan_sym");
+      CK(cudaEventRecord(ctx->evFork, ctx->stream));
+      CK(cudaStreamWaitEvent(ctx->streamAux, ctx->evFork, 0));
     }
+
+    k_plan_centres<<<(blocks + 255) / 256, 256, 0, planStream>>>(pl);
+    CKL("k_plan_centres");
+
+    if (hasAlpha)
+      k_plan_sym<4><<<planGrid, LIMG_PLAN_WARPS * 32, 0, planStream>>>(pl);
+    else
+      k_plan_sym<3><<<planGrid, LIMG_PLAN_WARPS * 32, 0, planStream>>>(pl);
+
+    CKL("k_plan_sym");
 
     if (async)
     {
