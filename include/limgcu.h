@@ -166,6 +166,38 @@ int limgcu_host_pass1(limgcu_ctx *ctx, const uint32_t *pIn, size_t sizeX, size_t
 int limgcu_host_merge(limgcu_ctx *ctx, const limgcu_decomp *table, size_t sizeX, size_t sizeY, int hasAlpha, limgcu_area *areas, uint32_t *area_count);
 double limgcu_host_compare(limgcu_ctx *ctx, const uint32_t *pImageA, const uint32_t *pImageB, size_t sizeX, size_t sizeY, int hasAlpha, double *pMeanSquaredError, double *pMaxPossibleSquaredError);
 
+/* .limg container ------------------------------------------------------------------------------------------------ */
+
+/* The reference defines no bitstream (it only accounts for one: limg.cpp:1629-1636, a per-area header plus
+ * rangeSize * ((8 - shiftA) + (8 - shiftB) + (8 - shiftC)) payload bits). Container "LIMGB200" version 1, little endian:
+ *
+ *   header (48 bytes)   char magic[8] = "LIMGB200"; u32 version = 1; u32 flags (bit 0: alpha); u32 sizeX, sizeY; u32 areaCount;
+ *                       u32 recordBytes (48 RGB / 60 RGBA); u64 payloadBytes; u64 reserved = 0
+ *   area table          areaCount records in emission order: u16 ox, oy, rx, ry (8x8-block units); u8 shift[3]; u8 stage;
+ *                       int16 dirA_min[ch], dirA_max[ch], dirB_offset[ch], dirB_mag[ch], dirC_offset[ch], dirC_mag[ch] (un-clamped)
+ *   payload             per area, in table order: factor A, factor B, factor C; per factor the area's pixels in area-contiguous
+ *                       order (row-major inside the pixel rectangle), (8 - shift) bits per code, LSB first; every 8-pixel run of a
+ *                       row starts on a byte boundary (a ragged last run is padded with zero codes). A dropped factor (shift 8)
+ *                       takes 0 bits for RGB and keeps its raw byte for RGBA (the reference's RGBA reconstruction reads it).
+ *
+ * The pixel rectangle of an area follows from its block rectangle (edge fit, limg.cpp:1722-1739). */
+
+/* worst-case size of a container for an image of this size */
+size_t limgcu_container_bound(size_t sizeX, size_t sizeY, int hasAlpha);
+/* parses and validates the header; any out pointer may be NULL. No device needed. */
+int limgcu_container_info(const void *data, size_t bytes, size_t *sizeX, size_t *sizeY, int *hasAlpha, uint32_t *areaCount, uint64_t *payloadBytes);
+/* encode (limg_blocked_encode3d_test's path; LIMGCU_FLAG_NO_MERGE for limg_encode3d_test's) straight into a container in host memory */
+int limgcu_host_encode_container(limgcu_ctx *ctx, const uint32_t *pIn, size_t sizeX, size_t sizeY, int hasAlpha, uint32_t errorFactor, uint32_t flags, void *out, size_t capacity,
+                                 size_t *written);
+/* container in host memory -> sizeX * sizeY pixels (bit-identical to the encoder's pDecoded) */
+int limgcu_host_decode_container(limgcu_ctx *ctx, const void *data, size_t bytes, uint32_t *pOut, size_t outPixels);
+/* device level: code planes <-> payload. d_offsets receives area_count + 1 byte offsets (the last one is the payload size);
+ * d_payload needs 3 * ceil(sizeX / 8) * 8 * sizeY bytes. d_area_count (device) may be NULL, then area_count (host value) is used. */
+int limgcu_pack_payload(limgcu_ctx *ctx, const limgcu_area *d_areas, const uint32_t *d_area_count, uint32_t area_count, const uint32_t *d_block_to_area, const uint8_t *d_codesA,
+                        const uint8_t *d_codesB, const uint8_t *d_codesC, size_t sizeX, size_t sizeY, int hasAlpha, uint8_t *d_payload, uint64_t *d_offsets);
+int limgcu_unpack_payload(limgcu_ctx *ctx, const limgcu_area *d_areas, uint32_t area_count, const uint32_t *d_block_to_area, const uint8_t *d_payload, uint64_t *d_offsets,
+                          size_t sizeX, size_t sizeY, int hasAlpha, uint8_t *d_codesA, uint8_t *d_codesB, uint8_t *d_codesC);
+
 #ifdef __cplusplus
 }
 #endif

@@ -43,6 +43,7 @@ SYMBOLS = (
     "limgcu_debug_counters", "limgcu_debug_wave", "limgcu_debug_predicate_check", "limgcu_debug_wave_rows", "limgcu_debug_set_decode_variant", "limgcu_pass1", "limgcu_merge", "limgcu_blocked_encode3d", "limgcu_decode", "limgcu_build_block_map", "limgcu_compare",
     "limgcu_host_blocked_encode3d", "limgcu_host_encode3d", "limgcu_host_encode_stream", "limgcu_host_decode",
     "limgcu_host_pass1", "limgcu_host_merge", "limgcu_host_compare",
+    "limgcu_container_bound", "limgcu_container_info", "limgcu_host_encode_container", "limgcu_host_decode_container", "limgcu_pack_payload", "limgcu_unpack_payload",
 )
 
 
@@ -82,6 +83,13 @@ def load():
     lib.limgcu_stream_handle.restype = vp
     lib.limgcu_sync.argtypes = [vp]
     lib.limgcu_launch_count.argtypes = [vp]
+    lib.limgcu_container_bound.argtypes = [C.c_size_t, C.c_size_t, C.c_int]
+    lib.limgcu_container_bound.restype = C.c_size_t
+    lib.limgcu_container_info.argtypes = [vp, sz, C.POINTER(sz), C.POINTER(sz), C.POINTER(i32), C.POINTER(u32), C.POINTER(C.c_uint64)]
+    lib.limgcu_host_encode_container.argtypes = [vp, vp, sz, sz, i32, u32, u32, vp, sz, C.POINTER(sz)]
+    lib.limgcu_host_decode_container.argtypes = [vp, vp, sz, vp, sz]
+    lib.limgcu_pack_payload.argtypes = [vp, vp, vp, u32, vp, vp, vp, vp, sz, sz, i32, vp, vp]
+    lib.limgcu_unpack_payload.argtypes = [vp, vp, u32, vp, vp, vp, sz, sz, i32, vp, vp, vp]
     lib.limgcu_debug_set_decode_variant.argtypes = [vp, C.c_int]
     lib.limgcu_launch_count.restype = C.c_uint64
     lib.limgcu_enable_phase_timing.argtypes = [vp, i32]

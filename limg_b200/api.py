@@ -142,6 +142,29 @@ class Codec:
             out["decoded"] = dec
         return out
 
+    def encode_container(self, img, has_alpha: bool, error_factor: int = 100, fast_bit_crushing: bool = True, no_merge: bool = False) -> bytes:
+        """Image -> "LIMGB200" container bytes (include/limgcu.h): header, area table, bit-packed codes."""
+        img = np.ascontiguousarray(img, dtype=np.uint32)
+        h, w = img.shape
+        buf = np.zeros(self.lib.limgcu_container_bound(w, h, int(has_alpha)), np.uint8)
+        n = C.c_size_t(0)
+        flags = (FLAG_FAST_BIT_CRUSH if fast_bit_crushing else 0) | (FLAG_NO_MERGE if no_merge else 0)
+        self._ck(self.lib.limgcu_host_encode_container(self.h, _vp(img), w, h, int(has_alpha), int(error_factor), flags, _vp(buf), buf.size, C.byref(n)), "limgcu_host_encode_container")
+        return buf[: n.value].tobytes()
+
+    def container_info(self, data: bytes) -> dict:
+        buf = np.frombuffer(data, np.uint8)
+        w, h, a, n, pb = C.c_size_t(0), C.c_size_t(0), C.c_int(0), C.c_uint32(0), C.c_uint64(0)
+        self._ck(self.lib.limgcu_container_info(_vp(buf), buf.size, C.byref(w), C.byref(h), C.byref(a), C.byref(n), C.byref(pb)), "limgcu_container_info")
+        return {"width": w.value, "height": h.value, "has_alpha": bool(a.value), "area_count": n.value, "payload_bytes": pb.value}
+
+    def decode_container(self, data: bytes) -> np.ndarray:
+        info = self.container_info(data)
+        buf = np.frombuffer(data, np.uint8)
+        out = np.zeros((info["height"], info["width"]), np.uint32)
+        self._ck(self.lib.limgcu_host_decode_container(self.h, _vp(buf), buf.size, _vp(out), out.size), "limgcu_host_decode_container")
+        return out
+
     def decode(self, areas, codesA, codesB, codesC, has_alpha: bool) -> np.ndarray:
         """Reconstruction from a stream (limg_decode_block_from_factors_3d per area, limg_decode.h:326)."""
         areas = np.ascontiguousarray(areas, dtype=AREA_DTYPE)

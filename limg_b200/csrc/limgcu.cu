@@ -5,6 +5,7 @@
 #include "kernels_wave.cuh"
 #include "kernels_stream.cuh"
 #include "kernels_decode.cuh"
+#include "kernels_container.cuh"
 #include "rsqrt_lut.h"
 
 #include <stdio.h>
@@ -57,6 +58,9 @@ struct limgcu_ctx
   uint32_t *dSrc = nullptr;
   uint32_t *dPlaneU32[9] = { nullptr };
   uint8_t *dPlaneU8[7] = { nullptr }; // factors A,B,C, bpp, codes A,B,C
+  uint8_t *dPayload = nullptr;        // bit-packed container payload (kernels_container.cuh)
+  unsigned long long *dPayloadOff = nullptr;
+  size_t capPayload = 0, capPayloadOff = 0;
 
   // wavefront merge (kernels_wave.cuh)
   uint32_t *dWaveZero = nullptr; // flags[8] ticket[2] candCount[2] pad[4] | progress[2*BY] | rowCounts[2*BY] | candBits[2*usedWords] | emitInfo[2*blocks]
@@ -303,7 +307,7 @@ extern "C" void limgcu_destroy(limgcu_ctx *ctx)
   void *ptrs[] = { ctx->dLut, ctx->dTable, ctx->dRec, ctx->dWindow, ctx->dAreas, ctx->dBlockToArea, ctx->dWork, ctx->dSmallList, ctx->dLargeList, ctx->dDemand,
                    ctx->dUsed, ctx->dScratchPx, ctx->dScratchFac, ctx->dCounters, ctx->dCompare, ctx->dSrc,
                    ctx->dExtSlot, ctx->dExtSeed, ctx->dExtBits, ctx->dExtHdr, ctx->dPlanCounters, ctx->dSymSlot, ctx->dSymSeed, ctx->dSymBits, ctx->dSymHdr, ctx->dSymStart, ctx->dSeedSym, ctx->dUnmasked,
-                   ctx->dWaveZero, ctx->dTau, ctx->dCandList, ctx->dRowLists, ctx->dWaveDbg, ctx->dWaveRows, ctx->dRowMeta, ctx->dReplayList, ctx->dReplayCount };
+                   ctx->dWaveZero, ctx->dTau, ctx->dCandList, ctx->dRowLists, ctx->dWaveDbg, ctx->dWaveRows, ctx->dRowMeta, ctx->dReplayList, ctx->dReplayCount, ctx->dPayload, ctx->dPayloadOff };
 
   for (void *p : ptrs)
     if (p) cudaFree(p);
@@ -1029,6 +1033,308 @@ extern "C" int limgcu_host_decode(limgcu_ctx *ctx, const limgcu_area *areas, uin
   rc = limgcu_build_block_map(ctx, ctx->dAreas, area_count, sizeX, sizeY, ctx->dBlockToArea);
   if (rc) return rc;
   rc = limgcu_decode(ctx, ctx->dAreas, ctx->dBlockToArea, ctx->dPlaneU8[4], ctx->dPlaneU8[5], ctx->dPlaneU8[6], sizeX, sizeY, hasAlpha, ctx->dPlaneU32[0]);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(pOut, ctx->dPlaneU32[0], n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return LIMGCU_SUCCESS;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------------
+// .limg container (layout in include/limgcu.h and kernels_container.cuh)
+// ---------------------------------------------------------------------------------------------------------------------------------
+
+#pragma pack(push, 1)
+struct ContainerHeader
+{
+  char magic[8]; // "LIMGB200"
+  uint32_t version, flags, sizeX, sizeY, areaCount, recordBytes;
+  uint64_t payloadBytes, reserved;
+};
+
+struct ContainerRecordHead
+{
+  uint16_t ox, oy, rx, ry; // 8x8-block units
+  uint8_t shift[3], stage;
+};
+#pragma pack(pop)
+
+static_assert(sizeof(ContainerHeader) == 48 && sizeof(ContainerRecordHead) == 12, "container layout");
+
+static const char kContainerMagic[8] = { 'L', 'I', 'M', 'G', 'B', '2', '0', '0' };
+
+static size_t container_record_bytes(int hasAlpha) { return sizeof(ContainerRecordHead) + 6 * (hasAlpha ? 4 : 3) * sizeof(int16_t); }
+static size_t container_payload_bound(size_t W, size_t H) { return 3 * ((W + 7) / 8) * 8 * H; }
+
+extern "C" size_t limgcu_container_bound(size_t sizeX, size_t sizeY, int hasAlpha)
+{
+  const size_t blocks = ((sizeX + 7) / 8) * ((sizeY + 7) / 8);
+  return sizeof(ContainerHeader) + blocks * container_record_bytes(hasAlpha) + container_payload_bound(sizeX, sizeY);
+}
+
+static int ensure_payload(limgcu_ctx *ctx, size_t W, size_t H)
+{
+  const size_t bytes = container_payload_bound(W, H) + 16, entries = ((W + 7) / 8) * ((H + 7) / 8) + 1;
+
+  if (bytes > ctx->capPayload)
+  {
+    CK(regrow(ctx->dPayload, bytes));
+    ctx->capPayload = bytes;
+  }
+
+  if (entries > ctx->capPayloadOff)
+  {
+    CK(regrow(ctx->dPayloadOff, entries));
+    ctx->capPayloadOff = entries;
+  }
+
+  return LIMGCU_SUCCESS;
+}
+
+extern "C" int limgcu_pack_payload(limgcu_ctx *ctx, const limgcu_area *d_areas, const uint32_t *d_area_count, uint32_t area_count, const uint32_t *d_block_to_area, const uint8_t *d_codesA,
+                                   const uint8_t *d_codesB, const uint8_t *d_codesC, size_t sizeX, size_t sizeY, int hasAlpha, uint8_t *d_payload, uint64_t *d_offsets)
+{
+  NEED(ctx); NEED(d_areas); NEED(d_block_to_area); NEED(d_codesA); NEED(d_codesB); NEED(d_codesC); NEED(d_payload); NEED(d_offsets);
+  int rc = check_image(ctx, sizeX, sizeY);
+  if (rc) return rc;
+  CK(cudaSetDevice(ctx->device));
+  const int W = (int)sizeX, H = (int)sizeY, BX = (W + 7) / 8;
+  const long long segs = (long long)BX * H;
+  const int vec = (W % 8 == 0) && ((((uintptr_t)d_codesA | (uintptr_t)d_codesB | (uintptr_t)d_codesC) & 7) == 0);
+  k_payload_scan<<<1, 1024, 0, ctx->stream>>>(d_areas, d_area_count, area_count, hasAlpha, reinterpret_cast<unsigned long long *>(d_offsets));
+  CKL("k_payload_scan");
+  k_container_pack<<<(unsigned)((segs + 255) / 256), 256, 0, ctx->stream>>>(d_areas, d_block_to_area, reinterpret_cast<const unsigned long long *>(d_offsets), d_codesA, d_codesB, d_codesC, W, H,
+                                                                             BX, hasAlpha, vec, d_payload);
+  CKL("k_container_pack");
+  return LIMGCU_SUCCESS;
+}
+
+extern "C" int limgcu_unpack_payload(limgcu_ctx *ctx, const limgcu_area *d_areas, uint32_t area_count, const uint32_t *d_block_to_area, const uint8_t *d_payload, uint64_t *d_offsets,
+                                     size_t sizeX, size_t sizeY, int hasAlpha, uint8_t *d_codesA, uint8_t *d_codesB, uint8_t *d_codesC)
+{
+  NEED(ctx); NEED(d_areas); NEED(d_block_to_area); NEED(d_codesA); NEED(d_codesB); NEED(d_codesC); NEED(d_payload); NEED(d_offsets);
+  int rc = check_image(ctx, sizeX, sizeY);
+  if (rc) return rc;
+  CK(cudaSetDevice(ctx->device));
+  const int W = (int)sizeX, H = (int)sizeY, BX = (W + 7) / 8;
+  const long long segs = (long long)BX * H;
+  const int vec = (W % 8 == 0) && ((((uintptr_t)d_codesA | (uintptr_t)d_codesB | (uintptr_t)d_codesC) & 7) == 0);
+  k_payload_scan<<<1, 1024, 0, ctx->stream>>>(d_areas, nullptr, area_count, hasAlpha, reinterpret_cast<unsigned long long *>(d_offsets));
+  CKL("k_payload_scan");
+  k_container_unpack<<<(unsigned)((segs + 255) / 256), 256, 0, ctx->stream>>>(d_areas, d_block_to_area, reinterpret_cast<const unsigned long long *>(d_offsets), d_payload, W, H, BX, hasAlpha, vec,
+                                                                               d_codesA, d_codesB, d_codesC);
+  CKL("k_container_unpack");
+  return LIMGCU_SUCCESS;
+}
+
+extern "C" int limgcu_container_info(const void *data, size_t bytes, size_t *sizeX, size_t *sizeY, int *hasAlpha, uint32_t *areaCount, uint64_t *payloadBytes)
+{
+  if (data == nullptr)
+    return LIMGCU_ERROR_ARGUMENT_NULL;
+
+  ContainerHeader h;
+
+  if (bytes < sizeof(h))
+    return LIMGCU_ERROR_OUT_OF_BOUNDS;
+
+  memcpy(&h, data, sizeof(h));
+
+  if (memcmp(h.magic, kContainerMagic, 8) != 0 || h.version != 1 || h.sizeX == 0 || h.sizeY == 0 || h.sizeX > 65528 || h.sizeY > 65528)
+    return LIMGCU_ERROR_INVALID_PARAMETER;
+
+  const int alpha = (int)(h.flags & 1u);
+  const uint64_t blocks = (uint64_t)((h.sizeX + 7) / 8) * ((h.sizeY + 7) / 8);
+
+  if (h.recordBytes != container_record_bytes(alpha) || h.areaCount == 0 || h.areaCount > blocks || h.payloadBytes > container_payload_bound(h.sizeX, h.sizeY))
+    return LIMGCU_ERROR_INVALID_PARAMETER;
+
+  if ((uint64_t)bytes < sizeof(h) + (uint64_t)h.areaCount * h.recordBytes + h.payloadBytes)
+    return LIMGCU_ERROR_OUT_OF_BOUNDS;
+
+  if (sizeX) *sizeX = h.sizeX;
+  if (sizeY) *sizeY = h.sizeY;
+  if (hasAlpha) *hasAlpha = alpha;
+  if (areaCount) *areaCount = h.areaCount;
+  if (payloadBytes) *payloadBytes = h.payloadBytes;
+  return LIMGCU_SUCCESS;
+}
+
+extern "C" int limgcu_host_encode_container(limgcu_ctx *ctx, const uint32_t *pIn, size_t sizeX, size_t sizeY, int hasAlpha, uint32_t errorFactor, uint32_t flags, void *out, size_t capacity,
+                                            size_t *written)
+{
+  NEED(ctx); NEED(pIn); NEED(out); NEED(written);
+  *written = 0;
+  int rc = check_image(ctx, sizeX, sizeY);
+  if (rc) return rc;
+  CK(cudaSetDevice(ctx->device));
+  const size_t n = sizeX * sizeY;
+  rc = ensure_staging(ctx, n);
+  if (rc) return rc;
+  rc = ensure_capacity(ctx, sizeX, sizeY);
+  if (rc) return rc;
+  rc = ensure_payload(ctx, sizeX, sizeY);
+  if (rc) return rc;
+
+  CK(cudaMemcpyAsync(ctx->dSrc, pIn, n * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+  limgcu_stream st;
+  memset(&st, 0, sizeof(st));
+  st.codesA = ctx->dPlaneU8[4]; st.codesB = ctx->dPlaneU8[5]; st.codesC = ctx->dPlaneU8[6];
+  rc = limgcu_blocked_encode3d(ctx, ctx->dSrc, sizeX, sizeY, hasAlpha, errorFactor, flags, &st, nullptr);
+  if (rc) return rc;
+  rc = limgcu_pack_payload(ctx, ctx->dAreas, ctx->dCounters + 1, 0, ctx->dBlockToArea, st.codesA, st.codesB, st.codesC, sizeX, sizeY, hasAlpha, ctx->dPayload,
+                           reinterpret_cast<uint64_t *>(ctx->dPayloadOff));
+  if (rc) return rc;
+
+  uint32_t count = 0, overflow[2] = { 0, 0 };
+  CK(cudaMemcpyAsync(&count, ctx->dCounters + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(overflow, ctx->dCounters + 27, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+
+  if (overflow[1])
+    return fail(ctx, LIMGCU_ERROR_OUT_OF_BOUNDS, "a block row emitted more rectangles than its list holds", cudaSuccess);
+
+  if (overflow[0])
+    return fail(ctx, LIMGCU_ERROR_GENERIC, "merge watchdog: a block row waited too long for the rows above", cudaSuccess);
+
+  unsigned long long payloadBytes = 0;
+  CK(cudaMemcpyAsync(&payloadBytes, ctx->dPayloadOff + count, sizeof(payloadBytes), cudaMemcpyDeviceToHost, ctx->stream));
+  limgcu_area *areas = static_cast<limgcu_area *>(malloc((size_t)count * sizeof(limgcu_area)));
+
+  if (areas == nullptr)
+    return fail(ctx, LIMGCU_ERROR_MEMORY_ALLOCATION_FAILURE, "host area table", cudaSuccess);
+
+  cudaError_t e = cudaMemcpyAsync(areas, ctx->dAreas, (size_t)count * sizeof(limgcu_area), cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+
+  const size_t recordBytes = container_record_bytes(hasAlpha), ch = hasAlpha ? 4 : 3;
+  const size_t total = sizeof(ContainerHeader) + (size_t)count * recordBytes + (size_t)payloadBytes;
+
+  if (e != cudaSuccess || total > capacity)
+  {
+    free(areas);
+    return e != cudaSuccess ? fail(ctx, LIMGCU_ERROR_CUDA, "area table D2H", e) : fail(ctx, LIMGCU_ERROR_OUT_OF_BOUNDS, "container buffer too small (limgcu_container_bound)", cudaSuccess);
+  }
+
+  uint8_t *o = static_cast<uint8_t *>(out);
+  ContainerHeader h;
+  memset(&h, 0, sizeof(h));
+  memcpy(h.magic, kContainerMagic, 8);
+  h.version = 1; h.flags = hasAlpha ? 1u : 0u; h.sizeX = (uint32_t)sizeX; h.sizeY = (uint32_t)sizeY; h.areaCount = count; h.recordBytes = (uint32_t)recordBytes; h.payloadBytes = payloadBytes;
+  memcpy(o, &h, sizeof(h));
+  o += sizeof(h);
+
+  for (uint32_t k = 0; k < count; k++)
+  {
+    const limgcu_area &a = areas[k];
+    ContainerRecordHead r = { (uint16_t)a.ox, (uint16_t)a.oy, (uint16_t)a.rx, (uint16_t)a.ry, { a.shift[0], a.shift[1], a.shift[2] }, (uint8_t)a.stage };
+    memcpy(o, &r, sizeof(r));
+    o += sizeof(r);
+    const int16_t *fields[6] = { a.decomp.dirA_min, a.decomp.dirA_max, a.decomp.dirB_offset, a.decomp.dirB_mag, a.decomp.dirC_offset, a.decomp.dirC_mag };
+
+    for (const int16_t *f : fields)
+    {
+      memcpy(o, f, ch * sizeof(int16_t));
+      o += ch * sizeof(int16_t);
+    }
+  }
+
+  free(areas);
+  CK(cudaMemcpyAsync(o, ctx->dPayload, (size_t)payloadBytes, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  *written = total;
+  return LIMGCU_SUCCESS;
+}
+
+extern "C" int limgcu_host_decode_container(limgcu_ctx *ctx, const void *data, size_t bytes, uint32_t *pOut, size_t outPixels)
+{
+  NEED(ctx); NEED(data); NEED(pOut);
+  size_t W = 0, H = 0;
+  int hasAlpha = 0;
+  uint32_t count = 0;
+  uint64_t payloadBytes = 0;
+  int rc = limgcu_container_info(data, bytes, &W, &H, &hasAlpha, &count, &payloadBytes);
+
+  if (rc)
+    return fail(ctx, rc, "not a valid LIMGB200 container", cudaSuccess);
+
+  if (outPixels < W * H)
+    return fail(ctx, LIMGCU_ERROR_OUT_OF_BOUNDS, "output buffer smaller than sizeX * sizeY", cudaSuccess);
+
+  CK(cudaSetDevice(ctx->device));
+  const size_t n = W * H, BX = (W + 7) / 8, BY = (H + 7) / 8;
+  rc = ensure_staging(ctx, n);
+  if (rc) return rc;
+  rc = ensure_capacity(ctx, W, H);
+  if (rc) return rc;
+  rc = ensure_payload(ctx, W, H);
+  if (rc) return rc;
+
+  // records -> area table; the rectangles must tile the block grid exactly (a corrupt table would make the kernels read out of bounds)
+  const size_t recordBytes = container_record_bytes(hasAlpha), ch = hasAlpha ? 4 : 3;
+  const uint8_t *p = static_cast<const uint8_t *>(data) + sizeof(ContainerHeader);
+  limgcu_area *areas = static_cast<limgcu_area *>(calloc(count, sizeof(limgcu_area)));
+  uint8_t *covered = static_cast<uint8_t *>(calloc(BX * BY, 1));
+  bool ok = areas != nullptr && covered != nullptr;
+  uint64_t expectPayload = 0, coveredBlocks = 0;
+
+  for (uint32_t k = 0; ok && k < count; k++)
+  {
+    ContainerRecordHead r;
+    memcpy(&r, p, sizeof(r));
+    p += sizeof(r);
+    limgcu_area &a = areas[k];
+    a.ox = r.ox; a.oy = r.oy; a.rx = r.rx; a.ry = r.ry; a.stage = r.stage;
+    ok = r.rx > 0 && r.ry > 0 && (size_t)r.ox + r.rx <= BX && (size_t)r.oy + r.ry <= BY && r.shift[0] <= 8 && r.shift[1] <= 8 && r.shift[2] <= 8;
+
+    if (!ok)
+      break;
+
+    a.px_x = a.ox * 8; a.px_y = a.oy * 8;
+    a.px_w = (uint32_t)((size_t)a.rx * 8 < W - a.px_x ? (size_t)a.rx * 8 : W - a.px_x);
+    a.px_h = (uint32_t)((size_t)a.ry * 8 < H - a.px_y ? (size_t)a.ry * 8 : H - a.px_y);
+    memcpy(a.shift, r.shift, 3);
+    int16_t *fields[6] = { a.decomp.dirA_min, a.decomp.dirA_max, a.decomp.dirB_offset, a.decomp.dirB_mag, a.decomp.dirC_offset, a.decomp.dirC_mag };
+
+    for (int16_t *f : fields)
+    {
+      memcpy(f, p, ch * sizeof(int16_t));
+      p += ch * sizeof(int16_t);
+    }
+
+    for (uint32_t y = a.oy; ok && y < a.oy + a.ry; y++)
+      for (uint32_t x = a.ox; x < a.ox + a.rx; x++)
+      {
+        if (covered[(size_t)y * BX + x]) { ok = false; break; }
+        covered[(size_t)y * BX + x] = 1;
+        coveredBlocks++;
+      }
+
+    expectPayload += (uint64_t)((a.px_w + 7) / 8) * a.px_h *
+                     (container_code_bits(a.shift[0], hasAlpha != 0) + container_code_bits(a.shift[1], hasAlpha != 0) + container_code_bits(a.shift[2], hasAlpha != 0));
+  }
+
+  ok = ok && coveredBlocks == (uint64_t)BX * BY && expectPayload == payloadBytes;
+  free(covered);
+
+  if (!ok)
+  {
+    free(areas);
+    return fail(ctx, LIMGCU_ERROR_INVALID_PARAMETER, "container: the area table does not tile the image or does not match the payload size", cudaSuccess);
+  }
+
+  cudaError_t e = cudaMemcpyAsync(ctx->dAreas, areas, (size_t)count * sizeof(limgcu_area), cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(ctx->dPayload, p, (size_t)payloadBytes, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream); // `areas` is pageable host memory that is freed below
+  free(areas);
+
+  if (e != cudaSuccess)
+    return fail(ctx, LIMGCU_ERROR_CUDA, "container H2D", e);
+
+  rc = limgcu_build_block_map(ctx, ctx->dAreas, count, W, H, ctx->dBlockToArea);
+  if (rc) return rc;
+  rc = limgcu_unpack_payload(ctx, ctx->dAreas, count, ctx->dBlockToArea, ctx->dPayload, reinterpret_cast<uint64_t *>(ctx->dPayloadOff), W, H, hasAlpha, ctx->dPlaneU8[4], ctx->dPlaneU8[5],
+                             ctx->dPlaneU8[6]);
+  if (rc) return rc;
+  rc = limgcu_decode(ctx, ctx->dAreas, ctx->dBlockToArea, ctx->dPlaneU8[4], ctx->dPlaneU8[5], ctx->dPlaneU8[6], W, H, hasAlpha, ctx->dPlaneU32[0]);
   if (rc) return rc;
   CK(cudaMemcpyAsync(pOut, ctx->dPlaneU32[0], n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));

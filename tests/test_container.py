@@ -1,0 +1,163 @@
+"""The "LIMGB200" container (include/limgcu.h): the numpy restatement (oracle/container.py) against the reference's golden outputs on the
+CPU, the header parser of the C ABI without a device, and -- on the GPU -- the encoder's bytes against the restatement's, bit for bit."""
+import ctypes as C
+import struct
+
+import numpy as np
+import pytest
+
+from oracle import container as oc
+from oracle import oracle as lo
+from tests import helpers as H
+
+
+def golden_area_table(g, dtype):
+    n = g["area_rect"].shape[0]
+    a = np.zeros(n, dtype=dtype)
+    for i, k in enumerate(("ox", "oy", "rx", "ry", "stage")):
+        a[k] = g["area_rect"][:, i]
+    for i, k in enumerate(("px_x", "px_y", "px_w", "px_h")):
+        a[k] = g["area_px"][:, i]
+    a["shift"] = g["area_shift"]
+    d = H.golden_area_decomps(g)
+    for name in d.dtype.names:
+        a["decomp"][name] = d[name]
+    return a
+
+
+def golden_container(g) -> bytes:
+    h, w = g["img"].shape
+    return oc.pack(w, h, bool(g["has_alpha"]), golden_area_table(g, lo.AREA_DTYPE), g["post"][0], g["post"][1], g["post"][2])
+
+
+@pytest.mark.parametrize("name", H.golden_image_cases())
+def test_container_of_reference_outputs_decodes_to_reference_pixels(name):
+    """reference areas + factor streams -> container bytes -> unpack -> oracle reconstruction == the reference's pDecoded"""
+    g = H.load_golden(name)
+    data = golden_container(g)
+    alpha = bool(g["has_alpha"])
+    u = oc.unpack(data, lo.AREA_DTYPE)
+    assert (u["width"], u["height"], u["has_alpha"]) == (g["img"].shape[1], g["img"].shape[0], alpha)
+    shifts = np.repeat(g["area_shift"], g["area_px"][:, 2].astype(np.int64) * g["area_px"][:, 3], axis=0)
+    for f, key in enumerate(("fa", "fb", "fc")):
+        kept = (shifts[:, f] < 8) | alpha  # an RGB factor without bits reads back as code 0 (its normal is zero, Q7)
+        assert np.array_equal(u[key][kept], g["post"][f][kept])
+        assert not u[key][~kept].any()
+    assert np.array_equal(oc.decode(data), g["plane_pDecoded"])
+    # the payload is exactly the bits the reference accounts for (limg.cpp:1632), rounded up to whole 8-pixel runs
+    bits = sum(((int(pw) + 7) // 8) * 8 * int(ph) * sum(oc.code_bits(int(s), alpha) for s in sh) for (_, _, pw, ph), sh in zip(g["area_px"], g["area_shift"]))
+    assert struct.unpack_from("<Q", data, 32)[0] * 8 == bits
+
+
+def test_ragged_runs_and_all_bit_widths_round_trip():
+    rng = np.random.default_rng(5)
+    for alpha in (False, True):
+        w, h = 37, 21
+        areas = np.zeros(15, dtype=lo.AREA_DTYPE)
+        k = 0
+        for by in range(3):
+            for bx in range(5):
+                a = areas[k]
+                a["ox"], a["oy"], a["rx"], a["ry"], a["stage"] = bx, by, 1, 1, 2
+                a["px_x"], a["px_y"], a["px_w"], a["px_h"] = bx * 8, by * 8, min(8, w - bx * 8), min(8, h - by * 8)
+                a["shift"] = [(k + j * 4) % 9 for j in range(3)]
+                for name in oc.FIELDS:
+                    a["decomp"][name][: 4 if alpha else 3] = rng.integers(-32768, 32768, 4 if alpha else 3)
+                k += 1
+        n = int((areas["px_w"].astype(np.int64) * areas["px_h"]).sum())
+        sh = np.repeat(areas["shift"], areas["px_w"].astype(np.int64) * areas["px_h"], axis=0)
+        streams = [(rng.integers(0, 256, n) >> np.where(sh[:, f] > 7, 0, sh[:, f])).astype(np.uint8) for f in range(3)]
+        data = oc.pack(w, h, alpha, areas, *streams)
+        u = oc.unpack(data, lo.AREA_DTYPE)
+        assert u["areas"].tobytes() == areas.tobytes()
+        for f, key in enumerate(("fa", "fb", "fc")):
+            kept = (sh[:, f] < 8) | alpha
+            assert np.array_equal(u[key][kept], streams[f][kept])
+
+
+def test_header_parser_of_the_c_abi_needs_no_device():
+    from limg_b200 import _lib
+    lib = _lib.load()
+    g = H.load_golden("rgba_photo_64x64")
+    data = golden_container(g)
+    buf = np.frombuffer(data, np.uint8)
+    w, h, a, n, pb = C.c_size_t(0), C.c_size_t(0), C.c_int(0), C.c_uint32(0), C.c_uint64(0)
+    args = (C.byref(w), C.byref(h), C.byref(a), C.byref(n), C.byref(pb))
+    assert lib.limgcu_container_info(buf.ctypes.data_as(C.c_void_p), buf.size, *args) == 0
+    assert (w.value, h.value, a.value, n.value) == (64, 64, 1, g["area_rect"].shape[0])
+    assert 48 + n.value * 60 + pb.value == len(data)
+    assert lib.limgcu_container_bound(64, 64, 1) >= len(data)
+    # truncated, wrong magic, wrong record size, area count beyond the block count
+    assert lib.limgcu_container_info(buf.ctypes.data_as(C.c_void_p), len(data) - 1, *args) == 103
+    for off, val in ((0, b"X"), (28, struct.pack("<I", 48)), (24, struct.pack("<I", 65))):
+        bad = bytearray(data)
+        bad[off:off + len(val)] = val
+        b = np.frombuffer(bytes(bad), np.uint8)
+        assert lib.limgcu_container_info(b.ctypes.data_as(C.c_void_p), b.size, *args) == 101
+    assert lib.limgcu_container_info(None, 0, *args) == 102
+
+
+# ---- GPU -------------------------------------------------------------------------------------------------------------------------
+
+@pytest.fixture(scope="module")
+def codec():
+    from limg_b200 import Codec
+    c = Codec(0)
+    yield c
+    c.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", H.golden_image_cases())
+def test_gpu_container_equals_the_restatement_built_from_reference_outputs(codec, name):
+    g = H.load_golden(name)
+    alpha = bool(g["has_alpha"])
+    want = golden_container(g)
+    # decoding a reference-produced container is bit exact (also for the AES-dithered one)
+    assert np.array_equal(codec.decode_container(want), g["plane_pDecoded"])
+    if bool(g["aes"]):
+        return  # the GPU dithers with the LCG: same areas and shifts, different noise
+    got = codec.encode_container(g["img"], alpha, int(g["error_factor"]), bool(g["fast"]))
+    assert got == want
+    assert codec.container_info(got)["area_count"] == g["area_rect"].shape[0]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(61, 37, False), (61, 37, True), (200, 136, False)])
+def test_gpu_container_ragged_sizes_vs_oracle(codec, shape):
+    from limg_b200 import synth
+    w, h, alpha = shape
+    img = synth.photo_like(w, h, 11, 4 if alpha else 3)
+    o = lo.blocked_encode3d(img, alpha, 100, True)
+    data = codec.encode_container(img, alpha)
+    assert np.array_equal(codec.decode_container(data), o["planes"]["pDecoded"])
+    assert np.array_equal(oc.decode(data), o["planes"]["pDecoded"])
+    u = oc.unpack(data, lo.AREA_DTYPE)
+    for k in ("ox", "oy", "rx", "ry", "stage", "px_x", "px_y", "px_w", "px_h", "shift"):
+        assert np.array_equal(u["areas"][k], o["areas"][k]), k
+
+
+@pytest.mark.gpu
+def test_gpu_container_rejects_a_table_that_does_not_tile(codec):
+    from limg_b200 import LimgError
+    g = H.load_golden("rgb_photo_96x64")
+    data = bytearray(golden_container(g))
+    data[48 + 4] = 0  # rx of the first record
+    with pytest.raises(LimgError):
+        codec.decode_container(bytes(data))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cfg", ["c2_4k_photo", "c3_8k_rgba"])
+def test_gpu_container_full_size_round_trip(codec, cfg):
+    from limg_b200 import synth
+    img, alpha = synth.CONFIGS[cfg]()
+    st = codec.encode_stream(img, alpha, 100, True, decoded=True)
+    data = codec.encode_container(img, alpha)
+    info = codec.container_info(data)
+    a = st["areas"]
+    assert info["area_count"] == len(a)
+    bits = np.where(a["shift"] > 7, 8 if alpha else 0, 8 - a["shift"].astype(np.int64)).sum(axis=1)
+    assert info["payload_bytes"] == int((((a["px_w"].astype(np.int64) + 7) // 8) * a["px_h"] * bits).sum())
+    assert len(data) < img.size * (4 if alpha else 3)  # smaller than the raw pixels
+    assert np.array_equal(codec.decode_container(data), st["decoded"])
