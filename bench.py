@@ -281,7 +281,20 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     codec = Codec(local_rank)
     stream = torch.cuda.ExternalStream(codec.stream, device=dev)
 
-    frame = make_frame(args.workload, rank)  # every rank its own frame (independent unit)
+    if args.mode == "rowband":
+        # one image cut into bands of whole block rows, one per rank: areas do not cross bands, every band restarts the
+        # dither chain -- by construction the reference run per band (tests/test_shard_gloo.py)
+        from limg_b200 import shard
+        full_h = h
+        y0, y1 = shard.row_bands(full_h, world)[rank]
+        if y1 <= y0:
+            raise SystemExit("bench.py: more ranks than block-row bands")
+        frame = np.ascontiguousarray(make_frame(args.workload, 0)[y0:y1])
+        h = y1 - y0
+        npx = w * h
+        by = (h + 7) // 8
+    else:
+        frame = make_frame(args.workload, rank)  # every rank its own frame (independent unit)
     d_src = torch.from_numpy(frame.view(np.int32)).to(dev)
     d_codes = [torch.empty((h, w), dtype=torch.uint8, device=dev) for _ in range(3)]
     d_areas = torch.empty(bx * by * AREA_DTYPE.itemsize, dtype=torch.uint8, device=dev)
@@ -370,16 +383,19 @@ def run_ours(args, rank: int, local_rank: int, world: int):
 
     # ---- max over ranks -----------------------------------------------------------------------------------------------
     t = torch.tensor([total_ms, sum(enc_ms), sum(dec_ms), e2e_s * 1e3], dtype=torch.float64, device=dev)
+    px_all = torch.tensor([float(npx)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(px_all, op=dist.ReduceOp.SUM)
     total_ms, enc_total, dec_total, e2e_ms = [float(x) for x in t.tolist()]
+    px_job = float(px_all.item())  # pixels all ranks process per step
 
     # self-check of the timed data against the round trip (cheap, outside the timed region)
     psnr, _, _ = codec.compare_device(d_src.data_ptr(), d_dec.data_ptr(), w, h, alpha)
 
     if rank == 0:
         peak, peak_src = measured_peaks()
-        mpx_total = npx * world * args.steps / 1e6
+        mpx_total = px_job * args.steps / 1e6
         value = mpx_total / (total_ms / 1e3)
         enc_step_ms = enc_total / args.steps
         dec_step_ms = dec_total / args.steps
@@ -388,15 +404,16 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         dominant = max(phase_acc, key=phase_acc.get)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong" if args.mode == "rowband" else "weak", "vs_baseline": None,
             "dtype": "f32+i32", "data": "synthetic",
             "config": {"workload": args.workload, "width": w, "height": h, "channels": 4 if alpha else 3, "error_factor": 100, "fast_bit_crushing": True,
-                       "dither": "lcg", "frames_per_rank_per_step": 1, "parallelism": "independent frames, one per GPU" if world > 1 else "single GPU",
+                       "dither": "lcg", "frames_per_rank_per_step": 1,
+                       "parallelism": ("row bands of one image, one per GPU (%d rows on rank 0)" % h) if args.mode == "rowband" else ("independent frames, one per GPU" if world > 1 else "single GPU"),
                        "step": "limgcu_blocked_encode3d (stream out) + limgcu_decode", "l2": "flushed between timed steps (512 MiB fill, untimed)"},
-            "encode_mpixel_s": npx * world / 1e6 / (enc_step_ms * 1e-3), "decode_mpixel_s": npx * world / 1e6 / (dec_step_ms * 1e-3),
+            "encode_mpixel_s": px_job / 1e6 / (enc_step_ms * 1e-3), "decode_mpixel_s": px_job / 1e6 / (dec_step_ms * 1e-3),
             "encode_ms": enc_step_ms, "decode_ms": dec_step_ms, "psnr_db": psnr,
             "clocks": clocks, "gpu_launches": int(launches),
-            "e2e": {"value": npx * world * args.steps / 1e6 / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+            "e2e": {"value": px_job * args.steps / 1e6 / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "path": "limgcu_host_encode_stream + limgcu_host_decode, pinned host buffers"},
             "roofline": {"bound": "hbm", "achieved": enc_gbs, "peak": peak, "unit": "GB/s", "frac": enc_gbs / peak,
                          # DRAM bytes of the dominant kernel (k_merge_wave) per launch from profiles/r1_d_ncu_wave_details.txt (4K photo only)
@@ -434,6 +451,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2_4k_photo", choices=sorted(WORKLOADS))
+    ap.add_argument("--mode", default="frames", choices=["frames", "rowband"], help="frames: one frame per rank (weak scaling); rowband: one image, one row band per rank")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
