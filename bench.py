@@ -175,9 +175,16 @@ def cpu_baseline(workload: str, threads: int, budget_s: float = 20.0) -> dict:
         t = ref.time_blocked(img, alpha, 100, True, threads, 1, False)  # one frame, also the warm-up
         reps = max(1, min(8, int(budget_s / max(t, 1e-3)) - 1))
         t = ref.time_blocked(img, alpha, 100, True, threads, reps, False)
-        return {"value": mpx / t, "unit": UNIT, "cores": threads, "kind": "reference",
-                "sample": "%d x limg_blocked_encode3d_test (encode + in-encoder decode) of one %dx%d frame, %d-thread limg_thread_pool, LCG dither" % (reps, w, h, threads),
-                "seconds_per_frame": t}
+        out = {"value": mpx / t, "unit": UNIT, "cores": threads, "kind": "reference",
+               "sample": "%d x limg_blocked_encode3d_test (encode + in-encoder decode) of one %dx%d frame, %d-thread limg_thread_pool, LCG dither" % (reps, w, h, threads),
+               "seconds_per_frame": t}
+        # the reference's only fully threaded path, limg_encode3d_test_perf (every 8x8 block its own area, no planes written)
+        tp = ref.time_blocked(img, alpha, 100, True, threads, 1, True)
+        tp = ref.time_blocked(img, alpha, 100, True, threads, max(1, min(8, int(5.0 / max(tp, 1e-3)))), True)
+        t1 = ref.time_blocked(img, alpha, 100, True, 0, 1, True)
+        out["unmerged_perf_path"] = {"value": mpx / tp, "unit": UNIT, "cores": threads, "single_thread_value": mpx / t1,
+                                     "sample": "limg_encode3d_test_perf of the same frame, %d-thread pool and pool-less" % threads}
+        return out
     from oracle import oracle as lo
     crop = img[: min(h, 1080), : min(w, 1920)]
     t0 = time.time()
@@ -353,6 +360,22 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     codec.enable_phase_timing(False)
     counters = codec.debug_counters()
 
+    # the non-merged encoder (limg_encode3d_test's path): every 8x8 block its own area, no area scan
+    ev_nm = []
+    with torch.cuda.stream(stream):
+        for i in range(5):
+            d_flush.fill_(i & 0xFF)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            codec.blocked_encode3d_device(d_src.data_ptr(), w, h, alpha, 100, True, True, st, None)
+            e1.record(stream)
+            ev_nm.append((e0, e1))
+    codec.sync()
+    unmerged_ms = statistics.median(a.elapsed_time(b) for a, b in ev_nm[1:])
+    codec.blocked_encode3d_device(d_src.data_ptr(), w, h, alpha, 100, True, False, st, None)  # leave the merged stream in the buffers
+    codec.decode_device(d_areas.data_ptr(), d_map.data_ptr(), d_codes[0].data_ptr(), d_codes[1].data_ptr(), d_codes[2].data_ptr(), w, h, alpha, d_dec.data_ptr())
+    codec.sync()
+
     # ---- end to end through the host-buffer C ABI, pinned host memory ----------------------------------------------
     h_src = torch.from_numpy(frame.view(np.int32)).pin_memory()
     h_codes = [torch.empty((h, w), dtype=torch.uint8).pin_memory() for _ in range(3)]
@@ -423,6 +446,8 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                          "phase_ms": {k: round(v, 4) for k, v in phase_acc.items()},
                          "note": "merge_scan = the row-pipelined greedy area scan (latency bound, not HBM bound); predicate_windows = the main-stream part of the "
                                  "predicate precompute (the speculative match bitmaps run on a second stream concurrently with the scan)"},
+            "unmerged_encode": {"encode_ms": unmerged_ms, "encode_mpixel_s": npx / 1e6 / (unmerged_ms * 1e-3), "hbm_frac": 7.0 * npx / (unmerged_ms * 1e-3) / 1e9 / peak,
+                                "what": "limgcu_blocked_encode3d with LIMGCU_FLAG_NO_MERGE (the path of limg_encode3d_test / _perf: every 8x8 block its own area), per GPU"},
             "merge": {"failed_first_tries": int(counters[24]), "areas": int(counters[1]), "merged_rectangles": int(counters[0])},
             "roofline_decode": {"bound": "hbm", "achieved": dec_gbs, "peak": peak, "unit": "GB/s", "frac": dec_gbs / peak, "traffic": None,
                                 "kernel": "k_decode_tile, 7 algorithmic B/px"},

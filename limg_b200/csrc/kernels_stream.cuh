@@ -13,7 +13,9 @@ namespace limg
 // chain and the LCG's O(log n) jump-ahead gives the state there, so the finalize pass needs no serial dependency.
 // ---------------------------------------------------------------------------------------------
 
-__global__ void __launch_bounds__(1024) k_dither_scan(limgcu_area *areas, const uint32_t *areaCount, const uint64_t *demand, LcgJumpTable jt, int restartEveryArea)
+// k_dither_scan (single CTA) only does the exclusive scan of the demand; the two jump-aheads per area are ~50 dependent 64-bit
+// multiply-adds each and run grid-wide in k_dither_states (both in one CTA took 71 us at 4K, the split takes < 10).
+__global__ void __launch_bounds__(1024) k_dither_scan(const uint32_t *areaCount, const uint64_t *demand, unsigned long long *before, int restartEveryArea)
 {
   __shared__ unsigned long long warpSums[33];
   const uint32_t count = *areaCount;
@@ -59,16 +61,23 @@ __global__ void __launch_bounds__(1024) k_dither_scan(limgcu_area *areas, const 
     __syncthreads();
 
     if (k < count)
-    {
-      const unsigned long long before = restartEveryArea ? 0ull : carry + warpSums[warp] + incl - v;
-      const uint64_t s0 = lcg_jump(LIMG_DITHER_SEED, before, jt);
-      areas[k].ditherBefore = s0;
-      areas[k].ditherAfter = lcg_jump(s0, v, jt);
-    }
+      before[k] = restartEveryArea ? 0ull : carry + warpSums[warp] + incl - v;
 
     carry += warpSums[32];
     __syncthreads();
   }
+}
+
+__global__ void __launch_bounds__(256) k_dither_states(limgcu_area *areas, const uint32_t *areaCount, const uint64_t *demand, const unsigned long long *before, LcgJumpTable jt)
+{
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+
+  if (k >= *areaCount)
+    return;
+
+  const uint64_t s0 = lcg_jump(LIMG_DITHER_SEED, before[k], jt);
+  areas[k].ditherBefore = s0;
+  areas[k].ditherAfter = lcg_jump(s0, demand[k], jt);
 }
 
 // ---------------------------------------------------------------------------------------------

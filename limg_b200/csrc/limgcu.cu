@@ -23,7 +23,7 @@ struct limgcu_ctx
   int device = 0;
   cudaStream_t stream = nullptr;
   cudaStream_t streamAux = nullptr; // the speculative match bitmaps are computed here while the scan already runs on `stream`
-  cudaEvent_t evFork = nullptr, evJoin = nullptr;
+  cudaEvent_t evFork = nullptr, evJoin = nullptr, evFork2 = nullptr, evJoin2 = nullptr;
   int planAsync = 1;                // LIMGCU_PLAN_ASYNC: 0 plan kernels on the main stream, 1 both on the second stream concurrently with the scan, 2 only k_plan_sym
   int planAsyncCtas = 2;            // LIMGCU_PLAN_CTAS: CTAs per SM of an asynchronous plan kernel (the scan needs room next to them)
   char err[512] = { 0 };
@@ -43,6 +43,7 @@ struct limgcu_ctx
   AreaWork *dWork = nullptr;
   uint32_t *dSmallList = nullptr, *dLargeList = nullptr;
   uint64_t *dDemand = nullptr;
+  unsigned long long *dDitherBefore = nullptr;
   uint32_t *dUsed = nullptr;
   uint32_t *dExtSlot = nullptr, *dExtSeed = nullptr, *dExtBits = nullptr, *dExtHdr = nullptr, *dPlanCounters = nullptr;
   uint4 *dSeedSym = nullptr;
@@ -128,6 +129,7 @@ static int ensure_capacity(limgcu_ctx *ctx, size_t W, size_t H)
     CK(regrow(ctx->dSmallList, blocks));
     CK(regrow(ctx->dLargeList, blocks));
     CK(regrow(ctx->dDemand, blocks));
+    CK(regrow(ctx->dDitherBefore, blocks));
     ctx->extCap = (uint32_t)(blocks / 2 > 1024 ? blocks / 2 : 1024);
     ctx->symCap = (uint32_t)(blocks > 1024 ? blocks : 1024);
     CK(regrow(ctx->dUnmasked, blocks));
@@ -250,6 +252,8 @@ extern "C" int limgcu_create(int device, limgcu_ctx **out)
     if (cudaStreamCreateWithPriority(&ctx->streamAux, cudaStreamNonBlocking, prLow) != cudaSuccess) return bail(LIMGCU_ERROR_CUDA);
     if (cudaEventCreateWithFlags(&ctx->evFork, cudaEventDisableTiming) != cudaSuccess) return bail(LIMGCU_ERROR_CUDA);
     if (cudaEventCreateWithFlags(&ctx->evJoin, cudaEventDisableTiming) != cudaSuccess) return bail(LIMGCU_ERROR_CUDA);
+    if (cudaEventCreateWithFlags(&ctx->evFork2, cudaEventDisableTiming) != cudaSuccess) return bail(LIMGCU_ERROR_CUDA);
+    if (cudaEventCreateWithFlags(&ctx->evJoin2, cudaEventDisableTiming) != cudaSuccess) return bail(LIMGCU_ERROR_CUDA);
   }
   cudaDeviceGetAttribute(&ctx->smCount, cudaDevAttrMultiProcessorCount, device);
 
@@ -307,7 +311,7 @@ extern "C" void limgcu_destroy(limgcu_ctx *ctx)
   void *ptrs[] = { ctx->dLut, ctx->dTable, ctx->dRec, ctx->dWindow, ctx->dAreas, ctx->dBlockToArea, ctx->dWork, ctx->dSmallList, ctx->dLargeList, ctx->dDemand,
                    ctx->dUsed, ctx->dScratchPx, ctx->dScratchFac, ctx->dCounters, ctx->dCompare, ctx->dSrc,
                    ctx->dExtSlot, ctx->dExtSeed, ctx->dExtBits, ctx->dExtHdr, ctx->dPlanCounters, ctx->dSymSlot, ctx->dSymSeed, ctx->dSymBits, ctx->dSymHdr, ctx->dSymStart, ctx->dSeedSym, ctx->dUnmasked,
-                   ctx->dWaveZero, ctx->dTau, ctx->dCandList, ctx->dRowLists, ctx->dWaveDbg, ctx->dWaveRows, ctx->dRowMeta, ctx->dReplayList, ctx->dReplayCount, ctx->dPayload, ctx->dPayloadOff };
+                   ctx->dWaveZero, ctx->dTau, ctx->dCandList, ctx->dRowLists, ctx->dWaveDbg, ctx->dWaveRows, ctx->dRowMeta, ctx->dReplayList, ctx->dReplayCount, ctx->dPayload, ctx->dPayloadOff, ctx->dDitherBefore };
 
   for (void *p : ptrs)
     if (p) cudaFree(p);
@@ -327,6 +331,8 @@ extern "C" void limgcu_destroy(limgcu_ctx *ctx)
 
   if (ctx->evFork) cudaEventDestroy(ctx->evFork);
   if (ctx->evJoin) cudaEventDestroy(ctx->evJoin);
+  if (ctx->evFork2) cudaEventDestroy(ctx->evFork2);
+  if (ctx->evJoin2) cudaEventDestroy(ctx->evJoin2);
 
   delete ctx;
 }
@@ -713,27 +719,36 @@ extern "C" int limgcu_blocked_encode3d(limgcu_ctx *ctx, const uint32_t *d_src, s
     const int gridLarge = ctx->smCount * 4, gridSmall = ctx->smCount * 6;
     const size_t smemLarge = 4096 + LIMG_CTA_STAGE_PX * 16 + 2 * LIMG_CTA_AREA_CAP * 4;
 
-    // large areas first: they are the long poles
+    // The large areas are the long poles (one CTA each, sequential sums): the warp-per-area kernel for the small ones runs next to them
+    // on the second stream.
+    CK(cudaEventRecord(ctx->evFork2, ctx->stream));
+    CK(cudaStreamWaitEvent(ctx->streamAux, ctx->evFork2, 0));
+
     if (hasAlpha)
     {
       k_encode_large<4><<<gridLarge, LIMG_ENCODE_THREADS, smemLarge, ctx->stream>>>(l);
       CKL("k_encode_large");
-      k_encode_small<4><<<gridSmall, LIMG_ENCODE_THREADS, 0, ctx->stream>>>(s);
+      k_encode_small<4><<<gridSmall, LIMG_ENCODE_THREADS, 0, ctx->streamAux>>>(s);
       CKL("k_encode_small");
     }
     else
     {
       k_encode_large<3><<<gridLarge, LIMG_ENCODE_THREADS, smemLarge, ctx->stream>>>(l);
       CKL("k_encode_large");
-      k_encode_small<3><<<gridSmall, LIMG_ENCODE_THREADS, 0, ctx->stream>>>(s);
+      k_encode_small<3><<<gridSmall, LIMG_ENCODE_THREADS, 0, ctx->streamAux>>>(s);
       CKL("k_encode_small");
     }
+
+    CK(cudaEventRecord(ctx->evJoin2, ctx->streamAux));
+    CK(cudaStreamWaitEvent(ctx->stream, ctx->evJoin2, 0));
   }
 
   if (ctx->timing) CK(cudaEventRecord(ctx->ev[PHASE_DITHER], ctx->stream));
 
-  k_dither_scan<<<1, 1024, 0, ctx->stream>>>(dAreas, ctx->dCounters + 1, ctx->dDemand, ctx->jt, 0);
+  k_dither_scan<<<1, 1024, 0, ctx->stream>>>(ctx->dCounters + 1, ctx->dDemand, ctx->dDitherBefore, 0);
   CKL("k_dither_scan");
+  k_dither_states<<<(unsigned)((((size_t)BX * e.BY) + 255) / 256), 256, 0, ctx->stream>>>(dAreas, ctx->dCounters + 1, ctx->dDemand, ctx->dDitherBefore, ctx->jt);
+  CKL("k_dither_states");
 
   if (ctx->timing) CK(cudaEventRecord(ctx->ev[PHASE_FINALIZE], ctx->stream));
 
