@@ -269,6 +269,57 @@ def north_star_8k_rgb(codec, stream, dev, d_flush, peak: float, iters: int = 5) 
             "decode_traffic": 190.9e6, "decode_algorithmic_bytes": 7 * w * h, "bytes_per_px": 7, "psnr_db": psnr, "iters": iters}
 
 
+def batch_1080p(local_rank: int, dev, d_flush, lanes: int = 4, steps: int = 6) -> dict:
+    """BASELINE.json config 5 on one GPU: a batch of independent 1920x1080 frames, `lanes` frames in flight on `lanes` contexts
+    (limg_b200/batch.py). Device-resident part: CUDA events from a common start to the last lane's end, L2 flushed between steps.
+    End to end: limgcu_batch_host_encode_containers + _decode_containers with host buffers (one host thread per lane), wall clock."""
+    import torch
+    from limg_b200 import AREA_DTYPE, BatchCodec, synth
+    w, h = 1920, 1080
+    bx, by = w // 8, (h + 7) // 8
+    batch = BatchCodec(local_rank, lanes)
+    main = torch.cuda.current_stream(dev)
+    frames = [synth.frame(i) for i in range(lanes)]
+    state = []
+    for c, f in zip(batch.codecs, frames):
+        codes = [torch.empty((h, w), dtype=torch.uint8, device=dev) for _ in range(3)]
+        t = {"codec": c, "stream": torch.cuda.ExternalStream(c.stream, device=dev), "src": torch.from_numpy(f.view(np.int32)).to(dev), "codes": codes,
+             "areas": torch.empty(bx * by * AREA_DTYPE.itemsize, dtype=torch.uint8, device=dev), "map": torch.empty(bx * by, dtype=torch.int32, device=dev),
+             "count": torch.zeros(1, dtype=torch.int32, device=dev), "dec": torch.empty((h, w), dtype=torch.int32, device=dev)}
+        t["st"] = {"areas": t["areas"].data_ptr(), "area_count": t["count"].data_ptr(), "block_to_area": t["map"].data_ptr(),
+                   "codesA": codes[0].data_ptr(), "codesB": codes[1].data_ptr(), "codesC": codes[2].data_ptr()}
+        state.append(t)
+    times = []
+    for it in range(steps + 2):
+        d_flush.fill_(it & 0xFF)
+        start, ends = torch.cuda.Event(enable_timing=True), []
+        torch.cuda.synchronize(dev)
+        start.record(main)
+        for t in state:
+            t["stream"].wait_event(start)
+        for t in state:
+            t["codec"].blocked_encode3d_device(t["src"].data_ptr(), w, h, False, 100, True, False, t["st"], None)
+            t["codec"].decode_device(t["areas"].data_ptr(), t["map"].data_ptr(), t["codes"][0].data_ptr(), t["codes"][1].data_ptr(), t["codes"][2].data_ptr(), w, h, False, t["dec"].data_ptr())
+            e = torch.cuda.Event(enable_timing=True)
+            e.record(t["stream"])
+            ends.append(e)
+        torch.cuda.synchronize(dev)
+        times.append(max(start.elapsed_time(e) for e in ends))
+    ms = statistics.median(times[2:])
+    host_frames = [synth.frame(i) for i in range(2 * lanes)]
+    batch.decode_containers(batch.encode_containers(host_frames, False))  # warm-up (allocations)
+    t0 = time.perf_counter()
+    dec = batch.decode_containers(batch.encode_containers(host_frames, False))
+    e2e_s = time.perf_counter() - t0
+    ok = all(np.array_equal(d, s["dec"].cpu().numpy().view(np.uint32)) for d, s in zip(dec[:lanes], state))
+    batch.close()
+    return {"workload": "%d x 1920x1080 RGB photo-like frames per step, %d lanes (contexts) on one GPU" % (lanes, lanes), "lanes": lanes, "ms_per_step": ms,
+            "value": lanes * w * h / 1e6 / (ms * 1e-3), "unit": UNIT,
+            "e2e": {"value": len(host_frames) * w * h / 1e6 / e2e_s, "unit": UNIT, "frames": len(host_frames),
+                    "path": "limgcu_batch_host_encode_containers + limgcu_batch_host_decode_containers, host buffers, one host thread per lane"},
+            "round_trip_equals_device_path": bool(ok)}
+
+
 def run_ours(args, rank: int, local_rank: int, world: int):
     import torch
     import torch.distributed as dist
@@ -457,6 +508,11 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                 line["north_star_8k_rgb"] = north_star_8k_rgb(codec, stream, dev, d_flush, peak)
             except Exception as e:  # an extra, never required for the headline line
                 line["north_star_8k_rgb"] = {"error": repr(e)}
+        if world == 1 and args.workload == "c2_4k_photo":
+            try:
+                line["batch_1080p"] = batch_1080p(local_rank, dev, d_flush)
+            except Exception as e:
+                line["batch_1080p"] = {"error": repr(e)}
         if world == 1 and not args.no_cpu_baseline:
             try:
                 line["cpu_baseline"] = cpu_baseline(args.workload, host_cores())

@@ -198,6 +198,17 @@ int limgcu_pack_payload(limgcu_ctx *ctx, const limgcu_area *d_areas, const uint3
 int limgcu_unpack_payload(limgcu_ctx *ctx, const limgcu_area *d_areas, uint32_t area_count, const uint32_t *d_block_to_area, const uint8_t *d_payload, uint64_t *d_offsets,
                           size_t sizeX, size_t sizeY, int hasAlpha, uint8_t *d_codesA, uint8_t *d_codesB, uint8_t *d_codesC);
 
+/* batches of independent frames (batch mode) ---------------------------------------------------------- */
+
+/* One frame does not fill a B200 (the area scan is a latency-bound chain), so a batch runs on `lanes` contexts at once -- of one device,
+ * or of several -- each driven by its own host thread; frame i is handled by ctxs[i % lanes], the frames of one lane in order. Every frame
+ * is an independent limg_blocked_encode3d_test call (own dither chain): results equal the one-at-a-time results bit for bit.
+ * Returns the first failing lane's code (limgcu_last_error of that lane's context has the text). */
+int limgcu_batch_host_encode_containers(limgcu_ctx *const *ctxs, int lanes, const uint32_t *const *frames, int count, size_t sizeX, size_t sizeY, int hasAlpha,
+                                        uint32_t errorFactor, uint32_t flags, void *const *outs, const size_t *capacities, size_t *written);
+int limgcu_batch_host_decode_containers(limgcu_ctx *const *ctxs, int lanes, const void *const *containers, const size_t *bytes, int count, uint32_t *const *outs,
+                                        const size_t *outPixels);
+
 #ifdef __cplusplus
 }
 #endif

@@ -6,3 +6,4 @@ the thin Python mirror of the reference's operator interface used by the tests a
 from . import synth  # noqa: F401
 from ._lib import AREA_DTYPE, DECOMP_DTYPE, LimgError  # noqa: F401
 from .api import Codec  # noqa: F401
+from .batch import BatchCodec  # noqa: F401

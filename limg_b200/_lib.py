@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "liblimgcu.so")
+LIB_PATH = os.environ.get("LIMGCU_LIB") or os.path.join(_HERE, "liblimgcu.so")  # LIMGCU_LIB: another build of the same library (profile counters)
 
 DECOMP_DTYPE = np.dtype([
     ("avg", "<f4", (4,)),
@@ -44,6 +44,7 @@ SYMBOLS = (
     "limgcu_host_blocked_encode3d", "limgcu_host_encode3d", "limgcu_host_encode_stream", "limgcu_host_decode",
     "limgcu_host_pass1", "limgcu_host_merge", "limgcu_host_compare",
     "limgcu_container_bound", "limgcu_container_info", "limgcu_host_encode_container", "limgcu_host_decode_container", "limgcu_pack_payload", "limgcu_unpack_payload",
+    "limgcu_batch_host_encode_containers", "limgcu_batch_host_decode_containers",
 )
 
 
@@ -90,6 +91,8 @@ def load():
     lib.limgcu_host_decode_container.argtypes = [vp, vp, sz, vp, sz]
     lib.limgcu_pack_payload.argtypes = [vp, vp, vp, u32, vp, vp, vp, vp, sz, sz, i32, vp, vp]
     lib.limgcu_unpack_payload.argtypes = [vp, vp, u32, vp, vp, vp, sz, sz, i32, vp, vp, vp]
+    lib.limgcu_batch_host_encode_containers.argtypes = [vp, i32, vp, i32, sz, sz, i32, u32, u32, vp, vp, vp]
+    lib.limgcu_batch_host_decode_containers.argtypes = [vp, i32, vp, vp, i32, vp, vp]
     lib.limgcu_debug_set_decode_variant.argtypes = [vp, C.c_int]
     lib.limgcu_launch_count.restype = C.c_uint64
     lib.limgcu_enable_phase_timing.argtypes = [vp, i32]

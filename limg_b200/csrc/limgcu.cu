@@ -13,6 +13,8 @@
 #include <string.h>
 #include <math.h>
 #include <new>
+#include <thread>
+#include <vector>
 
 using namespace limg;
 
@@ -1354,6 +1356,60 @@ extern "C" int limgcu_host_decode_container(limgcu_ctx *ctx, const void *data, s
   CK(cudaMemcpyAsync(pOut, ctx->dPlaneU32[0], n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   return LIMGCU_SUCCESS;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------------
+// batches of independent frames: `lanes` contexts of one (or several) devices, one host thread each; frame i runs on lane i % lanes
+// ---------------------------------------------------------------------------------------------------------------------------------
+
+template <class Fn>
+static int run_lanes(limgcu_ctx *const *ctxs, int lanes, int count, Fn &&fn)
+{
+  if (ctxs == nullptr || lanes < 1 || count < 0)
+    return LIMGCU_ERROR_INVALID_PARAMETER;
+
+  for (int j = 0; j < lanes; j++)
+    if (ctxs[j] == nullptr)
+      return LIMGCU_ERROR_ARGUMENT_NULL;
+
+  std::vector<int> rc((size_t)lanes, LIMGCU_SUCCESS);
+  std::vector<std::thread> threads;
+  const int used = lanes < count ? lanes : count;
+
+  for (int j = 0; j < used; j++)
+    threads.emplace_back([&, j]() {
+      for (int i = j; i < count && rc[j] == LIMGCU_SUCCESS; i += lanes)
+        rc[j] = fn(ctxs[j], i);
+    });
+
+  for (auto &t : threads)
+    t.join();
+
+  for (int j = 0; j < used; j++)
+    if (rc[j] != LIMGCU_SUCCESS)
+      return rc[j]; // limgcu_last_error of that lane's context has the text
+
+  return LIMGCU_SUCCESS;
+}
+
+extern "C" int limgcu_batch_host_encode_containers(limgcu_ctx *const *ctxs, int lanes, const uint32_t *const *frames, int count, size_t sizeX, size_t sizeY, int hasAlpha,
+                                                   uint32_t errorFactor, uint32_t flags, void *const *outs, const size_t *capacities, size_t *written)
+{
+  if (frames == nullptr || outs == nullptr || capacities == nullptr || written == nullptr)
+    return LIMGCU_ERROR_ARGUMENT_NULL;
+
+  return run_lanes(ctxs, lanes, count, [&](limgcu_ctx *ctx, int i) {
+    return limgcu_host_encode_container(ctx, frames[i], sizeX, sizeY, hasAlpha, errorFactor, flags, outs[i], capacities[i], &written[i]);
+  });
+}
+
+extern "C" int limgcu_batch_host_decode_containers(limgcu_ctx *const *ctxs, int lanes, const void *const *containers, const size_t *bytes, int count, uint32_t *const *outs,
+                                                   const size_t *outPixels)
+{
+  if (containers == nullptr || bytes == nullptr || outs == nullptr || outPixels == nullptr)
+    return LIMGCU_ERROR_ARGUMENT_NULL;
+
+  return run_lanes(ctxs, lanes, count, [&](limgcu_ctx *ctx, int i) { return limgcu_host_decode_container(ctx, containers[i], bytes[i], outs[i], outPixels[i]); });
 }
 
 extern "C" int limgcu_host_pass1(limgcu_ctx *ctx, const uint32_t *pIn, size_t sizeX, size_t sizeY, int hasAlpha, limgcu_decomp *table)

@@ -161,3 +161,23 @@ def test_gpu_container_full_size_round_trip(codec, cfg):
     assert info["payload_bytes"] == int((((a["px_w"].astype(np.int64) + 7) // 8) * a["px_h"] * bits).sum())
     assert len(data) < img.size * (4 if alpha else 3)  # smaller than the raw pixels
     assert np.array_equal(codec.decode_container(data), st["decoded"])
+
+
+@pytest.mark.gpu
+def test_gpu_batch_of_frames_equals_one_at_a_time(codec):
+    """Batch mode: frames on several contexts at once through the C batch entry points == the frames one at a time."""
+    from limg_b200 import BatchCodec, synth
+    frames = [synth.photo_like(320, 200, 60 + i, 3) for i in range(7)]
+    want = [codec.encode_container(f, False) for f in frames]
+    b = BatchCodec(0, lanes=3)
+    try:
+        got = b.encode_containers(frames, False)
+        assert got == want
+        decoded = b.decode_containers(got)
+        for d, w_ in zip(decoded, want):
+            assert np.array_equal(d, codec.decode_container(w_))
+        streams = b.encode_streams(frames, False, decoded=True)
+        for s, d in zip(streams, decoded):
+            assert np.array_equal(s["decoded"], d)
+    finally:
+        b.close()

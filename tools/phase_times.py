@@ -4,7 +4,7 @@ import numpy as np, torch
 from limg_b200 import Codec, synth
 c = Codec(0)
 c.enable_phase_timing(True)
-for name in ("c1_512_gradient","c5_1080p_frame0","c2_4k_photo","c4_4k_flatui","c3_8k_rgba"):
+for name in (sys.argv[1].split(",") if len(sys.argv) > 1 else ("c1_512_gradient","c5_1080p_frame0","c2_4k_photo","c4_4k_flatui","c3_8k_rgba")):
     img, alpha = synth.CONFIGS[name]()
     h,w = img.shape
     d = torch.from_numpy(img.view(np.int32)).cuda()
