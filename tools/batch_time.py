@@ -52,4 +52,6 @@ for lanes in lanes_list:
         torch.cuda.synchronize()
         times.append(max(start.elapsed_time(e) for e in ends))
     ms = statistics.median(times[2:])
-    print("%s lanes %d: %.3f ms per step of %d frames -> %.0f Mpx/s (%.2f ms per frame)" % (name, lanes, ms, lanes, lanes * w * h / ms / 1e3, ms / lanes))
+    fails = [int(l.codec.debug_counters()[24]) for l in ls]
+    flags = [l.codec.debug_counters()[24:29].tolist() for l in ls]
+    print("%s lanes %d: %.3f ms per step of %d frames -> %.0f Mpx/s (%.2f ms per frame); tries that failed in the last step, per lane: %s; step times %s" % (name, lanes, ms, lanes, lanes * w * h / ms / 1e3, ms / lanes, flags, [round(t, 2) for t in times]))
