@@ -11,9 +11,10 @@
  *   - `pThreadPool` is accepted and ignored. For limg_encode3d_test the reference restarts its dither chain per y-band of the
  *     pool (limg.cpp:1893, 2114-2134), so its output depends on the pool size; this implementation always produces the
  *     pool-less result (pThreadPool == nullptr).
- *   - The dither generator is the reference's PCG-style LCG (limg.cpp:799-822), i.e. what the reference computes on hosts
- *     without AES-NI. On AES-NI hosts the reference picks an AES round chain instead (limg.cpp:824-879); area maps,
- *     shifts and endpoints are identical either way, the factor bytes differ.
+ *   - The dither generator follows the reference's own rule (limg.cpp:881-887): the AES round chain (limg.cpp:824-879) on hosts with
+ *     SSE4.1 + AES-NI, the PCG-style LCG (limg.cpp:799-822) otherwise, so the output equals the reference run on the same host.
+ *     The AES chain has no skip-ahead and is walked on the host once the GPU has found the shifts (a few ms per 4K frame);
+ *     LIMGCU_DITHER=lcg selects the LCG everywhere (area maps, shifts and endpoints are identical either way, the factor bytes differ).
  *   - limg_encode_test (the legacy one-factor codec, not reachable from the CLI) returns limg_error_Generic.
  *   - Null pointers are rejected with limg_error_ArgumentNull (the reference dereferences them).
  */

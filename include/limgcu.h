@@ -91,7 +91,11 @@ typedef struct limgcu_stream
 enum
 {
   LIMGCU_FLAG_FAST_BIT_CRUSH = 1u << 0,  /* reference `fastBitCrushing` (limg.h:46); clear = --accurate-bit-crushing */
-  LIMGCU_FLAG_NO_MERGE = 1u << 1         /* every 8x8 block is its own area (limg_encode3d_test) */
+  LIMGCU_FLAG_NO_MERGE = 1u << 1,        /* every 8x8 block is its own area (limg_encode3d_test) */
+  LIMGCU_FLAG_DITHER_AES = 1u << 2       /* the dither noise of a reference running on a host with SSE4.1 + AES-NI (limg.cpp:824-879) instead of the
+                                            LCG it uses elsewhere (limg.cpp:799-822). The AES-round chain has no skip-ahead: it is walked on the host
+                                            (AES-NI when the host has it, software otherwise) once the shifts are known, so a call with this flag
+                                            synchronises with the stream. Areas, shifts and decompositions are the same in both modes. */
 };
 
 typedef struct limgcu_ctx limgcu_ctx;
@@ -105,6 +109,10 @@ int limgcu_device_count(void);
 int limgcu_set_rsqrt_lut(limgcu_ctx *ctx, const uint16_t *lut2048);
 void *limgcu_stream_handle(limgcu_ctx *ctx); /* cudaStream_t */
 int limgcu_sync(limgcu_ctx *ctx);
+/* dither generator of the entry points that have no flags argument (limgcu_host_blocked_encode3d, limgcu_host_encode3d): 0 = LCG (default),
+ * 1 = AES (as LIMGCU_FLAG_DITHER_AES). limgcu_host_has_aesni: 1 when the reference itself would pick the AES generator on this host. */
+int limgcu_set_dither_mode(limgcu_ctx *ctx, int aes);
+int limgcu_host_has_aesni(void);
 /* number of kernels launched through this context since creation (bench.py's gpu_launches) */
 uint64_t limgcu_launch_count(const limgcu_ctx *ctx);
 /* milliseconds the kernels of one named phase took during the last limgcu_*encode3d call when profiling was enabled

@@ -35,11 +35,12 @@ PLANES_U8 = ("pFactorsA", "pFactorsB", "pFactorsC", "pBlockError", "pBitsPerPixe
 
 FLAG_FAST_BIT_CRUSH = 1
 FLAG_NO_MERGE = 2
+FLAG_DITHER_AES = 4
 
 # every symbol include/limgcu.h declares (tests/test_abi.py checks the header against this list and the .so)
 SYMBOLS = (
     "limgcu_create", "limgcu_destroy", "limgcu_last_error", "limgcu_device_count", "limgcu_set_rsqrt_lut",
-    "limgcu_stream_handle", "limgcu_sync", "limgcu_launch_count", "limgcu_enable_phase_timing", "limgcu_phase_ms",
+    "limgcu_stream_handle", "limgcu_sync", "limgcu_set_dither_mode", "limgcu_host_has_aesni", "limgcu_launch_count", "limgcu_enable_phase_timing", "limgcu_phase_ms",
     "limgcu_debug_counters", "limgcu_debug_wave", "limgcu_debug_predicate_check", "limgcu_debug_wave_rows", "limgcu_debug_set_decode_variant", "limgcu_pass1", "limgcu_merge", "limgcu_blocked_encode3d", "limgcu_decode", "limgcu_build_block_map", "limgcu_compare",
     "limgcu_host_blocked_encode3d", "limgcu_host_encode3d", "limgcu_host_encode_stream", "limgcu_host_decode",
     "limgcu_host_pass1", "limgcu_host_merge", "limgcu_host_compare",
@@ -84,6 +85,8 @@ def load():
     lib.limgcu_stream_handle.restype = vp
     lib.limgcu_sync.argtypes = [vp]
     lib.limgcu_launch_count.argtypes = [vp]
+    lib.limgcu_set_dither_mode.argtypes = [vp, i32]
+    lib.limgcu_host_has_aesni.restype = i32
     lib.limgcu_container_bound.argtypes = [C.c_size_t, C.c_size_t, C.c_int]
     lib.limgcu_container_bound.restype = C.c_size_t
     lib.limgcu_container_info.argtypes = [vp, sz, C.POINTER(sz), C.POINTER(sz), C.POINTER(i32), C.POINTER(u32), C.POINTER(C.c_uint64)]

@@ -11,7 +11,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import AREA_DTYPE, DECOMP_DTYPE, FLAG_FAST_BIT_CRUSH, FLAG_NO_MERGE, PLANE_ORDER, PLANES_U8, LimgError, Planes, Stream
+from ._lib import AREA_DTYPE, DECOMP_DTYPE, FLAG_DITHER_AES, FLAG_FAST_BIT_CRUSH, FLAG_NO_MERGE, PLANE_ORDER, PLANES_U8, LimgError, Planes, Stream
 
 PHASES = ("pass1", "predicate_windows", "merge_scan", "area_encode", "dither_scan", "finalize")
 
@@ -29,6 +29,7 @@ class Codec:
             raise LimgError(f"limgcu_create(device={device}) failed with {rc} (200 = no CUDA device; there is no CPU fallback)")
         self.h = h
         self.device = device
+        self.aes = False
 
     def close(self):
         if getattr(self, "h", None):
@@ -54,6 +55,11 @@ class Codec:
 
     def launch_count(self) -> int:
         return int(self.lib.limgcu_launch_count(self.h))
+
+    def set_dither_mode(self, aes: bool):
+        """Dither generator: False = the reference's LCG (default), True = its AES-round chain (what it uses on hosts with AES-NI)."""
+        self.aes = bool(aes)
+        self._ck(self.lib.limgcu_set_dither_mode(self.h, int(self.aes)), "limgcu_set_dither_mode")
 
     def set_decode_variant(self, variant: int):
         self._ck(self.lib.limgcu_debug_set_decode_variant(self.h, int(variant)), "limgcu_debug_set_decode_variant")
@@ -134,7 +140,7 @@ class Codec:
         codes = [np.zeros((h, w), np.uint8) for _ in range(3)]
         dec = np.zeros((h, w), np.uint32) if decoded else None
         n = C.c_uint32(0)
-        flags = (FLAG_FAST_BIT_CRUSH if fast_bit_crushing else 0) | (FLAG_NO_MERGE if no_merge else 0)
+        flags = (FLAG_FAST_BIT_CRUSH if fast_bit_crushing else 0) | (FLAG_NO_MERGE if no_merge else 0) | (FLAG_DITHER_AES if self.aes else 0)
         self._ck(self.lib.limgcu_host_encode_stream(self.h, _vp(img), w, h, int(has_alpha), int(error_factor), flags, _vp(areas), C.byref(n),
                                                     _vp(codes[0]), _vp(codes[1]), _vp(codes[2]), _vp(dec)), "limgcu_host_encode_stream")
         out = {"areas": areas[: n.value].copy(), "codesA": codes[0], "codesB": codes[1], "codesC": codes[2], "width": w, "height": h, "has_alpha": has_alpha}
@@ -148,7 +154,7 @@ class Codec:
         h, w = img.shape
         buf = np.zeros(self.lib.limgcu_container_bound(w, h, int(has_alpha)), np.uint8)
         n = C.c_size_t(0)
-        flags = (FLAG_FAST_BIT_CRUSH if fast_bit_crushing else 0) | (FLAG_NO_MERGE if no_merge else 0)
+        flags = (FLAG_FAST_BIT_CRUSH if fast_bit_crushing else 0) | (FLAG_NO_MERGE if no_merge else 0) | (FLAG_DITHER_AES if self.aes else 0)
         self._ck(self.lib.limgcu_host_encode_container(self.h, _vp(img), w, h, int(has_alpha), int(error_factor), flags, _vp(buf), buf.size, C.byref(n)), "limgcu_host_encode_container")
         return buf[: n.value].tobytes()
 
@@ -205,7 +211,7 @@ class Codec:
         pl = Planes()
         for k in PLANE_ORDER:
             setattr(pl, k, (planes or {}).get(k))
-        flags = (FLAG_FAST_BIT_CRUSH if fast_bit_crushing else 0) | (FLAG_NO_MERGE if no_merge else 0)
+        flags = (FLAG_FAST_BIT_CRUSH if fast_bit_crushing else 0) | (FLAG_NO_MERGE if no_merge else 0) | (FLAG_DITHER_AES if self.aes else 0)
         self._ck(self.lib.limgcu_blocked_encode3d(self.h, d_src, w, h, int(has_alpha), int(error_factor), flags, C.byref(st), C.byref(pl)), "limgcu_blocked_encode3d")
 
     def decode_device(self, d_areas: int, d_block_to_area: int, d_codesA: int, d_codesB: int, d_codesC: int, w: int, h: int, has_alpha: bool, d_dst: int):

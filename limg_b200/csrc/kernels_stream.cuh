@@ -68,6 +68,18 @@ __global__ void __launch_bounds__(1024) k_dither_scan(const uint32_t *areaCount,
   }
 }
 
+// AES mode: the chain states around every area come from the host
+__global__ void __launch_bounds__(256) k_set_dither_states(limgcu_area *areas, const unsigned long long *before, const unsigned long long *after, uint32_t count)
+{
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+
+  if (k >= count)
+    return;
+
+  areas[k].ditherBefore = before[k];
+  areas[k].ditherAfter = after[k];
+}
+
 __global__ void __launch_bounds__(256) k_dither_states(limgcu_area *areas, const uint32_t *areaCount, const uint64_t *demand, const unsigned long long *before, LcgJumpTable jt)
 {
   const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -95,6 +107,8 @@ struct FinalizeArgs
   uint8_t *codesA, *codesB, *codesC;
   limgcu_planes planes;
   LcgJumpTable jt;
+  const uint8_t *noise;                // AES mode: one noise byte per pixel and dithered plane, area-contiguous (dither_aes_host.cpp); else nullptr
+  const unsigned long long *noiseOff;  // [3 * area + plane] -> offset into noise
   int vec; // W % 8 == 0 and every plane pointer 32-byte aligned: 128-bit loads / stores
 };
 
@@ -204,7 +218,16 @@ __global__ void __launch_bounds__(256) k_finalize(FinalizeArgs a)
 #pragma unroll
     for (int pl = 0; pl < 3; pl++)
     {
-      if (sh[pl] != 0 && sh[pl] != 8)
+      if (sh[pl] != 0 && sh[pl] != 8 && a.noise != nullptr)
+      {
+        const uint8_t *nz = a.noise + a.noiseOff[3 * (size_t)k + pl] + i0;
+
+#pragma unroll
+        for (int j = 0; j < 8; j++)
+          if (j < npx)
+            codes[pl][j] = dither_one(codes[pl][j], nz[j], sh[pl]);
+      }
+      else if (sh[pl] != 0 && sh[pl] != 8)
       {
         uint64_t h = lcg_jump(ar->ditherBefore, planeIndex * n + i0, a.jt);
 

@@ -4,6 +4,8 @@
 #include "../../include/limgcu.h"
 
 #include <math.h>
+#include <stdlib.h>
+#include <string.h>
 #include <mutex>
 #include <thread>
 
@@ -36,8 +38,19 @@ int g_device = 0;
 // one process-wide context, created on first use; calls are serialised (the reference is not re-entrant on a shared pool either)
 limgcu_ctx *context()
 {
-  if (g_ctx == nullptr && limgcu_create(g_device, &g_ctx) != LIMGCU_SUCCESS)
-    g_ctx = nullptr;
+  if (g_ctx == nullptr)
+  {
+    if (limgcu_create(g_device, &g_ctx) != LIMGCU_SUCCESS)
+    {
+      g_ctx = nullptr;
+      return nullptr;
+    }
+
+    // The reference picks its dither generator from the host CPU (limg.cpp:881-887: AES rounds with SSE4.1 + AES-NI, the LCG otherwise);
+    // the drop-in follows the same rule so that it reproduces the reference run on this host. LIMGCU_DITHER=lcg / aes overrides it.
+    const char *mode = getenv("LIMGCU_DITHER");
+    limgcu_set_dither_mode(g_ctx, mode ? (strcmp(mode, "aes") == 0) : limgcu_host_has_aesni());
+  }
 
   return g_ctx;
 }

@@ -18,6 +18,13 @@
 
 using namespace limg;
 
+namespace limg
+{
+// dither_aes_host.cpp
+uint64_t aes_dither_chain_host(const limgcu_area *areas, uint32_t count, uint64_t seed, uint8_t *noise, uint64_t *planeOff, uint64_t *before, uint64_t *after, bool forceSoftware);
+bool host_has_aesni();
+}
+
 enum { PHASE_PASS1 = 0, PHASE_WINDOW, PHASE_SCAN, PHASE_ENCODE, PHASE_DITHER, PHASE_FINALIZE, PHASE_COUNT };
 
 struct limgcu_ctx
@@ -46,6 +53,13 @@ struct limgcu_ctx
   uint32_t *dSmallList = nullptr, *dLargeList = nullptr;
   uint64_t *dDemand = nullptr;
   unsigned long long *dDitherBefore = nullptr;
+  // AES dither mode (dither_aes_host.cpp): pinned host staging + device copies, allocated on first use
+  int ditherAes = 0;                 // limgcu_set_dither_mode / LIMGCU_DITHER=aes: default generator of the entry points without a flags argument
+  int aesForceSoftware = 0;          // LIMGCU_AES_SOFTWARE=1: software AES rounds even on a host with AES-NI (test hook)
+  limgcu_area *hAreas = nullptr;
+  uint8_t *hNoise = nullptr, *dNoise = nullptr;
+  unsigned long long *hNoiseOff = nullptr, *dNoiseOff = nullptr, *hStates = nullptr, *dStates = nullptr;
+  size_t capAesBlocks = 0, capAesPixels = 0;
   uint32_t *dUsed = nullptr;
   uint32_t *dExtSlot = nullptr, *dExtSeed = nullptr, *dExtBits = nullptr, *dExtHdr = nullptr, *dPlanCounters = nullptr;
   uint4 *dSeedSym = nullptr;
@@ -288,6 +302,8 @@ extern "C" int limgcu_create(int device, limgcu_ctx **out)
   if (const char *v = getenv("LIMGCU_PLAN_CTAS")) ctx->planAsyncCtas = atoi(v) < 1 ? 1 : (atoi(v) > 8 ? 8 : atoi(v));
   if (const char *v = getenv("LIMGCU_MERGE_GAP")) ctx->mergeGap = atoi(v) < 0 ? 0 : atoi(v);
   if (const char *v = getenv("LIMGCU_DECODE_VARIANT")) ctx->decodeVariant = atoi(v);
+  if (const char *v = getenv("LIMGCU_DITHER")) ctx->ditherAes = !strcmp(v, "aes") ? 1 : 0;
+  if (const char *v = getenv("LIMGCU_AES_SOFTWARE")) ctx->aesForceSoftware = atoi(v);
   if (const char *v = getenv("LIMGCU_MERGE_SPEC")) ctx->mergeSpec = atoi(v) < 0 ? 0 : atoi(v);
 
   for (auto &e : ctx->ev)
@@ -317,6 +333,11 @@ extern "C" void limgcu_destroy(limgcu_ctx *ctx)
 
   for (void *p : ptrs)
     if (p) cudaFree(p);
+
+  void *aesDev[] = { ctx->dNoise, ctx->dNoiseOff, ctx->dStates };
+  void *aesHost[] = { ctx->hAreas, ctx->hNoise, ctx->hNoiseOff, ctx->hStates };
+  for (void *p : aesDev) if (p) cudaFree(p);
+  for (void *p : aesHost) if (p) cudaFreeHost(p);
 
   for (auto p : ctx->dPlaneU32) if (p) cudaFree(p);
   for (auto p : ctx->dPlaneU8) if (p) cudaFree(p);
@@ -682,6 +703,52 @@ extern "C" int limgcu_merge(limgcu_ctx *ctx, const limgcu_decomp *d_table, size_
   return LIMGCU_SUCCESS;
 }
 
+template <class T>
+static cudaError_t regrow_host(T *&p, size_t count)
+{
+  if (p)
+    cudaFreeHost(p);
+
+  p = nullptr;
+  return cudaMallocHost(reinterpret_cast<void **>(&p), count * sizeof(T));
+}
+
+static int ensure_aes(limgcu_ctx *ctx, size_t W, size_t H)
+{
+  const size_t blocks = ((W + 7) / 8) * ((H + 7) / 8), pixels = W * H;
+
+  if (blocks > ctx->capAesBlocks)
+  {
+    CK(regrow_host(ctx->hAreas, blocks));
+    CK(regrow_host(ctx->hNoiseOff, 3 * blocks));
+    CK(regrow_host(ctx->hStates, 2 * blocks));
+    CK(regrow(ctx->dNoiseOff, 3 * blocks));
+    CK(regrow(ctx->dStates, 2 * blocks));
+    ctx->capAesBlocks = blocks;
+  }
+
+  if (pixels > ctx->capAesPixels)
+  {
+    CK(regrow_host(ctx->hNoise, 3 * pixels));
+    CK(regrow(ctx->dNoise, 3 * pixels));
+    ctx->capAesPixels = pixels;
+  }
+
+  return LIMGCU_SUCCESS;
+}
+
+extern "C" int limgcu_set_dither_mode(limgcu_ctx *ctx, int aes)
+{
+  if (!ctx) return LIMGCU_ERROR_ARGUMENT_NULL;
+  ctx->ditherAes = aes ? 1 : 0;
+  return LIMGCU_SUCCESS;
+}
+
+extern "C" int limgcu_host_has_aesni(void)
+{
+  return host_has_aesni() ? 1 : 0;
+}
+
 extern "C" int limgcu_blocked_encode3d(limgcu_ctx *ctx, const uint32_t *d_src, size_t sizeX, size_t sizeY, int hasAlpha, uint32_t errorFactor, uint32_t flags,
                                        const limgcu_stream *stream, const limgcu_planes *planes)
 {
@@ -747,10 +814,42 @@ extern "C" int limgcu_blocked_encode3d(limgcu_ctx *ctx, const uint32_t *d_src, s
 
   if (ctx->timing) CK(cudaEventRecord(ctx->ev[PHASE_DITHER], ctx->stream));
 
-  k_dither_scan<<<1, 1024, 0, ctx->stream>>>(ctx->dCounters + 1, ctx->dDemand, ctx->dDitherBefore, 0);
-  CKL("k_dither_scan");
-  k_dither_states<<<(unsigned)((((size_t)BX * e.BY) + 255) / 256), 256, 0, ctx->stream>>>(dAreas, ctx->dCounters + 1, ctx->dDemand, ctx->dDitherBefore, ctx->jt);
-  CKL("k_dither_states");
+  const bool ditherAes = (flags & LIMGCU_FLAG_DITHER_AES) != 0;
+
+  if (ditherAes)
+  {
+    // The AES-round chain cannot be jumped: bring the area table (shifts, pixel rectangles) to the host, walk the chain there
+    // (dither_aes_host.cpp), send the noise stream back. This synchronises with the stream.
+    rc = ensure_aes(ctx, sizeX, sizeY);
+    if (rc) return rc;
+    uint32_t count = 0;
+    CK(cudaMemcpyAsync(&count, ctx->dCounters + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+
+    if ((size_t)count > ctx->capAesBlocks)
+      return fail(ctx, LIMGCU_ERROR_OUT_OF_BOUNDS, "more areas than blocks", cudaSuccess);
+
+    CK(cudaMemcpyAsync(ctx->hAreas, dAreas, (size_t)count * sizeof(limgcu_area), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    const uint64_t noiseBytes = aes_dither_chain_host(ctx->hAreas, count, LIMG_DITHER_SEED, ctx->hNoise, reinterpret_cast<uint64_t *>(ctx->hNoiseOff),
+                                                      reinterpret_cast<uint64_t *>(ctx->hStates), reinterpret_cast<uint64_t *>(ctx->hStates) + count, ctx->aesForceSoftware != 0);
+    CK(cudaMemcpyAsync(ctx->dNoise, ctx->hNoise, (size_t)noiseBytes, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->dNoiseOff, ctx->hNoiseOff, 3 * (size_t)count * sizeof(unsigned long long), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->dStates, ctx->hStates, 2 * (size_t)count * sizeof(unsigned long long), cudaMemcpyHostToDevice, ctx->stream));
+
+    if (count)
+    {
+      k_set_dither_states<<<(count + 255) / 256, 256, 0, ctx->stream>>>(dAreas, ctx->dStates, ctx->dStates + count, count);
+      CKL("k_set_dither_states");
+    }
+  }
+  else
+  {
+    k_dither_scan<<<1, 1024, 0, ctx->stream>>>(ctx->dCounters + 1, ctx->dDemand, ctx->dDitherBefore, 0);
+    CKL("k_dither_scan");
+    k_dither_states<<<(unsigned)((((size_t)BX * e.BY) + 255) / 256), 256, 0, ctx->stream>>>(dAreas, ctx->dCounters + 1, ctx->dDemand, ctx->dDitherBefore, ctx->jt);
+    CKL("k_dither_states");
+  }
 
   if (ctx->timing) CK(cudaEventRecord(ctx->ev[PHASE_FINALIZE], ctx->stream));
 
@@ -764,6 +863,8 @@ extern "C" int limgcu_blocked_encode3d(limgcu_ctx *ctx, const uint32_t *d_src, s
 
   f.planes.pBlockError = nullptr; // never written (Q12)
   f.jt = ctx->jt;
+  f.noise = ditherAes ? ctx->dNoise : nullptr;
+  f.noiseOff = ditherAes ? ctx->dNoiseOff : nullptr;
   f.vec = (W % 8 == 0) && aligned32(d_src) && aligned32(f.codesA) && aligned32(f.codesB) && aligned32(f.codesC) && aligned32(f.planes.pDecoded) &&
           aligned32(f.planes.pFactorsA) && aligned32(f.planes.pFactorsB) && aligned32(f.planes.pFactorsC) && aligned32(f.planes.pBitsPerPixel) &&
           aligned32(f.planes.pShiftABCX) && aligned32(f.planes.pColAMin) && aligned32(f.planes.pColAMax) && aligned32(f.planes.pColBMin) &&
@@ -999,7 +1100,9 @@ static int host_encode(limgcu_ctx *ctx, const uint32_t *pIn, size_t W, size_t H,
 
 extern "C" int limgcu_host_blocked_encode3d(limgcu_ctx *ctx, const uint32_t *pIn, size_t sizeX, size_t sizeY, int hasAlpha, const limgcu_planes *pInfo, uint32_t errorFactor, int fastBitCrushing)
 {
-  return host_encode(ctx, pIn, sizeX, sizeY, hasAlpha, pInfo, errorFactor, fastBitCrushing ? LIMGCU_FLAG_FAST_BIT_CRUSH : 0, nullptr, nullptr, nullptr, nullptr, nullptr);
+  NEED(ctx);
+  return host_encode(ctx, pIn, sizeX, sizeY, hasAlpha, pInfo, errorFactor, (fastBitCrushing ? LIMGCU_FLAG_FAST_BIT_CRUSH : 0) | (ctx->ditherAes ? LIMGCU_FLAG_DITHER_AES : 0), nullptr, nullptr,
+                     nullptr, nullptr, nullptr);
 }
 
 extern "C" int limgcu_host_encode3d(limgcu_ctx *ctx, const uint32_t *pIn, size_t sizeX, size_t sizeY, int hasAlpha, const limgcu_planes *pInfo, uint32_t errorFactor, int fastBitCrushing)
@@ -1015,7 +1118,9 @@ extern "C" int limgcu_host_encode3d(limgcu_ctx *ctx, const uint32_t *pIn, size_t
     p.pBlockError = nullptr;
   }
 
-  return host_encode(ctx, pIn, sizeX, sizeY, hasAlpha, pInfo ? &p : nullptr, errorFactor, (fastBitCrushing ? LIMGCU_FLAG_FAST_BIT_CRUSH : 0) | LIMGCU_FLAG_NO_MERGE, nullptr, nullptr, nullptr, nullptr, nullptr);
+  NEED(ctx);
+  return host_encode(ctx, pIn, sizeX, sizeY, hasAlpha, pInfo ? &p : nullptr, errorFactor,
+                     (fastBitCrushing ? LIMGCU_FLAG_FAST_BIT_CRUSH : 0) | LIMGCU_FLAG_NO_MERGE | (ctx->ditherAes ? LIMGCU_FLAG_DITHER_AES : 0), nullptr, nullptr, nullptr, nullptr, nullptr);
 }
 
 extern "C" int limgcu_host_encode_stream(limgcu_ctx *ctx, const uint32_t *pIn, size_t sizeX, size_t sizeY, int hasAlpha, uint32_t errorFactor, uint32_t flags,

@@ -395,3 +395,73 @@ def test_decode_variants_on_adversarial_streams(codec, lo, shape):
             assert np.array_equal(got, want), "decode variant %d" % v
     finally:
         codec.set_decode_variant(20)
+
+
+# ---- AES dither mode (limg.cpp:824-879: what the reference computes on hosts with AES-NI) ------------------------------------------
+
+@pytest.fixture()
+def aes_codec(codec):
+    codec.set_dither_mode(True)
+    yield codec
+    codec.set_dither_mode(False)
+
+
+def test_aes_mode_reproduces_the_reference_run_with_aesni(aes_codec):
+    """The golden produced by the real reference with its AES-NI dither: every plane, the stream, the dither chain states and the container."""
+    g = H.load_golden("rgb_photo_96x64_aes")
+    assert bool(g["aes"])
+    planes = aes_codec.blocked_encode3d_test(g["img"], False, None, int(g["error_factor"]), bool(g["fast"]))
+    for k in H.PLANES:
+        assert np.array_equal(planes[k], g["plane_" + k]), k
+    st = aes_codec.encode_stream(g["img"], False, int(g["error_factor"]), bool(g["fast"]), decoded=True)
+    assert_areas_equal(st["areas"], golden_areas(g))
+    a, b, c = scatter_streams(g)
+    assert np.array_equal(st["codesA"], a) and np.array_equal(st["codesB"], b) and np.array_equal(st["codesC"], c)
+    assert np.array_equal(st["decoded"], g["plane_pDecoded"])
+    psnr, mse, _ = aes_codec.compare(g["img"], st["decoded"], False)
+    assert abs(psnr - float(g["psnr"])) < 1e-9
+    from oracle import container as oc
+    from tests.test_container import golden_container
+    assert aes_codec.encode_container(g["img"], False, int(g["error_factor"]), bool(g["fast"])) == golden_container(g)
+
+
+@pytest.mark.parametrize("case", [("photo", 200, 136, False, "fast"), ("photo", 61, 37, True, "fast"), ("gradient", 128, 128, False, "accurate"), ("flatui", 256, 144, False, "fast"),
+                                  ("photo", 320, 200, True, "ef37")])
+def test_aes_mode_vs_oracle(aes_codec, lo, case):
+    kind, w, h, alpha, mode = case
+    img = {"photo": lambda: synth.photo_like(w, h, 21, 4 if alpha else 3), "gradient": lambda: synth.gradient_noise(w, h, 5), "flatui": lambda: synth.flat_ui(w, h, 4, 30)}[kind]()
+    ef = 37 if mode == "ef37" else 100
+    fast = mode != "accurate"
+    o = lo.blocked_encode3d(img, alpha, ef, fast, lo.DITHER_AES)
+    planes = aes_codec.blocked_encode3d_test(img, alpha, None, ef, fast)
+    for k in H.PLANES:
+        assert np.array_equal(planes[k], o["planes"][k]), k
+    st = aes_codec.encode_stream(img, alpha, ef, fast)
+    assert_areas_equal(st["areas"], o["areas"])
+    # and it differs from the LCG result only in the noise
+    aes_codec.set_dither_mode(False)
+    lcg = aes_codec.encode_stream(img, alpha, ef, fast)
+    aes_codec.set_dither_mode(True)
+    assert_areas_equal(lcg["areas"], o["areas"], dither=False)
+
+
+def test_aes_mode_software_rounds_equal_aesni(monkeypatch):
+    """Hosts without AES-NI walk the chain with table-based AES rounds: same bytes."""
+    from limg_b200 import Codec
+    img = synth.photo_like(160, 96, 31, 3)
+    out = []
+    for soft in ("0", "1"):
+        monkeypatch.setenv("LIMGCU_AES_SOFTWARE", soft)
+        c = Codec(0)
+        c.set_dither_mode(True)
+        out.append(c.encode_container(img, False))
+        c.close()
+    assert out[0] == out[1]
+
+
+def test_unmerged_encoder_aes_vs_oracle(aes_codec, lo):
+    img = synth.photo_like(200, 136, 8, 3)
+    o = lo.encode3d(img, False, 100, True, lo.DITHER_AES, 0)
+    p = aes_codec.encode3d_test(img, False, None, 100, True)
+    for k, v in o.items():
+        assert np.array_equal(p[k], v), k
