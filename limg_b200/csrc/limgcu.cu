@@ -1149,14 +1149,47 @@ extern "C" int limgcu_host_decode(limgcu_ctx *ctx, const limgcu_area *areas, uin
     return fail(ctx, LIMGCU_ERROR_OUT_OF_BOUNDS, "more areas than blocks", cudaSuccess);
 
   CK(cudaMemcpyAsync(ctx->dAreas, areas, (size_t)area_count * sizeof(limgcu_area), cudaMemcpyHostToDevice, ctx->stream));
-  CK(cudaMemcpyAsync(ctx->dPlaneU8[4], codesA, n, cudaMemcpyHostToDevice, ctx->stream));
-  CK(cudaMemcpyAsync(ctx->dPlaneU8[5], codesB, n, cudaMemcpyHostToDevice, ctx->stream));
-  CK(cudaMemcpyAsync(ctx->dPlaneU8[6], codesC, n, cudaMemcpyHostToDevice, ctx->stream));
   rc = limgcu_build_block_map(ctx, ctx->dAreas, area_count, sizeX, sizeY, ctx->dBlockToArea);
   if (rc) return rc;
-  rc = limgcu_decode(ctx, ctx->dAreas, ctx->dBlockToArea, ctx->dPlaneU8[4], ctx->dPlaneU8[5], ctx->dPlaneU8[6], sizeX, sizeY, hasAlpha, ctx->dPlaneU32[0]);
-  if (rc) return rc;
-  CK(cudaMemcpyAsync(pOut, ctx->dPlaneU32[0], n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+
+  // Bands of block rows, alternating between the two streams: the code upload of band i + 1 runs while band i is reconstructed and
+  // downloaded (uploads and downloads use different copy engines; with pinned host buffers the call is bound by the 4 B/px download).
+  const size_t BX = (sizeX + 7) / 8, BY = (sizeY + 7) / 8;
+  const size_t bands = BY >= 64 ? 4 : 1, rowsPerBand = (BY + bands - 1) / bands;
+  CK(cudaEventRecord(ctx->evFork2, ctx->stream));
+  CK(cudaStreamWaitEvent(ctx->streamAux, ctx->evFork2, 0));
+  cudaStream_t main = ctx->stream;
+
+  for (size_t b = 0; b < bands; b++)
+  {
+    const size_t by0 = b * rowsPerBand, by1 = by0 + rowsPerBand < BY ? by0 + rowsPerBand : BY;
+
+    if (by0 >= by1)
+      break;
+
+    const size_t y0 = by0 * 8, y1 = by1 * 8 < sizeY ? by1 * 8 : sizeY, off = y0 * sizeX, cnt = (y1 - y0) * sizeX;
+    ctx->stream = (b & 1) ? ctx->streamAux : main; // limgcu_decode launches on ctx->stream
+    cudaError_t e = cudaMemcpyAsync(ctx->dPlaneU8[4] + off, codesA + off, cnt, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(ctx->dPlaneU8[5] + off, codesB + off, cnt, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(ctx->dPlaneU8[6] + off, codesC + off, cnt, cudaMemcpyHostToDevice, ctx->stream);
+
+    if (e == cudaSuccess)
+      rc = limgcu_decode(ctx, ctx->dAreas, ctx->dBlockToArea + by0 * BX, ctx->dPlaneU8[4] + off, ctx->dPlaneU8[5] + off, ctx->dPlaneU8[6] + off, sizeX, y1 - y0, hasAlpha, ctx->dPlaneU32[0] + off);
+
+    if (e == cudaSuccess && rc == LIMGCU_SUCCESS)
+      e = cudaMemcpyAsync(pOut + off, ctx->dPlaneU32[0] + off, cnt * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream);
+
+    ctx->stream = main;
+
+    if (e != cudaSuccess)
+      return fail(ctx, LIMGCU_ERROR_CUDA, "banded decode", e);
+
+    if (rc)
+      return rc;
+  }
+
+  CK(cudaEventRecord(ctx->evJoin2, ctx->streamAux));
+  CK(cudaStreamWaitEvent(ctx->stream, ctx->evJoin2, 0));
   CK(cudaStreamSynchronize(ctx->stream));
   return LIMGCU_SUCCESS;
 }

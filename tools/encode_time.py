@@ -6,6 +6,8 @@ from limg_b200 import Codec, synth, AREA_DTYPE
 names = sys.argv[1].split(",") if len(sys.argv) > 1 else ["c2_4k_photo", "c4_4k_flatui", "c5_1080p_frame0", "c3_8k_rgba"]
 iters = int(sys.argv[2]) if len(sys.argv) > 2 else 8
 c = Codec(0)
+if len(sys.argv) > 3 and sys.argv[3] == "aes":
+    c.set_dither_mode(True)  # the reference's AES-round dither chain, walked on the host (dither_aes_host.cpp)
 stream = torch.cuda.ExternalStream(c.stream)
 flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
 out = []
