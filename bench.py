@@ -490,8 +490,9 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             "e2e": {"value": px_job * args.steps / 1e6 / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "path": "limgcu_host_encode_stream + limgcu_host_decode, pinned host buffers"},
             "roofline": {"bound": "hbm", "achieved": enc_gbs, "peak": peak, "unit": "GB/s", "frac": enc_gbs / peak,
-                         # DRAM bytes of the dominant kernel (k_merge_wave) per launch from profiles/r1_d_ncu_wave_details.txt (4K photo only)
-                         "traffic": 7.19e6 if args.workload == "c2_4k_photo" else None,
+                         # DRAM bytes of the dominant kernel (k_merge_wave) per launch, ncu --set full, profiles/r1_k_ncu_wave_details.txt (4K photo only):
+                         # 10.12 MB read + 256 B written (the scan lives in L2; the pass-1 records it reads are 8.3 MB)
+                         "traffic": 10.12e6 if args.workload == "c2_4k_photo" else None,
                          "kernel": "encode path (all kernels of limgcu_blocked_encode3d), 7 algorithmic B/px", "peak_source": peak_src,
                          "dominant_kernel": dominant, "dominant_share": phase_acc[dominant] / max(sum(phase_acc.values()), 1e-9),
                          "phase_ms": {k: round(v, 4) for k, v in phase_acc.items()},
