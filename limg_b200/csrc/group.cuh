@@ -140,15 +140,47 @@ __device__ __forceinline__ f4 unit_direction(const f4 &v, const uint16_t *__rest
 template <int WARPS>
 __device__ __forceinline__ void ordered_accumulate(const float4 *stage, int count, float &acc)
 {
-  // lanes 0..3 of the group's first warp: acc is channel `lane` of the running sum.
+  // lanes 0..3 of the group's first warp: acc is channel `lane` of the running sum. The sum is one dependent chain of FADDs (4 cycles each)
+  // in the reference's pixel order; the loads of the next eight terms are issued before the current eight are added, so the chain never
+  // waits for shared memory.
   const int t = group_tid<WARPS>();
 
   if (t < 4)
   {
     const float *s = reinterpret_cast<const float *>(stage) + t;
+    int i = 0;
 
-#pragma unroll 8
-    for (int i = 0; i < count; i++)
+    if (count >= 8)
+    {
+      float v[8];
+
+#pragma unroll
+      for (int k = 0; k < 8; k++)
+        v[k] = s[k * 4];
+
+      for (i = 8; i + 8 <= count; i += 8)
+      {
+        float nx[8];
+
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+          nx[k] = s[(i + k) * 4];
+
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+          acc = fadd(acc, v[k]);
+
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+          v[k] = nx[k];
+      }
+
+#pragma unroll
+      for (int k = 0; k < 8; k++)
+        acc = fadd(acc, v[k]);
+    }
+
+    for (; i < count; i++)
       acc = fadd(acc, s[i * 4]);
   }
 }

@@ -93,6 +93,8 @@ struct EncodeArgs
   uint32_t *workCounter;      // dynamic scheduling
   const uint32_t *list;       // area indices of this size class
   const uint32_t *listCount;
+  const uint32_t *hugeCount;  // k_encode_large: list[0 .. huge) from the front, then list[listCap - 1 - i] for the other listCount entries
+  uint32_t listCap;
   CrushParams cp;
 };
 
@@ -203,7 +205,7 @@ __global__ void __launch_bounds__(LIMG_ENCODE_THREADS) k_encode_large(EncodeArgs
   load_lut(sLut, a.lut);
   __syncthreads();
 
-  const uint32_t count = *a.listCount;
+  const uint32_t huge = *a.hugeCount, count = huge + *a.listCount;
 
   while (true)
   {
@@ -217,7 +219,7 @@ __global__ void __launch_bounds__(LIMG_ENCODE_THREADS) k_encode_large(EncodeArgs
     if (j >= count)
       break;
 
-    const uint32_t k = a.list[j];
+    const uint32_t k = j < huge ? a.list[j] : a.list[a.listCap - 1u - (j - huge)];
     const AreaWork w = a.work[k];
     uint32_t *px = w.n <= LIMG_CTA_AREA_CAP ? sPx : a.scratchPx + w.scratchOff;
     uint32_t *fac = w.n <= LIMG_CTA_AREA_CAP ? sFac : a.scratchFac + w.scratchOff;

@@ -67,7 +67,7 @@ struct limgcu_ctx
   uint16_t *dUnmasked = nullptr;
   uint32_t extCap = 0, symCap = 0;
   uint32_t *dScratchPx = nullptr, *dScratchFac = nullptr;
-  uint32_t *dCounters = nullptr; // [16]: 0 merged, 1 areaCount, 2 smallCount, 3 largeCount, 4 workSmall, 5 workLarge, 8.. stats
+  uint32_t *dCounters = nullptr; // [32]: 0 merged, 1 areaCount, 2 smallCount, 3 largeCount (fits shared memory), 4 workSmall, 5 workLarge, 6 scratchTop, 7 hugeCount, 8.. stats
   unsigned long long *dCompare = nullptr;
 
   // host-buffer staging
@@ -674,7 +674,8 @@ static int launch_merge(limgcu_ctx *ctx, const limgcu_decomp *dTable, size_t W, 
   p.rowLeft = ctx->dRowMeta; p.rowBase = ctx->dRowMeta + BY;
   p.mergedCount = ctx->dCounters + 0; p.areaCount = ctx->dCounters + 1;
   p.blockToArea = dBlockToArea; p.work = ctx->dWork; p.smallList = ctx->dSmallList; p.largeList = ctx->dLargeList;
-  p.smallCount = ctx->dCounters + 2; p.largeCount = ctx->dCounters + 3; p.scratchTop = ctx->dCounters + 6;
+  p.smallCount = ctx->dCounters + 2; p.largeCount = ctx->dCounters + 3; p.hugeCount = ctx->dCounters + 7; p.scratchTop = ctx->dCounters + 6;
+  p.largeCap = (uint32_t)ctx->capBlocks;
   k_prepare_rowleft<<<BY, 32, 0, ctx->stream>>>(p);
   CKL("k_prepare_rowleft");
   k_prepare_collect<<<BY, 128, 0, ctx->stream>>>(p);
@@ -784,7 +785,7 @@ extern "C" int limgcu_blocked_encode3d(limgcu_ctx *ctx, const uint32_t *d_src, s
     EncodeArgs s = e;
     s.workCounter = ctx->dCounters + 4; s.list = ctx->dSmallList; s.listCount = ctx->dCounters + 2;
     EncodeArgs l = e;
-    l.workCounter = ctx->dCounters + 5; l.list = ctx->dLargeList; l.listCount = ctx->dCounters + 3;
+    l.workCounter = ctx->dCounters + 5; l.list = ctx->dLargeList; l.listCount = ctx->dCounters + 3; l.hugeCount = ctx->dCounters + 7; l.listCap = (uint32_t)ctx->capBlocks;
     const int gridLarge = ctx->smCount * 4, gridSmall = ctx->smCount * 6;
     const size_t smemLarge = 4096 + LIMG_CTA_STAGE_PX * 16 + 2 * LIMG_CTA_AREA_CAP * 4;
 
