@@ -415,14 +415,36 @@ __device__ __forceinline__ bool group_trial(const uint32_t *px, const uint32_t *
 
   int32_t acc = 0;
   bool fail = false;
-
-  for (uint32_t i = group_tid<WARPS>(); i < n; i += THREADS)
-  {
+  auto one = [&](uint32_t i) {
     const uint32_t f = fac[i];
     const int32_t eA = (int32_t)((f & 0xFF) >> sA), eB = (int32_t)(((f >> 8) & 0xFF) >> sB), eC = (int32_t)(((f >> 16) & 0xFF) >> sC);
     const int32_t err = trial_error(px[i], recon_channel(r, 0, eA, eB, eC), recon_channel(r, 1, eA, eB, eC), recon_channel(r, 2, eA, eB, eC));
     acc += err;
     fail |= (uint64_t)(int64_t)err > cp.maxPixelError;
+  };
+
+  constexpr uint32_t CHUNK = THREADS * 4;
+
+  if (WARPS > 1 && n > 2 * CHUNK)
+  {
+    // Big areas: a trial that fails does so because some pixel exceeds the per-pixel bound (the reference returns at the first such pixel,
+    // limg_bit_crush_simd.h:431-440, without a block error), and with too coarse a shift that happens within the first few hundred pixels:
+    // the CTA looks at the flag after every CHUNK pixels and stops. A passing trial is unchanged (same sum).
+    for (uint32_t base = 0; base < n; base += CHUNK)
+    {
+      const uint32_t end = min(n, base + CHUNK);
+
+      for (uint32_t i = base + group_tid<WARPS>(); i < end; i += THREADS)
+        one(i);
+
+      if (__syncthreads_or(fail))
+        return false;
+    }
+  }
+  else
+  {
+    for (uint32_t i = group_tid<WARPS>(); i < n; i += THREADS)
+      one(i);
   }
 
   group_sum_any<WARPS>(acc, fail, gs, parity);
