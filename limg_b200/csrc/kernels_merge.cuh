@@ -362,22 +362,45 @@ __device__ bool predicate_warp(const PredRec &a, const PredRec &b)
 template <int CH>
 __global__ void __launch_bounds__(256) k_pred_window(const PredRec *__restrict__ rec, int BX, int BY, uint32_t *__restrict__ window /* 2 words per block */)
 {
+  // A warp's 32 candidates are four runs of eight consecutive records (8 x 144 B each). Loading them lane by lane is 9 x 32 scattered
+  // 16-byte requests (the kernel was bound by L1: 73 % busy against 52 % issue); the warp copies the four runs into shared memory with
+  // coalesced 16-byte loads instead and every lane then reads its own record from there (stride 36 words: conflict free per quarter warp).
+  constexpr int REC16 = (int)(sizeof(PredRec) / 16);
+  __shared__ uint4 sCand[8][32 * REC16];
   const int pair = blockIdx.x * 8 + (threadIdx.x >> 5); // (seed, half) pairs: 8 per CTA
   const int seed = pair >> 1, half = pair & 1;
 
   if (seed >= BX * BY)
     return;
 
-  const int lane = threadIdx.x & 31;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int o = half * 32 + lane;
   const int dx = o & 7, dy = o >> 3;
   const int sy = seed / BX, sx = seed - sy * BX;
+  const int cols = min(8, BX - sx);
+  uint4 *mine = sCand[warp];
+
+#pragma unroll
+  for (int r = 0; r < 4; r++)
+  {
+    const int y = sy + half * 4 + r;
+
+    if (y < BY)
+    {
+      const uint4 *src = reinterpret_cast<const uint4 *>(rec + (size_t)y * BX + sx);
+
+      for (int i = lane; i < cols * REC16; i += 32)
+        mine[r * 8 * REC16 + i] = __ldg(src + i);
+    }
+  }
+
+  __syncwarp();
   bool m = false;
 
   if (o == 0)
     m = true;
   else if (sx + dx < BX && sy + dy < BY)
-    m = predicate_thread<CH>(rec[seed], rec[(size_t)(sy + dy) * BX + sx + dx]);
+    m = predicate_thread<CH>(rec[seed], *reinterpret_cast<const PredRec *>(mine + lane * REC16));
 
   const uint32_t bits = __ballot_sync(0xFFFFFFFFu, m);
 
