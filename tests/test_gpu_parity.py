@@ -465,3 +465,50 @@ def test_unmerged_encoder_aes_vs_oracle(aes_codec, lo):
     p = aes_codec.encode3d_test(img, False, None, 100, True)
     for k, v in o.items():
         assert np.array_equal(p[k], v), k
+
+
+# ---- randomised sizes / contents / settings against the oracle ------------------------------------------------------------------------
+
+def _fuzz_cases(n=36):
+    rng = np.random.default_rng(20260)
+    cases = []
+    while len(cases) < n:
+        w, h = int(rng.integers(1, 150)), int(rng.integers(1, 110))
+        wr, hr = (w % 8) or 8, (h % 8) or 8
+        if min(w, 8) * min(h, 8) < 4 or wr * hr < 4:
+            continue  # areas of fewer than 4 pixels: the reference's channel sum over-reads (limg.cpp:478-490), outside the parity contract
+        cases.append((w, h, bool(rng.integers(0, 2)), int(rng.choice([0, 12, 50, 100, 100, 100, 255])), bool(rng.integers(0, 4)), bool(rng.integers(0, 3) == 0), int(rng.integers(0, 4)),
+                      int(rng.integers(0, 1 << 30))))
+    return cases
+
+
+@pytest.mark.parametrize("case", _fuzz_cases(), ids=lambda c: "%dx%d%s_ef%d_%s_%s_k%d" % (c[0], c[1], "a" if c[2] else "", c[3], "fast" if c[4] else "acc", "aes" if c[5] else "lcg", c[6]))
+def test_random_images_vs_oracle(codec, lo, case):
+    """Odd sizes down to a single block, smooth / noisy / flat / random content, every setting: all planes, the stream and the container."""
+    w, h, alpha, ef, fast, aes, kind, seed = case
+    rng = np.random.default_rng(seed)
+    ch = 4 if alpha else 3
+    if kind == 0:
+        img = synth.photo_like(w, h, seed % 1000, ch)
+    elif kind == 1:
+        img = rng.integers(0, 2 ** 32, (h, w), dtype=np.uint64).astype(np.uint32)  # white noise, alpha byte included
+    elif kind == 2:
+        base = rng.integers(0, 256, 4).astype(np.uint32)
+        img = np.full((h, w), base[0] | (base[1] << 8) | (base[2] << 16) | (base[3] << 24), np.uint32)
+        img[h // 3:, w // 2:] ^= np.uint32(0x00102030)  # two flat regions
+    else:
+        img = synth.gradient_noise(w, h, seed % 1000)
+        if alpha:
+            img = (img & np.uint32(0x00FFFFFF)) | (rng.integers(0, 256, (h, w)).astype(np.uint32) << 24)
+    codec.set_dither_mode(aes)
+    try:
+        o = lo.blocked_encode3d(img, alpha, ef, fast, lo.DITHER_AES if aes else lo.DITHER_LCG)
+        planes = codec.blocked_encode3d_test(img, alpha, None, ef, fast)
+        for k in H.PLANES:
+            assert np.array_equal(planes[k], o["planes"][k]), k
+        st = codec.encode_stream(img, alpha, ef, fast)
+        assert_areas_equal(st["areas"], o["areas"])
+        assert np.array_equal(codec.decode(st["areas"], st["codesA"], st["codesB"], st["codesC"], alpha), o["planes"]["pDecoded"])
+        assert np.array_equal(codec.decode_container(codec.encode_container(img, alpha, ef, fast)), o["planes"]["pDecoded"])
+    finally:
+        codec.set_dither_mode(False)
