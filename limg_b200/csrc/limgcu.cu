@@ -32,7 +32,8 @@ struct limgcu_ctx
   int device = 0;
   cudaStream_t stream = nullptr;
   cudaStream_t streamAux = nullptr; // the speculative match bitmaps are computed here while the scan already runs on `stream`
-  cudaEvent_t evFork = nullptr, evJoin = nullptr, evFork2 = nullptr, evJoin2 = nullptr;
+  cudaEvent_t evFork = nullptr, evJoin = nullptr, evFork2 = nullptr, evJoin2 = nullptr, evBand[4] = { nullptr, nullptr, nullptr, nullptr };
+  const uint32_t *hostSrc = nullptr; // set by host_encode: limgcu_blocked_encode3d uploads d_src from here in bands, pass 1 of band i under the upload of band i + 1
   int planAsync = 1;                // LIMGCU_PLAN_ASYNC: 0 plan kernels on the main stream, 1 both on the second stream concurrently with the scan, 2 only k_plan_sym
   int planAsyncCtas = 2;            // LIMGCU_PLAN_CTAS: CTAs per SM of an asynchronous plan kernel (the scan needs room next to them)
   char err[512] = { 0 };
@@ -270,6 +271,8 @@ extern "C" int limgcu_create(int device, limgcu_ctx **out)
     if (cudaEventCreateWithFlags(&ctx->evJoin, cudaEventDisableTiming) != cudaSuccess) return bail(LIMGCU_ERROR_CUDA);
     if (cudaEventCreateWithFlags(&ctx->evFork2, cudaEventDisableTiming) != cudaSuccess) return bail(LIMGCU_ERROR_CUDA);
     if (cudaEventCreateWithFlags(&ctx->evJoin2, cudaEventDisableTiming) != cudaSuccess) return bail(LIMGCU_ERROR_CUDA);
+    for (auto &e : ctx->evBand)
+      if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return bail(LIMGCU_ERROR_CUDA);
   }
   cudaDeviceGetAttribute(&ctx->smCount, cudaDevAttrMultiProcessorCount, device);
 
@@ -356,6 +359,7 @@ extern "C" void limgcu_destroy(limgcu_ctx *ctx)
   if (ctx->evJoin) cudaEventDestroy(ctx->evJoin);
   if (ctx->evFork2) cudaEventDestroy(ctx->evFork2);
   if (ctx->evJoin2) cudaEventDestroy(ctx->evJoin2);
+  for (auto e : ctx->evBand) if (e) cudaEventDestroy(e);
 
   delete ctx;
 }
@@ -767,8 +771,45 @@ extern "C" int limgcu_blocked_encode3d(limgcu_ctx *ctx, const uint32_t *d_src, s
 
   if (ctx->timing) CK(cudaEventRecord(ctx->ev[PHASE_PASS1], ctx->stream));
 
-  rc = launch_pass1(ctx, d_src, sizeX, sizeY, hasAlpha, ctx->dTable);
-  if (rc) return rc;
+  const size_t BYall = (sizeY + 7) / 8;
+
+  if (ctx->hostSrc != nullptr && BYall >= 64)
+  {
+    // host-buffer entry points: the source is uploaded in four bands of block rows on the second stream, pass 1 of a band starts as soon as
+    // its rows are there (the fit of an 8x8 block needs nothing else), so only the last band's pass 1 is not hidden under the upload
+    const uint32_t *hostSrc = ctx->hostSrc;
+    ctx->hostSrc = nullptr;
+    const size_t rowsPerBand = (BYall + 3) / 4;
+    CK(cudaEventRecord(ctx->evFork2, ctx->stream));
+    CK(cudaStreamWaitEvent(ctx->streamAux, ctx->evFork2, 0));
+
+    for (size_t b = 0; b < 4; b++)
+    {
+      const size_t by0 = b * rowsPerBand, by1 = by0 + rowsPerBand < BYall ? by0 + rowsPerBand : BYall;
+
+      if (by0 >= by1)
+        break;
+
+      const size_t y0 = by0 * 8, y1 = by1 * 8 < sizeY ? by1 * 8 : sizeY;
+      uint32_t *dBand = const_cast<uint32_t *>(d_src) + y0 * sizeX;
+      CK(cudaMemcpyAsync(dBand, hostSrc + y0 * sizeX, (y1 - y0) * sizeX * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->streamAux));
+      CK(cudaEventRecord(ctx->evBand[b], ctx->streamAux));
+      CK(cudaStreamWaitEvent(ctx->stream, ctx->evBand[b], 0));
+      rc = launch_pass1(ctx, dBand, sizeX, y1 - y0, hasAlpha, ctx->dTable + by0 * (size_t)BX);
+      if (rc) return rc;
+    }
+  }
+  else
+  {
+    if (ctx->hostSrc != nullptr)
+    {
+      CK(cudaMemcpyAsync(const_cast<uint32_t *>(d_src), ctx->hostSrc, sizeX * sizeY * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+      ctx->hostSrc = nullptr;
+    }
+
+    rc = launch_pass1(ctx, d_src, sizeX, sizeY, hasAlpha, ctx->dTable);
+    if (rc) return rc;
+  }
 
   rc = launch_merge(ctx, ctx->dTable, sizeX, sizeY, hasAlpha, dAreas, dBlockToArea, noMerge);
   if (rc) return rc;
@@ -1039,7 +1080,7 @@ static int host_encode(limgcu_ctx *ctx, const uint32_t *pIn, size_t W, size_t H,
   rc = ensure_capacity(ctx, W, H);
   if (rc) return rc;
 
-  CK(cudaMemcpyAsync(ctx->dSrc, pIn, n * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+  ctx->hostSrc = pIn; // uploaded by limgcu_blocked_encode3d, in bands under pass 1
 
   limgcu_planes dev;
   memset(&dev, 0, sizeof(dev));
@@ -1064,6 +1105,7 @@ static int host_encode(limgcu_ctx *ctx, const uint32_t *pIn, size_t W, size_t H,
   st.codesC = codesC ? ctx->dPlaneU8[6] : nullptr;
 
   rc = limgcu_blocked_encode3d(ctx, ctx->dSrc, W, H, hasAlpha, errorFactor, flags, &st, &dev);
+  ctx->hostSrc = nullptr;
   if (rc) return rc;
 
   for (int i = 0; i < 9; i++)
@@ -1330,11 +1372,12 @@ extern "C" int limgcu_host_encode_container(limgcu_ctx *ctx, const uint32_t *pIn
   rc = ensure_payload(ctx, sizeX, sizeY);
   if (rc) return rc;
 
-  CK(cudaMemcpyAsync(ctx->dSrc, pIn, n * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+  ctx->hostSrc = pIn; // uploaded by limgcu_blocked_encode3d, in bands under pass 1
   limgcu_stream st;
   memset(&st, 0, sizeof(st));
   st.codesA = ctx->dPlaneU8[4]; st.codesB = ctx->dPlaneU8[5]; st.codesC = ctx->dPlaneU8[6];
   rc = limgcu_blocked_encode3d(ctx, ctx->dSrc, sizeX, sizeY, hasAlpha, errorFactor, flags, &st, nullptr);
+  ctx->hostSrc = nullptr;
   if (rc) return rc;
   rc = limgcu_pack_payload(ctx, ctx->dAreas, ctx->dCounters + 1, 0, ctx->dBlockToArea, st.codesA, st.codesB, st.codesC, sizeX, sizeY, hasAlpha, ctx->dPayload,
                            reinterpret_cast<uint64_t *>(ctx->dPayloadOff));
