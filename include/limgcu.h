@@ -206,6 +206,23 @@ int limgcu_pack_payload(limgcu_ctx *ctx, const limgcu_area *d_areas, const uint3
 int limgcu_unpack_payload(limgcu_ctx *ctx, const limgcu_area *d_areas, uint32_t area_count, const uint32_t *d_block_to_area, const uint8_t *d_payload, uint64_t *d_offsets,
                           size_t sizeX, size_t sizeY, int hasAlpha, uint8_t *d_codesA, uint8_t *d_codesB, uint8_t *d_codesC);
 
+/* whole-image-exact row bands ------------------------------------------------------------------- */
+
+/* One very large image on several GPUs with the SAME result as one limg_blocked_encode3d_test call over the whole image (areas may cross
+ * the bands, one dither chain). Every rank holds the whole source (all-gathered over NVLink) and runs, with its own context:
+ *   1. limgcu_pass1 on its band of block rows -> all-gather of the table (64 B per block)
+ *   2. limgcu_merge on the full table: the scan is deterministic, every rank gets the identical area table and block map
+ *   3. limgcu_encode_areas: refit + shift search of the areas whose first block row lies in [rowLo, rowHi) (the rank's band);
+ *      d_results receives limgcu_area_result_words() uint32 per area, zero for the areas of other ranks
+ *   4. SUM all-reduce of d_results over the ranks (every area has exactly one owner)
+ *   5. limgcu_finalize_rows: results -> area table, dither chain states of all areas, codes / planes of the pixel rows [yLo, yHi)
+ * The collectives are the caller's (limg_b200/shard.py: torch.distributed over NCCL). LCG dither only. limgcu_finalize_rows synchronises. */
+size_t limgcu_area_result_words(void);
+int limgcu_encode_areas(limgcu_ctx *ctx, const uint32_t *d_src, size_t sizeX, size_t sizeY, int hasAlpha, uint32_t errorFactor, uint32_t flags, const limgcu_decomp *d_table,
+                        limgcu_area *d_areas, uint32_t rowLo, uint32_t rowHi, uint32_t *d_results);
+int limgcu_finalize_rows(limgcu_ctx *ctx, const uint32_t *d_src, size_t sizeX, size_t sizeY, int hasAlpha, uint32_t flags, limgcu_area *d_areas, const uint32_t *d_results,
+                         const uint32_t *d_block_to_area, const limgcu_stream *stream, const limgcu_planes *planes, size_t yLo, size_t yHi);
+
 /* batches of independent frames (batch mode) ---------------------------------------------------------- */
 
 /* One frame does not fill a B200 (the area scan is a latency-bound chain), so a batch runs on `lanes` contexts at once -- of one device,

@@ -46,6 +46,7 @@ SYMBOLS = (
     "limgcu_host_pass1", "limgcu_host_merge", "limgcu_host_compare",
     "limgcu_container_bound", "limgcu_container_info", "limgcu_host_encode_container", "limgcu_host_decode_container", "limgcu_pack_payload", "limgcu_unpack_payload",
     "limgcu_batch_host_encode_containers", "limgcu_batch_host_decode_containers",
+    "limgcu_area_result_words", "limgcu_encode_areas", "limgcu_finalize_rows",
 )
 
 
@@ -94,6 +95,9 @@ def load():
     lib.limgcu_host_decode_container.argtypes = [vp, vp, sz, vp, sz]
     lib.limgcu_pack_payload.argtypes = [vp, vp, vp, u32, vp, vp, vp, vp, sz, sz, i32, vp, vp]
     lib.limgcu_unpack_payload.argtypes = [vp, vp, u32, vp, vp, vp, sz, sz, i32, vp, vp, vp]
+    lib.limgcu_area_result_words.restype = sz
+    lib.limgcu_encode_areas.argtypes = [vp, vp, sz, sz, i32, u32, u32, vp, vp, u32, u32, vp]
+    lib.limgcu_finalize_rows.argtypes = [vp, vp, sz, sz, i32, u32, vp, vp, vp, C.POINTER(Stream), C.POINTER(Planes), sz, sz]
     lib.limgcu_batch_host_encode_containers.argtypes = [vp, i32, vp, i32, sz, sz, i32, u32, u32, vp, vp, vp]
     lib.limgcu_batch_host_decode_containers.argtypes = [vp, i32, vp, vp, i32, vp, vp]
     lib.limgcu_debug_set_decode_variant.argtypes = [vp, C.c_int]

@@ -95,6 +95,7 @@ struct EncodeArgs
   const uint32_t *listCount;
   const uint32_t *hugeCount;  // k_encode_large: list[0 .. huge) from the front, then list[listCap - 1 - i] for the other listCount entries
   uint32_t listCap;
+  uint32_t rowLo, rowHi;      // only areas whose first block row lies in [rowLo, rowHi) are encoded (row-band sharding; the default is everything)
   CrushParams cp;
 };
 
@@ -186,7 +187,13 @@ __global__ void __launch_bounds__(LIMG_ENCODE_THREADS) k_encode_small(EncodeArgs
     if (j >= count)
       break;
 
-    encode_area_group<CH, 1>(a, a.list[j], sPx[warp], sFac[warp], sLut, sStage[warp], 64, &sGs[warp]);
+    const uint32_t k = a.list[j];
+    const uint32_t oy = a.areas[k].oy;
+
+    if (oy < a.rowLo || oy >= a.rowHi)
+      continue;
+
+    encode_area_group<CH, 1>(a, k, sPx[warp], sFac[warp], sLut, sStage[warp], 64, &sGs[warp]);
   }
 }
 
@@ -220,6 +227,11 @@ __global__ void __launch_bounds__(LIMG_ENCODE_THREADS) k_encode_large(EncodeArgs
       break;
 
     const uint32_t k = j < huge ? a.list[j] : a.list[a.listCap - 1u - (j - huge)];
+    const uint32_t oy = a.areas[k].oy;
+
+    if (oy < a.rowLo || oy >= a.rowHi)
+      continue;
+
     const AreaWork w = a.work[k];
     uint32_t *px = w.n <= LIMG_CTA_AREA_CAP ? sPx : a.scratchPx + w.scratchOff;
     uint32_t *fac = w.n <= LIMG_CTA_AREA_CAP ? sFac : a.scratchFac + w.scratchOff;

@@ -68,6 +68,53 @@ __global__ void __launch_bounds__(1024) k_dither_scan(const uint32_t *areaCount,
   }
 }
 
+// Row-band sharding (limgcu_encode_areas / limgcu_finalize_rows): what the per-area encode produced, as 20 words per area that are zero
+// for the areas another rank owns, so that a SUM all-reduce over the ranks assembles the complete table.
+#define LIMG_AREA_RESULT_WORDS 20
+
+__global__ void __launch_bounds__(256) k_pack_area_results(const limgcu_area *areas, const uint32_t *areaCount, const uint64_t *demand, uint32_t rowLo, uint32_t rowHi, uint32_t *out)
+{
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+
+  if (k >= *areaCount)
+    return;
+
+  uint32_t *o = out + (size_t)k * LIMG_AREA_RESULT_WORDS;
+  const limgcu_area &a = areas[k];
+  const bool mine = a.oy >= rowLo && a.oy < rowHi;
+  const uint32_t *d = reinterpret_cast<const uint32_t *>(&a.decomp);
+
+  for (int i = 0; i < 16; i++)
+    o[i] = mine ? d[i] : 0u;
+
+  o[16] = mine ? ((uint32_t)a.shift[0] | ((uint32_t)a.shift[1] << 8) | ((uint32_t)a.shift[2] << 16)) : 0u;
+  o[17] = mine ? (uint32_t)demand[k] : 0u;
+  o[18] = mine ? (uint32_t)(demand[k] >> 32) : 0u;
+  o[19] = mine ? 1u : 0u; // after the all-reduce: exactly one owner per area
+}
+
+__global__ void __launch_bounds__(256) k_unpack_area_results(limgcu_area *areas, const uint32_t *areaCount, uint64_t *demand, const uint32_t *in, uint32_t *badOwners)
+{
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+
+  if (k >= *areaCount)
+    return;
+
+  const uint32_t *r = in + (size_t)k * LIMG_AREA_RESULT_WORDS;
+  limgcu_area &a = areas[k];
+  uint32_t *d = reinterpret_cast<uint32_t *>(&a.decomp);
+
+  for (int i = 0; i < 16; i++)
+    d[i] = r[i];
+
+  a.shift[0] = (uint8_t)(r[16] & 0xFF); a.shift[1] = (uint8_t)((r[16] >> 8) & 0xFF); a.shift[2] = (uint8_t)((r[16] >> 16) & 0xFF);
+  a.pad = 0;
+  demand[k] = (uint64_t)r[17] | ((uint64_t)r[18] << 32);
+
+  if (r[19] != 1u)
+    atomicAdd(badOwners, 1u);
+}
+
 // AES mode: the chain states around every area come from the host
 __global__ void __launch_bounds__(256) k_set_dither_states(limgcu_area *areas, const unsigned long long *before, const unsigned long long *after, uint32_t count)
 {
@@ -109,6 +156,7 @@ struct FinalizeArgs
   LcgJumpTable jt;
   const uint8_t *noise;                // AES mode: one noise byte per pixel and dithered plane, area-contiguous (dither_aes_host.cpp); else nullptr
   const unsigned long long *noiseOff;  // [3 * area + plane] -> offset into noise
+  int yLo, yHi; // pixel rows handled by this launch (row-band sharding; the default is the whole image)
   int vec; // W % 8 == 0 and every plane pointer 32-byte aligned: 128-bit loads / stores
 };
 
@@ -162,11 +210,11 @@ __global__ void __launch_bounds__(256) k_finalize(FinalizeArgs a)
   const int segsPerRow = (a.W + 7) >> 3;
   const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
 
-  if (s >= (long long)segsPerRow * a.H)
+  if (s >= (long long)segsPerRow * (a.yHi - a.yLo))
     return;
 
-  const int y = (int)(s / segsPerRow);
-  const int bx = (int)(s - (long long)y * segsPerRow);
+  const int y = a.yLo + (int)(s / segsPerRow);
+  const int bx = (int)(s - (long long)(y - a.yLo) * segsPerRow);
   const int x0 = bx * 8;
   const int npx = min(8, a.W - x0);
   const size_t rowOff = (size_t)y * a.W + x0;

@@ -754,6 +754,140 @@ extern "C" int limgcu_host_has_aesni(void)
   return host_has_aesni() ? 1 : 0;
 }
 
+// per-area encode (k_encode_large on the main stream, k_encode_small next to it on the second one) of the areas whose first block row lies in
+// [rowLo, rowHi); the lists and the work table are the ones launch_merge left in the context
+static int launch_area_encode(limgcu_ctx *ctx, const uint32_t *d_src, int W, int H, int hasAlpha, uint32_t errorFactor, uint32_t flags, limgcu_area *dAreas, const limgcu_decomp *dTable,
+                              uint32_t rowLo, uint32_t rowHi)
+{
+  const int BX = (W + 7) / 8;
+  EncodeArgs e;
+  e.src = d_src; e.W = W; e.H = H; e.BX = BX; e.BY = (H + 7) / 8; e.lut = ctx->dLut; e.table = dTable;
+  e.areas = dAreas; e.areaCount = ctx->dCounters + 1; e.work = ctx->dWork; e.ditherDemand = ctx->dDemand;
+  e.scratchPx = ctx->dScratchPx; e.scratchFac = ctx->dScratchFac;
+  e.cp = make_crush_params(errorFactor, (flags & LIMGCU_FLAG_FAST_BIT_CRUSH) ? 1 : 0);
+  e.rowLo = rowLo; e.rowHi = rowHi; e.hugeCount = nullptr; e.listCap = 0;
+
+  {
+    EncodeArgs s = e;
+    s.workCounter = ctx->dCounters + 4; s.list = ctx->dSmallList; s.listCount = ctx->dCounters + 2;
+    EncodeArgs l = e;
+    l.workCounter = ctx->dCounters + 5; l.list = ctx->dLargeList; l.listCount = ctx->dCounters + 3; l.hugeCount = ctx->dCounters + 7; l.listCap = (uint32_t)ctx->capBlocks;
+    const int gridLarge = ctx->smCount * 4, gridSmall = ctx->smCount * 6;
+    const size_t smemLarge = 4096 + LIMG_CTA_STAGE_PX * 16 + 2 * LIMG_CTA_AREA_CAP * 4;
+
+    // The large areas are the long poles (one CTA each, sequential sums): the warp-per-area kernel for the small ones runs next to them
+    // on the second stream.
+    CK(cudaEventRecord(ctx->evFork2, ctx->stream));
+    CK(cudaStreamWaitEvent(ctx->streamAux, ctx->evFork2, 0));
+
+    if (hasAlpha)
+    {
+      k_encode_large<4><<<gridLarge, LIMG_ENCODE_THREADS, smemLarge, ctx->stream>>>(l);
+      CKL("k_encode_large");
+      k_encode_small<4><<<gridSmall, LIMG_ENCODE_THREADS, 0, ctx->streamAux>>>(s);
+      CKL("k_encode_small");
+    }
+    else
+    {
+      k_encode_large<3><<<gridLarge, LIMG_ENCODE_THREADS, smemLarge, ctx->stream>>>(l);
+      CKL("k_encode_large");
+      k_encode_small<3><<<gridSmall, LIMG_ENCODE_THREADS, 0, ctx->streamAux>>>(s);
+      CKL("k_encode_small");
+    }
+
+    CK(cudaEventRecord(ctx->evJoin2, ctx->streamAux));
+    CK(cudaStreamWaitEvent(ctx->stream, ctx->evJoin2, 0));
+  }
+
+  return LIMGCU_SUCCESS;
+}
+
+// dither chain states of every area (LCG: scan + jump-ahead on the device; AES: chain walked on the host), then the fused projection +
+// dither + bit-crush + plane writer for the pixel rows [yLo, yHi)
+static int launch_dither_finalize(limgcu_ctx *ctx, const uint32_t *d_src, size_t sizeX, size_t sizeY, int hasAlpha, uint32_t flags, limgcu_area *dAreas, const uint32_t *dBlockToArea,
+                                  const limgcu_stream *stream, const limgcu_planes *planes, size_t yLo, size_t yHi)
+{
+  const int W = (int)sizeX, H = (int)sizeY, BX = (W + 7) / 8;
+  int rc = LIMGCU_SUCCESS;
+  struct { int BY; } e = { (H + 7) / 8 };
+  const bool ditherAes = (flags & LIMGCU_FLAG_DITHER_AES) != 0;
+
+  if (ditherAes)
+  {
+    // The AES-round chain cannot be jumped: bring the area table (shifts, pixel rectangles) to the host, walk the chain there
+    // (dither_aes_host.cpp), send the noise stream back. This synchronises with the stream.
+    rc = ensure_aes(ctx, sizeX, sizeY);
+    if (rc) return rc;
+    uint32_t count = 0;
+    CK(cudaMemcpyAsync(&count, ctx->dCounters + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+
+    if ((size_t)count > ctx->capAesBlocks)
+      return fail(ctx, LIMGCU_ERROR_OUT_OF_BOUNDS, "more areas than blocks", cudaSuccess);
+
+    CK(cudaMemcpyAsync(ctx->hAreas, dAreas, (size_t)count * sizeof(limgcu_area), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    const uint64_t noiseBytes = aes_dither_chain_host(ctx->hAreas, count, LIMG_DITHER_SEED, ctx->hNoise, reinterpret_cast<uint64_t *>(ctx->hNoiseOff),
+                                                      reinterpret_cast<uint64_t *>(ctx->hStates), reinterpret_cast<uint64_t *>(ctx->hStates) + count, ctx->aesForceSoftware != 0);
+    CK(cudaMemcpyAsync(ctx->dNoise, ctx->hNoise, (size_t)noiseBytes, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->dNoiseOff, ctx->hNoiseOff, 3 * (size_t)count * sizeof(unsigned long long), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->dStates, ctx->hStates, 2 * (size_t)count * sizeof(unsigned long long), cudaMemcpyHostToDevice, ctx->stream));
+
+    if (count)
+    {
+      k_set_dither_states<<<(count + 255) / 256, 256, 0, ctx->stream>>>(dAreas, ctx->dStates, ctx->dStates + count, count);
+      CKL("k_set_dither_states");
+    }
+  }
+  else
+  {
+    k_dither_scan<<<1, 1024, 0, ctx->stream>>>(ctx->dCounters + 1, ctx->dDemand, ctx->dDitherBefore, 0);
+    CKL("k_dither_scan");
+    k_dither_states<<<(unsigned)((((size_t)BX * e.BY) + 255) / 256), 256, 0, ctx->stream>>>(dAreas, ctx->dCounters + 1, ctx->dDemand, ctx->dDitherBefore, ctx->jt);
+    CKL("k_dither_states");
+  }
+
+  if (ctx->timing) CK(cudaEventRecord(ctx->ev[PHASE_FINALIZE], ctx->stream));
+
+  FinalizeArgs f;
+  memset(&f, 0, sizeof(f));
+  f.src = d_src; f.W = W; f.H = H; f.BX = BX; f.areas = dAreas; f.blockToArea = dBlockToArea;
+  f.codesA = stream ? stream->codesA : nullptr; f.codesB = stream ? stream->codesB : nullptr; f.codesC = stream ? stream->codesC : nullptr;
+
+  if (planes)
+    f.planes = *planes;
+
+  f.planes.pBlockError = nullptr; // never written (Q12)
+  f.jt = ctx->jt;
+  f.yLo = (int)yLo; f.yHi = (int)yHi;
+  f.noise = ditherAes ? ctx->dNoise : nullptr;
+  f.noiseOff = ditherAes ? ctx->dNoiseOff : nullptr;
+  f.vec = (W % 8 == 0) && aligned32(d_src) && aligned32(f.codesA) && aligned32(f.codesB) && aligned32(f.codesC) && aligned32(f.planes.pDecoded) &&
+          aligned32(f.planes.pFactorsA) && aligned32(f.planes.pFactorsB) && aligned32(f.planes.pFactorsC) && aligned32(f.planes.pBitsPerPixel) &&
+          aligned32(f.planes.pShiftABCX) && aligned32(f.planes.pColAMin) && aligned32(f.planes.pColAMax) && aligned32(f.planes.pColBMin) &&
+          aligned32(f.planes.pColBMax) && aligned32(f.planes.pColCMin) && aligned32(f.planes.pColCMax) && aligned32(f.planes.pBlockIndex);
+
+  const bool anyOut = f.codesA || f.codesB || f.codesC || f.planes.pDecoded || f.planes.pFactorsA || f.planes.pFactorsB || f.planes.pFactorsC ||
+                      f.planes.pBitsPerPixel || f.planes.pShiftABCX || f.planes.pColAMin || f.planes.pColAMax || f.planes.pColBMin || f.planes.pColBMax ||
+                      f.planes.pColCMin || f.planes.pColCMax || f.planes.pBlockIndex;
+
+  if (anyOut) // limg_encode3d_test_perf writes nothing (limg.cpp:2141-2173)
+  {
+    const long long segs = (long long)((W + 7) / 8) * (long long)(yHi - yLo);
+    const int grid = (int)((segs + 255) / 256);
+
+    if (hasAlpha)
+      k_finalize<4><<<grid, 256, 0, ctx->stream>>>(f);
+    else
+      k_finalize<3><<<grid, 256, 0, ctx->stream>>>(f);
+
+    CKL("k_finalize");
+  }
+
+  (void)rc;
+  return LIMGCU_SUCCESS;
+}
+
 extern "C" int limgcu_blocked_encode3d(limgcu_ctx *ctx, const uint32_t *d_src, size_t sizeX, size_t sizeY, int hasAlpha, uint32_t errorFactor, uint32_t flags,
                                        const limgcu_stream *stream, const limgcu_planes *planes)
 {
@@ -816,118 +950,13 @@ extern "C" int limgcu_blocked_encode3d(limgcu_ctx *ctx, const uint32_t *d_src, s
 
   if (ctx->timing) CK(cudaEventRecord(ctx->ev[PHASE_ENCODE], ctx->stream));
 
-  EncodeArgs e;
-  e.src = d_src; e.W = W; e.H = H; e.BX = BX; e.BY = (H + 7) / 8; e.lut = ctx->dLut; e.table = ctx->dTable;
-  e.areas = dAreas; e.areaCount = ctx->dCounters + 1; e.work = ctx->dWork; e.ditherDemand = ctx->dDemand;
-  e.scratchPx = ctx->dScratchPx; e.scratchFac = ctx->dScratchFac;
-  e.cp = make_crush_params(errorFactor, (flags & LIMGCU_FLAG_FAST_BIT_CRUSH) ? 1 : 0);
-
-  {
-    EncodeArgs s = e;
-    s.workCounter = ctx->dCounters + 4; s.list = ctx->dSmallList; s.listCount = ctx->dCounters + 2;
-    EncodeArgs l = e;
-    l.workCounter = ctx->dCounters + 5; l.list = ctx->dLargeList; l.listCount = ctx->dCounters + 3; l.hugeCount = ctx->dCounters + 7; l.listCap = (uint32_t)ctx->capBlocks;
-    const int gridLarge = ctx->smCount * 4, gridSmall = ctx->smCount * 6;
-    const size_t smemLarge = 4096 + LIMG_CTA_STAGE_PX * 16 + 2 * LIMG_CTA_AREA_CAP * 4;
-
-    // The large areas are the long poles (one CTA each, sequential sums): the warp-per-area kernel for the small ones runs next to them
-    // on the second stream.
-    CK(cudaEventRecord(ctx->evFork2, ctx->stream));
-    CK(cudaStreamWaitEvent(ctx->streamAux, ctx->evFork2, 0));
-
-    if (hasAlpha)
-    {
-      k_encode_large<4><<<gridLarge, LIMG_ENCODE_THREADS, smemLarge, ctx->stream>>>(l);
-      CKL("k_encode_large");
-      k_encode_small<4><<<gridSmall, LIMG_ENCODE_THREADS, 0, ctx->streamAux>>>(s);
-      CKL("k_encode_small");
-    }
-    else
-    {
-      k_encode_large<3><<<gridLarge, LIMG_ENCODE_THREADS, smemLarge, ctx->stream>>>(l);
-      CKL("k_encode_large");
-      k_encode_small<3><<<gridSmall, LIMG_ENCODE_THREADS, 0, ctx->streamAux>>>(s);
-      CKL("k_encode_small");
-    }
-
-    CK(cudaEventRecord(ctx->evJoin2, ctx->streamAux));
-    CK(cudaStreamWaitEvent(ctx->stream, ctx->evJoin2, 0));
-  }
+  rc = launch_area_encode(ctx, d_src, W, H, hasAlpha, errorFactor, flags, dAreas, ctx->dTable, 0u, 0xFFFFFFFFu);
+  if (rc) return rc;
 
   if (ctx->timing) CK(cudaEventRecord(ctx->ev[PHASE_DITHER], ctx->stream));
 
-  const bool ditherAes = (flags & LIMGCU_FLAG_DITHER_AES) != 0;
-
-  if (ditherAes)
-  {
-    // The AES-round chain cannot be jumped: bring the area table (shifts, pixel rectangles) to the host, walk the chain there
-    // (dither_aes_host.cpp), send the noise stream back. This synchronises with the stream.
-    rc = ensure_aes(ctx, sizeX, sizeY);
-    if (rc) return rc;
-    uint32_t count = 0;
-    CK(cudaMemcpyAsync(&count, ctx->dCounters + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-
-    if ((size_t)count > ctx->capAesBlocks)
-      return fail(ctx, LIMGCU_ERROR_OUT_OF_BOUNDS, "more areas than blocks", cudaSuccess);
-
-    CK(cudaMemcpyAsync(ctx->hAreas, dAreas, (size_t)count * sizeof(limgcu_area), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    const uint64_t noiseBytes = aes_dither_chain_host(ctx->hAreas, count, LIMG_DITHER_SEED, ctx->hNoise, reinterpret_cast<uint64_t *>(ctx->hNoiseOff),
-                                                      reinterpret_cast<uint64_t *>(ctx->hStates), reinterpret_cast<uint64_t *>(ctx->hStates) + count, ctx->aesForceSoftware != 0);
-    CK(cudaMemcpyAsync(ctx->dNoise, ctx->hNoise, (size_t)noiseBytes, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->dNoiseOff, ctx->hNoiseOff, 3 * (size_t)count * sizeof(unsigned long long), cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->dStates, ctx->hStates, 2 * (size_t)count * sizeof(unsigned long long), cudaMemcpyHostToDevice, ctx->stream));
-
-    if (count)
-    {
-      k_set_dither_states<<<(count + 255) / 256, 256, 0, ctx->stream>>>(dAreas, ctx->dStates, ctx->dStates + count, count);
-      CKL("k_set_dither_states");
-    }
-  }
-  else
-  {
-    k_dither_scan<<<1, 1024, 0, ctx->stream>>>(ctx->dCounters + 1, ctx->dDemand, ctx->dDitherBefore, 0);
-    CKL("k_dither_scan");
-    k_dither_states<<<(unsigned)((((size_t)BX * e.BY) + 255) / 256), 256, 0, ctx->stream>>>(dAreas, ctx->dCounters + 1, ctx->dDemand, ctx->dDitherBefore, ctx->jt);
-    CKL("k_dither_states");
-  }
-
-  if (ctx->timing) CK(cudaEventRecord(ctx->ev[PHASE_FINALIZE], ctx->stream));
-
-  FinalizeArgs f;
-  memset(&f, 0, sizeof(f));
-  f.src = d_src; f.W = W; f.H = H; f.BX = BX; f.areas = dAreas; f.blockToArea = dBlockToArea;
-  f.codesA = stream ? stream->codesA : nullptr; f.codesB = stream ? stream->codesB : nullptr; f.codesC = stream ? stream->codesC : nullptr;
-
-  if (planes)
-    f.planes = *planes;
-
-  f.planes.pBlockError = nullptr; // never written (Q12)
-  f.jt = ctx->jt;
-  f.noise = ditherAes ? ctx->dNoise : nullptr;
-  f.noiseOff = ditherAes ? ctx->dNoiseOff : nullptr;
-  f.vec = (W % 8 == 0) && aligned32(d_src) && aligned32(f.codesA) && aligned32(f.codesB) && aligned32(f.codesC) && aligned32(f.planes.pDecoded) &&
-          aligned32(f.planes.pFactorsA) && aligned32(f.planes.pFactorsB) && aligned32(f.planes.pFactorsC) && aligned32(f.planes.pBitsPerPixel) &&
-          aligned32(f.planes.pShiftABCX) && aligned32(f.planes.pColAMin) && aligned32(f.planes.pColAMax) && aligned32(f.planes.pColBMin) &&
-          aligned32(f.planes.pColBMax) && aligned32(f.planes.pColCMin) && aligned32(f.planes.pColCMax) && aligned32(f.planes.pBlockIndex);
-
-  const bool anyOut = f.codesA || f.codesB || f.codesC || f.planes.pDecoded || f.planes.pFactorsA || f.planes.pFactorsB || f.planes.pFactorsC ||
-                      f.planes.pBitsPerPixel || f.planes.pShiftABCX || f.planes.pColAMin || f.planes.pColAMax || f.planes.pColBMin || f.planes.pColBMax ||
-                      f.planes.pColCMin || f.planes.pColCMax || f.planes.pBlockIndex;
-
-  if (anyOut) // limg_encode3d_test_perf writes nothing (limg.cpp:2141-2173)
-  {
-    const long long segs = (long long)((W + 7) / 8) * H;
-    const int grid = (int)((segs + 255) / 256);
-
-    if (hasAlpha)
-      k_finalize<4><<<grid, 256, 0, ctx->stream>>>(f);
-    else
-      k_finalize<3><<<grid, 256, 0, ctx->stream>>>(f);
-
-    CKL("k_finalize");
-  }
+  rc = launch_dither_finalize(ctx, d_src, sizeX, sizeY, hasAlpha, flags, dAreas, dBlockToArea, stream, planes, 0, sizeY);
+  if (rc) return rc;
 
   if (stream && stream->area_count)
     CK(cudaMemcpyAsync(stream->area_count, ctx->dCounters + 1, sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream));
@@ -940,6 +969,67 @@ extern "C" int limgcu_blocked_encode3d(limgcu_ctx *ctx, const uint32_t *d_src, s
     for (int i = 0; i < PHASE_COUNT; i++)
       CK(cudaEventElapsedTime(&ctx->phaseMs[i], ctx->ev[i], ctx->ev[i + 1]));
   }
+
+  return LIMGCU_SUCCESS;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------------
+// phased encode for whole-image-exact row-band sharding: pass 1 per band (limgcu_pass1) -> all-gather of the
+// table -> the identical scan on every rank (limgcu_merge) -> limgcu_encode_areas for the areas a rank owns -> SUM all-reduce of the
+// per-area results -> limgcu_finalize_rows for the rank's pixel rows. The collectives are the caller's (limg_b200/shard.py uses NCCL).
+// ---------------------------------------------------------------------------------------------------------------------------------
+
+extern "C" size_t limgcu_area_result_words(void) { return LIMG_AREA_RESULT_WORDS; }
+
+extern "C" int limgcu_encode_areas(limgcu_ctx *ctx, const uint32_t *d_src, size_t sizeX, size_t sizeY, int hasAlpha, uint32_t errorFactor, uint32_t flags, const limgcu_decomp *d_table,
+                                   limgcu_area *d_areas, uint32_t rowLo, uint32_t rowHi, uint32_t *d_results)
+{
+  NEED(ctx); NEED(d_src); NEED(d_table); NEED(d_areas); NEED(d_results);
+  int rc = check_image(ctx, sizeX, sizeY);
+  if (rc) return rc;
+  CK(cudaSetDevice(ctx->device));
+
+  if (ctx->capBlocks < ((sizeX + 7) / 8) * ((sizeY + 7) / 8))
+    return fail(ctx, LIMGCU_ERROR_INVALID_PARAMETER, "limgcu_encode_areas: call limgcu_merge for this image first", cudaSuccess);
+
+  rc = launch_area_encode(ctx, d_src, (int)sizeX, (int)sizeY, hasAlpha, errorFactor, flags, d_areas, d_table, rowLo, rowHi);
+  if (rc) return rc;
+  const size_t blocks = ((sizeX + 7) / 8) * ((sizeY + 7) / 8);
+  k_pack_area_results<<<(unsigned)((blocks + 255) / 256), 256, 0, ctx->stream>>>(d_areas, ctx->dCounters + 1, ctx->dDemand, rowLo, rowHi, d_results);
+  CKL("k_pack_area_results");
+  return LIMGCU_SUCCESS;
+}
+
+extern "C" int limgcu_finalize_rows(limgcu_ctx *ctx, const uint32_t *d_src, size_t sizeX, size_t sizeY, int hasAlpha, uint32_t flags, limgcu_area *d_areas, const uint32_t *d_results,
+                                    const uint32_t *d_block_to_area, const limgcu_stream *stream, const limgcu_planes *planes, size_t yLo, size_t yHi)
+{
+  NEED(ctx); NEED(d_src); NEED(d_areas); NEED(d_results); NEED(d_block_to_area);
+  int rc = check_image(ctx, sizeX, sizeY);
+  if (rc) return rc;
+
+  if (yLo > yHi || yHi > sizeY)
+    return fail(ctx, LIMGCU_ERROR_OUT_OF_BOUNDS, "limgcu_finalize_rows: row range", cudaSuccess);
+
+  if (flags & LIMGCU_FLAG_DITHER_AES)
+    return fail(ctx, LIMGCU_ERROR_INVALID_PARAMETER, "limgcu_finalize_rows: the AES dither chain is not available in the sharded path", cudaSuccess);
+
+  CK(cudaSetDevice(ctx->device));
+  const size_t blocks = ((sizeX + 7) / 8) * ((sizeY + 7) / 8);
+  CK(cudaMemsetAsync(ctx->dCounters + 30, 0, sizeof(uint32_t), ctx->stream));
+  k_unpack_area_results<<<(unsigned)((blocks + 255) / 256), 256, 0, ctx->stream>>>(d_areas, ctx->dCounters + 1, ctx->dDemand, d_results, ctx->dCounters + 30);
+  CKL("k_unpack_area_results");
+  rc = launch_dither_finalize(ctx, d_src, sizeX, sizeY, hasAlpha, flags, d_areas, d_block_to_area, stream, planes, yLo, yHi);
+  if (rc) return rc;
+
+  if (stream && stream->area_count)
+    CK(cudaMemcpyAsync(stream->area_count, ctx->dCounters + 1, sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream));
+
+  uint32_t bad = 0;
+  CK(cudaMemcpyAsync(&bad, ctx->dCounters + 30, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+
+  if (bad)
+    return fail(ctx, LIMGCU_ERROR_GENERIC, "limgcu_finalize_rows: some areas were encoded by no rank or by several (row ranges must partition the block rows)", cudaSuccess);
 
   return LIMGCU_SUCCESS;
 }

@@ -50,3 +50,91 @@ def gather_to_rank0(obj, rank: int, world: int):
     out = [None] * world if rank == 0 else None
     dist.gather_object(obj, out, dst=0)
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------------------------------
+# whole-image-exact row bands (C ABI: limgcu_pass1 / limgcu_merge / limgcu_encode_areas / limgcu_finalize_rows)
+# ---------------------------------------------------------------------------------------------------------------------------------
+
+class RowBandExact:
+    """One rank of the exact row-band encode: the same stream as ONE encode of the whole image (areas may cross the bands, one dither chain).
+
+    The exchange steps are SUM all-reduces over buffers that are zero wherever another rank contributes (pass-1 table: 64 B per block;
+    per-area results: 80 B per area), so that bands of unequal height need no padding; with integer views the sum is exact. The scan runs
+    redundantly on every rank (it is deterministic), the per-area refit + shift search and the per-pixel finalize are sharded.
+    Phases: pass1() -> [all-reduce table] -> merge_and_encode() -> [all-reduce results] -> finalize(). `encode_rowbands_exact` drives them
+    with torch.distributed; the tests drive several ranks on one GPU by hand."""
+
+    def __init__(self, codec, d_src, width: int, height: int, has_alpha: bool, rank: int, world: int, error_factor: int = 100, fast_bit_crushing: bool = True):
+        import torch
+        from ._lib import AREA_DTYPE, FLAG_FAST_BIT_CRUSH
+        self.codec, self.src, self.w, self.h, self.alpha = codec, d_src, width, height, bool(has_alpha)
+        self.rank, self.world, self.ef = rank, world, int(error_factor)
+        self.flags = FLAG_FAST_BIT_CRUSH if fast_bit_crushing else 0
+        self.bx, self.by = (width + 7) // 8, (height + 7) // 8
+        self.y0, self.y1 = row_bands(height, world)[rank]
+        self.row_lo, self.row_hi = self.y0 // BLOCK, (self.y1 + BLOCK - 1) // BLOCK
+        dev = d_src.device
+        blocks = self.bx * self.by
+        words = int(codec.lib.limgcu_area_result_words())
+        self.table = torch.zeros(blocks * 16, dtype=torch.int32, device=dev)      # limgcu_decomp[blocks], 64 B each
+        self.results = torch.zeros(blocks * words, dtype=torch.int32, device=dev)
+        self.areas = torch.zeros(blocks * AREA_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+        self.count = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.block_to_area = torch.zeros(blocks, dtype=torch.int32, device=dev)
+        self.codes = [torch.zeros((height, width), dtype=torch.uint8, device=dev) for _ in range(3)]  # only rows [y0, y1) are written
+
+    def _ck(self, rc, what):
+        self.codec._ck(rc, what)
+
+    def pass1(self):
+        """three-factor fit of the blocks of this rank's band -> its rows of the table (the rest stays zero)"""
+        if self.y1 > self.y0:
+            lib, c = self.codec.lib, self.codec
+            self._ck(lib.limgcu_pass1(c.h, self.src.data_ptr() + self.y0 * self.w * 4, self.w, self.y1 - self.y0, int(self.alpha), self.table.data_ptr() + self.row_lo * self.bx * 64), "limgcu_pass1")
+        self.codec.sync()
+        return self.table
+
+    def merge_and_encode(self):
+        """the identical scan on the complete table, then refit + shift search of the areas that start in this rank's block rows"""
+        lib, c = self.codec.lib, self.codec
+        self._ck(lib.limgcu_merge(c.h, self.table.data_ptr(), self.w, self.h, int(self.alpha), self.areas.data_ptr(), self.count.data_ptr(), self.block_to_area.data_ptr()), "limgcu_merge")
+        self._ck(lib.limgcu_encode_areas(c.h, self.src.data_ptr(), self.w, self.h, int(self.alpha), self.ef, self.flags, self.table.data_ptr(), self.areas.data_ptr(), self.row_lo, self.row_hi,
+                                         self.results.data_ptr()), "limgcu_encode_areas")
+        self.codec.sync()
+        return self.results
+
+    def finalize(self):
+        """complete per-area results -> area table, dither chain, codes of this rank's pixel rows"""
+        from ._lib import Stream
+        import ctypes as C
+        lib, c = self.codec.lib, self.codec
+        st = Stream()
+        st.areas, st.area_count, st.block_to_area = self.areas.data_ptr(), self.count.data_ptr(), self.block_to_area.data_ptr()
+        st.codesA, st.codesB, st.codesC = (t.data_ptr() for t in self.codes)
+        self._ck(lib.limgcu_finalize_rows(c.h, self.src.data_ptr(), self.w, self.h, int(self.alpha), self.flags, self.areas.data_ptr(), self.results.data_ptr(), self.block_to_area.data_ptr(),
+                                          C.byref(st), None, self.y0, self.y1), "limgcu_finalize_rows")
+        return self
+
+    def area_table(self):
+        import numpy as np
+        from ._lib import AREA_DTYPE
+        n = int(self.count.item())
+        return np.frombuffer(self.areas.cpu().numpy().tobytes(), dtype=AREA_DTYPE, count=n).copy()
+
+
+def encode_rowbands_exact(codec, d_src, width: int, height: int, has_alpha: bool, rank: int, world: int, error_factor: int = 100, fast_bit_crushing: bool = True) -> RowBandExact:
+    """All ranks call this with the whole source in device memory (all-gather it first if every rank holds only its band). Returns the rank's
+    RowBandExact: the complete area table and the codes of its own pixel rows."""
+    import torch
+    r = RowBandExact(codec, d_src, width, height, has_alpha, rank, world, error_factor, fast_bit_crushing)
+    table = r.pass1()
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(table)
+        torch.cuda.synchronize(d_src.device)
+    results = r.merge_and_encode()
+    if world > 1:
+        dist.all_reduce(results)
+        torch.cuda.synchronize(d_src.device)
+    return r.finalize()

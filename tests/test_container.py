@@ -181,3 +181,40 @@ def test_gpu_batch_of_frames_equals_one_at_a_time(codec):
             assert np.array_equal(s["decoded"], d)
     finally:
         b.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", [(640, 360, False, 1), (640, 360, False, 3), (328, 200, True, 2), (1920, 1080, False, 4)])
+def test_gpu_exact_row_bands_equal_the_whole_image_encode(codec, case):
+    """the phased, sharded encode (ranks simulated by contexts on one GPU, the all-reduces done by hand) gives the same area
+    table (decompositions, shifts, dither chain) and the same codes as one encode of the whole image."""
+    import torch
+    from limg_b200 import Codec, shard, synth
+    w, h, alpha, world = case
+    img = synth.photo_like(w, h, 17, 4 if alpha else 3)
+    want = codec.encode_stream(img, alpha, 100, True)
+    d_src = torch.from_numpy(img.view(np.int32)).cuda()
+    codecs = [Codec(0) for _ in range(world)]
+    try:
+        ranks = [shard.RowBandExact(c, d_src, w, h, alpha, r, world) for r, c in enumerate(codecs)]
+        table = sum(r.pass1() for r in ranks)          # the SUM all-reduce
+        for r in ranks:
+            r.table.copy_(table)
+        results = sum(r.merge_and_encode() for r in ranks)
+        for r in ranks:
+            r.results.copy_(results)
+        codes = [np.zeros((h, w), np.uint8) for _ in range(3)]
+        for r in ranks:
+            r.finalize()
+            for k in range(3):
+                codes[k][r.y0:r.y1] = r.codes[k][r.y0:r.y1].cpu().numpy()
+        got = ranks[0].area_table()
+        assert len(got) == len(want["areas"])
+        for name in got.dtype.names:
+            assert got[name].tobytes() == want["areas"][name].tobytes(), name
+        assert ranks[-1].area_table().tobytes() == got.tobytes()
+        for k, name in enumerate(("codesA", "codesB", "codesC")):
+            assert np.array_equal(codes[k], want[name]), name
+    finally:
+        for c in codecs:
+            c.close()
