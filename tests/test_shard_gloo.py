@@ -48,6 +48,13 @@ def test_partitions():
     assert bands[0] == (0, 544) and bands[-1][1] == 4320 and all(b[0] % 8 == 0 for b in bands)
     assert sum(y1 - y0 for y0, y1 in bands) == 4320
     assert shard.row_bands(20, 4) == [(0, 8), (8, 16), (16, 20), (20, 20)]
+    # exact row-band mode: the block-row ranges [y0 // 8, ceil(y1 / 8)) of the ranks own every block row exactly once
+    for h in (8, 20, 200, 1080, 2160, 4320, 4321):
+        for world in (1, 2, 3, 4, 8):
+            owners = []
+            for y0, y1 in shard.row_bands(h, world):
+                owners += list(range(y0 // 8, (y1 + 7) // 8)) if y1 > y0 else []
+            assert owners == list(range((h + 7) // 8)), (h, world)
 
 
 @pytest.mark.timeout(300)
