@@ -9,6 +9,7 @@ namespace limg
 
 #define LIMG_SMALL_AREA_PX 256   // <= 4 blocks: one warp, everything in shared memory
 #define LIMG_CTA_AREA_CAP 4096   // <= 64 blocks: one CTA, pixels + factors in shared memory; above: global scratch
+#define LIMG_HUGE_AREA_PX 16384  // above: a 512-thread CTA per area, started first (k_encode_large<CH, 512, true>)
 #define LIMG_CTA_STAGE_PX 1024
 #define LIMG_ENCODE_THREADS 256
 
@@ -93,8 +94,10 @@ struct EncodeArgs
   uint32_t *workCounter;      // dynamic scheduling
   const uint32_t *list;       // area indices of this size class
   const uint32_t *listCount;
-  const uint32_t *hugeCount;  // k_encode_large: list[0 .. huge) from the front, then list[listCap - 1 - i] for the other listCount entries
+  const uint32_t *hugeCount;  // k_encode_large: list[0 .. huge) from the front (huge areas), list[listCap - 1 - i] for the other listCount entries
   uint32_t listCap;
+  const uint32_t *bigCount;   // k_encode_large<.., false>: first the bigList[listCap - 1 - i] entries (areas beyond shared memory), then the list's
+  const uint32_t *bigList;
   uint32_t rowLo, rowHi;      // only areas whose first block row lies in [rowLo, rowHi) are encoded (row-band sharding; the default is everything)
   CrushParams cp;
 };
@@ -197,10 +200,13 @@ __global__ void __launch_bounds__(LIMG_ENCODE_THREADS) k_encode_small(EncodeArgs
   }
 }
 
-template <int CH>
-__global__ void __launch_bounds__(LIMG_ENCODE_THREADS) k_encode_large(EncodeArgs a)
+// THREADS = 256 for the areas that fit into shared memory (four CTAs per SM), 512 for the huge ones (list[0 .. huge)): a huge area is a long pole
+// on ONE SM, and twice the warps roughly double the issue rate its trials get there. first / last select the part of the list:
+// HUGE: jobs [0, huge) from the front; otherwise the other listCount entries from the back.
+template <int CH, int THREADS, bool HUGE>
+__global__ void __launch_bounds__(THREADS) k_encode_large(EncodeArgs a)
 {
-  constexpr int WARPS = LIMG_ENCODE_THREADS / 32;
+  constexpr int WARPS = THREADS / 32;
   extern __shared__ __align__(16) unsigned char dynSmem[];
   uint16_t *sLut = reinterpret_cast<uint16_t *>(dynSmem);
   float4 *sStage = reinterpret_cast<float4 *>(dynSmem + 4096);
@@ -212,7 +218,8 @@ __global__ void __launch_bounds__(LIMG_ENCODE_THREADS) k_encode_large(EncodeArgs
   load_lut(sLut, a.lut);
   __syncthreads();
 
-  const uint32_t huge = *a.hugeCount, count = huge + *a.listCount;
+  const uint32_t big = HUGE ? 0u : *a.bigCount;
+  const uint32_t count = HUGE ? *a.hugeCount : big + *a.listCount;
 
   while (true)
   {
@@ -226,7 +233,7 @@ __global__ void __launch_bounds__(LIMG_ENCODE_THREADS) k_encode_large(EncodeArgs
     if (j >= count)
       break;
 
-    const uint32_t k = j < huge ? a.list[j] : a.list[a.listCap - 1u - (j - huge)];
+    const uint32_t k = HUGE ? a.list[j] : (j < big ? a.bigList[a.listCap - 1u - j] : a.list[a.listCap - 1u - (j - big)]);
     const uint32_t oy = a.areas[k].oy;
 
     if (oy < a.rowLo || oy >= a.rowHi)

@@ -817,7 +817,7 @@ struct PrepareArgs
   uint32_t *blockToArea;
   AreaWork *work;
   uint32_t *smallList, *largeList;
-  uint32_t *smallCount, *largeCount, *hugeCount, *scratchTop; // largeCount: 256 < n <= LIMG_CTA_AREA_CAP, hugeCount: above
+  uint32_t *smallCount, *largeCount, *bigCount, *hugeCount, *scratchTop; // large: 256 < n <= LIMG_CTA_AREA_CAP, big: up to LIMG_HUGE_AREA_PX, huge: above
   uint32_t largeCap;         // entries of largeList
 };
 
@@ -963,13 +963,15 @@ __global__ void __launch_bounds__(256) k_prepare_geometry(PrepareArgs a)
     // area-contiguous scratch: any disjoint ranges do (the areas tile the image, so they fit into one image-sized buffer)
     a.work[k].scratchOff = n > LIMG_SMALL_AREA_PX ? atomicAdd(a.scratchTop, n) : 0u;
 
-    // The areas that do not fit into shared memory are the long poles of k_encode_large (their reference-order sums are one dependent
-    // chain per area): they go to the front of the list so that every one of them starts in the first wave of CTAs; the others fill the
-    // list from the back.
+    // Huge areas are the long poles of the per-area encode (their reference-order sums are one dependent chain per area, their trials run
+    // on one SM): they go to the front of the list and get a kernel of their own with 512-thread CTAs that starts first; the others fill
+    // the list from the back.
     if (n <= LIMG_SMALL_AREA_PX)
       a.smallList[atomicAdd(a.smallCount, 1u)] = k;
-    else if (n > LIMG_CTA_AREA_CAP)
+    else if (n > LIMG_HUGE_AREA_PX)
       a.largeList[atomicAdd(a.hugeCount, 1u)] = k;
+    else if (n > LIMG_CTA_AREA_CAP)
+      a.smallList[a.largeCap - 1u - atomicAdd(a.bigCount, 1u)] = k; // the free end of the small list (small + big <= areas <= blocks): first in the 256-thread kernel
     else
       a.largeList[a.largeCap - 1u - atomicAdd(a.largeCount, 1u)] = k;
   }

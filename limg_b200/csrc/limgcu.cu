@@ -32,6 +32,8 @@ struct limgcu_ctx
   int device = 0;
   cudaStream_t stream = nullptr;
   cudaStream_t streamAux = nullptr; // the speculative match bitmaps are computed here while the scan already runs on `stream`
+  cudaStream_t streamAux2 = nullptr; // high priority: the huge areas of the per-area encode (huge / large / small areas run side by side)
+  cudaEvent_t evJoin3 = nullptr;
   cudaEvent_t evFork = nullptr, evJoin = nullptr, evFork2 = nullptr, evJoin2 = nullptr, evBand[4] = { nullptr, nullptr, nullptr, nullptr };
   const uint32_t *hostSrc = nullptr; // set by host_encode: limgcu_blocked_encode3d uploads d_src from here in bands, pass 1 of band i under the upload of band i + 1
   int planAsync = 1;                // LIMGCU_PLAN_ASYNC: 0 plan kernels on the main stream, 1 both on the second stream concurrently with the scan, 2 only k_plan_sym
@@ -68,7 +70,7 @@ struct limgcu_ctx
   uint16_t *dUnmasked = nullptr;
   uint32_t extCap = 0, symCap = 0;
   uint32_t *dScratchPx = nullptr, *dScratchFac = nullptr;
-  uint32_t *dCounters = nullptr; // [32]: 0 merged, 1 areaCount, 2 smallCount, 3 largeCount (fits shared memory), 4 workSmall, 5 workLarge, 6 scratchTop, 7 hugeCount, 8.. stats
+  uint32_t *dCounters = nullptr; // [32]: 0 merged, 1 areaCount, 2 smallCount, 3 largeCount (fits shared memory), 4 workSmall, 5 workLarge, 6 scratchTop, 7 hugeCount, 8.. stats, 24..28 + 31 scan flags, 29 bigCount, 30 work counter of the huge areas
   unsigned long long *dCompare = nullptr;
 
   // host-buffer staging
@@ -267,6 +269,8 @@ extern "C" int limgcu_create(int device, limgcu_ctx **out)
     cudaDeviceGetStreamPriorityRange(&prLow, &prHigh);
     if (cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prHigh) != cudaSuccess) return bail(LIMGCU_ERROR_CUDA);
     if (cudaStreamCreateWithPriority(&ctx->streamAux, cudaStreamNonBlocking, prLow) != cudaSuccess) return bail(LIMGCU_ERROR_CUDA);
+    if (cudaStreamCreateWithPriority(&ctx->streamAux2, cudaStreamNonBlocking, prHigh) != cudaSuccess) return bail(LIMGCU_ERROR_CUDA);
+    if (cudaEventCreateWithFlags(&ctx->evJoin3, cudaEventDisableTiming) != cudaSuccess) return bail(LIMGCU_ERROR_CUDA);
     if (cudaEventCreateWithFlags(&ctx->evFork, cudaEventDisableTiming) != cudaSuccess) return bail(LIMGCU_ERROR_CUDA);
     if (cudaEventCreateWithFlags(&ctx->evJoin, cudaEventDisableTiming) != cudaSuccess) return bail(LIMGCU_ERROR_CUDA);
     if (cudaEventCreateWithFlags(&ctx->evFork2, cudaEventDisableTiming) != cudaSuccess) return bail(LIMGCU_ERROR_CUDA);
@@ -312,8 +316,13 @@ extern "C" int limgcu_create(int device, limgcu_ctx **out)
   for (auto &e : ctx->ev)
     if (cudaEventCreate(&e) != cudaSuccess) return bail(LIMGCU_ERROR_CUDA);
 
-  cudaFuncSetAttribute(k_encode_large<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 + LIMG_CTA_STAGE_PX * 16 + 2 * LIMG_CTA_AREA_CAP * 4);
-  cudaFuncSetAttribute(k_encode_large<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 + LIMG_CTA_STAGE_PX * 16 + 2 * LIMG_CTA_AREA_CAP * 4);
+  {
+    const int smemLarge = 4096 + LIMG_CTA_STAGE_PX * 16 + 2 * LIMG_CTA_AREA_CAP * 4;
+    cudaFuncSetAttribute(k_encode_large<3, LIMG_ENCODE_THREADS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smemLarge);
+    cudaFuncSetAttribute(k_encode_large<4, LIMG_ENCODE_THREADS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smemLarge);
+    cudaFuncSetAttribute(k_encode_large<3, 512, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smemLarge);
+    cudaFuncSetAttribute(k_encode_large<4, 512, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smemLarge);
+  }
 
   *out = ctx;
   return LIMGCU_SUCCESS;
@@ -359,6 +368,8 @@ extern "C" void limgcu_destroy(limgcu_ctx *ctx)
   if (ctx->evJoin) cudaEventDestroy(ctx->evJoin);
   if (ctx->evFork2) cudaEventDestroy(ctx->evFork2);
   if (ctx->evJoin2) cudaEventDestroy(ctx->evJoin2);
+  if (ctx->evJoin3) cudaEventDestroy(ctx->evJoin3);
+  if (ctx->streamAux2) cudaStreamDestroy(ctx->streamAux2);
   for (auto e : ctx->evBand) if (e) cudaEventDestroy(e);
 
   delete ctx;
@@ -678,7 +689,7 @@ static int launch_merge(limgcu_ctx *ctx, const limgcu_decomp *dTable, size_t W, 
   p.rowLeft = ctx->dRowMeta; p.rowBase = ctx->dRowMeta + BY;
   p.mergedCount = ctx->dCounters + 0; p.areaCount = ctx->dCounters + 1;
   p.blockToArea = dBlockToArea; p.work = ctx->dWork; p.smallList = ctx->dSmallList; p.largeList = ctx->dLargeList;
-  p.smallCount = ctx->dCounters + 2; p.largeCount = ctx->dCounters + 3; p.hugeCount = ctx->dCounters + 7; p.scratchTop = ctx->dCounters + 6;
+  p.smallCount = ctx->dCounters + 2; p.largeCount = ctx->dCounters + 3; p.hugeCount = ctx->dCounters + 7; p.bigCount = ctx->dCounters + 29; p.scratchTop = ctx->dCounters + 6;
   p.largeCap = (uint32_t)ctx->capBlocks;
   k_prepare_rowleft<<<BY, 32, 0, ctx->stream>>>(p);
   CKL("k_prepare_rowleft");
@@ -765,13 +776,13 @@ static int launch_area_encode(limgcu_ctx *ctx, const uint32_t *d_src, int W, int
   e.areas = dAreas; e.areaCount = ctx->dCounters + 1; e.work = ctx->dWork; e.ditherDemand = ctx->dDemand;
   e.scratchPx = ctx->dScratchPx; e.scratchFac = ctx->dScratchFac;
   e.cp = make_crush_params(errorFactor, (flags & LIMGCU_FLAG_FAST_BIT_CRUSH) ? 1 : 0);
-  e.rowLo = rowLo; e.rowHi = rowHi; e.hugeCount = nullptr; e.listCap = 0;
+  e.rowLo = rowLo; e.rowHi = rowHi; e.hugeCount = nullptr; e.listCap = 0; e.bigCount = nullptr; e.bigList = nullptr;
 
   {
     EncodeArgs s = e;
     s.workCounter = ctx->dCounters + 4; s.list = ctx->dSmallList; s.listCount = ctx->dCounters + 2;
     EncodeArgs l = e;
-    l.workCounter = ctx->dCounters + 5; l.list = ctx->dLargeList; l.listCount = ctx->dCounters + 3; l.hugeCount = ctx->dCounters + 7; l.listCap = (uint32_t)ctx->capBlocks;
+    l.workCounter = ctx->dCounters + 5; l.list = ctx->dLargeList; l.listCount = ctx->dCounters + 3; l.hugeCount = ctx->dCounters + 7; l.listCap = (uint32_t)ctx->capBlocks; l.bigCount = ctx->dCounters + 29; l.bigList = ctx->dSmallList;
     const int gridLarge = ctx->smCount * 4, gridSmall = ctx->smCount * 6;
     const size_t smemLarge = 4096 + LIMG_CTA_STAGE_PX * 16 + 2 * LIMG_CTA_AREA_CAP * 4;
 
@@ -779,17 +790,28 @@ static int launch_area_encode(limgcu_ctx *ctx, const uint32_t *d_src, int W, int
     // on the second stream.
     CK(cudaEventRecord(ctx->evFork2, ctx->stream));
     CK(cudaStreamWaitEvent(ctx->streamAux, ctx->evFork2, 0));
+    CK(cudaStreamWaitEvent(ctx->streamAux2, ctx->evFork2, 0));
 
+    EncodeArgs hg = l;
+    hg.workCounter = ctx->dCounters + 30; // free until limgcu_finalize_rows (which clears it first)
+    const int gridHuge = ctx->smCount * 2;
+
+    // three kernels side by side: huge areas (512 threads each, launched first) on the third stream, the other CTA-sized areas on the main
+    // stream (both high priority: the long poles start first), the warp-sized ones on the low-priority second stream
     if (hasAlpha)
     {
-      k_encode_large<4><<<gridLarge, LIMG_ENCODE_THREADS, smemLarge, ctx->stream>>>(l);
+      k_encode_large<4, 512, true><<<gridHuge, 512, smemLarge, ctx->streamAux2>>>(hg);
+      CKL("k_encode_huge");
+      k_encode_large<4, LIMG_ENCODE_THREADS, false><<<gridLarge, LIMG_ENCODE_THREADS, smemLarge, ctx->stream>>>(l);
       CKL("k_encode_large");
       k_encode_small<4><<<gridSmall, LIMG_ENCODE_THREADS, 0, ctx->streamAux>>>(s);
       CKL("k_encode_small");
     }
     else
     {
-      k_encode_large<3><<<gridLarge, LIMG_ENCODE_THREADS, smemLarge, ctx->stream>>>(l);
+      k_encode_large<3, 512, true><<<gridHuge, 512, smemLarge, ctx->streamAux2>>>(hg);
+      CKL("k_encode_huge");
+      k_encode_large<3, LIMG_ENCODE_THREADS, false><<<gridLarge, LIMG_ENCODE_THREADS, smemLarge, ctx->stream>>>(l);
       CKL("k_encode_large");
       k_encode_small<3><<<gridSmall, LIMG_ENCODE_THREADS, 0, ctx->streamAux>>>(s);
       CKL("k_encode_small");
@@ -797,6 +819,8 @@ static int launch_area_encode(limgcu_ctx *ctx, const uint32_t *d_src, int W, int
 
     CK(cudaEventRecord(ctx->evJoin2, ctx->streamAux));
     CK(cudaStreamWaitEvent(ctx->stream, ctx->evJoin2, 0));
+    CK(cudaEventRecord(ctx->evJoin3, ctx->streamAux2));
+    CK(cudaStreamWaitEvent(ctx->stream, ctx->evJoin3, 0));
   }
 
   return LIMGCU_SUCCESS;
