@@ -215,11 +215,14 @@ __global__ void __launch_bounds__(THREADS) k_encode_large(EncodeArgs a)
   __shared__ GroupScratch<WARPS> sGs;
   __shared__ uint32_t sJob;
 
-  load_lut(sLut, a.lut);
-  __syncthreads();
-
   const uint32_t big = HUGE ? 0u : *a.bigCount;
   const uint32_t count = HUGE ? *a.hugeCount : big + *a.listCount;
+
+  if (count == 0)
+    return; // photo-like content has no huge areas: nothing to stage
+
+  load_lut(sLut, a.lut);
+  __syncthreads();
 
   while (true)
   {

@@ -32,8 +32,6 @@ struct limgcu_ctx
   int device = 0;
   cudaStream_t stream = nullptr;
   cudaStream_t streamAux = nullptr; // the speculative match bitmaps are computed here while the scan already runs on `stream`
-  cudaStream_t streamAux2 = nullptr; // high priority: the huge areas of the per-area encode (huge / large / small areas run side by side)
-  cudaEvent_t evJoin3 = nullptr;
   cudaEvent_t evFork = nullptr, evJoin = nullptr, evFork2 = nullptr, evJoin2 = nullptr, evBand[4] = { nullptr, nullptr, nullptr, nullptr };
   const uint32_t *hostSrc = nullptr; // set by host_encode: limgcu_blocked_encode3d uploads d_src from here in bands, pass 1 of band i under the upload of band i + 1
   int planAsync = 1;                // LIMGCU_PLAN_ASYNC: 0 plan kernels on the main stream, 1 both on the second stream concurrently with the scan, 2 only k_plan_sym
@@ -269,8 +267,6 @@ extern "C" int limgcu_create(int device, limgcu_ctx **out)
     cudaDeviceGetStreamPriorityRange(&prLow, &prHigh);
     if (cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prHigh) != cudaSuccess) return bail(LIMGCU_ERROR_CUDA);
     if (cudaStreamCreateWithPriority(&ctx->streamAux, cudaStreamNonBlocking, prLow) != cudaSuccess) return bail(LIMGCU_ERROR_CUDA);
-    if (cudaStreamCreateWithPriority(&ctx->streamAux2, cudaStreamNonBlocking, prHigh) != cudaSuccess) return bail(LIMGCU_ERROR_CUDA);
-    if (cudaEventCreateWithFlags(&ctx->evJoin3, cudaEventDisableTiming) != cudaSuccess) return bail(LIMGCU_ERROR_CUDA);
     if (cudaEventCreateWithFlags(&ctx->evFork, cudaEventDisableTiming) != cudaSuccess) return bail(LIMGCU_ERROR_CUDA);
     if (cudaEventCreateWithFlags(&ctx->evJoin, cudaEventDisableTiming) != cudaSuccess) return bail(LIMGCU_ERROR_CUDA);
     if (cudaEventCreateWithFlags(&ctx->evFork2, cudaEventDisableTiming) != cudaSuccess) return bail(LIMGCU_ERROR_CUDA);
@@ -368,8 +364,6 @@ extern "C" void limgcu_destroy(limgcu_ctx *ctx)
   if (ctx->evJoin) cudaEventDestroy(ctx->evJoin);
   if (ctx->evFork2) cudaEventDestroy(ctx->evFork2);
   if (ctx->evJoin2) cudaEventDestroy(ctx->evJoin2);
-  if (ctx->evJoin3) cudaEventDestroy(ctx->evJoin3);
-  if (ctx->streamAux2) cudaStreamDestroy(ctx->streamAux2);
   for (auto e : ctx->evBand) if (e) cudaEventDestroy(e);
 
   delete ctx;
@@ -790,37 +784,35 @@ static int launch_area_encode(limgcu_ctx *ctx, const uint32_t *d_src, int W, int
     // on the second stream.
     CK(cudaEventRecord(ctx->evFork2, ctx->stream));
     CK(cudaStreamWaitEvent(ctx->streamAux, ctx->evFork2, 0));
-    CK(cudaStreamWaitEvent(ctx->streamAux2, ctx->evFork2, 0));
 
     EncodeArgs hg = l;
     hg.workCounter = ctx->dCounters + 30; // free until limgcu_finalize_rows (which clears it first)
     const int gridHuge = ctx->smCount * 2;
 
-    // three kernels side by side: huge areas (512 threads each, launched first) on the third stream, the other CTA-sized areas on the main
-    // stream (both high priority: the long poles start first), the warp-sized ones on the low-priority second stream
+    // The CTA-sized areas on the second stream; on the main stream the huge areas (512 threads each) and, behind them, the warp-sized ones
+    // (a handful of launches next to each other without a third stream: four contexts with two streams each are exactly the eight
+    // hardware queues of the default CUDA_DEVICE_MAX_CONNECTIONS, a third stream per context cost the batch mode 17 %).
     if (hasAlpha)
     {
-      k_encode_large<4, 512, true><<<gridHuge, 512, smemLarge, ctx->streamAux2>>>(hg);
-      CKL("k_encode_huge");
-      k_encode_large<4, LIMG_ENCODE_THREADS, false><<<gridLarge, LIMG_ENCODE_THREADS, smemLarge, ctx->stream>>>(l);
+      k_encode_large<4, LIMG_ENCODE_THREADS, false><<<gridLarge, LIMG_ENCODE_THREADS, smemLarge, ctx->streamAux>>>(l);
       CKL("k_encode_large");
-      k_encode_small<4><<<gridSmall, LIMG_ENCODE_THREADS, 0, ctx->streamAux>>>(s);
+      k_encode_large<4, 512, true><<<gridHuge, 512, smemLarge, ctx->stream>>>(hg);
+      CKL("k_encode_huge");
+      k_encode_small<4><<<gridSmall, LIMG_ENCODE_THREADS, 0, ctx->stream>>>(s);
       CKL("k_encode_small");
     }
     else
     {
-      k_encode_large<3, 512, true><<<gridHuge, 512, smemLarge, ctx->streamAux2>>>(hg);
-      CKL("k_encode_huge");
-      k_encode_large<3, LIMG_ENCODE_THREADS, false><<<gridLarge, LIMG_ENCODE_THREADS, smemLarge, ctx->stream>>>(l);
+      k_encode_large<3, LIMG_ENCODE_THREADS, false><<<gridLarge, LIMG_ENCODE_THREADS, smemLarge, ctx->streamAux>>>(l);
       CKL("k_encode_large");
-      k_encode_small<3><<<gridSmall, LIMG_ENCODE_THREADS, 0, ctx->streamAux>>>(s);
+      k_encode_large<3, 512, true><<<gridHuge, 512, smemLarge, ctx->stream>>>(hg);
+      CKL("k_encode_huge");
+      k_encode_small<3><<<gridSmall, LIMG_ENCODE_THREADS, 0, ctx->stream>>>(s);
       CKL("k_encode_small");
     }
 
     CK(cudaEventRecord(ctx->evJoin2, ctx->streamAux));
     CK(cudaStreamWaitEvent(ctx->stream, ctx->evJoin2, 0));
-    CK(cudaEventRecord(ctx->evJoin3, ctx->streamAux2));
-    CK(cudaStreamWaitEvent(ctx->stream, ctx->evJoin3, 0));
   }
 
   return LIMGCU_SUCCESS;
