@@ -57,6 +57,29 @@ def make_frame(workload: str, index: int) -> np.ndarray:
     return synth.gradient_noise(w, h, 1234 + index)
 
 
+class stdout_to_stderr:
+    """NCCL prints its version banner on stdout when the communicator is created; rank 0's stdout must carry the JSON line only."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
+def init_distributed(dev):
+    import torch
+    import torch.distributed as dist
+    with stdout_to_stderr():
+        dist.init_process_group("nccl", device_id=dev)
+        dist.barrier()  # creates the communicator (and prints the banner) now
+        torch.cuda.synchronize(dev)
+
+
 def measured_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -332,7 +355,7 @@ def run_rowband_exact(args, rank: int, local_rank: int, world: int):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        init_distributed(dev)
     w, h, alpha, _ = WORKLOADS[args.workload]
     codec = Codec(local_rank)
     frame = make_frame(args.workload, 0)
@@ -410,7 +433,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        init_distributed(dev)
 
     w, h, alpha, _ = WORKLOADS[args.workload]
     npx = w * h
