@@ -7,7 +7,7 @@
  *                   device; work is enqueued on the context's stream and is stream ordered. No hidden
  *                   synchronisation except where a function returns a host value (documented per function).
  *   limgcu_host_*   host-buffer entry points with the reference's argument meaning (H2D, kernels, D2H inside).
- *                   include/limg.h declares the reference's own C++ signatures on top of these.
+ *                   include/limg_dropin.h declares the reference's own C++ signatures on top of these.
  *
  * There is NO CPU fallback: every entry point fails with LIMGCU_ERROR_NO_DEVICE / a CUDA error if the
  * kernels cannot run.
@@ -109,6 +109,11 @@ int limgcu_device_count(void);
 int limgcu_set_rsqrt_lut(limgcu_ctx *ctx, const uint16_t *lut2048);
 void *limgcu_stream_handle(limgcu_ctx *ctx); /* cudaStream_t */
 int limgcu_sync(limgcu_ctx *ctx);
+/* Synchronises with the stream and reports the hard errors of the last merge scan that the stream-ordered device entry points
+ * (limgcu_merge, limgcu_blocked_encode3d, limgcu_encode_areas) cannot return themselves: LIMGCU_ERROR_GENERIC (watchdog: a block
+ * row waited too long) or LIMGCU_ERROR_OUT_OF_BOUNDS (a row's rectangle list overflowed); the area map is then truncated and nothing
+ * computed from it is valid. The host-buffer entry points and limgcu_finalize_rows check the same flags themselves. */
+int limgcu_status(limgcu_ctx *ctx);
 /* dither generator of the entry points that have no flags argument (limgcu_host_blocked_encode3d, limgcu_host_encode3d): 0 = LCG (default),
  * 1 = AES (as LIMGCU_FLAG_DITHER_AES). limgcu_host_has_aesni: 1 when the reference itself would pick the AES generator on this host. */
 int limgcu_set_dither_mode(limgcu_ctx *ctx, int aes);

@@ -53,6 +53,11 @@ class Codec:
     def sync(self):
         self._ck(self.lib.limgcu_sync(self.h), "limgcu_sync")
 
+    def status(self):
+        """Synchronises and raises if the last merge scan flagged a hard error (watchdog, row-list overflow): the stream-ordered
+        device entry points cannot report those themselves."""
+        self._ck(self.lib.limgcu_status(self.h), "limgcu_status")
+
     def launch_count(self) -> int:
         return int(self.lib.limgcu_launch_count(self.h))
 

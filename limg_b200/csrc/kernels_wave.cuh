@@ -6,11 +6,15 @@
 // gets a LOGICAL TIME T = (seed raster index, attempt number); the sequential result is the unique record in which every seed's
 // decision equals what limg_encode_find_block_3d does against the mask { blocks owned by a rectangle with time < T }.
 //
-//   k_merge_wave    one warp per block row (rows handed out by ticket, so a row's predecessor is always running). A row walks
-//                   its candidate seeds left to right against the LIVE mask in global memory (L2). Before a seed's decision
-//                   stands, the row above must have committed every seed left of (right edge of everything the seed probed +
-//                   margin); by induction the rows further up are further ahead. That lag rule is a heuristic: the four-way
-//                   centre-third regrowth can reach arbitrarily far to the left, so
+//   wave_scan_rows  one warp per block row (rows handed out by ticket, so a row's predecessor is always running). A row walks
+//                   its candidate seeds left to right against the LIVE mask. Before a seed's decision stands, the row above
+//                   must have committed every seed left of (right edge of everything the seed probed + margin); by induction
+//                   the rows further up are further ahead. That lag rule is a heuristic: the four-way centre-third regrowth
+//                   can reach arbitrarily far to the left, so the record is verified (below). The mask, the rows' progress
+//                   words and the tickets live in a BACK END: k_merge_cta (kernels_cta.cuh) keeps them in the shared memory
+//                   of one thread-block cluster (every CTA holds a replica it reads locally; writes go to all replicas), which
+//                   is what the encoder uses; k_merge_wave keeps them in global memory (L2): any image size, any grid, and
+//                   the strictly sequential last resort.
 //   k_merge_verify  replays EVERY candidate seed, fully in parallel, against the mask "owner time < my time" built from the
 //                   per-block owner times the wave wrote, and compares with what the wave recorded. All equal (and no
 //                   rectangle overlap, detected by the atomicOr of the claims)  =>  the record is self-consistent  =>  it is
@@ -92,8 +96,8 @@ __device__ __forceinline__ int ld_acquire_s32(const int *p)
 }
 
 // Polling uses relaxed (strong, L2-coherent) loads: an acquire load costs an L1 invalidation (CCTL.IVALL) plus a fence on every
-// poll. Everything read after a satisfied poll is itself a relaxed gpu-scope load issued behind the branch on the polled value,
-// and the producer fences between its claims and its progress store.
+// poll. The producer fences between its claims and its progress store; the consumer fences (acquire_fence() of the back end)
+// between a progress read and the look at the mask that can make a decision final, and only then.
 __device__ __forceinline__ int ld_relaxed_s32(const int *p)
 {
   int v;
@@ -106,6 +110,11 @@ __device__ __forceinline__ void st_relaxed_s32(int *p, int v)
   asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
 }
 
+__device__ __forceinline__ void fence_acq_rel_gpu()
+{
+  asm volatile("fence.acq_rel.gpu;" ::: "memory");
+}
+
 #define LIMG_SNAP_UP 8 // a seed's mask snapshot covers block rows y - 8 .. y + 23, one per lane
 
 // 96 in-use bits per lane: row (r0 + lane), columns [32 * w0, 32 * w0 + 96)
@@ -115,10 +124,11 @@ struct Snapshot
   int r0, w0;
 };
 
-// the live in-use mask (global memory, read at L2)
-struct LiveMask
+// the live in-use mask: [BY][wordsPerRow] words behind a loader (global memory read at L2, or shared memory)
+template <class Words>
+struct WordMask
 {
-  const uint32_t *used;
+  Words ld; // ld(i): word i of the mask, a strong (never cached stale) read
   int wordsPerRow, BX, BY;
 
   // 32 in-use bits of row y starting at column x (x may be negative); everything outside the grid rows reads as in use
@@ -127,17 +137,17 @@ struct LiveMask
     if (y < 0 || y >= BY)
       return 0xFFFFFFFFu;
 
-    const uint32_t *row = used + (size_t)y * wordsPerRow;
+    const int row = y * wordsPerRow;
 
     if (x < 0)
     {
       const int s = -x; // 1..31
-      return (ld_relaxed_u32(row) << s) | ((1u << s) - 1u);
+      return (ld(row) << s) | ((1u << s) - 1u);
     }
 
     const int w0 = x >> 5, s = x & 31;
-    const uint32_t lo = ld_relaxed_u32(row + w0);
-    const uint32_t hi = s ? ld_relaxed_u32(row + w0 + 1) : 0u; // rows are padded; columns >= BX are never set
+    const uint32_t lo = ld(row + w0);
+    const uint32_t hi = s ? ld(row + w0 + 1) : 0u; // rows are padded; columns >= BX are never set
     return __funnelshift_r(lo, hi, s);
   }
 
@@ -149,17 +159,25 @@ struct LiveMask
       return;
     }
 
-    const uint32_t *row = used + (size_t)y * wordsPerRow + w0;
-    out[0] = ld_relaxed_u32(row);
-    out[1] = ld_relaxed_u32(row + 1);
-    out[2] = ld_relaxed_u32(row + 2);
+    const int row = y * wordsPerRow + w0;
+    out[0] = ld(row);
+    out[1] = ld(row + 1);
+    out[2] = ld(row + 2);
   }
 
   __device__ __forceinline__ bool is_used(int x, int y) const
   {
-    return (ld_relaxed_u32(used + (size_t)y * wordsPerRow + (x >> 5)) >> (x & 31)) & 1u;
+    return (ld(y * wordsPerRow + (x >> 5)) >> (x & 31)) & 1u;
   }
 };
+
+struct GlobalWords
+{
+  const uint32_t *used;
+  __device__ __forceinline__ uint32_t operator()(int i) const { return ld_relaxed_u32(used + i); }
+};
+
+typedef WordMask<GlobalWords> LiveMask;
 
 // the mask the sequential scan shows a seed at logical time T: blocks owned by an earlier rectangle
 struct TimeMask
@@ -804,7 +822,9 @@ __device__ __forceinline__ uint2 pack_rect(int ox, int oy, int rx, int ry)
 // next column >= x of row y whose candidate bit is set and which can still emit given a fresh read of the in-use bits: in stage 0
 // its whole 3 x 3 corner must be free (limg.cpp:1424 keeps nothing smaller), in stage 1 the block and its right or lower neighbour.
 // In-use bits at columns >= x of these rows only ever come from logically earlier rectangles, so skipping is exact. BX if none.
-__device__ __forceinline__ int wave_next_candidate(const uint32_t *candRow, const uint32_t *usedRow, int wordsPerRow, int nWords, int x, int BX, int stage, int lane)
+// `used(dy, w)` returns in-use word w of block row y + dy (rows are padded by two zero words).
+template <class UsedWord>
+__device__ __forceinline__ int wave_next_candidate(const uint32_t *candRow, UsedWord used, int nWords, int x, int BX, int stage, int lane)
 {
   for (int w0 = x >> 5; w0 < nWords; w0 += 32)
   {
@@ -814,13 +834,13 @@ __device__ __forceinline__ int wave_next_candidate(const uint32_t *candRow, cons
     if (w < nWords)
     {
       // rows are padded with zero words, and candidates never sit in the last block rows (their 3 x 3 corner / lower neighbour is inside the grid)
-      const unsigned long long u0 = ld_relaxed_u32(usedRow + w) | ((unsigned long long)ld_relaxed_u32(usedRow + w + 1) << 32);
+      const unsigned long long u0 = used(0, w) | ((unsigned long long)used(0, w + 1) << 32);
       bits = __ldg(candRow + w);
 
       if (stage == 0 && bits) // a candidate bit in this word: block rows y + 1 and y + 2 exist
       {
-        const unsigned long long u1 = ld_relaxed_u32(usedRow + wordsPerRow + w) | ((unsigned long long)ld_relaxed_u32(usedRow + wordsPerRow + w + 1) << 32);
-        const unsigned long long u2 = ld_relaxed_u32(usedRow + 2 * wordsPerRow + w) | ((unsigned long long)ld_relaxed_u32(usedRow + 2 * wordsPerRow + w + 1) << 32);
+        const unsigned long long u1 = used(1, w) | ((unsigned long long)used(1, w + 1) << 32);
+        const unsigned long long u2 = used(2, w) | ((unsigned long long)used(2, w + 1) << 32);
         const unsigned long long u = u0 | u1 | u2;
         bits &= (uint32_t)~(u | (u >> 1) | (u >> 2));
       }
@@ -847,52 +867,112 @@ __device__ __forceinline__ int wave_next_candidate(const uint32_t *candRow, cons
   return BX;
 }
 
-// Waits until every one of the 32 rows above row y has committed all seeds left of `need` (LIMG_WAVE_DONE satisfies every need):
-// one acquire load per lane, warp minimum. Rows further up are assumed to be further along (they are whenever the rectangles
-// are less than 32 rows tall; the verification pass covers the rest).
 #define LIMG_WAVE_SPIN_LIMIT (1u << 22) // watchdog: a wait that long (seconds) is a bug; flag it instead of hanging the GPU
 
-__device__ __forceinline__ int wave_wait(const int *progress, int y, int need, uint32_t &polls, uint32_t *flags)
+// Order in which the block rows of the two merge stages are handed out. A stage-1 row needs stage 0 to be done down to `gap` rows
+// below it, so stage 1 can follow stage 0 at that distance: tickets 0 .. lead-1 are the first `lead` rows of stage 0, then the
+// stages alternate (stage-0 row lead + k, stage-1 row k), then the last `lead` rows of stage 1. Whatever a row waits for (the rows
+// above it in its own stage, stage-0 rows down to row + gap < row + lead) has an earlier ticket, so its owner is running or done.
+// lead >= BY gives the plain order: all of stage 0, then all of stage 1.
+__device__ __forceinline__ void wave_ticket_row(int t, int BY, int lead, int &stage, int &y)
 {
-  const int r = y - 1 - (int)(threadIdx.x & 31);
-  int v;
+  lead = min(lead, BY);
 
-  for (uint32_t spins = 0;; spins++)
+  if (t < lead)
   {
-    v = r >= 0 ? ld_acquire_s32(progress + r) : LIMG_WAVE_DONE;
-    v = __reduce_min_sync(0xFFFFFFFFu, v);
-
-    if (v >= need)
-      break;
-
-    if (spins > LIMG_WAVE_SPIN_LIMIT)
-    {
-      flags[3] = 1;
-      return LIMG_WAVE_DONE;
-    }
-
-    polls++;
-    __nanosleep(v + 64 < need ? 400 : 20);
+    stage = 0;
+    y = t;
   }
-
-  return v;
+  else if (t < 2 * BY - lead)
+  {
+    const int k = t - lead;
+    stage = k & 1;
+    y = stage ? (k >> 1) : lead + (k >> 1);
+  }
+  else
+  {
+    stage = 1;
+    y = t - BY;
+  }
 }
 
-// Both merge stages in one launch: tickets 0 .. BY-1 are the block rows of stage 0, tickets BY .. 2BY-1 the rows of stage 1. A
-// stage-1 row starts once stage 0 is done with every row down to `stageGap` rows below it (the centre-third regrowth of a stage-0
-// seed further down would have to reach that far up to matter, which the verification pass would notice).
-// `attempt` numbers the tries of the host: the kernel runs only if flags[0] == attempt, i.e. every earlier try failed.
-template <int CH>
-__global__ void __launch_bounds__(LIMG_WAVE_WARPS * 32) k_merge_wave(WaveArgs a, int attempt, int sequential)
+// The scan's shared state (in-use mask, row progress, tickets) in GLOBAL memory, read and written at L2: any grid, any image size.
+struct WaveGlobal
 {
-  if (a.flags[0] != (uint32_t)attempt)
-    return;
+  typedef LiveMask Mask;
+  const WaveArgs &a;
 
-  __shared__ uint32_t sScratch[LIMG_WAVE_WARPS][32];
+  __device__ __forceinline__ Mask mask() const { return LiveMask{ GlobalWords{ a.used }, a.wordsPerRow, a.BX, a.BY }; }
+
+  __device__ __forceinline__ int take_ticket(int lane) const
+  {
+    int t = 0;
+
+    if (lane == 0)
+      t = (int)atomicAdd(&a.ticket[0], 1u);
+
+    return __shfl_sync(0xFFFFFFFFu, t, 0);
+  }
+
+  __device__ __forceinline__ uint32_t stage0_rows_done() const { return ld_relaxed_u32(&a.ticket[1]); }
+  // everything read after this fence is at least as new as what was read before it
+  __device__ __forceinline__ void acquire_fence() const { fence_acq_rel_gpu(); }
+  __device__ __forceinline__ int progress(int stage, int row) const { return ld_relaxed_s32(a.progress + (size_t)stage * a.BY + row); }
+  __device__ __forceinline__ int progress_acquire(int stage, int row) const { return ld_acquire_s32(a.progress + (size_t)stage * a.BY + row); }
+
+  __device__ __forceinline__ void publish(int stage, int y, int v, int lane) const
+  {
+    if (lane == 0)
+      st_relaxed_s32(a.progress + (size_t)stage * a.BY + y, v);
+  }
+
+  __device__ __forceinline__ uint32_t used_word(int y, int w) const { return ld_relaxed_u32(a.used + (size_t)y * a.wordsPerRow + w); }
+
+  // claim the blocks of a rectangle; visible to this warp's next look at the mask and to everybody who later reads a progress
+  // value published after it
+  __device__ __forceinline__ void claim(int eox, int eoy, int erx, int ery, int lane) const
+  {
+    for (int rr = lane; rr < ery; rr += 32)
+    {
+      uint32_t *row = a.used + (size_t)(eoy + rr) * a.wordsPerRow;
+
+      for (int xx = eox; xx < eox + erx;)
+      {
+        const int w0 = xx >> 5, b0 = xx & 31;
+        const int cnt = min(32 - b0, eox + erx - xx);
+        const uint32_t m = (cnt == 32 ? 0xFFFFFFFFu : ((1u << cnt) - 1u)) << b0;
+        atomicOr(&row[w0], m);
+        xx += cnt;
+      }
+    }
+
+    __threadfence();
+    __syncwarp();
+  }
+
+  // rows finish in order (a row publishes DONE only after every row above it did): the count of finished stage-0 rows
+  __device__ __forceinline__ void stage0_row_done(int y, int lane) const
+  {
+    if (lane == 0)
+    {
+      __threadfence();
+      atomicMax(&a.ticket[1], (uint32_t)(y + 1));
+    }
+  }
+};
+
+// One warp per block row, rows by ticket, both merge stages in one launch. A stage-1 row starts once stage 0 is done with every
+// row down to `stageGap` rows below it (the centre-third regrowth of a stage-0 seed further down would have to reach that far up to
+// matter, which the verification pass would notice). `attempt` numbers the tries of the host. `scratch`: 32 words of shared memory
+// private to the warp. `sequential`: rows strictly one after the other (the reference's order).
+template <int CH, class Backend>
+__device__ void wave_scan_rows(const WaveArgs &a, const Backend &be, int attempt, int sequential, uint32_t *scratch)
+{
   const int lane = threadIdx.x & 31;
-  WaveScan<CH, LiveMask> scan{ a, LiveMask{ a.used, a.wordsPerRow, a.BX, a.BY }, lane, 0 };
-  scan.scratch = sScratch[threadIdx.x >> 5];
+  WaveScan<CH, typename Backend::Mask> scan{ a, be.mask(), lane, 0 };
+  scan.scratch = scratch;
   const int nWords = (a.BX + 31) >> 5;
+  const int lead = sequential ? a.BY : a.stageGap + 8;
   uint32_t nExp[2] = { 0, 0 }, nReexp[2] = { 0, 0 }, nPolls[2] = { 0, 0 }, nOnDemand[2] = { 0, 0 };
   long long tNext = 0, tWait = 0, tExpand = 0, tClaim = 0, tPre = 0, tc;
   long long cSeedStart = 0, cPre = 0, cWait = 0, cExp = 0, cClaim = 0, cTotal[2] = { 0, 0 }, cParts[2][4] = { { 0, 0, 0, 0 }, { 0, 0, 0, 0 } };
@@ -901,19 +981,13 @@ __global__ void __launch_bounds__(LIMG_WAVE_WARPS * 32) k_merge_wave(WaveArgs a,
 
   for (;;)
   {
-    int y = 0;
+    const int t = be.take_ticket(lane);
 
-    if (lane == 0)
-      y = (int)atomicAdd(&a.ticket[0], 1u);
-
-    y = __shfl_sync(0xFFFFFFFFu, y, 0);
-
-    if (y >= 2 * a.BY)
+    if (t >= 2 * a.BY)
       break;
 
-    const int stage = y >= a.BY ? 1 : 0;
-    y -= stage * a.BY;
-    int *progress = a.progress + (size_t)stage * a.BY;
+    int stage, y;
+    wave_ticket_row(t, a.BY, lead, stage, y);
     const uint32_t *cand = a.candBits + (size_t)stage * a.BY * a.wordsPerRow;
     uint2 *lists = a.rowLists + (size_t)stage * a.BY * a.listCap;
     uint32_t *emitInfo = a.emitInfo + (size_t)stage * a.BX * a.BY;
@@ -929,16 +1003,15 @@ __global__ void __launch_bounds__(LIMG_WAVE_WARPS * 32) k_merge_wave(WaveArgs a,
       {
         uint32_t spins = 0;
 
-        while (ld_relaxed_u32(&a.ticket[1]) < need)
+        while (be.stage0_rows_done() < need)
         {
           if (++spins > (LIMG_WAVE_SPIN_LIMIT << 3)) { a.flags[3] = 1; break; }
           __nanosleep(200);
         }
-
-        __threadfence();
       }
 
       __syncwarp();
+      be.acquire_fence();
     }
 
     if (sequential && y > 0)
@@ -948,7 +1021,7 @@ __global__ void __launch_bounds__(LIMG_WAVE_WARPS * 32) k_merge_wave(WaveArgs a,
       {
         uint32_t spins = 0;
 
-        while (ld_acquire_s32(progress + y - 1) != LIMG_WAVE_DONE)
+        while (be.progress_acquire(stage, y - 1) != LIMG_WAVE_DONE)
         {
           if (++spins > (LIMG_WAVE_SPIN_LIMIT << 3)) { a.flags[3] = 1; break; }
           __nanosleep(100);
@@ -956,6 +1029,7 @@ __global__ void __launch_bounds__(LIMG_WAVE_WARPS * 32) k_merge_wave(WaveArgs a,
       }
 
       __syncwarp();
+      be.acquire_fence();
     }
 
     uint32_t *rowT = (LIMG_WAVE_PROFILE && a.dbgRows) ? a.dbgRows + ((size_t)stage * a.BY + y) * 4 : nullptr;
@@ -964,7 +1038,6 @@ __global__ void __launch_bounds__(LIMG_WAVE_WARPS * 32) k_merge_wave(WaveArgs a,
       rowT[0] = global_ns();
 
     const uint32_t *candRow = cand + (size_t)y * a.wordsPerRow;
-    const uint32_t *usedRow = a.used + (size_t)y * a.wordsPerRow;
     uint2 *list = lists + (size_t)y * a.listCap;
     uint32_t count = 0;
     int x = 0, published = 0, nEvents = 0, xEvent = 0;
@@ -977,17 +1050,20 @@ __global__ void __launch_bounds__(LIMG_WAVE_WARPS * 32) k_merge_wave(WaveArgs a,
 
       if (v > published)
       {
-        if (lane == 0)
-          st_relaxed_s32(progress + y, v);
-
+        be.publish(stage, y, v, lane);
         published = v;
       }
+    };
+
+    auto rows_above = [&]() -> int {
+      const int row = y - 1 - lane;
+      return __reduce_min_sync(0xFFFFFFFFu, row >= 0 ? be.progress(stage, row) : LIMG_WAVE_DONE);
     };
 
     for (;;)
     {
       tc = wave_clock();
-      x = wave_next_candidate(candRow, usedRow, a.wordsPerRow, nWords, x, a.BX, stage, lane);
+      x = wave_next_candidate(candRow, [&](int dy, int w) { return be.used_word(y + dy, w); }, nWords, x, a.BX, stage, lane);
 
       // every seed left of x is decided, and its claims were fenced when they were made
       publish(x >= a.BX ? LIMG_WAVE_DONE : x);
@@ -1010,7 +1086,8 @@ __global__ void __launch_bounds__(LIMG_WAVE_WARPS * 32) k_merge_wave(WaveArgs a,
       {
         // Speculate while the rows above are not far enough: the seed is expanded against the mask as it is NOW and expanded again
         // only when a bit it consulted changes. Once the rows above have passed everything it consulted (+ margin), a snapshot
-        // taken after that observation which agrees with the one the expansion used makes the expansion final.
+        // taken after that observation (and after an acquire fence) which agrees with the one the expansion used makes the
+        // expansion final.
         WaveResult r;
         Snapshot used;
         bool have = false, taken = false, unstable = false;
@@ -1022,8 +1099,7 @@ __global__ void __launch_bounds__(LIMG_WAVE_WARPS * 32) k_merge_wave(WaveArgs a,
 
           if (y > 0 && !sequential)
           {
-            const int row = y - 1 - lane;
-            p = __reduce_min_sync(0xFFFFFFFFu, row >= 0 ? ld_relaxed_s32(progress + row) : LIMG_WAVE_DONE);
+            p = rows_above();
             pAbove = p;
             publish(x);
           }
@@ -1039,6 +1115,13 @@ __global__ void __launch_bounds__(LIMG_WAVE_WARPS * 32) k_merge_wave(WaveArgs a,
             __nanosleep(p + 64 < x ? 400 : 20);
             continue;
           }
+
+          // The fence orders the mask reads below behind the progress read above (PTX does not order two loads by a branch between
+          // them); it is only paid for when this look at the mask can be the final one.
+          const bool final = have ? p >= min(r.boxR + a.margin, a.BX) : p >= min(x + 1 + a.margin + 8, a.BX);
+
+          if (final)
+            be.acquire_fence();
 
           const Snapshot sn = scan.snapshot(x, y); // after the progress read
           tWait += wave_clock() - tc;
@@ -1065,7 +1148,7 @@ __global__ void __launch_bounds__(LIMG_WAVE_WARPS * 32) k_merge_wave(WaveArgs a,
               atomicAdd(&a.dbg[stage * 16 + min(15, 63 - __clzll((dt >> 8) | 1))], 1u);
           }
 
-          if (p >= min(r.boxR + a.margin, a.BX))
+          if (final && p >= min(r.boxR + a.margin, a.BX))
           {
             if (LIMG_WAVE_PROFILE && a.dbg && lane == 0 && stage == 0)
             {
@@ -1080,6 +1163,9 @@ __global__ void __launch_bounds__(LIMG_WAVE_WARPS * 32) k_merge_wave(WaveArgs a,
           }
 
           if (spins > LIMG_WAVE_SPIN_LIMIT) { a.flags[3] = 1; break; }
+
+          if (p >= min(r.boxR + a.margin, a.BX))
+            continue; // far enough, but this look was not fenced: look again at once
 
           nPolls[stage]++;
           __nanosleep(p + 64 < x ? 400 : 20);
@@ -1098,24 +1184,7 @@ __global__ void __launch_bounds__(LIMG_WAVE_WARPS * 32) k_merge_wave(WaveArgs a,
         // claim: in-use bits and owner times. Two rectangles that overlap (a failed speculation) leave one of them with a foreign
         // owner time on a block, which the verification pass sees.
         tc = wave_clock();
-
-        for (int rr = lane; rr < ery; rr += 32)
-        {
-          uint32_t *row = a.used + (size_t)(eoy + rr) * a.wordsPerRow;
-
-          for (int xx = eox; xx < eox + erx;)
-          {
-            const int w0 = xx >> 5, b0 = xx & 31;
-            const int cnt = min(32 - b0, eox + erx - xx);
-            const uint32_t m = (cnt == 32 ? 0xFFFFFFFFu : ((1u << cnt) - 1u)) << b0;
-            atomicOr(&row[w0], m);
-            xx += cnt;
-          }
-        }
-
-        // the claim is visible to this warp's next look at the mask and to everybody who later reads the progress store
-        __threadfence();
-        __syncwarp();
+        be.claim(eox, eoy, erx, ery, lane);
 
         // hand over to the rows below as early as possible: a right/down rectangle decides every seed up to its right edge
         if (r.kind == 1 && x + r.rx < a.BX)
@@ -1167,15 +1236,15 @@ __global__ void __launch_bounds__(LIMG_WAVE_WARPS * 32) k_merge_wave(WaveArgs a,
 
       if (rowT && lane == 0)
       {
-        const uint32_t t = global_ns();
-        if (rowT[1] == 0) rowT[1] = t;
-        rowT[2] = t;
+        const uint32_t tn = global_ns();
+        if (rowT[1] == 0) rowT[1] = tn;
+        rowT[2] = tn;
 
         if (stage == 0 && y >= a.eventRow && y < a.eventRow + 4 && nEvents < 64)
         {
           uint32_t *ev = a.dbgRows + (size_t)8 * a.BY + ((size_t)(y - a.eventRow) * 64 + nEvents) * 2;
           ev[0] = (uint32_t)xEvent | ((uint32_t)(claimed ? 1 : 0) << 16);
-          ev[1] = t;
+          ev[1] = tn;
           nEvents++;
         }
       }
@@ -1194,24 +1263,19 @@ __global__ void __launch_bounds__(LIMG_WAVE_WARPS * 32) k_merge_wave(WaveArgs a,
     // the row is done, but it keeps relaying the progress of the rows above until they are done too
     for (uint32_t spins = 0; published != LIMG_WAVE_DONE; spins++)
     {
-      const int row = y - 1 - lane;
-      pAbove = __reduce_min_sync(0xFFFFFFFFu, row >= 0 ? ld_relaxed_s32(progress + row) : LIMG_WAVE_DONE);
+      pAbove = rows_above();
       publish(LIMG_WAVE_DONE);
 
       if (published == LIMG_WAVE_DONE)
         break;
 
-      if (spins > LIMG_WAVE_SPIN_LIMIT) { a.flags[3] = 1; if (lane == 0) st_relaxed_s32(progress + y, LIMG_WAVE_DONE); break; }
+      if (spins > LIMG_WAVE_SPIN_LIMIT) { a.flags[3] = 1; be.publish(stage, y, LIMG_WAVE_DONE, lane); break; }
 
       __nanosleep(100);
     }
 
-    // rows finish in order (a row publishes DONE only after every row above it did): the count of finished stage-0 rows
-    if (stage == 0 && lane == 0)
-    {
-      __threadfence();
-      atomicMax(&a.ticket[1], (uint32_t)(y + 1));
-    }
+    if (stage == 0)
+      be.stage0_row_done(y, lane);
 
     nOnDemand[stage] += scan.nOnDemand - onDemandBefore;
   }
@@ -1266,6 +1330,18 @@ __global__ void __launch_bounds__(LIMG_WAVE_WARPS * 32) k_merge_wave(WaveArgs a,
       atomicAdd(&a.dbg[50], scan.nFourNoSym);
     }
   }
+}
+
+// The scan over the live mask in global memory: any image size; with `sequential` (one CTA) it is the reference's order, the last resort
+// of the host's tries. `attempt`: the kernel runs only if flags[0] == attempt, i.e. every earlier try failed.
+template <int CH>
+__global__ void __launch_bounds__(LIMG_WAVE_WARPS * 32) k_merge_wave(WaveArgs a, int attempt, int sequential)
+{
+  if (a.flags[0] != (uint32_t)attempt)
+    return;
+
+  __shared__ uint32_t sScratch[LIMG_WAVE_WARPS][32];
+  wave_scan_rows<CH>(a, WaveGlobal{ a }, attempt, sequential, sScratch[threadIdx.x >> 5]);
 }
 
 // Verification, part 1 (one THREAD per candidate seed): most candidates were in use before their turn came, or could not emit

@@ -3,6 +3,7 @@
 #include "kernels_fit.cuh"
 #include "kernels_merge.cuh"
 #include "kernels_wave.cuh"
+#include "kernels_cta.cuh"
 #include "kernels_stream.cuh"
 #include "kernels_decode.cuh"
 #include "kernels_container.cuh"
@@ -93,6 +94,8 @@ struct limgcu_ctx
 
   int mergeExt = 1;                  // LIMGCU_MERGE_EXT=0 disables the speculative match bitmaps (everything beyond the 8x8 window on demand)
   int mergeMode = 0;                 // LIMGCU_MERGE_MODE: 0 wave (pipelined rows + verification), 1 seq (rows strictly in sequence)
+  int scanCluster = 8;               // LIMGCU_SCAN_CLUSTER: CTAs of the cluster that runs the scan with its state in shared memory (k_merge_cta); 0 = scan over the mask in global memory (k_merge_wave)
+  int scanSmemLimit = 0;             // bytes of dynamic shared memory a CTA may opt in to (the mask replica has to fit)
   int planExtW = 16, planSymL = 6, planSymR = 12, planSymD = 16; // LIMGCU_PLAN_EXTW / SYML / SYMR / SYMD: size caps of the speculative bitmaps
   int mergeGap = 16;                 // LIMGCU_MERGE_GAP: block rows stage 1 stays behind stage 0
   int mergeWideMargin = 64;          // margin (and stage gap) of the second try
@@ -295,6 +298,7 @@ extern "C" int limgcu_create(int device, limgcu_ctx **out)
   if (const char *v = getenv("LIMGCU_MERGE_EXT")) ctx->mergeExt = atoi(v);
 
   if (const char *v = getenv("LIMGCU_MERGE_MODE")) ctx->mergeMode = !strcmp(v, "seq") ? 1 : 0;
+  if (const char *v = getenv("LIMGCU_SCAN_CLUSTER")) ctx->scanCluster = atoi(v) < 0 ? 0 : (atoi(v) > 8 ? 8 : atoi(v));
   if (const char *v = getenv("LIMGCU_MERGE_MARGIN")) ctx->mergeMargin = atoi(v) < 0 ? 0 : atoi(v);
   if (const char *v = getenv("LIMGCU_PLAN_EXTW")) ctx->planExtW = atoi(v) < 8 ? 8 : (atoi(v) > 32 ? 32 : atoi(v));
   if (const char *v = getenv("LIMGCU_PLAN_SYML")) ctx->planSymL = atoi(v) < 1 ? 1 : (atoi(v) > 8 ? 8 : atoi(v));
@@ -318,6 +322,9 @@ extern "C" int limgcu_create(int device, limgcu_ctx **out)
     cudaFuncSetAttribute(k_encode_large<4, LIMG_ENCODE_THREADS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smemLarge);
     cudaFuncSetAttribute(k_encode_large<3, 512, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smemLarge);
     cudaFuncSetAttribute(k_encode_large<4, 512, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smemLarge);
+    cudaDeviceGetAttribute(&ctx->scanSmemLimit, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+    cudaFuncSetAttribute(k_merge_cta<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->scanSmemLimit);
+    cudaFuncSetAttribute(k_merge_cta<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->scanSmemLimit);
   }
 
   *out = ctx;
@@ -627,12 +634,41 @@ static int launch_merge(limgcu_ctx *ctx, const limgcu_decomp *dTable, size_t W, 
         CKL("k_merge_reset");
       }
 
-      if (hasAlpha)
-        k_merge_wave<4><<<sequential ? 1 : waveGrid, LIMG_WAVE_WARPS * 32, 0, ctx->stream>>>(wa, attempt, sequential);
-      else
-        k_merge_wave<3><<<sequential ? 1 : waveGrid, LIMG_WAVE_WARPS * 32, 0, ctx->stream>>>(wa, attempt, sequential);
+      // The pipelined tries run as ONE thread-block cluster with the mask, the progress words and the tickets replicated in the shared
+      // memory of its CTAs (k_merge_cta), if a replica fits; the scan over global memory is for larger images and for the sequential try.
+      const size_t ctaSmem = merge_cta_smem_words(BY, wordsPerRow) * sizeof(uint32_t);
 
-      CKL("k_merge_wave");
+      if (!sequential && ctx->scanCluster > 0 && ctaSmem <= (size_t)ctx->scanSmemLimit)
+      {
+        cudaLaunchConfig_t cfg = {};
+        cudaLaunchAttribute attr[1];
+        cfg.gridDim = dim3((unsigned)ctx->scanCluster);
+        cfg.blockDim = dim3(LIMG_CTA_WARPS * 32);
+        cfg.dynamicSmemBytes = ctaSmem;
+        cfg.stream = ctx->stream;
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = (unsigned)ctx->scanCluster;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+
+        if (hasAlpha)
+          CK(cudaLaunchKernelEx(&cfg, k_merge_cta<4>, wa, attempt));
+        else
+          CK(cudaLaunchKernelEx(&cfg, k_merge_cta<3>, wa, attempt));
+
+        CKL("k_merge_cta");
+      }
+      else
+      {
+        if (hasAlpha)
+          k_merge_wave<4><<<sequential ? 1 : waveGrid, LIMG_WAVE_WARPS * 32, 0, ctx->stream>>>(wa, attempt, sequential);
+        else
+          k_merge_wave<3><<<sequential ? 1 : waveGrid, LIMG_WAVE_WARPS * 32, 0, ctx->stream>>>(wa, attempt, sequential);
+
+        CKL("k_merge_wave");
+      }
 
       if (async && attempt == 0)
         CK(cudaStreamWaitEvent(ctx->stream, ctx->evJoin, 0)); // everything after the first scan sees the complete bitmaps
@@ -694,6 +730,28 @@ static int launch_merge(limgcu_ctx *ctx, const limgcu_decomp *dTable, size_t W, 
   k_prepare_blockmap<<<(blocks + 255) / 256, 256, 0, ctx->stream>>>(p);
   CKL("k_prepare_blockmap");
   return LIMGCU_SUCCESS;
+}
+
+// hard errors of the last merge scan (dCounters[27]: watchdog, [28]: a row list overflowed): the area map is truncated, nothing downstream is valid
+static int scan_flags_error(limgcu_ctx *ctx, const uint32_t f[2])
+{
+  if (f[1])
+    return fail(ctx, LIMGCU_ERROR_OUT_OF_BOUNDS, "a block row emitted more rectangles than its list holds", cudaSuccess);
+
+  if (f[0])
+    return fail(ctx, LIMGCU_ERROR_GENERIC, "merge watchdog: a block row waited too long for the rows above", cudaSuccess);
+
+  return LIMGCU_SUCCESS;
+}
+
+extern "C" int limgcu_status(limgcu_ctx *ctx)
+{
+  NEED(ctx);
+  CK(cudaSetDevice(ctx->device));
+  uint32_t f[2] = { 0, 0 };
+  CK(cudaMemcpyAsync(f, ctx->dCounters + 27, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return scan_flags_error(ctx, f);
 }
 
 extern "C" int limgcu_merge(limgcu_ctx *ctx, const limgcu_decomp *d_table, size_t sizeX, size_t sizeY, int hasAlpha, limgcu_area *d_areas, uint32_t *d_area_count, uint32_t *d_block_to_area)
@@ -1040,9 +1098,13 @@ extern "C" int limgcu_finalize_rows(limgcu_ctx *ctx, const uint32_t *d_src, size
   if (stream && stream->area_count)
     CK(cudaMemcpyAsync(stream->area_count, ctx->dCounters + 1, sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream));
 
-  uint32_t bad = 0;
+  uint32_t bad = 0, scanFlags[2] = { 0, 0 };
   CK(cudaMemcpyAsync(&bad, ctx->dCounters + 30, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(scanFlags, ctx->dCounters + 27, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
+
+  if (int e = scan_flags_error(ctx, scanFlags))
+    return e;
 
   if (bad)
     return fail(ctx, LIMGCU_ERROR_GENERIC, "limgcu_finalize_rows: some areas were encoded by no rank or by several (row ranges must partition the block rows)", cudaSuccess);
@@ -1229,11 +1291,8 @@ static int host_encode(limgcu_ctx *ctx, const uint32_t *pIn, size_t W, size_t H,
   CK(cudaMemcpyAsync(overflow, ctx->dCounters + 27, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
 
-  if (overflow[1])
-    return fail(ctx, LIMGCU_ERROR_OUT_OF_BOUNDS, "a block row emitted more rectangles than its list holds", cudaSuccess);
-
-  if (overflow[0])
-    return fail(ctx, LIMGCU_ERROR_GENERIC, "merge watchdog: a block row waited too long for the rows above", cudaSuccess);
+  if (int bad = scan_flags_error(ctx, overflow))
+    return bad;
 
   if (areas)
   {
@@ -1494,11 +1553,8 @@ extern "C" int limgcu_host_encode_container(limgcu_ctx *ctx, const uint32_t *pIn
   CK(cudaMemcpyAsync(overflow, ctx->dCounters + 27, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
 
-  if (overflow[1])
-    return fail(ctx, LIMGCU_ERROR_OUT_OF_BOUNDS, "a block row emitted more rectangles than its list holds", cudaSuccess);
-
-  if (overflow[0])
-    return fail(ctx, LIMGCU_ERROR_GENERIC, "merge watchdog: a block row waited too long for the rows above", cudaSuccess);
+  if (int bad = scan_flags_error(ctx, overflow))
+    return bad;
 
   unsigned long long payloadBytes = 0;
   CK(cudaMemcpyAsync(&payloadBytes, ctx->dPayloadOff + count, sizeof(payloadBytes), cudaMemcpyDeviceToHost, ctx->stream));
@@ -1736,11 +1792,8 @@ extern "C" int limgcu_host_merge(limgcu_ctx *ctx, const limgcu_decomp *table, si
   CK(cudaMemcpyAsync(overflow, ctx->dCounters + 27, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
 
-  if (overflow[1])
-    return fail(ctx, LIMGCU_ERROR_OUT_OF_BOUNDS, "a block row emitted more rectangles than its list holds", cudaSuccess);
-
-  if (overflow[0])
-    return fail(ctx, LIMGCU_ERROR_GENERIC, "merge watchdog: a block row waited too long for the rows above", cudaSuccess);
+  if (int bad = scan_flags_error(ctx, overflow))
+    return bad;
 
   CK(cudaMemcpyAsync(areas, ctx->dAreas, (size_t)count * sizeof(limgcu_area), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));

@@ -29,6 +29,14 @@ def row_bands(height: int, world: int) -> List[Tuple[int, int]]:
     return bands
 
 
+def band_block_rows(y0: int, y1: int) -> Tuple[int, int]:
+    """Block rows [lo, hi) a band of pixel rows [y0, y1) owns in the exact row-band mode; an empty band (more ranks than block rows)
+    owns none, whatever the image height is."""
+    if y1 <= y0:
+        return (0, 0)
+    return (y0 // BLOCK, (y1 + BLOCK - 1) // BLOCK)
+
+
 def encode_frames_sharded(frames: Sequence, encode_fn: Callable, rank: int, world: int) -> List[Tuple[int, object]]:
     """Encodes this rank's frames; returns [(frame index, result)]."""
     return [(i, encode_fn(frames[i])) for i in frames_for_rank(len(frames), rank, world)]
@@ -73,7 +81,7 @@ class RowBandExact:
         self.flags = FLAG_FAST_BIT_CRUSH if fast_bit_crushing else 0
         self.bx, self.by = (width + 7) // 8, (height + 7) // 8
         self.y0, self.y1 = row_bands(height, world)[rank]
-        self.row_lo, self.row_hi = self.y0 // BLOCK, (self.y1 + BLOCK - 1) // BLOCK
+        self.row_lo, self.row_hi = band_block_rows(self.y0, self.y1)
         dev = d_src.device
         blocks = self.bx * self.by
         words = int(codec.lib.limgcu_area_result_words())
@@ -83,6 +91,8 @@ class RowBandExact:
         self.count = torch.zeros(1, dtype=torch.int32, device=dev)
         self.block_to_area = torch.zeros(blocks, dtype=torch.int32, device=dev)
         self.codes = [torch.zeros((height, width), dtype=torch.uint8, device=dev) for _ in range(3)]  # only rows [y0, y1) are written
+        # the buffers were zeroed on torch's stream; the codec launches on its own stream
+        torch.cuda.current_stream(dev).synchronize()
 
     def _ck(self, rc, what):
         self.codec._ck(rc, what)
@@ -101,7 +111,7 @@ class RowBandExact:
         self._ck(lib.limgcu_merge(c.h, self.table.data_ptr(), self.w, self.h, int(self.alpha), self.areas.data_ptr(), self.count.data_ptr(), self.block_to_area.data_ptr()), "limgcu_merge")
         self._ck(lib.limgcu_encode_areas(c.h, self.src.data_ptr(), self.w, self.h, int(self.alpha), self.ef, self.flags, self.table.data_ptr(), self.areas.data_ptr(), self.row_lo, self.row_hi,
                                          self.results.data_ptr()), "limgcu_encode_areas")
-        self.codec.sync()
+        self.codec.status()  # synchronises; a timed-out or truncated scan must not be shared with the other ranks
         return self.results
 
     def finalize(self):

@@ -184,7 +184,7 @@ def test_gpu_batch_of_frames_equals_one_at_a_time(codec):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("case", [(640, 360, False, 1), (640, 360, False, 3), (328, 200, True, 2), (1920, 1080, False, 4)])
+@pytest.mark.parametrize("case", [(640, 360, False, 1), (640, 360, False, 3), (328, 200, True, 2), (1920, 1080, False, 4), (200, 36, False, 8)])
 def test_gpu_exact_row_bands_equal_the_whole_image_encode(codec, case):
     """the phased, sharded encode (ranks simulated by contexts on one GPU, the all-reduces done by hand) gives the same area
     table (decompositions, shifts, dither chain) and the same codes as one encode of the whole image."""

@@ -234,6 +234,52 @@ def test_full_size_properties(codec, cfg):
     assert (psnr > 30.0) if not alpha else (psnr > 10.0)  # RGBA path of the reference is defective (Q6/Q7): ~13-25 dB
 
 
+def _trace_areas(tr, lo):
+    """areas of oracle/ref.py::blocked_trace -> the stream's area records (limg_b200.AREA_DTYPE)"""
+    from limg_b200 import AREA_DTYPE
+    r = tr["areas"]
+    a = np.zeros(len(r), dtype=AREA_DTYPE)
+    for k in ("ox", "oy", "rx", "ry", "stage", "px_x", "px_y", "px_w", "px_h", "shift", "ditherBefore", "ditherAfter"):
+        a[k] = r[k]
+    a["decomp"]["avg"] = r["avg"]
+    for i, name in enumerate(lo.FIELDS):
+        a["decomp"][name] = r["dec"][:, i, :]
+    return a
+
+
+@pytest.mark.parametrize("cfg", ["c2_4k_photo", "c4_4k_flatui", "c3_8k_rgba"])
+def test_full_size_bit_exact_vs_reference(codec, lo, ref_lib, cfg):
+    """BASELINE.json's full-size configs against the REAL reference (oracle/_ref/libref.so, limg.cpp:2329-2453 run on this
+    host): pass-1 table, area table (rectangles, stages, order, shifts, int16 decompositions, dither chain), the three code
+    planes, all 13 API planes, the standalone decode and the PSNR, bit for bit."""
+    img, alpha = synth.CONFIGS[cfg]()
+    h, w = img.shape
+    tr = ref_lib.blocked_trace(img, alpha, 100, True)
+    assert codec.pass1(img, alpha).tobytes() == lo.decomp_from_ref(tr["pass1"], alpha).tobytes()
+    st = codec.encode_stream(img, alpha, 100, True, decoded=True)
+    want = _trace_areas(tr, lo)
+    assert_areas_equal(st["areas"], want)
+    # the reference's factor streams are area-contiguous: scatter them into image layout
+    planes = [np.zeros((h, w), np.uint8) for _ in range(3)]
+    off = 0
+    for x, y, pw, ph in zip(want["px_x"], want["px_y"], want["px_w"], want["px_h"]):
+        n = int(pw) * int(ph)
+        for k in range(3):
+            planes[k][y:y + ph, x:x + pw] = tr["post"][k][off:off + n].reshape(ph, pw)
+        off += n
+    assert off == h * w
+    for k, name in enumerate(("codesA", "codesB", "codesC")):
+        assert np.array_equal(st[name], planes[k]), name
+    assert np.array_equal(st["decoded"], tr["planes"]["pDecoded"])
+    assert np.array_equal(codec.decode(st["areas"], st["codesA"], st["codesB"], st["codesC"], alpha), tr["planes"]["pDecoded"])
+    got = codec.blocked_encode3d_test(img, alpha, None, 100, True)
+    for k in H.PLANES:
+        assert np.array_equal(got[k], tr["planes"][k]), k
+    psnr, mse, _ = codec.compare(img, st["decoded"], alpha)
+    rpsnr, rmse, _ = ref_lib.compare(img, tr["planes"]["pDecoded"], alpha)
+    assert abs(psnr - rpsnr) < 1e-9 and abs(mse - rmse) < 1e-9
+
+
 def test_compare_matches_oracle(codec, lo):
     rng = np.random.default_rng(5)
     a = rng.integers(0, 2 ** 32, (97, 131), dtype=np.uint64).astype(np.uint32)

@@ -49,12 +49,15 @@ def test_partitions():
     assert sum(y1 - y0 for y0, y1 in bands) == 4320
     assert shard.row_bands(20, 4) == [(0, 8), (8, 16), (16, 20), (20, 20)]
     # exact row-band mode: the block-row ranges [y0 // 8, ceil(y1 / 8)) of the ranks own every block row exactly once
-    for h in (8, 20, 200, 1080, 2160, 4320, 4321):
+    # (also with more ranks than block rows and a ragged height: the empty bands own nothing)
+    for h in (8, 20, 36, 200, 1080, 2160, 4320, 4321):
         for world in (1, 2, 3, 4, 8):
             owners = []
             for y0, y1 in shard.row_bands(h, world):
-                owners += list(range(y0 // 8, (y1 + 7) // 8)) if y1 > y0 else []
+                lo, hi = shard.band_block_rows(y0, y1)
+                owners += list(range(lo, hi))
             assert owners == list(range((h + 7) // 8)), (h, world)
+    assert [shard.band_block_rows(*b) for b in shard.row_bands(36, 8)] == [(0, 1), (1, 2), (2, 3), (3, 4), (4, 5), (0, 0), (0, 0), (0, 0)]
 
 
 @pytest.mark.timeout(300)
