@@ -8,7 +8,7 @@
 //   reads   are local shared-memory loads (~30 cycles): the poll of the 32 rows above, the 32 x 96 snapshot, the candidate search;
 //   writes  (the claim of a rectangle, a progress value, the finished-rows count) go to every replica through distributed shared
 //           memory (red / st .shared::cluster), ordered by one cluster-scope fence between a claim and the progress that follows it;
-//   tickets come from rank 0's counter (one remote atomic per block row).
+//   rows    are handed out from rank 0's counters (one remote read and one remote atomic per block row).
 // What nobody waits for during the scan (owner times, the rows' rectangle lists, per-seed emission info) still goes to global
 // memory and is consumed by the verification and the area preparation as before; the final mask is written back by rank 0.
 // A cluster of 8 CTAs x 8 warps keeps 64 block rows in flight, about what the wavefront can use at 4K (BX / lag).
@@ -44,6 +44,13 @@ __device__ __forceinline__ void cluster_red_or(uint32_t caddr, uint32_t v) { asm
 __device__ __forceinline__ void cluster_red_max(uint32_t caddr, uint32_t v) { asm volatile("red.relaxed.cluster.shared::cluster.max.u32 [%0], %1;" :: "r"(caddr), "r"(v) : "memory"); }
 __device__ __forceinline__ void cluster_st(uint32_t caddr, uint32_t v) { asm volatile("st.relaxed.cluster.shared::cluster.u32 [%0], %1;" :: "r"(caddr), "r"(v) : "memory"); }
 
+__device__ __forceinline__ uint32_t cluster_ld(uint32_t caddr)
+{
+  uint32_t v;
+  asm volatile("ld.relaxed.cluster.shared::cluster.u32 %0, [%1];" : "=r"(v) : "r"(caddr) : "memory");
+  return v;
+}
+
 __device__ __forceinline__ uint32_t cluster_atom_add(uint32_t caddr, uint32_t v)
 {
   uint32_t r;
@@ -65,22 +72,21 @@ struct WaveCluster
 {
   typedef WordMask<SharedWords> Mask;
   const WaveArgs &a;
-  uint32_t sUsed, sProgress, sMisc; // this CTA's replica: mask [BY][wordsPerRow], progress [2][BY], misc { ticket (rank 0's counts), finished stage-0 rows }
+  uint32_t sUsed, sProgress, sMisc; // this CTA's replica: mask [BY][wordsPerRow], progress [2][BY], counters[4] (kernels_wave.cuh; the hand-out counters that count are rank 0's)
   uint32_t ranks;
 
   __device__ __forceinline__ Mask mask() const { return Mask{ SharedWords{ sUsed }, a.wordsPerRow, a.BX, a.BY }; }
 
-  __device__ __forceinline__ int take_ticket(int lane) const
+  // the hand-out counters are rank 0's; the done counters are replicated
+  __device__ __forceinline__ uint32_t peek_next(int stage) const { return cluster_ld(cluster_map(sMisc + 8u * (uint32_t)stage, 0)); }
+  __device__ __forceinline__ uint32_t take_next(int stage) const { return cluster_atom_add(cluster_map(sMisc + 8u * (uint32_t)stage, 0), 1u); }
+  __device__ __forceinline__ uint32_t done_rows(int stage) const { return lds_volatile(sMisc + 8u * (uint32_t)stage + 4u); }
+
+  __device__ __forceinline__ void set_done_rows(int stage, uint32_t n, int lane) const
   {
-    int t = 0;
-
-    if (lane == 0)
-      t = (int)cluster_atom_add(cluster_map(sMisc, 0), 1u);
-
-    return __shfl_sync(0xFFFFFFFFu, t, 0);
+    if ((uint32_t)lane < ranks)
+      cluster_red_max(cluster_map(sMisc + 8u * (uint32_t)stage + 4u, (uint32_t)lane), n);
   }
-
-  __device__ __forceinline__ uint32_t stage0_rows_done() const { return lds_volatile(sMisc + 4); }
 
   __device__ __forceinline__ void fence() const
   {
@@ -91,8 +97,16 @@ struct WaveCluster
   }
 
   __device__ __forceinline__ void acquire_fence() const { fence(); }
+
+  __device__ __forceinline__ void fence_sc() const
+  {
+    if (ranks == 1)
+      asm volatile("fence.sc.cta;" ::: "memory");
+    else
+      asm volatile("fence.sc.cluster;" ::: "memory");
+  }
+
   __device__ __forceinline__ int progress(int stage, int row) const { return (int)lds_volatile(sProgress + 4u * (uint32_t)(stage * a.BY + row)); }
-  __device__ __forceinline__ int progress_acquire(int stage, int row) const { return progress(stage, row); }
 
   // one lane per replica; a row's progress words are always written by the same lane, so every replica sees them in order
   __device__ __forceinline__ void publish(int stage, int y, int v, int lane) const
@@ -125,14 +139,6 @@ struct WaveCluster
     // every replica has the claim before any replica sees a progress value published after it
     fence();
     __syncwarp();
-  }
-
-  __device__ __forceinline__ void stage0_row_done(int y, int lane) const
-  {
-    fence();
-
-    if ((uint32_t)lane < ranks)
-      cluster_red_max(cluster_map(sMisc + 4, (uint32_t)lane), (uint32_t)(y + 1));
   }
 };
 

@@ -478,7 +478,8 @@ __global__ void __launch_bounds__(256, 4) k_decode(const limgcu_area *__restrict
 }
 
 // block map from an area table produced elsewhere
-__global__ void k_block_map(const limgcu_area *__restrict__ areas, uint32_t count, int BX, uint32_t *__restrict__ blockToArea)
+// (a rectangle that leaves the block grid is clipped: a table from outside never makes this kernel write out of bounds)
+__global__ void k_block_map(const limgcu_area *__restrict__ areas, uint32_t count, int BX, int BY, uint32_t *__restrict__ blockToArea)
 {
   const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
 
@@ -486,9 +487,11 @@ __global__ void k_block_map(const limgcu_area *__restrict__ areas, uint32_t coun
     return;
 
   const limgcu_area ar = areas[k];
+  const uint32_t x0 = min(ar.ox, (uint32_t)BX), y0 = min(ar.oy, (uint32_t)BY);
+  const uint32_t x1 = x0 + min(ar.rx, (uint32_t)BX - x0), y1 = y0 + min(ar.ry, (uint32_t)BY - y0);
 
-  for (uint32_t yy = ar.oy; yy < ar.oy + ar.ry; yy++)
-    for (uint32_t xx = ar.ox; xx < ar.ox + ar.rx; xx++)
+  for (uint32_t yy = y0; yy < y1; yy++)
+    for (uint32_t xx = x0; xx < x1; xx++)
       blockToArea[(size_t)yy * BX + xx] = k;
 }
 

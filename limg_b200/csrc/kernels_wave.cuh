@@ -66,7 +66,7 @@ struct WaveArgs
   uint32_t *used;            // [BY][wordsPerRow] live in-use bits (rows padded by two zero words)
   uint32_t *tau;             // [blocks] logical time of the rectangle that owns the block
   int *progress;             // [2][BY] column up to which the row's seeds are committed (LIMG_WAVE_DONE when finished)
-  uint32_t *ticket;          // [0] row tickets of both stages, [1] number of finished stage-0 rows
+  uint32_t *ticket;          // counters[4]: next stage-0 row, done stage-0 rows, next stage-1 row, done stage-1 rows
   uint2 *rowLists;           // [2][BY][listCap] (ox | oy << 16, rx | ry << 16) in emission order
   uint32_t *rowCounts;       // [2][BY]
   uint32_t *emitInfo;        // [2][blocks] per seed: first entry in its row list << 8 | number of entries
@@ -869,56 +869,125 @@ __device__ __forceinline__ int wave_next_candidate(const uint32_t *candRow, Used
 
 #define LIMG_WAVE_SPIN_LIMIT (1u << 22) // watchdog: a wait that long (seconds) is a bug; flag it instead of hanging the GPU
 
-// Order in which the block rows of the two merge stages are handed out. A stage-1 row needs stage 0 to be done down to `gap` rows
-// below it, so stage 1 can follow stage 0 at that distance: tickets 0 .. lead-1 are the first `lead` rows of stage 0, then the
-// stages alternate (stage-0 row lead + k, stage-1 row k), then the last `lead` rows of stage 1. Whatever a row waits for (the rows
-// above it in its own stage, stage-0 rows down to row + gap < row + lead) has an earlier ticket, so its owner is running or done.
-// lead >= BY gives the plain order: all of stage 0, then all of stage 1.
-__device__ __forceinline__ void wave_ticket_row(int t, int BY, int lead, int &stage, int &y)
-{
-  lead = min(lead, BY);
+// ---- how the rows of the scan coordinate (both back ends) -----------------------------------------------------------------
+// Per stage: a counter of rows handed out, one progress word per row (the column up to which the row's seeds are decided and their
+// claims fenced; LIMG_WAVE_DONE when the row is finished) and a counter of DONE rows: every row below it is finished. A row that
+// needs to know how far the rows above are takes the minimum of the progress words of the rows from the done counter up to itself:
+// no row relays anybody else's progress, so the information is as fresh as one read, and a finished row's warp is free at once.
+// Rows are handed out dynamically: the next stage-1 row if stage 0 is already done down to `stageGap` rows below it, else the
+// next stage-0 row, else (stage 0 handed out completely) the next stage-1 row. Whatever a row waits for (rows above it in its own
+// stage, stage-0 rows when every stage-0 row is handed out) is therefore held by a running warp or finished.
+// counters[4] = { next stage-0 row, done stage-0 rows, next stage-1 row, done stage-1 rows }.
 
-  if (t < lead)
+__device__ __forceinline__ void fence_sc_gpu() { asm volatile("fence.sc.gpu;" ::: "memory"); }
+
+// common part of the back ends' take_row(): lane 0 decides, the warp gets (stage, row) or false when nothing is left
+template <class Backend>
+__device__ __forceinline__ bool wave_take_row(const Backend &be, int BY, int gap, int sequential, int lane, int &stage, int &y)
+{
+  int packed = -1;
+
+  if (lane == 0)
   {
-    stage = 0;
-    y = t;
+    const int next1 = (int)be.peek_next(1);
+
+    if (next1 < BY && (int)be.done_rows(0) >= (sequential ? BY : min(next1 + gap + 1, BY)))
+    {
+      const int k = (int)be.take_next(1);
+
+      if (k < BY)
+        packed = (k << 1) | 1;
+    }
+
+    if (packed < 0 && (int)be.peek_next(0) < BY)
+    {
+      const int k = (int)be.take_next(0);
+
+      if (k < BY)
+        packed = k << 1;
+    }
+
+    if (packed < 0)
+    {
+      const int k = (int)be.take_next(1);
+
+      if (k < BY)
+        packed = (k << 1) | 1;
+    }
   }
-  else if (t < 2 * BY - lead)
+
+  packed = __shfl_sync(0xFFFFFFFFu, packed, 0);
+  stage = packed & 1;
+  y = packed >> 1;
+  return packed >= 0;
+}
+
+// minimum of the progress words of the unfinished rows above row y (LIMG_WAVE_DONE if there is none)
+template <class Backend>
+__device__ __forceinline__ int wave_rows_above(const Backend &be, int stage, int y, int lane)
+{
+  const int base = (int)be.done_rows(stage); // read first: rows finishing meanwhile only add reads
+  int p = LIMG_WAVE_DONE;
+
+  for (int r0 = y - 1; r0 >= base; r0 -= 32)
   {
-    const int k = t - lead;
-    stage = k & 1;
-    y = stage ? (k >> 1) : lead + (k >> 1);
+    const int r = r0 - lane;
+
+    if (r >= base)
+      p = min(p, be.progress(stage, r));
   }
-  else
+
+  return __reduce_min_sync(0xFFFFFFFFu, p);
+}
+
+// after the row published LIMG_WAVE_DONE: move the stage's done counter over every leading finished row. Two rows that finish at the
+// same time must not both miss the other's DONE word (store, sequentially consistent fence, then the reads).
+template <class Backend>
+__device__ __forceinline__ void wave_advance_done(const Backend &be, int stage, int BY, int lane)
+{
+  be.fence_sc();
+  const int before = (int)be.done_rows(stage);
+  int b = before;
+
+  for (;;)
   {
-    stage = 1;
-    y = t - BY;
+    const bool done = b + lane < BY && be.progress(stage, b + lane) == LIMG_WAVE_DONE;
+    const uint32_t notDone = ~__ballot_sync(0xFFFFFFFFu, done);
+    const int n = notDone ? __ffs(notDone) - 1 : 32;
+    b += n;
+
+    if (n < 32)
+      break;
+  }
+
+  if (b > before)
+  {
+    be.acquire_fence(); // what the finished rows claimed is visible to whoever sees the new count
+    be.set_done_rows(stage, (uint32_t)b, lane);
   }
 }
 
-// The scan's shared state (in-use mask, row progress, tickets) in GLOBAL memory, read and written at L2: any grid, any image size.
+// The scan's shared state (in-use mask, row progress, counters) in GLOBAL memory, read and written at L2: any grid, any image size.
 struct WaveGlobal
 {
   typedef LiveMask Mask;
   const WaveArgs &a;
 
   __device__ __forceinline__ Mask mask() const { return LiveMask{ GlobalWords{ a.used }, a.wordsPerRow, a.BX, a.BY }; }
+  __device__ __forceinline__ uint32_t peek_next(int stage) const { return ld_relaxed_u32(&a.ticket[2 * stage]); }
+  __device__ __forceinline__ uint32_t take_next(int stage) const { return atomicAdd(&a.ticket[2 * stage], 1u); }
+  __device__ __forceinline__ uint32_t done_rows(int stage) const { return ld_relaxed_u32(&a.ticket[2 * stage + 1]); }
 
-  __device__ __forceinline__ int take_ticket(int lane) const
+  __device__ __forceinline__ void set_done_rows(int stage, uint32_t n, int lane) const
   {
-    int t = 0;
-
     if (lane == 0)
-      t = (int)atomicAdd(&a.ticket[0], 1u);
-
-    return __shfl_sync(0xFFFFFFFFu, t, 0);
+      atomicMax(&a.ticket[2 * stage + 1], n);
   }
 
-  __device__ __forceinline__ uint32_t stage0_rows_done() const { return ld_relaxed_u32(&a.ticket[1]); }
   // everything read after this fence is at least as new as what was read before it
   __device__ __forceinline__ void acquire_fence() const { fence_acq_rel_gpu(); }
+  __device__ __forceinline__ void fence_sc() const { fence_sc_gpu(); }
   __device__ __forceinline__ int progress(int stage, int row) const { return ld_relaxed_s32(a.progress + (size_t)stage * a.BY + row); }
-  __device__ __forceinline__ int progress_acquire(int stage, int row) const { return ld_acquire_s32(a.progress + (size_t)stage * a.BY + row); }
 
   __device__ __forceinline__ void publish(int stage, int y, int v, int lane) const
   {
@@ -949,16 +1018,6 @@ struct WaveGlobal
     __threadfence();
     __syncwarp();
   }
-
-  // rows finish in order (a row publishes DONE only after every row above it did): the count of finished stage-0 rows
-  __device__ __forceinline__ void stage0_row_done(int y, int lane) const
-  {
-    if (lane == 0)
-    {
-      __threadfence();
-      atomicMax(&a.ticket[1], (uint32_t)(y + 1));
-    }
-  }
 };
 
 // One warp per block row, rows by ticket, both merge stages in one launch. A stage-1 row starts once stage 0 is done with every
@@ -972,7 +1031,6 @@ __device__ void wave_scan_rows(const WaveArgs &a, const Backend &be, int attempt
   WaveScan<CH, typename Backend::Mask> scan{ a, be.mask(), lane, 0 };
   scan.scratch = scratch;
   const int nWords = (a.BX + 31) >> 5;
-  const int lead = sequential ? a.BY : a.stageGap + 8;
   uint32_t nExp[2] = { 0, 0 }, nReexp[2] = { 0, 0 }, nPolls[2] = { 0, 0 }, nOnDemand[2] = { 0, 0 };
   long long tNext = 0, tWait = 0, tExpand = 0, tClaim = 0, tPre = 0, tc;
   long long cSeedStart = 0, cPre = 0, cWait = 0, cExp = 0, cClaim = 0, cTotal[2] = { 0, 0 }, cParts[2][4] = { { 0, 0, 0, 0 }, { 0, 0, 0, 0 } };
@@ -981,13 +1039,11 @@ __device__ void wave_scan_rows(const WaveArgs &a, const Backend &be, int attempt
 
   for (;;)
   {
-    const int t = be.take_ticket(lane);
+    int stage, y;
 
-    if (t >= 2 * a.BY)
+    if (!wave_take_row(be, a.BY, a.stageGap, sequential, lane, stage, y))
       break;
 
-    int stage, y;
-    wave_ticket_row(t, a.BY, lead, stage, y);
     const uint32_t *cand = a.candBits + (size_t)stage * a.BY * a.wordsPerRow;
     uint2 *lists = a.rowLists + (size_t)stage * a.BY * a.listCap;
     uint32_t *emitInfo = a.emitInfo + (size_t)stage * a.BX * a.BY;
@@ -1003,7 +1059,7 @@ __device__ void wave_scan_rows(const WaveArgs &a, const Backend &be, int attempt
       {
         uint32_t spins = 0;
 
-        while (be.stage0_rows_done() < need)
+        while (be.done_rows(0) < need)
         {
           if (++spins > (LIMG_WAVE_SPIN_LIMIT << 3)) { a.flags[3] = 1; break; }
           __nanosleep(200);
@@ -1021,7 +1077,7 @@ __device__ void wave_scan_rows(const WaveArgs &a, const Backend &be, int attempt
       {
         uint32_t spins = 0;
 
-        while (be.progress_acquire(stage, y - 1) != LIMG_WAVE_DONE)
+        while ((int)be.done_rows(stage) < y)
         {
           if (++spins > (LIMG_WAVE_SPIN_LIMIT << 3)) { a.flags[3] = 1; break; }
           __nanosleep(100);
@@ -1041,23 +1097,14 @@ __device__ void wave_scan_rows(const WaveArgs &a, const Backend &be, int attempt
     uint2 *list = lists + (size_t)y * a.listCap;
     uint32_t count = 0;
     int x = 0, published = 0, nEvents = 0, xEvent = 0;
-    int pAbove = (y == 0 || sequential) ? LIMG_WAVE_DONE : 0; // last observed minimum over the rows above
 
-    // a row never claims to be further than the rows above it: the published values fall monotonically from row to row, so
-    // looking at the 32 rows above is as good as looking at all of them
+    // the row's own progress: every seed left of `own` is decided, and its claims were fenced when they were made
     auto publish = [&](int own) {
-      const int v = min(own, pAbove);
-
-      if (v > published)
+      if (own > published)
       {
-        be.publish(stage, y, v, lane);
-        published = v;
+        be.publish(stage, y, own, lane);
+        published = own;
       }
-    };
-
-    auto rows_above = [&]() -> int {
-      const int row = y - 1 - lane;
-      return __reduce_min_sync(0xFFFFFFFFu, row >= 0 ? be.progress(stage, row) : LIMG_WAVE_DONE);
     };
 
     for (;;)
@@ -1065,7 +1112,6 @@ __device__ void wave_scan_rows(const WaveArgs &a, const Backend &be, int attempt
       tc = wave_clock();
       x = wave_next_candidate(candRow, [&](int dy, int w) { return be.used_word(y + dy, w); }, nWords, x, a.BX, stage, lane);
 
-      // every seed left of x is decided, and its claims were fenced when they were made
       publish(x >= a.BX ? LIMG_WAVE_DONE : x);
       tNext += wave_clock() - tc;
 
@@ -1098,11 +1144,7 @@ __device__ void wave_scan_rows(const WaveArgs &a, const Backend &be, int attempt
           int p = LIMG_WAVE_DONE;
 
           if (y > 0 && !sequential)
-          {
-            p = rows_above();
-            pAbove = p;
-            publish(x);
-          }
+            p = wave_rows_above(be, stage, y, lane);
 
           if (p < min(x + 1 + a.margin - a.specAhead, a.BX))
           {
@@ -1260,22 +1302,8 @@ __device__ void wave_scan_rows(const WaveArgs &a, const Backend &be, int attempt
     if (rowT && lane == 0)
       rowT[3] = global_ns();
 
-    // the row is done, but it keeps relaying the progress of the rows above until they are done too
-    for (uint32_t spins = 0; published != LIMG_WAVE_DONE; spins++)
-    {
-      pAbove = rows_above();
-      publish(LIMG_WAVE_DONE);
-
-      if (published == LIMG_WAVE_DONE)
-        break;
-
-      if (spins > LIMG_WAVE_SPIN_LIMIT) { a.flags[3] = 1; be.publish(stage, y, LIMG_WAVE_DONE, lane); break; }
-
-      __nanosleep(100);
-    }
-
-    if (stage == 0)
-      be.stage0_row_done(y, lane);
+    // the row published LIMG_WAVE_DONE when it ran out of candidates
+    wave_advance_done(be, stage, a.BY, lane);
 
     nOnDemand[stage] += scan.nOnDemand - onDemandBefore;
   }
@@ -1556,7 +1584,7 @@ __global__ void __launch_bounds__(256) k_merge_reset(WaveArgs a, int attempt)
       a.rowCounts[b] = 0;
     }
 
-    if (b < 2)
+    if (b < 4)
       a.ticket[b] = 0;
   }
 }

@@ -45,7 +45,7 @@ struct limgcu_ctx
   LcgJumpTable jt;
 
   // per-image working set, grown on demand
-  size_t capBlocks = 0, capPixels = 0, capUsedWords = 0;
+  size_t capBlocks = 0, capDecodeBlocks = 0, capPixels = 0, capUsedWords = 0;
   limgcu_decomp *dTable = nullptr;
   PredRec *dRec = nullptr;
   uint32_t *dWindow = nullptr;
@@ -73,7 +73,7 @@ struct limgcu_ctx
   unsigned long long *dCompare = nullptr;
 
   // host-buffer staging
-  size_t capStagePixels = 0;
+  size_t capStagePixels = 0, capDecodeStagePixels = 0;
   uint32_t *dSrc = nullptr;
   uint32_t *dPlaneU32[9] = { nullptr };
   uint8_t *dPlaneU8[7] = { nullptr }; // factors A,B,C, bpp, codes A,B,C
@@ -82,7 +82,7 @@ struct limgcu_ctx
   size_t capPayload = 0, capPayloadOff = 0;
 
   // wavefront merge (kernels_wave.cuh)
-  uint32_t *dWaveZero = nullptr; // flags[8] ticket[2] candCount[2] pad[4] | progress[2*BY] | rowCounts[2*BY] | candBits[2*usedWords] | emitInfo[2*blocks]
+  uint32_t *dWaveZero = nullptr; // flags[8] pad[2] candCount[2] counters[4] | progress[2*BY] | rowCounts[2*BY] | candBits[2*usedWords] | emitInfo[2*blocks]
   uint32_t *dReplayList = nullptr, *dReplayCount = nullptr;
   uint32_t *dTau = nullptr, *dCandList = nullptr, *dWaveDbg = nullptr, *dWaveRows = nullptr;
   size_t capWaveRows = 0;
@@ -129,7 +129,33 @@ static cudaError_t regrow(T *&p, size_t count)
     cudaFree(p);
 
   p = nullptr;
-  return cudaMalloc(reinterpret_cast<void **>(&p), count * sizeof(T));
+  const cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&p), count * sizeof(T));
+
+  if (e != cudaSuccess)
+  {
+    p = nullptr;
+    cudaGetLastError(); // a failed allocation must not be reported again by the next launch check
+  }
+
+  return e;
+}
+
+// A capacity is set to 0 before its buffers are freed, so a failed allocation leaves the context consistent (the next call allocates again).
+
+// what the decoders need per block: the area table and the block map
+static int ensure_decode_capacity(limgcu_ctx *ctx, size_t W, size_t H)
+{
+  const size_t blocks = ((W + 7) / 8) * ((H + 7) / 8);
+
+  if (blocks > ctx->capDecodeBlocks)
+  {
+    ctx->capDecodeBlocks = 0;
+    CK(regrow(ctx->dAreas, blocks));
+    CK(regrow(ctx->dBlockToArea, blocks));
+    ctx->capDecodeBlocks = blocks;
+  }
+
+  return LIMGCU_SUCCESS;
 }
 
 static int ensure_capacity(limgcu_ctx *ctx, size_t W, size_t H)
@@ -137,14 +163,15 @@ static int ensure_capacity(limgcu_ctx *ctx, size_t W, size_t H)
   const size_t BX = (W + 7) / 8, BY = (H + 7) / 8;
   const size_t blocks = BX * BY, pixels = W * H;
   const size_t usedWords = BY * ((BX + 31) / 32 + 2);
+  int rc = ensure_decode_capacity(ctx, W, H);
+  if (rc) return rc;
 
   if (blocks > ctx->capBlocks)
   {
+    ctx->capBlocks = 0;
     CK(regrow(ctx->dTable, blocks));
     CK(regrow(ctx->dRec, blocks));
     CK(regrow(ctx->dWindow, blocks * 2));
-    CK(regrow(ctx->dAreas, blocks));
-    CK(regrow(ctx->dBlockToArea, blocks));
     CK(regrow(ctx->dWork, blocks));
     CK(regrow(ctx->dSmallList, blocks));
     CK(regrow(ctx->dLargeList, blocks));
@@ -176,18 +203,21 @@ static int ensure_capacity(limgcu_ctx *ctx, size_t W, size_t H)
 
     if (waveZero > ctx->capWaveZero)
     {
+      ctx->capWaveZero = 0;
       CK(regrow(ctx->dWaveZero, waveZero));
       ctx->capWaveZero = waveZero;
     }
 
     if (4 * BY > ctx->capRowMeta)
     {
+      ctx->capRowMeta = 0;
       CK(regrow(ctx->dRowMeta, 4 * BY));
       ctx->capRowMeta = 4 * BY;
     }
 
     if (rowLists > ctx->capRowLists)
     {
+      ctx->capRowLists = 0;
       CK(regrow(ctx->dRowLists, rowLists));
       ctx->capRowLists = rowLists;
     }
@@ -195,12 +225,14 @@ static int ensure_capacity(limgcu_ctx *ctx, size_t W, size_t H)
 
   if (usedWords > ctx->capUsedWords)
   {
+    ctx->capUsedWords = 0;
     CK(regrow(ctx->dUsed, usedWords));
     ctx->capUsedWords = usedWords;
   }
 
   if (pixels > ctx->capPixels)
   {
+    ctx->capPixels = 0;
     CK(regrow(ctx->dScratchPx, pixels));
     CK(regrow(ctx->dScratchFac, pixels));
     ctx->capPixels = pixels;
@@ -209,18 +241,38 @@ static int ensure_capacity(limgcu_ctx *ctx, size_t W, size_t H)
   return LIMGCU_SUCCESS;
 }
 
+// what the host-buffer decoders stage per pixel: the three code planes and the output (7 B/px; the encoders' staging is 47 B/px)
+static int ensure_decode_staging(limgcu_ctx *ctx, size_t pixels)
+{
+  if (pixels <= ctx->capDecodeStagePixels)
+    return LIMGCU_SUCCESS;
+
+  ctx->capDecodeStagePixels = 0;
+  CK(regrow(ctx->dPlaneU32[0], pixels));
+
+  for (int i = 4; i < 7; i++)
+    CK(regrow(ctx->dPlaneU8[i], pixels));
+
+  ctx->capDecodeStagePixels = pixels;
+  return LIMGCU_SUCCESS;
+}
+
 static int ensure_staging(limgcu_ctx *ctx, size_t pixels)
 {
+  int rc = ensure_decode_staging(ctx, pixels);
+  if (rc) return rc;
+
   if (pixels <= ctx->capStagePixels)
     return LIMGCU_SUCCESS;
 
+  ctx->capStagePixels = 0;
   CK(regrow(ctx->dSrc, pixels));
 
-  for (auto &p : ctx->dPlaneU32)
-    CK(regrow(p, pixels));
+  for (int i = 1; i < 9; i++)
+    CK(regrow(ctx->dPlaneU32[i], pixels));
 
-  for (auto &p : ctx->dPlaneU8)
-    CK(regrow(p, pixels));
+  for (int i = 0; i < 4; i++)
+    CK(regrow(ctx->dPlaneU8[i], pixels));
 
   ctx->capStagePixels = pixels;
   return LIMGCU_SUCCESS;
@@ -298,7 +350,7 @@ extern "C" int limgcu_create(int device, limgcu_ctx **out)
   if (const char *v = getenv("LIMGCU_MERGE_EXT")) ctx->mergeExt = atoi(v);
 
   if (const char *v = getenv("LIMGCU_MERGE_MODE")) ctx->mergeMode = !strcmp(v, "seq") ? 1 : 0;
-  if (const char *v = getenv("LIMGCU_SCAN_CLUSTER")) ctx->scanCluster = atoi(v) < 0 ? 0 : (atoi(v) > 8 ? 8 : atoi(v));
+  if (const char *v = getenv("LIMGCU_SCAN_CLUSTER")) ctx->scanCluster = atoi(v) < 0 ? 0 : (atoi(v) > 16 ? 16 : atoi(v));
   if (const char *v = getenv("LIMGCU_MERGE_MARGIN")) ctx->mergeMargin = atoi(v) < 0 ? 0 : atoi(v);
   if (const char *v = getenv("LIMGCU_PLAN_EXTW")) ctx->planExtW = atoi(v) < 8 ? 8 : (atoi(v) > 32 ? 32 : atoi(v));
   if (const char *v = getenv("LIMGCU_PLAN_SYML")) ctx->planSymL = atoi(v) < 1 ? 1 : (atoi(v) > 8 ? 8 : atoi(v));
@@ -325,6 +377,8 @@ extern "C" int limgcu_create(int device, limgcu_ctx **out)
     cudaDeviceGetAttribute(&ctx->scanSmemLimit, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     cudaFuncSetAttribute(k_merge_cta<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->scanSmemLimit);
     cudaFuncSetAttribute(k_merge_cta<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->scanSmemLimit);
+    cudaFuncSetAttribute(k_merge_cta<3>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1); // LIMGCU_SCAN_CLUSTER=16
+    cudaFuncSetAttribute(k_merge_cta<4>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
   }
 
   *out = ctx;
@@ -493,7 +547,7 @@ static int launch_merge(limgcu_ctx *ctx, const limgcu_decomp *dTable, size_t W, 
 
     const size_t usedWords = (size_t)BY * wordsPerRow;
     uint32_t *wz = ctx->dWaveZero;
-    uint32_t *wFlags = wz, *wTicket = wz + 8, *wCandCount = wz + 10;
+    uint32_t *wFlags = wz, *wCandCount = wz + 10, *wTicket = wz + 12;
     int *wProgress = reinterpret_cast<int *>(wz + 16);
     uint32_t *wRowCounts = wz + 16 + 2 * BY, *wCandBits = wz + 16 + 4 * BY, *wEmitInfo = wCandBits + 2 * usedWords;
     CK(cudaMemsetAsync(wz, 0, (16 + 4 * (size_t)BY + 2 * usedWords + 2 * (size_t)blocks) * sizeof(uint32_t), ctx->stream));
@@ -787,6 +841,7 @@ static int ensure_aes(limgcu_ctx *ctx, size_t W, size_t H)
 
   if (blocks > ctx->capAesBlocks)
   {
+    ctx->capAesBlocks = 0;
     CK(regrow_host(ctx->hAreas, blocks));
     CK(regrow_host(ctx->hNoiseOff, 3 * blocks));
     CK(regrow_host(ctx->hStates, 2 * blocks));
@@ -797,6 +852,7 @@ static int ensure_aes(limgcu_ctx *ctx, size_t W, size_t H)
 
   if (pixels > ctx->capAesPixels)
   {
+    ctx->capAesPixels = 0;
     CK(regrow_host(ctx->hNoise, 3 * pixels));
     CK(regrow(ctx->dNoise, 3 * pixels));
     ctx->capAesPixels = pixels;
@@ -945,7 +1001,7 @@ static int launch_dither_finalize(limgcu_ctx *ctx, const uint32_t *d_src, size_t
                       f.planes.pBitsPerPixel || f.planes.pShiftABCX || f.planes.pColAMin || f.planes.pColAMax || f.planes.pColBMin || f.planes.pColBMax ||
                       f.planes.pColCMin || f.planes.pColCMax || f.planes.pBlockIndex;
 
-  if (anyOut) // limg_encode3d_test_perf writes nothing (limg.cpp:2141-2173)
+  if (anyOut && yHi > yLo) // limg_encode3d_test_perf writes nothing (limg.cpp:2141-2173); an empty row band (sharded path) has no rows to write
   {
     const long long segs = (long long)((W + 7) / 8) * (long long)(yHi - yLo);
     const int grid = (int)((segs + 255) / 256);
@@ -1117,13 +1173,17 @@ extern "C" int limgcu_build_block_map(limgcu_ctx *ctx, const limgcu_area *d_area
   NEED(ctx); NEED(d_areas); NEED(d_block_to_area);
   CK(cudaSetDevice(ctx->device));
 
+  // A block no rectangle covers maps to area 0, which exists: a table that does not tile the grid (the host entry points reject one,
+  // area_table_valid()) decodes to garbage but never indexes outside the table.
+  const size_t BX = (sizeX + 7) / 8, BY = (sizeY + 7) / 8;
+  CK(cudaMemsetAsync(d_block_to_area, 0, BX * BY * sizeof(uint32_t), ctx->stream));
+
   if (area_count)
   {
-    k_block_map<<<(area_count + 255) / 256, 256, 0, ctx->stream>>>(d_areas, area_count, (int)((sizeX + 7) / 8), d_block_to_area);
+    k_block_map<<<(area_count + 255) / 256, 256, 0, ctx->stream>>>(d_areas, area_count, (int)BX, (int)BY, d_block_to_area);
     CKL("k_block_map");
   }
 
-  (void)sizeY;
   return LIMGCU_SUCCESS;
 }
 
@@ -1340,6 +1400,46 @@ extern "C" int limgcu_host_encode_stream(limgcu_ctx *ctx, const uint32_t *pIn, s
   return host_encode(ctx, pIn, sizeX, sizeY, hasAlpha, &p, errorFactor, flags, areas, area_count, codesA, codesB, codesC);
 }
 
+// Host-side check of an area table that comes from outside (a stream handed to the decoder, a container): the kernels index the block
+// map, the code planes and the table itself with what it says. Every rectangle lies inside the block grid, the rectangles cover every
+// block exactly once, the shifts are at most 8 and the pixel rectangles are the ones the block rectangles imply.
+static bool area_table_valid(const limgcu_area *areas, uint32_t count, size_t W, size_t H)
+{
+  const size_t BX = (W + 7) / 8, BY = (H + 7) / 8;
+
+  if (count == 0 || (size_t)count > BX * BY)
+    return false;
+
+  std::vector<uint8_t> covered(BX * BY, 0);
+  size_t coveredBlocks = 0;
+
+  for (uint32_t k = 0; k < count; k++)
+  {
+    const limgcu_area &a = areas[k];
+
+    if (a.rx == 0 || a.ry == 0 || (size_t)a.ox + a.rx > BX || (size_t)a.oy + a.ry > BY || a.shift[0] > 8 || a.shift[1] > 8 || a.shift[2] > 8)
+      return false;
+
+    const size_t pw = (size_t)a.rx * 8 < W - (size_t)a.ox * 8 ? (size_t)a.rx * 8 : W - (size_t)a.ox * 8;
+    const size_t ph = (size_t)a.ry * 8 < H - (size_t)a.oy * 8 ? (size_t)a.ry * 8 : H - (size_t)a.oy * 8;
+
+    if (a.px_x != a.ox * 8 || a.px_y != a.oy * 8 || a.px_w != pw || a.px_h != ph)
+      return false;
+
+    for (uint32_t y = a.oy; y < a.oy + a.ry; y++)
+      for (uint32_t x = a.ox; x < a.ox + a.rx; x++)
+      {
+        if (covered[(size_t)y * BX + x])
+          return false;
+
+        covered[(size_t)y * BX + x] = 1;
+        coveredBlocks++;
+      }
+  }
+
+  return coveredBlocks == BX * BY;
+}
+
 extern "C" int limgcu_host_decode(limgcu_ctx *ctx, const limgcu_area *areas, uint32_t area_count, const uint8_t *codesA, const uint8_t *codesB, const uint8_t *codesC,
                                   size_t sizeX, size_t sizeY, int hasAlpha, uint32_t *pOut)
 {
@@ -1348,14 +1448,14 @@ extern "C" int limgcu_host_decode(limgcu_ctx *ctx, const limgcu_area *areas, uin
   if (rc) return rc;
   CK(cudaSetDevice(ctx->device));
   const size_t n = sizeX * sizeY;
-  rc = ensure_staging(ctx, n);
-  if (rc) return rc;
-  rc = ensure_capacity(ctx, sizeX, sizeY);
-  if (rc) return rc;
 
-  if ((size_t)area_count > ctx->capBlocks)
-    return fail(ctx, LIMGCU_ERROR_OUT_OF_BOUNDS, "more areas than blocks", cudaSuccess);
+  if (!area_table_valid(areas, area_count, sizeX, sizeY))
+    return fail(ctx, LIMGCU_ERROR_INVALID_PARAMETER, "limgcu_host_decode: the area table does not tile the image (or a shift is above 8)", cudaSuccess);
 
+  rc = ensure_decode_staging(ctx, n);
+  if (rc) return rc;
+  rc = ensure_decode_capacity(ctx, sizeX, sizeY);
+  if (rc) return rc;
   CK(cudaMemcpyAsync(ctx->dAreas, areas, (size_t)area_count * sizeof(limgcu_area), cudaMemcpyHostToDevice, ctx->stream));
   rc = limgcu_build_block_map(ctx, ctx->dAreas, area_count, sizeX, sizeY, ctx->dBlockToArea);
   if (rc) return rc;
@@ -1434,18 +1534,21 @@ extern "C" size_t limgcu_container_bound(size_t sizeX, size_t sizeY, int hasAlph
   return sizeof(ContainerHeader) + blocks * container_record_bytes(hasAlpha) + container_payload_bound(sizeX, sizeY);
 }
 
-static int ensure_payload(limgcu_ctx *ctx, size_t W, size_t H)
+// payloadBytes == 0: room for the largest payload an image of this size can have (the encoder does not know it in advance)
+static int ensure_payload(limgcu_ctx *ctx, size_t W, size_t H, size_t payloadBytes = 0)
 {
-  const size_t bytes = container_payload_bound(W, H) + 16, entries = ((W + 7) / 8) * ((H + 7) / 8) + 1;
+  const size_t bytes = (payloadBytes ? payloadBytes : container_payload_bound(W, H)) + 16, entries = ((W + 7) / 8) * ((H + 7) / 8) + 1;
 
   if (bytes > ctx->capPayload)
   {
+    ctx->capPayload = 0;
     CK(regrow(ctx->dPayload, bytes));
     ctx->capPayload = bytes;
   }
 
   if (entries > ctx->capPayloadOff)
   {
+    ctx->capPayloadOff = 0;
     CK(regrow(ctx->dPayloadOff, entries));
     ctx->capPayloadOff = entries;
   }
@@ -1620,38 +1723,31 @@ extern "C" int limgcu_host_decode_container(limgcu_ctx *ctx, const void *data, s
   if (outPixels < W * H)
     return fail(ctx, LIMGCU_ERROR_OUT_OF_BOUNDS, "output buffer smaller than sizeX * sizeY", cudaSuccess);
 
-  CK(cudaSetDevice(ctx->device));
+  // Nothing is allocated from what the (unauthenticated) header claims before the table is known to be sound: records -> area table; the
+  // rectangles must tile the block grid exactly and the payload must have the size the table implies.
   const size_t n = W * H, BX = (W + 7) / 8, BY = (H + 7) / 8;
-  rc = ensure_staging(ctx, n);
-  if (rc) return rc;
-  rc = ensure_capacity(ctx, W, H);
-  if (rc) return rc;
-  rc = ensure_payload(ctx, W, H);
-  if (rc) return rc;
-
-  // records -> area table; the rectangles must tile the block grid exactly (a corrupt table would make the kernels read out of bounds)
   const size_t recordBytes = container_record_bytes(hasAlpha), ch = hasAlpha ? 4 : 3;
   const uint8_t *p = static_cast<const uint8_t *>(data) + sizeof(ContainerHeader);
-  limgcu_area *areas = static_cast<limgcu_area *>(calloc(count, sizeof(limgcu_area)));
-  uint8_t *covered = static_cast<uint8_t *>(calloc(BX * BY, 1));
-  bool ok = areas != nullptr && covered != nullptr;
-  uint64_t expectPayload = 0, coveredBlocks = 0;
 
-  for (uint32_t k = 0; ok && k < count; k++)
+  if ((size_t)count > BX * BY || bytes < sizeof(ContainerHeader) + (size_t)count * recordBytes + payloadBytes)
+    return fail(ctx, LIMGCU_ERROR_INVALID_PARAMETER, "container: more areas than blocks, or shorter than its table and payload", cudaSuccess);
+
+  limgcu_area *areas = static_cast<limgcu_area *>(calloc(count ? count : 1, sizeof(limgcu_area)));
+
+  if (areas == nullptr)
+    return fail(ctx, LIMGCU_ERROR_MEMORY_ALLOCATION_FAILURE, "container: area table", cudaSuccess);
+
+  for (uint32_t k = 0; k < count; k++)
   {
     ContainerRecordHead r;
     memcpy(&r, p, sizeof(r));
     p += sizeof(r);
     limgcu_area &a = areas[k];
     a.ox = r.ox; a.oy = r.oy; a.rx = r.rx; a.ry = r.ry; a.stage = r.stage;
-    ok = r.rx > 0 && r.ry > 0 && (size_t)r.ox + r.rx <= BX && (size_t)r.oy + r.ry <= BY && r.shift[0] <= 8 && r.shift[1] <= 8 && r.shift[2] <= 8;
-
-    if (!ok)
-      break;
-
     a.px_x = a.ox * 8; a.px_y = a.oy * 8;
-    a.px_w = (uint32_t)((size_t)a.rx * 8 < W - a.px_x ? (size_t)a.rx * 8 : W - a.px_x);
-    a.px_h = (uint32_t)((size_t)a.ry * 8 < H - a.px_y ? (size_t)a.ry * 8 : H - a.px_y);
+    // (garbage for a rectangle outside the grid, which area_table_valid() rejects below)
+    a.px_w = (uint32_t)((size_t)a.rx * 8 < W - (size_t)a.px_x ? (size_t)a.rx * 8 : W - (size_t)a.px_x);
+    a.px_h = (uint32_t)((size_t)a.ry * 8 < H - (size_t)a.px_y ? (size_t)a.ry * 8 : H - (size_t)a.px_y);
     memcpy(a.shift, r.shift, 3);
     int16_t *fields[6] = { a.decomp.dirA_min, a.decomp.dirA_max, a.decomp.dirB_offset, a.decomp.dirB_mag, a.decomp.dirC_offset, a.decomp.dirC_mag };
 
@@ -1660,26 +1756,36 @@ extern "C" int limgcu_host_decode_container(limgcu_ctx *ctx, const void *data, s
       memcpy(f, p, ch * sizeof(int16_t));
       p += ch * sizeof(int16_t);
     }
+  }
 
-    for (uint32_t y = a.oy; ok && y < a.oy + a.ry; y++)
-      for (uint32_t x = a.ox; x < a.ox + a.rx; x++)
-      {
-        if (covered[(size_t)y * BX + x]) { ok = false; break; }
-        covered[(size_t)y * BX + x] = 1;
-        coveredBlocks++;
-      }
+  bool ok = area_table_valid(areas, count, W, H);
+  uint64_t expectPayload = 0;
 
+  for (uint32_t k = 0; ok && k < count; k++)
+  {
+    const limgcu_area &a = areas[k];
     expectPayload += (uint64_t)((a.px_w + 7) / 8) * a.px_h *
                      (container_code_bits(a.shift[0], hasAlpha != 0) + container_code_bits(a.shift[1], hasAlpha != 0) + container_code_bits(a.shift[2], hasAlpha != 0));
   }
 
-  ok = ok && coveredBlocks == (uint64_t)BX * BY && expectPayload == payloadBytes;
-  free(covered);
+  ok = ok && expectPayload == payloadBytes;
 
   if (!ok)
   {
     free(areas);
     return fail(ctx, LIMGCU_ERROR_INVALID_PARAMETER, "container: the area table does not tile the image or does not match the payload size", cudaSuccess);
+  }
+
+  // only what the decode needs: three code planes, the output, the area table, the block map, the payload
+  CK(cudaSetDevice(ctx->device));
+  rc = ensure_decode_staging(ctx, n);
+  if (rc == LIMGCU_SUCCESS) rc = ensure_decode_capacity(ctx, W, H);
+  if (rc == LIMGCU_SUCCESS) rc = ensure_payload(ctx, W, H, (size_t)payloadBytes + 1);
+
+  if (rc)
+  {
+    free(areas);
+    return rc;
   }
 
   cudaError_t e = cudaMemcpyAsync(ctx->dAreas, areas, (size_t)count * sizeof(limgcu_area), cudaMemcpyHostToDevice, ctx->stream);

@@ -148,6 +148,59 @@ def test_gpu_container_rejects_a_table_that_does_not_tile(codec):
 
 
 @pytest.mark.gpu
+def test_gpu_container_that_claims_a_huge_image_is_rejected_before_anything_is_allocated(codec):
+    """A ~100-byte file whose header claims 65528 x 65528 pixels: the table is validated on the host first, nothing is allocated from the
+    header's claim, and the context decodes a sound container right afterwards."""
+    from limg_b200 import LimgError
+    g = H.load_golden("rgb_photo_96x64")
+    good = golden_container(g)
+    magic, version, flags, w, h, count, rec, payload, rsv = oc.HEADER.unpack(good[:48])
+    # one record, claims to cover a block rectangle that is not the whole (huge) grid: must fail in validation
+    fake = oc.HEADER.pack(magic, version, flags, 65528, 65528, 1, rec, 0, rsv) + good[48:48 + rec]
+    launches = codec.launch_count()
+    with pytest.raises(LimgError):
+        _decode_raw(codec, fake, 65528 * 65528)
+    assert codec.launch_count() == launches  # no kernel ran
+    assert np.array_equal(codec.decode_container(good), g["plane_pDecoded"])
+
+
+def _decode_raw(codec, data, out_pixels):
+    """limgcu_host_decode_container with a caller-declared output size but a tiny real buffer: valid only for inputs that must be rejected"""
+    from limg_b200 import LimgError
+    out = np.zeros(16, np.uint32)
+    rc = codec.lib.limgcu_host_decode_container(codec.h, data, len(data), out.ctypes.data_as(C.c_void_p), C.c_size_t(out_pixels))
+    if rc != 0:
+        raise LimgError("limgcu_host_decode_container failed with %d: %s" % (rc, codec.lib.limgcu_last_error(codec.h).decode()))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("what", ["outside", "overlap", "gap", "shift", "pixels", "count"])
+def test_gpu_stream_decode_rejects_a_bad_area_table(codec, what):
+    """limgcu_host_decode validates a caller-supplied table before a kernel indexes the block map and the planes with it."""
+    from limg_b200 import LimgError
+    from limg_b200 import synth
+    img = synth.photo_like(96, 64, 5, 3)
+    st = codec.encode_stream(img, False, 100, True)
+    a = st["areas"].copy()
+    k = int(np.argmax(a["rx"] * a["ry"]))
+    if what == "outside":
+        a["ox"][k] = 4000
+    elif what == "overlap":
+        a["ox"][0], a["oy"][0], a["px_x"][0], a["px_y"][0] = a["ox"][1], a["oy"][1], a["px_x"][1], a["px_y"][1]
+    elif what == "gap":
+        a = a[:-1]
+    elif what == "shift":
+        a["shift"][k, 1] = 9
+    elif what == "pixels":
+        a["px_w"][k] += 8
+    elif what == "count":
+        a = a[:0]
+    with pytest.raises(LimgError):
+        codec.decode(a, st["codesA"], st["codesB"], st["codesC"], False)
+    assert np.array_equal(codec.decode(st["areas"], st["codesA"], st["codesB"], st["codesC"], False), codec.encode_stream(img, False, 100, True, decoded=True)["decoded"])
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("cfg", ["c2_4k_photo", "c3_8k_rgba"])
 def test_gpu_container_full_size_round_trip(codec, cfg):
     from limg_b200 import synth
