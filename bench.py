@@ -80,6 +80,20 @@ def init_distributed(dev):
         torch.cuda.synchronize(dev)
 
 
+PHASE_KERNELS = {"pass1": "k_pass1", "predicate_windows": "k_pred_records + k_pred_window + k_plan_seeds", "merge_scan": "k_merge_cta (+ k_merge_verify, k_prepare_*)",
+                 "area_encode": "k_encode_small + k_encode_large", "dither_scan": "k_dither_scan + k_dither_states", "finalize": "k_finalize"}
+
+
+def ncu_traffic(workload: str, phase: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the phase's main kernel, from the ncu --set full capture recorded in
+    profiles/ncu_traffic.json ({workload: {phase: {"bytes": ..., "source": "profiles/<file>"}}}); None when no capture of this build exists."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            return json.load(f)[workload][phase]
+    except Exception:
+        return None
+
+
 def measured_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -180,6 +194,12 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(self.reasons), "samples": len(sm), "source": self.source}
 
 
+def common_config(workload: str) -> dict:
+    """The keys both arms print under "config" (identical for `ours` and `--impl reference`); everything arm-specific goes under "notes"."""
+    w, h, alpha, _ = WORKLOADS[workload]
+    return {"workload": workload, "width": w, "height": h, "channels": 4 if alpha else 3, "error_factor": 100, "fast_bit_crushing": True}
+
+
 def host_cores() -> int:
     try:
         return len(os.sched_getaffinity(0))
@@ -199,8 +219,13 @@ def cpu_baseline(workload: str, threads: int, budget_s: float = 20.0) -> dict:
         reps = max(1, min(8, int(budget_s / max(t, 1e-3)) - 1))
         t = ref.time_blocked(img, alpha, 100, True, threads, reps, False)
         out = {"value": mpx / t, "unit": UNIT, "cores": threads, "kind": "reference",
-               "sample": "%d x limg_blocked_encode3d_test (encode + in-encoder decode) of one %dx%d frame, %d-thread limg_thread_pool, LCG dither" % (reps, w, h, threads),
+               "sample": "%d x limg_blocked_encode3d_test (encode + in-encoder decode) of one %dx%d frame, %d-thread limg_thread_pool (only pass 1 of the reference "
+                         "uses the pool; the merge, refit and bit-crush search run on one core), LCG dither" % (reps, w, h, threads),
                "seconds_per_frame": t}
+        try:
+            out["frame_parallel"] = cpu_frame_parallel(workload, max(1, min(threads, 32)))
+        except Exception as e:
+            out["frame_parallel"] = {"value": None, "unit": UNIT, "processes": 0, "sample": repr(e)}
         # the reference's only fully threaded path, limg_encode3d_test_perf (every 8x8 block its own area, no planes written)
         tp = ref.time_blocked(img, alpha, 100, True, threads, 1, True)
         tp = ref.time_blocked(img, alpha, 100, True, threads, max(1, min(8, int(5.0 / max(tp, 1e-3)))), True)
@@ -217,6 +242,34 @@ def cpu_baseline(workload: str, threads: int, budget_s: float = 20.0) -> dict:
             "sample": "1 x oracle lo_blocked_encode3d on a %dx%d crop (scalar C port, 1 thread)" % (crop.shape[1], crop.shape[0]), "seconds_per_frame": t}
 
 
+def _frame_parallel_worker(job):
+    """one reference process: limg_blocked_encode3d_test of one frame, pool-less (the reference's merge path uses one core after pass 1 anyway)"""
+    workload, index = job
+    from oracle import ref
+    w, h, alpha, _ = WORKLOADS[workload]
+    img = make_frame(workload, index % 4)
+    ref.set_modes(True, False)
+    t0 = time.time()
+    ref.time_blocked(img, alpha, 100, True, 0, 1, False)
+    return t0, time.time()
+
+
+def cpu_frame_parallel(workload: str, procs: int) -> dict:
+    """What the CPU box does on a BATCH of frames: `procs` reference processes side by side, one frame each (the reference's own thread pool
+    only helps pass 1; frames are independent). Aggregate Mpixel/s from the first start to the last end."""
+    import multiprocessing as mp
+    from oracle import ref
+    if not ref.available():
+        return {"value": None, "unit": UNIT, "processes": 0, "sample": "oracle/_ref/libref.so not present"}
+    w, h, alpha, _ = WORKLOADS[workload]
+    with mp.get_context("spawn").Pool(procs) as pool:
+        pool.map(_frame_parallel_worker, [(workload, i) for i in range(procs)])          # start-up (imports, page faults) outside the sample
+        spans = pool.map(_frame_parallel_worker, [(workload, i) for i in range(procs)], chunksize=1)
+    dt = max(e for _, e in spans) - min(b for b, _ in spans)
+    return {"value": procs * w * h / 1e6 / dt, "unit": UNIT, "processes": procs,
+            "sample": "%d processes x 1 frame of %dx%d through limg_blocked_encode3d_test (pool-less each), wall clock first start to last end" % (procs, w, h)}
+
+
 def run_reference(args, rank: int, world: int):
     """--impl reference: the reference's CPU path on the same workload; rank 0 only."""
     if rank != 0:
@@ -228,8 +281,9 @@ def run_reference(args, rank: int, world: int):
     img = make_frame(args.workload, 0)
     line = {"impl": "reference", "metric": METRIC, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32+i32", "data": "synthetic",
-            "config": {"workload": args.workload, "width": w, "height": h, "channels": 4 if alpha else 3, "error_factor": 100, "fast_bit_crushing": True,
-                       "step": "limg_blocked_encode3d_test: encode + in-encoder decode of one frame (the reference has no standalone decoder)"}}
+            "config": common_config(args.workload),
+            "notes": {"step": "limg_blocked_encode3d_test: encode + in-encoder decode of one frame, all 13 API planes written (the reference has no standalone decoder, no stream)",
+                      "dither": "lcg"}}
     if ref.available():
         ref.set_modes(True, False)
         ref.time_blocked(img, alpha, 100, True, threads, max(1, min(args.warmup, 1)), False)
@@ -251,6 +305,56 @@ def run_reference(args, rank: int, world: int):
                  "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
                  "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
     print(json.dumps(line), flush=True)
+
+
+DROPIN_PLANES_U32 = ("pDecoded", "pShiftABCX", "pColAMin", "pColAMax", "pColBMin", "pColBMax", "pColCMin", "pColCMax", "pBlockIndex")
+DROPIN_PLANES_U8 = ("pFactorsA", "pFactorsB", "pFactorsC", "pBitsPerPixel")
+DROPIN_ORDER = ("pDecoded", "pFactorsA", "pFactorsB", "pFactorsC", "pBlockError", "pBitsPerPixel", "pShiftABCX", "pColAMin", "pColAMax", "pColBMin", "pColBMax", "pColCMin",
+                "pColCMax", "pBlockIndex")  # limg_blocked_encode3d_info, limg.h:39-44
+
+
+def e2e_dropin(lib, frame: np.ndarray, alpha: bool, device: int, steps: int) -> dict:
+    """What a user of the reference gets after swapping the library: the reference's own C++ entry point limg_blocked_encode3d_test
+    (limg.h:46, main.cpp:255) through the drop-in (limg_api.cpp), host source in, ALL 13 host planes out (40 B/px device-to-host; pBlockError is
+    written by neither implementation), wall clock per blocking call. Both dither generators: the drop-in picks like the reference does (AES
+    rounds on a host with AES-NI: walked on the host, the call synchronises in the middle), LIMGCU_DITHER=lcg selects the device-side LCG."""
+    import ctypes as C
+    import torch
+    h, w = frame.shape
+    fn = getattr(lib, "_Z26limg_blocked_encode3d_testPKjmmbP26limg_blocked_encode3d_infojP16limg_thread_poolb")
+    fn.restype = C.c_int
+    fn.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_bool, C.c_void_p, C.c_uint32, C.c_void_p, C.c_bool]
+    set_device = getattr(lib, "_Z20limg_b200_set_devicei")
+    set_device.restype = C.c_int
+    set_dither = getattr(lib, "_Z25limg_b200_set_dither_modei")
+    set_dither.restype = C.c_int
+    lib.limgcu_host_has_aesni.restype = C.c_int
+
+    class Info(C.Structure):
+        _fields_ = [(k, C.c_void_p) for k in DROPIN_ORDER]
+
+    src = torch.from_numpy(frame.view(np.int32)).pin_memory()
+    planes = {k: torch.empty((h, w), dtype=torch.int32).pin_memory() for k in DROPIN_PLANES_U32}
+    planes.update({k: torch.empty((h, w), dtype=torch.uint8).pin_memory() for k in DROPIN_PLANES_U8})
+    info = Info(**{k: planes[k].data_ptr() for k in planes})
+    assert set_device(device) == 0
+    out = {"entry_point": "limg_blocked_encode3d_test (C++ symbol of include/limg_dropin.h), 13 host planes, pinned host buffers",
+           "h2d_bytes_per_step": 4 * h * w, "d2h_bytes_per_step": (4 * len(DROPIN_PLANES_U32) + len(DROPIN_PLANES_U8)) * h * w,
+           "host_has_aesni": bool(lib.limgcu_host_has_aesni())}
+    for name, mode in (("lcg", 0), ("aes", 1)):
+        set_dither(mode)
+        for _ in range(2):
+            assert fn(src.data_ptr(), w, h, alpha, C.byref(info), 100, None, True) == 0
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            assert fn(src.data_ptr(), w, h, alpha, C.byref(info), 100, None, True) == 0
+        dt = (time.perf_counter() - t0) / steps
+        out[name] = {"ms_per_call": dt * 1e3, "value": h * w / 1e6 / dt, "unit": "Mpixel/s (encode + in-encoder decode, as the reference's step)"}
+    picked = "aes" if set_dither(-1) == 1 else "lcg"
+    out["default_on_this_host"] = picked
+    out["value"] = out[picked]["value"]
+    out["unit"] = "Mpixel/s"
+    return out
 
 
 def north_star_8k_rgb(codec, stream, dev, d_flush, peak: float, iters: int = 5) -> dict:
@@ -288,8 +392,8 @@ def north_star_8k_rgb(codec, stream, dev, d_flush, peak: float, iters: int = 5) 
     return {"workload": "7680x4320 RGB photo-like synthetic (seed 1), one frame", "encode_ms": enc, "decode_ms": dec,
             "encode_mpixel_s": w * h / 1e6 / (enc * 1e-3), "decode_mpixel_s": w * h / 1e6 / (dec * 1e-3),
             "encode_hbm_frac": gbs(enc) / peak, "decode_hbm_frac": gbs(dec) / peak, "peak_gbs": peak,
-            # dram__bytes_read.sum + dram__bytes_write.sum of k_decode_tile at this size (profiles/r1_f_ncu_decode_details.txt): 108.6 + 82.3 MB
-            "decode_traffic": 190.9e6, "decode_algorithmic_bytes": 7 * w * h, "bytes_per_px": 7, "psnr_db": psnr, "iters": iters}
+            "decode_traffic": (ncu_traffic("north_star_8k_rgb", "decode") or {}).get("bytes"), "decode_traffic_source": (ncu_traffic("north_star_8k_rgb", "decode") or {}).get("source"),
+            "decode_algorithmic_bytes": 7 * w * h, "bytes_per_px": 7, "psnr_db": psnr, "iters": iters}
 
 
 def batch_1080p(local_rank: int, dev, d_flush, lanes: int = 4, steps: int = 6) -> dict:
@@ -578,28 +682,33 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         enc_gbs = 7.0 * npx / (enc_step_ms * 1e-3) / 1e9
         dec_gbs = 7.0 * npx / (dec_step_ms * 1e-3) / 1e9
         dominant = max(phase_acc, key=phase_acc.get)
+        dom_ms = phase_acc[dominant]
+        dom_gbs = 7.0 * npx / (dom_ms * 1e-3) / 1e9
+        traffic = ncu_traffic(args.workload, dominant)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong" if args.mode == "rowband" else "weak", "vs_baseline": None,
             "dtype": "f32+i32", "data": "synthetic",
-            "config": {"workload": args.workload, "width": w, "height": h, "channels": 4 if alpha else 3, "error_factor": 100, "fast_bit_crushing": True,
-                       "dither": "lcg", "frames_per_rank_per_step": 1,
-                       "parallelism": ("row bands of one image, one per GPU (%d rows on rank 0)" % h) if args.mode == "rowband" else ("independent frames, one per GPU" if world > 1 else "single GPU"),
-                       "step": "limgcu_blocked_encode3d (stream out) + limgcu_decode", "l2": "flushed between timed steps (512 MiB fill, untimed)"},
+            "config": common_config(args.workload),
+            "notes": {"dither": "lcg", "frames_per_rank_per_step": 1,
+                      "parallelism": ("row bands of one image, one per GPU (%d rows on rank 0)" % h) if args.mode == "rowband" else ("independent frames, one per GPU" if world > 1 else "single GPU"),
+                      "step": "limgcu_blocked_encode3d (stream out: area table + three code planes) + limgcu_decode", "l2": "flushed between timed steps (512 MiB fill, untimed)",
+                      "warmup": "at least 3 warm-up steps are always run"},
             "encode_mpixel_s": px_job / 1e6 / (enc_step_ms * 1e-3), "decode_mpixel_s": px_job / 1e6 / (dec_step_ms * 1e-3),
             "encode_ms": enc_step_ms, "decode_ms": dec_step_ms, "psnr_db": psnr,
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": px_job * args.steps / 1e6 / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "path": "limgcu_host_encode_stream + limgcu_host_decode, pinned host buffers"},
-            "roofline": {"bound": "hbm", "achieved": enc_gbs, "peak": peak, "unit": "GB/s", "frac": enc_gbs / peak,
-                         # DRAM bytes of the dominant kernel (k_merge_wave) per launch, ncu --set full, profiles/r1_k_ncu_wave_details.txt (4K photo only):
-                         # 10.12 MB read + 256 B written (the scan lives in L2; the pass-1 records it reads are 8.3 MB)
-                         "traffic": 10.12e6 if args.workload == "c2_4k_photo" else None,
-                         "kernel": "encode path (all kernels of limgcu_blocked_encode3d), 7 algorithmic B/px", "peak_source": peak_src,
-                         "dominant_kernel": dominant, "dominant_share": phase_acc[dominant] / max(sum(phase_acc.values()), 1e-9),
+            # the DOMINANT kernel phase of the encode (CUDA events around its kernels on the codec's stream): 7 algorithmic B/px of the frame over its duration
+            "roofline": {"bound": "hbm", "achieved": dom_gbs, "peak": peak, "unit": "GB/s", "frac": dom_gbs / peak,
+                         "traffic": traffic["bytes"] if traffic else None, "traffic_source": traffic["source"] if traffic else None,
+                         "kernel": PHASE_KERNELS.get(dominant, dominant), "phase": dominant, "ms": dom_ms,
+                         "share_of_encode": dom_ms / max(sum(phase_acc.values()), 1e-9), "algorithmic_bytes": 7 * npx, "peak_source": peak_src,
                          "phase_ms": {k: round(v, 4) for k, v in phase_acc.items()},
-                         "note": "merge_scan = the row-pipelined greedy area scan (latency bound, not HBM bound); predicate_windows = the main-stream part of the "
-                                 "predicate precompute (the speculative match bitmaps run on a second stream concurrently with the scan)"},
+                         "note": "merge_scan = the row-pipelined greedy area scan + its verification (latency bound: a dependency chain, not HBM bound); predicate_windows = "
+                                 "the main-stream part of the predicate precompute (the speculative match bitmaps run on a second stream concurrently with the scan)"},
+            "roofline_encode_path": {"bound": "hbm", "achieved": enc_gbs, "peak": peak, "unit": "GB/s", "frac": enc_gbs / peak,
+                                     "kernel": "all kernels of limgcu_blocked_encode3d, 7 algorithmic B/px"},
             "unmerged_encode": {"encode_ms": unmerged_ms, "encode_mpixel_s": npx / 1e6 / (unmerged_ms * 1e-3), "hbm_frac": 7.0 * npx / (unmerged_ms * 1e-3) / 1e9 / peak,
                                 "what": "limgcu_blocked_encode3d with LIMGCU_FLAG_NO_MERGE (the path of limg_encode3d_test / _perf: every 8x8 block its own area), per GPU"},
             "merge": {"failed_first_tries": int(counters[24]), "areas": int(counters[1]), "merged_rectangles": int(counters[0])},
@@ -616,6 +725,10 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                 line["batch_1080p"] = batch_1080p(local_rank, dev, d_flush)
             except Exception as e:
                 line["batch_1080p"] = {"error": repr(e)}
+        try:
+            line["e2e_dropin"] = e2e_dropin(codec.lib, frame, alpha, local_rank, max(3, min(args.steps, 10)))
+        except Exception as e:
+            line["e2e_dropin"] = {"error": repr(e)}
         if world == 1 and not args.no_cpu_baseline:
             try:
                 line["cpu_baseline"] = cpu_baseline(args.workload, host_cores())

@@ -83,5 +83,9 @@ double limg_compare(const uint32_t *pImageA, const uint32_t *pImageB, const size
 
 /* Additions (not in the reference): select the CUDA device used by the wrappers above (default 0). */
 limg_result limg_b200_set_device(const int device);
+/* Dither generator of the wrappers above: 1 = the AES-round chain the reference uses on a host with AES-NI (limg.cpp:824-879; walked on the
+ * host, the call synchronises), 0 = the reference's LCG (limg.cpp:799-822; fully on the device), -1 = decide like the reference does from
+ * the host CPU (limg.cpp:881-887), which is the default. Returns the generator now in use (1 / 0) or -1 without a device. */
+int limg_b200_set_dither_mode(const int aes);
 
 #endif /* LIMG_DROPIN_H */

@@ -137,7 +137,10 @@ struct WaveCluster
     }
 
     // every replica has the claim before any replica sees a progress value published after it
-    fence();
+    if (a.experiment & 2)
+      asm volatile("fence.acq_rel.cta;" ::: "memory");
+    else
+      fence();
     __syncwarp();
   }
 };
@@ -147,7 +150,7 @@ __host__ __device__ inline size_t merge_cta_smem_words(int BY, int wordsPerRow) 
 
 // One cluster (gridDim.x == cluster size), LIMG_CTA_WARPS warps per CTA. `attempt`: runs only if flags[0] == attempt (uniform over the cluster).
 template <int CH>
-__global__ void __launch_bounds__(LIMG_CTA_WARPS * 32) k_merge_cta(WaveArgs a, int attempt)
+__global__ void __launch_bounds__(LIMG_CTA_WARPS * 32) k_merge_cta(const __grid_constant__ WaveArgs a, int attempt)
 {
   if (a.flags[0] != (uint32_t)attempt)
     return;

@@ -79,6 +79,7 @@ struct WaveArgs
   int symMaxL, symMaxR, symMaxD; // size caps of a centre bitmap built on the fly (same as the plan's)
   int stageGap;              // block rows stage 1 stays behind stage 0
   int specAhead;             // a seed is expanded speculatively once the rows above are within this many columns of where they have to be
+  int experiment;            // LIMGCU_SCAN_EXPERIMENT (measurement only, never set by default): 1 no acquire fence before the final look, 2 claims fenced at CTA scope only, 4 re-speculate on every poll
 };
 
 __device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t *p)
@@ -227,9 +228,21 @@ struct WaveResult
   int boxR;               // exclusive right edge of every column whose in-use bits were consulted
 };
 
+// first level of a seed's immutable data: what is indexed by the seed itself. Loaded one candidate ahead (the loads are in flight
+// while the row decides the seed before); the second level (bitmaps behind the slots) is SeedPre.
+struct SeedLinks
+{
+  int x;          // the candidate the loads were issued for (-1: none)
+  uint32_t slot;  // extSlot
+  uint32_t u;     // unmasked rx | ry << 8
+  uint32_t w0, w1; // the seed's 8x8 match word (warp uniform)
+  uint4 links;    // bitmap slots of the predicted centre and the three to its left
+};
+
 // everything about a seed that does not depend on the mask: loaded while the row waits for the rows above
 struct SeedPre
 {
+  uint32_t w0, w1;  // the seed's 8x8 match word: bit dy * 8 + dx (warp uniform)
   uint32_t rowBits; // lane: match bits of the seed for block row y + lane, columns x ..
   int vx1, vy1;     // known part of it: [0, vx1) x [0, vy1)
   int pcx, pcy;     // centre the mask-free growth predicts (-1: none)
@@ -259,21 +272,24 @@ struct WaveScan
   uint32_t nOnDemand;
   long long tOnDemand = 0, tFour = 0; // profile: clock cycles inside on-demand strips / the four-way regrowth
   uint32_t *scratch = nullptr;        // 32 words of shared memory private to the warp
-  const Snapshot *cur = nullptr;      // the mask snapshot the running expansion is based on
+  Snapshot cur = { { 0, 0, 0 }, 0, 0 }; // the mask snapshot the running expansion is based on (a copy: a pointer would put every snapshot into local memory)
+  bool haveCur = false;
   bool volatileReads = false;         // the running expansion read in-use bits that the snapshot does not hold
   int cause = 0;                      // who asks for on-demand strips: 0 seed growth, 1 four-way with a bitmap, 2 four-way without
   uint32_t nStrips[3] = { 0, 0, 0 };
   long long tStrips[3] = { 0, 0, 0 };
   uint32_t nFour = 0, nFourMiss = 0, nFourNoSym = 0, nBuilt = 0;
+  long long tSeedFast = 0, tSeedGeneral = 0, tSym = 0, tRegion = 0, tGrow4 = 0; // profile: where an expansion's cycles go
+  uint32_t nSeedFast = 0, nSeedGeneral = 0;
 
   __device__ bool strip_unused(int x0, int y0, int w, int h)
   {
     bool any = false;
 
-    if (cur && y0 >= cur->r0 && y0 + h <= cur->r0 + 32 && x0 >= cur->w0 * 32 && x0 + w <= cur->w0 * 32 + 96)
+    if (haveCur && y0 >= cur.r0 && y0 + h <= cur.r0 + 32 && x0 >= cur.w0 * 32 && x0 + w <= cur.w0 * 32 + 96)
     {
       // inside the snapshot: lane = row, test the columns of the strip
-      const int row = cur->r0 + lane, b0 = x0 - cur->w0 * 32;
+      const int row = cur.r0 + lane, b0 = x0 - cur.w0 * 32;
 
       if (row >= y0 && row < y0 + h)
       {
@@ -284,7 +300,7 @@ struct WaveScan
           if (hi > lo)
           {
             const uint32_t m = (hi - lo >= 32 ? 0xFFFFFFFFu : ((1u << (hi - lo)) - 1u)) << lo;
-            any |= (cur->w[j] & m) != 0;
+            any |= (cur.w[j] & m) != 0;
           }
         }
       }
@@ -373,8 +389,7 @@ struct WaveScan
 
     const long long dt = wave_clock() - t0;
     tOnDemand += dt;
-    nStrips[cause]++;
-    tStrips[cause] += dt;
+    if (LIMG_WAVE_PROFILE) { nStrips[cause]++; tStrips[cause] += dt; }
     return good;
   }
 
@@ -384,8 +399,7 @@ struct WaveScan
     const bool ok = strip_unused(x0, y0, w, h) && strip_matches(seed, x0, y0, w, h);
     const long long dt = wave_clock() - t0;
     tOnDemand += dt;
-    nStrips[cause]++;
-    tStrips[cause] += dt;
+    if (LIMG_WAVE_PROFILE) { nStrips[cause]++; tStrips[cause] += dt; }
     return ok;
   }
 
@@ -478,25 +492,39 @@ struct WaveScan
     }
   }
 
-  __device__ SeedPre prefetch(int x, int y, int stage) const
+  // first level: issue the loads, consume nothing
+  __device__ __forceinline__ SeedLinks prefetch_links(int x, int y, int stage) const
+  {
+    SeedLinks l;
+    const int seed = y * a.BX + x;
+    l.x = x;
+    l.slot = ld_relaxed_u32(&a.extSlot[seed]);
+    l.u = *(const volatile uint16_t *)&a.unmasked[seed];
+    const uint2 w = __ldg(reinterpret_cast<const uint2 *>(a.window) + seed);
+    l.w0 = w.x;
+    l.w1 = w.y;
+    l.links = (a.seedSym && stage == 0) ? __ldg(&a.seedSym[seed]) : make_uint4(LIMG_NO_SLOT, LIMG_NO_SLOT, LIMG_NO_SLOT, LIMG_NO_SLOT);
+    return l;
+  }
+
+  // second level: the bitmaps behind the slots (consumes the first level)
+  __device__ SeedPre prefetch_bitmaps(const SeedLinks &l, int y, int stage) const
   {
     SeedPre p;
-    const int seed = y * a.BX + x;
-    const uint32_t slot = ld_relaxed_u32(&a.extSlot[seed]);
-    const uint32_t u = *(const volatile uint16_t *)&a.unmasked[seed];
-    const uint32_t wv = lane < 8 ? __ldg(&a.window[(size_t)seed * 2 + (lane >> 2)]) : 0u;
-    const uint4 links = (a.seedSym && stage == 0) ? __ldg(&a.seedSym[seed]) : make_uint4(LIMG_NO_SLOT, LIMG_NO_SLOT, LIMG_NO_SLOT, LIMG_NO_SLOT);
+    const int x = l.x;
+    p.w0 = l.w0;
+    p.w1 = l.w1;
 
-    if (slot >= LIMG_SLOT_PENDING)
+    if (l.slot >= LIMG_SLOT_PENDING)
     {
-      p.rowBits = (wv >> (8 * (lane & 3))) & 0xFFu;
+      p.rowBits = lane < 8 ? ((lane < 4 ? l.w0 >> (8 * lane) : l.w1 >> (8 * (lane - 4))) & 0xFFu) : 0u;
       p.vx1 = 8;
       p.vy1 = 8;
     }
     else
     {
-      const uint32_t h = ld_relaxed_u32(&a.extHdr[slot]);
-      p.rowBits = ld_relaxed_u32(&a.extBits[(size_t)slot * 32 + lane]);
+      const uint32_t h = ld_relaxed_u32(&a.extHdr[l.slot]);
+      p.rowBits = ld_relaxed_u32(&a.extBits[(size_t)l.slot * 32 + lane]);
       p.vx1 = (h >> 16) & 0xFF;
       p.vy1 = h >> 24;
     }
@@ -507,7 +535,7 @@ struct WaveScan
     p.ccx = p.ccy = -1;
     p.cRow = 0;
     p.cHdr = 0;
-    const int prx = u & 0xFF, pry = u >> 8;
+    const int prx = l.u & 0xFF, pry = l.u >> 8;
 
     p.alt[0] = p.alt[1] = p.alt[2] = LIMG_NO_SLOT;
 
@@ -518,8 +546,8 @@ struct WaveScan
 
       if (a.seedSym)
       {
-        p.alt[0] = links.y; p.alt[1] = links.z; p.alt[2] = links.w;
-        load_sym_slot(links.x, p.symRow, p.symHdr);
+        p.alt[0] = l.links.y; p.alt[1] = l.links.z; p.alt[2] = l.links.w;
+        load_sym_slot(l.links.x, p.symRow, p.symHdr);
       }
       else
       {
@@ -528,6 +556,207 @@ struct WaveScan
     }
 
     return p;
+  }
+
+  __device__ SeedPre prefetch(int x, int y, int stage) const
+  {
+    return prefetch_bitmaps(prefetch_links(x, y, stage), y, stage);
+  }
+
+  // ---- growth from run lengths -----------------------------------------------------------------------------------------------
+  // A growing rectangle only ever contains blocks that matched and were free, so "the next strip joins" is a statement about how
+  // far the run of available blocks of every row reaches: the rectangle grows right while the shortest run of its rows reaches the
+  // new column, and a row joins below (or above) if its run covers the rectangle's width. With one run length per row, four bits
+  // each, packed into a 64-bit word that every lane holds, a strip test is a few uniform integer operations on registers: no ballot,
+  // no shuffle, no loop over the strip (the ballot version spent ~130 cycles per test; a single warp issues one dependent
+  // instruction every 5-6 cycles). Same sequence of tests, same results as grow() (limg.cpp:1315-1383); both functions return false,
+  // with nothing decided, when a test would leave the known part of the bitmap or the 16 rows / 15 columns the packing holds.
+
+  // nibble i of the result = v (0..15) of lane first + i, for 16 lanes
+  __device__ __forceinline__ unsigned long long pack_nibbles16(uint32_t v, int first) const
+  {
+    const int i = lane - first;
+    const uint32_t lo = __reduce_or_sync(0xFFFFFFFFu, (i >= 0 && i < 8) ? v << (4 * i) : 0u);
+    const uint32_t hi = __reduce_or_sync(0xFFFFFFFFu, (i >= 8 && i < 16) ? v << (4 * (i - 8)) : 0u);
+    return (unsigned long long)lo | ((unsigned long long)hi << 32);
+  }
+
+  static __device__ __forceinline__ int nibble(unsigned long long packed, int i) { return (int)((packed >> (4 * i)) & 15ull); }
+
+  // right/down growth of seed (x, y). availRow: lane = block row y + lane, bit = column x + bit (matches the seed and is free);
+  // known part [0, kx) x [0, ky).
+  __device__ __forceinline__ bool grow_seed_runs(uint32_t availRow, int kx, int ky, int x, int y, int minSide, int &rx, int &ry) const
+  {
+    const unsigned long long runs = pack_nibbles16((uint32_t)min(__ffs((int)~availRow) - 1 & 63, 15), 0); // ~0 -> ffs 0 -> 63 -> 15
+    int shortest = nibble(runs, 0);
+    bool right = true, down = true;
+    rx = 1;
+    ry = 1;
+
+    while (right || down)
+    {
+      if (right)
+      {
+        bool ok = x + rx + 1 < a.BX;
+
+        if (ok)
+        {
+          if (rx >= kx || rx >= 15)
+            return false;
+
+          ok = shortest > rx;
+        }
+
+        if (ok) rx++; else right = false;
+      }
+
+      if (down)
+      {
+        bool ok = y + ry + 1 < a.BY;
+
+        if (ok)
+        {
+          if (ry >= ky || ry >= 16)
+            return false;
+
+          const int run = nibble(runs, ry);
+          ok = run >= rx;
+
+          if (ok)
+            shortest = min(shortest, run);
+        }
+
+        if (ok) ry++; else down = false;
+      }
+
+      if (minSide && ((!right && rx < minSide) || (!down && ry < minSide)))
+        break;
+    }
+
+    return true;
+  }
+
+  // four-way growth around centre (cx, cy) from the untested start rectangle [cx, cx + rx) x [cy, cy + ry) (limg.cpp:1428-1433).
+  // avail: lane = block row cy - 8 + lane, bit = column cx - 8 + bit; hdr: known part. Runs are measured from the start rectangle's
+  // edges outwards (its own blocks are never tested); a row that joins must also be available across the start rectangle's columns.
+  __device__ __forceinline__ bool grow_centre_runs(uint32_t avail, uint32_t hdr, int cx, int cy, int &ox, int &oy, int &rx, int &ry) const
+  {
+    const int B = LIMG_SYM_BACK;
+    const int vx0 = (int)(hdr & 0xFF), vy0 = (int)((hdr >> 8) & 0xFF), vx1 = (int)((hdr >> 16) & 0xFF), vy1 = (int)(hdr >> 24);
+    const int sx = rx, sy = ry; // start size
+
+    if (sx > 7 || sy > 7 || !hdr)
+      return false;
+
+    const uint32_t beyond = avail >> (B + sx);   // bit 0 = first column right of the start rectangle
+    const uint32_t before = avail << (32 - B);   // bit 31 = first column left of it
+    const unsigned long long runsR = pack_nibbles16((uint32_t)min(__ffs((int)~beyond) - 1, 15), 0);
+    const unsigned long long runsL = pack_nibbles16((uint32_t)__clz((int)~before), 0); // <= 8
+    const uint32_t across = (1u << sx) - 1u;
+    const uint32_t middle = __ballot_sync(0xFFFFFFFFu, ((avail >> B) & across) == across);
+    int shortR = 15, shortL = 15;
+
+    for (int i = 0; i < sy; i++)
+    {
+      shortR = min(shortR, nibble(runsR, B + i));
+      shortL = min(shortL, nibble(runsL, B + i));
+    }
+
+    // rectangle in bitmap coordinates: columns [c0, c0 + w), rows [r0, r0 + h)
+    int c0 = B, r0 = B, w = sx, h = sy;
+    const int ax = cx - B, ay = cy - B;
+    bool right = true, down = true, up = true, left = true;
+
+    auto row_joins = [&](int r) -> bool {
+      return ((middle >> r) & 1u) && nibble(runsL, r) >= B - c0 && nibble(runsR, r) >= c0 + w - (B + sx);
+    };
+
+    while (right || down || up || left)
+    {
+      if (right)
+      {
+        bool ok = ax + c0 + w + 1 < a.BX;
+
+        if (ok)
+        {
+          const int need = c0 + w - (B + sx) + 1;
+
+          if (c0 + w >= vx1 || need > 15)
+            return false;
+
+          ok = shortR >= need;
+        }
+
+        if (ok) w++; else right = false;
+      }
+
+      if (down)
+      {
+        bool ok = ay + r0 + h + 1 < a.BY;
+
+        if (ok)
+        {
+          const int r = r0 + h;
+
+          if (r >= vy1 || r >= 16 || c0 + w - (B + sx) > 15)
+            return false;
+
+          ok = row_joins(r);
+
+          if (ok)
+          {
+            shortR = min(shortR, nibble(runsR, r));
+            shortL = min(shortL, nibble(runsL, r));
+          }
+        }
+
+        if (ok) h++; else down = false;
+      }
+
+      if (up)
+      {
+        bool ok = ay + r0 > 0;
+
+        if (ok)
+        {
+          const int r = r0 - 1;
+
+          if (r < vy0 || c0 + w - (B + sx) > 15)
+            return false;
+
+          ok = row_joins(r);
+
+          if (ok)
+          {
+            shortR = min(shortR, nibble(runsR, r));
+            shortL = min(shortL, nibble(runsL, r));
+          }
+        }
+
+        if (ok) { r0--; h++; } else up = false;
+      }
+
+      if (left)
+      {
+        bool ok = ax + c0 > 0;
+
+        if (ok)
+        {
+          if (c0 - 1 < vx0)
+            return false;
+
+          ok = shortL >= B - (c0 - 1);
+        }
+
+        if (ok) { c0--; w++; } else left = false;
+      }
+    }
+
+    ox = ax + c0;
+    oy = ay + r0;
+    rx = w;
+    ry = h;
+    return true;
   }
 
   // alternating growth of the rectangle (ox, oy, rx, ry) of seed block `seed` (limg.cpp:1294-1388): right and down, and also up
@@ -705,14 +934,31 @@ struct WaveScan
   {
     WaveResult r;
     Region g;
-    cur = &sn;
+    cur = sn;
+    haveCur = true;
     volatileReads = false;
     g.ax = x; g.ay = y; g.vx0 = x; g.vy0 = y; g.vx1 = x + pre.vx1; g.vy1 = y + pre.vy1;
+
+    const long long ts0 = wave_clock();
+
     g.avail = pre.rowBits & ~region_used(sn, x, y, pre.vy1);
-    int ox = x, oy = y;
-    r.rx = 1;
-    r.ry = 1;
-    grow(y * a.BX + x, g, false, stage == 0 ? 3 : 0, ox, oy, r.rx, r.ry);
+
+    if (!grow_seed_runs(g.avail, pre.vx1, pre.vy1, x, y, stage == 0 ? 3 : 0, r.rx, r.ry))
+    {
+      const long long ts1 = wave_clock();
+      int ox = x, oy = y;
+      r.rx = 1;
+      r.ry = 1;
+      grow(y * a.BX + x, g, false, stage == 0 ? 3 : 0, ox, oy, r.rx, r.ry);
+      tSeedGeneral += wave_clock() - ts1;
+      nSeedGeneral++;
+    }
+    else
+    {
+      tSeedFast += wave_clock() - ts0;
+      nSeedFast++;
+    }
+
     r.kind = 0;
     r.cox = r.coy = r.crx = r.cry = 0;
     r.attempted = 0;
@@ -776,6 +1022,8 @@ struct WaveScan
 
         if (!symHdr) nFourNoSym++;
         cause = symHdr ? 1 : 2;
+        const long long tr0 = wave_clock();
+        tSym += tr0 - t0;
 
         Region c;
         c.ax = cox - LIMG_SYM_BACK; c.ay = coy - LIMG_SYM_BACK;
@@ -783,7 +1031,13 @@ struct WaveScan
         c.vx1 = c.ax + (int)((symHdr >> 16) & 0xFF); c.vy1 = c.ay + (int)(symHdr >> 24);
         c.avail = symHdr ? (symRow & ~region_used(sn, c.ax, c.ay, (int)(symHdr >> 24))) : 0u;
         const int centre = coy * a.BX + cox;
-        grow(centre, c, true, 0, cox, coy, crx, cry);
+        const long long tg0 = wave_clock();
+        tRegion += tg0 - tr0;
+
+        if (!grow_centre_runs(c.avail, symHdr, cox, coy, cox, coy, crx, cry))
+          grow(centre, c, true, 0, cox, coy, crx, cry);
+
+        tGrow4 += wave_clock() - tg0;
         r.cox = cox; r.coy = coy; r.crx = crx; r.cry = cry;
         r.attempted = 1;
         r.kind = (crx * cry > r.rx * r.ry) ? 2 : 1;
@@ -1049,6 +1303,7 @@ __device__ void wave_scan_rows(const WaveArgs &a, const Backend &be, int attempt
     uint32_t *emitInfo = a.emitInfo + (size_t)stage * a.BX * a.BY;
     const uint32_t base = stage ? LIMG_TAU_STAGE1 : 0u;
     const uint32_t onDemandBefore = scan.nOnDemand;
+    uint32_t rowExp = 0, rowReexp = 0, rowPolls = 0; // (arrays indexed by `stage` would live in local memory)
 
     if (stage == 1)
     {
@@ -1097,6 +1352,21 @@ __device__ void wave_scan_rows(const WaveArgs &a, const Backend &be, int attempt
     uint2 *list = lists + (size_t)y * a.listCap;
     uint32_t count = 0;
     int x = 0, published = 0, nEvents = 0, xEvent = 0;
+    SeedLinks ahead;
+    ahead.x = -1;
+
+    // issue the loads of the candidate that will probably come next: the first live candidate right of `from`
+    auto look_ahead = [&](int from) {
+      if (ahead.x != -1) // -2: looked, and there is none
+        return;
+
+      const int xn = from < a.BX ? wave_next_candidate(candRow, [&](int dy, int w) { return be.used_word(y + dy, w); }, nWords, from, a.BX, stage, lane) : a.BX;
+
+      if (xn < a.BX)
+        ahead = scan.prefetch_links(xn, y, stage);
+      else
+        ahead.x = -2;
+    };
 
     // the row's own progress: every seed left of `own` is decided, and its claims were fenced when they were made
     auto publish = [&](int own) {
@@ -1120,7 +1390,9 @@ __device__ void wave_scan_rows(const WaveArgs &a, const Backend &be, int attempt
 
       tc = wave_clock();
       cSeedStart = tc;
-      SeedPre pre = scan.prefetch(x, y, stage);
+      // the seed's links were loaded while the row decided the seed before, if the guess of the next candidate was right
+      SeedPre pre = scan.prefetch_bitmaps(ahead.x == x ? ahead : scan.prefetch_links(x, y, stage), y, stage);
+      ahead.x = -1;
       tPre += wave_clock() - tc;
       cPre = wave_clock() - tc; cWait = 0; cExp = 0; cClaim = 0; cIters = 0;
       const uint32_t first = count;
@@ -1153,8 +1425,8 @@ __device__ void wave_scan_rows(const WaveArgs &a, const Backend &be, int attempt
 
             if (spins > LIMG_WAVE_SPIN_LIMIT) { a.flags[3] = 1; taken = true; break; }
 
-            nPolls[stage]++;
-            __nanosleep(p + 64 < x ? 400 : 20);
+            rowPolls++;
+            if (p + 64 < x) __nanosleep(200);
             continue;
           }
 
@@ -1162,7 +1434,20 @@ __device__ void wave_scan_rows(const WaveArgs &a, const Backend &be, int attempt
           // them); it is only paid for when this look at the mask can be the final one.
           const bool final = have ? p >= min(r.boxR + a.margin, a.BX) : p >= min(x + 1 + a.margin + 8, a.BX);
 
-          if (final)
+          if (have && !final && !(a.experiment & 4))
+          {
+            // the speculative result stands until the look that can make it final: a poll is two shared-memory reads, not a snapshot and a comparison
+            tWait += wave_clock() - tc;
+
+            if (spins > LIMG_WAVE_SPIN_LIMIT) { a.flags[3] = 1; break; }
+
+            look_ahead(r.kind == 1 ? x + r.rx : x + 1);
+            rowPolls++;
+            if (p + 64 < x) __nanosleep(200);
+            continue;
+          }
+
+          if (final && !(a.experiment & 1))
             be.acquire_fence();
 
           const Snapshot sn = scan.snapshot(x, y); // after the progress read
@@ -1175,13 +1460,13 @@ __device__ void wave_scan_rows(const WaveArgs &a, const Backend &be, int attempt
           {
             tc = wave_clock();
 
-            if (have) nReexp[stage]++;
+            if (have) rowReexp++;
 
             r = scan.expand(x, y, stage, pre, sn);
             unstable = scan.volatileReads; // it read in-use bits outside the snapshot: only good if the rows above had already passed
             used = sn;
             have = true;
-            nExp[stage]++;
+            rowExp++;
             const long long dt = wave_clock() - tc;
             tExpand += dt;
             cExp += dt;
@@ -1206,11 +1491,14 @@ __device__ void wave_scan_rows(const WaveArgs &a, const Backend &be, int attempt
 
           if (spins > LIMG_WAVE_SPIN_LIMIT) { a.flags[3] = 1; break; }
 
+          // the seed has to wait: the next candidate's links can be on their way meanwhile
+          look_ahead(r.kind == 1 ? x + r.rx : x + 1);
+
           if (p >= min(r.boxR + a.margin, a.BX))
             continue; // far enough, but this look was not fenced: look again at once
 
-          nPolls[stage]++;
-          __nanosleep(p + 64 < x ? 400 : 20);
+          rowPolls++;
+          if (p + 64 < x) __nanosleep(200);
         }
 
         if (taken || r.kind == 0)
@@ -1246,6 +1534,9 @@ __device__ void wave_scan_rows(const WaveArgs &a, const Backend &be, int attempt
 
         count++;
         claimed = true;
+
+        if (r.kind == 1)
+          look_ahead(x + r.rx);
         tClaim += wave_clock() - tc;
         cClaim += wave_clock() - tc;
 
@@ -1306,6 +1597,9 @@ __device__ void wave_scan_rows(const WaveArgs &a, const Backend &be, int attempt
     wave_advance_done(be, stage, a.BY, lane);
 
     nOnDemand[stage] += scan.nOnDemand - onDemandBefore;
+    nExp[stage] += rowExp;
+    nReexp[stage] += rowReexp;
+    nPolls[stage] += rowPolls;
   }
 
   if (failed && !sequential && lane == 0)
@@ -1353,6 +1647,13 @@ __device__ void wave_scan_rows(const WaveArgs &a, const Backend &be, int attempt
       }
 
       atomicAdd(&a.dbg[53], scan.nBuilt);
+      atomicAdd(&a.dbg[224], (uint32_t)(scan.tSeedFast >> 10));
+      atomicAdd(&a.dbg[225], (uint32_t)(scan.tSeedGeneral >> 10));
+      atomicAdd(&a.dbg[226], (uint32_t)(scan.tSym >> 10));
+      atomicAdd(&a.dbg[227], (uint32_t)(scan.tRegion >> 10));
+      atomicAdd(&a.dbg[228], (uint32_t)(scan.tGrow4 >> 10));
+      atomicAdd(&a.dbg[230], scan.nSeedFast);
+      atomicAdd(&a.dbg[231], scan.nSeedGeneral);
       atomicAdd(&a.dbg[48], scan.nFour);
       atomicAdd(&a.dbg[49], scan.nFourMiss);
       atomicAdd(&a.dbg[50], scan.nFourNoSym);
@@ -1363,7 +1664,7 @@ __device__ void wave_scan_rows(const WaveArgs &a, const Backend &be, int attempt
 // The scan over the live mask in global memory: any image size; with `sequential` (one CTA) it is the reference's order, the last resort
 // of the host's tries. `attempt`: the kernel runs only if flags[0] == attempt, i.e. every earlier try failed.
 template <int CH>
-__global__ void __launch_bounds__(LIMG_WAVE_WARPS * 32) k_merge_wave(WaveArgs a, int attempt, int sequential)
+__global__ void __launch_bounds__(LIMG_WAVE_WARPS * 32) k_merge_wave(const __grid_constant__ WaveArgs a, int attempt, int sequential)
 {
   if (a.flags[0] != (uint32_t)attempt)
     return;
@@ -1435,7 +1736,7 @@ __global__ void __launch_bounds__(256) k_merge_verify_filter(WaveArgs a, int sta
 // Verification, part 2 (one WARP per remaining seed): replays the seed against the mask at its logical time and compares with the
 // wave's record.
 template <int CH>
-__global__ void __launch_bounds__(256) k_merge_verify(WaveArgs a, int stage, int attempt, const uint32_t *replayList, const uint32_t *replayCount)
+__global__ void __launch_bounds__(256) k_merge_verify(const __grid_constant__ WaveArgs a, int stage, int attempt, const uint32_t *replayList, const uint32_t *replayCount)
 {
   if (a.flags[0] != (uint32_t)attempt)
     return; // this try did not run, or already failed

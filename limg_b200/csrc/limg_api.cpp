@@ -83,6 +83,19 @@ limg_result limg_b200_set_device(const int device)
   return context() ? limg_success : limg_error_Generic;
 }
 
+int limg_b200_set_dither_mode(const int aes)
+{
+  std::lock_guard<std::mutex> lock(g_mutex);
+  limgcu_ctx *ctx = context();
+
+  if (ctx == nullptr)
+    return -1;
+
+  const int mode = aes < 0 ? limgcu_host_has_aesni() : (aes ? 1 : 0);
+  limgcu_set_dither_mode(ctx, mode);
+  return mode;
+}
+
 limg_result limg_encode_test(const uint32_t *, const size_t, const size_t, const bool, limg_encode_info *, const uint32_t)
 {
   return limg_error_Generic; // legacy one-factor codec: out of scope

@@ -95,6 +95,7 @@ struct limgcu_ctx
   int mergeExt = 1;                  // LIMGCU_MERGE_EXT=0 disables the speculative match bitmaps (everything beyond the 8x8 window on demand)
   int mergeMode = 0;                 // LIMGCU_MERGE_MODE: 0 wave (pipelined rows + verification), 1 seq (rows strictly in sequence)
   int scanCluster = 8;               // LIMGCU_SCAN_CLUSTER: CTAs of the cluster that runs the scan with its state in shared memory (k_merge_cta); 0 = scan over the mask in global memory (k_merge_wave)
+  int scanExperiment = 0;            // LIMGCU_SCAN_EXPERIMENT: measurement switches of the scan (WaveArgs::experiment), 0 in production
   int scanSmemLimit = 0;             // bytes of dynamic shared memory a CTA may opt in to (the mask replica has to fit)
   int planExtW = 16, planSymL = 6, planSymR = 12, planSymD = 16; // LIMGCU_PLAN_EXTW / SYML / SYMR / SYMD: size caps of the speculative bitmaps
   int mergeGap = 16;                 // LIMGCU_MERGE_GAP: block rows stage 1 stays behind stage 0
@@ -350,6 +351,7 @@ extern "C" int limgcu_create(int device, limgcu_ctx **out)
   if (const char *v = getenv("LIMGCU_MERGE_EXT")) ctx->mergeExt = atoi(v);
 
   if (const char *v = getenv("LIMGCU_MERGE_MODE")) ctx->mergeMode = !strcmp(v, "seq") ? 1 : 0;
+  if (const char *v = getenv("LIMGCU_SCAN_EXPERIMENT")) ctx->scanExperiment = atoi(v);
   if (const char *v = getenv("LIMGCU_SCAN_CLUSTER")) ctx->scanCluster = atoi(v) < 0 ? 0 : (atoi(v) > 16 ? 16 : atoi(v));
   if (const char *v = getenv("LIMGCU_MERGE_MARGIN")) ctx->mergeMargin = atoi(v) < 0 ? 0 : atoi(v);
   if (const char *v = getenv("LIMGCU_PLAN_EXTW")) ctx->planExtW = atoi(v) < 8 ? 8 : (atoi(v) > 32 ? 32 : atoi(v));
@@ -641,7 +643,7 @@ static int launch_merge(limgcu_ctx *ctx, const limgcu_decomp *dTable, size_t W, 
     w.BX = BX; w.BY = BY; w.wordsPerRow = wordsPerRow;
     w.used = ctx->dUsed; w.tau = ctx->dTau; w.progress = wProgress; w.ticket = wTicket;
     w.rowLists = ctx->dRowLists; w.rowCounts = wRowCounts; w.emitInfo = wEmitInfo; w.flags = wFlags; w.stats = ctx->dCounters + 8;
-    w.listCap = 2 * BX; w.margin = ctx->mergeMargin; w.stageGap = ctx->mergeGap; w.symMaxL = ctx->planSymL; w.symMaxR = ctx->planSymR; w.symMaxD = ctx->planSymD; w.specAhead = ctx->mergeSpec; w.dbg = ctx->dWaveDbg;
+    w.listCap = 2 * BX; w.margin = ctx->mergeMargin; w.stageGap = ctx->mergeGap; w.symMaxL = ctx->planSymL; w.symMaxR = ctx->planSymR; w.symMaxD = ctx->planSymD; w.specAhead = ctx->mergeSpec; w.dbg = ctx->dWaveDbg; w.experiment = ctx->scanExperiment;
     CK(cudaMemsetAsync(ctx->dWaveDbg, 0, 256 * sizeof(uint32_t), ctx->stream));
     w.dbgRows = nullptr;
     w.eventRow = ctx->waveRowTimes > 1 ? ctx->waveRowTimes : 0;

@@ -25,6 +25,7 @@ for name in (sys.argv[1].split(",") if len(sys.argv) > 1 else ("c1_512_gradient"
     print("   on-demand strips [seed, 4way+bitmap, 4way no bitmap]: n %s kcyc %s | - %s %s | four-way attempts %d, centre mispredicted %d, no bitmap %d, built on the fly %d" % (dbg[32:35].tolist(), dbg[36:39].tolist(), dbg[40:43].tolist(), dbg[44:47].tolist(), dbg[48], dbg[49], dbg[50], dbg[53]))
     print("   strips outside the known part [left, up, right, down]: seed %s 4way+bitmap %s 4way-no-bitmap %s ; known reach (blocks from centre) when right/down left it: %s" % (dbg[64:68].tolist(), dbg[68:72].tolist(), dbg[72:76].tolist(), dbg[80:96].tolist()))
     print("   stage 0 at commit: rows above ahead by (x4 columns) %s ; probe box width (x2) %s ; immediate %d waited %d" % (dbg[128:160].tolist(), dbg[160:192].tolist(), dbg[192], dbg[193]))
+    print("   expansion parts (kcycles): seed growth in the 8x8 word %d (%d seeds), general seed growth %d (%d seeds), centre bitmap lookup/build %d, centre region %d, four-way growth %d" % (dbg[224], dbg[230], dbg[225], dbg[231], dbg[226], dbg[227], dbg[228]))
     for st in range(2):
         o = dbg[200 + st * 8: 208 + st * 8].astype(float)
         if o[0] > 0:
