@@ -8,9 +8,9 @@
  * limg_error_Generic.
  *
  * Behavioural notes (also in INTEGRATION.md):
- *   - `pThreadPool` is accepted and ignored. For limg_encode3d_test the reference restarts its dither chain per y-band of the
- *     pool (limg.cpp:1893, 2114-2134), so its output depends on the pool size; this implementation always produces the
- *     pool-less result (pThreadPool == nullptr).
+ *   - `pThreadPool` is a token: nothing runs on host threads. For limg_encode3d_test the reference restarts its dither chain per
+ *     y-band of the pool (limg.cpp:1893, 2108-2137), so its output depends on the pool size; the wrapper reproduces the run with a
+ *     pool of limg_thread_pool_thread_count(pThreadPool) threads (and the pool-less run for nullptr).
  *   - The dither generator follows the reference's own rule (limg.cpp:881-887): the AES round chain (limg.cpp:824-879) on hosts with
  *     SSE4.1 + AES-NI, the PCG-style LCG (limg.cpp:799-822) otherwise, so the output equals the reference run on the same host.
  *     The AES chain has no skip-ahead and is walked on the host once the GPU has found the shifts (a few ms per 4K frame);

@@ -118,6 +118,10 @@ int limgcu_status(limgcu_ctx *ctx);
  * 1 = AES (as LIMGCU_FLAG_DITHER_AES). limgcu_host_has_aesni: 1 when the reference itself would pick the AES generator on this host. */
 int limgcu_set_dither_mode(limgcu_ctx *ctx, int aes);
 int limgcu_host_has_aesni(void);
+/* The reference's non-merged encoder (limg_encode3d_test, limg.cpp:2108-2137) restarts its dither chain at the top of every y-band of its thread
+ * pool, so its output depends on the pool size: `threads` > 0 reproduces the run with a pool of that many threads in the NO_MERGE paths
+ * (limgcu_host_encode3d, LIMGCU_FLAG_NO_MERGE), 0 (default) the pool-less run. The blocked (merged) encoder has one chain either way. */
+int limgcu_set_pool_threads(limgcu_ctx *ctx, int threads);
 /* number of kernels launched through this context since creation (bench.py's gpu_launches) */
 uint64_t limgcu_launch_count(const limgcu_ctx *ctx);
 /* milliseconds the kernels of one named phase took during the last limgcu_*encode3d call when profiling was enabled

@@ -40,7 +40,7 @@ FLAG_DITHER_AES = 4
 # every symbol include/limgcu.h declares (tests/test_abi.py checks the header against this list and the .so)
 SYMBOLS = (
     "limgcu_create", "limgcu_destroy", "limgcu_last_error", "limgcu_device_count", "limgcu_set_rsqrt_lut",
-    "limgcu_stream_handle", "limgcu_sync", "limgcu_status", "limgcu_set_dither_mode", "limgcu_host_has_aesni", "limgcu_launch_count", "limgcu_enable_phase_timing", "limgcu_phase_ms",
+    "limgcu_stream_handle", "limgcu_sync", "limgcu_status", "limgcu_set_dither_mode", "limgcu_set_pool_threads", "limgcu_host_has_aesni", "limgcu_launch_count", "limgcu_enable_phase_timing", "limgcu_phase_ms",
     "limgcu_debug_counters", "limgcu_debug_wave", "limgcu_debug_predicate_check", "limgcu_debug_wave_rows", "limgcu_debug_set_decode_variant", "limgcu_pass1", "limgcu_merge", "limgcu_blocked_encode3d", "limgcu_decode", "limgcu_build_block_map", "limgcu_compare",
     "limgcu_host_blocked_encode3d", "limgcu_host_encode3d", "limgcu_host_encode_stream", "limgcu_host_decode",
     "limgcu_host_pass1", "limgcu_host_merge", "limgcu_host_compare",
@@ -88,6 +88,7 @@ def load():
     lib.limgcu_status.argtypes = [vp]
     lib.limgcu_launch_count.argtypes = [vp]
     lib.limgcu_set_dither_mode.argtypes = [vp, i32]
+    lib.limgcu_set_pool_threads.argtypes = [vp, i32]
     lib.limgcu_host_has_aesni.restype = i32
     lib.limgcu_container_bound.argtypes = [C.c_size_t, C.c_size_t, C.c_int]
     lib.limgcu_container_bound.restype = C.c_size_t

@@ -127,14 +127,19 @@ class Codec:
         self._ck(self.lib.limgcu_host_blocked_encode3d(self.h, _vp(img), w, h, int(has_alpha), C.byref(s), int(error_factor), int(fast_bit_crushing)), "limg_blocked_encode3d_test")
         return planes
 
-    def encode3d_test(self, img, has_alpha: bool, planes: dict | None = None, error_factor: int = 100, fast_bit_crushing: bool = True) -> dict:
-        """limg_encode3d_test (limg.h:35) with pThreadPool == nullptr: one dither chain over all blocks in raster order."""
+    def encode3d_test(self, img, has_alpha: bool, planes: dict | None = None, error_factor: int = 100, fast_bit_crushing: bool = True, pool_threads: int = 0) -> dict:
+        """limg_encode3d_test (limg.h:35): every 8x8 block its own area. pool_threads == 0: pThreadPool == nullptr, one dither chain over all blocks
+        in raster order; > 0: the reference's run with a pool of that many threads (one chain per y-band, limg.cpp:2108-2137)."""
         img = np.ascontiguousarray(img, dtype=np.uint32)
         h, w = img.shape
         names = [k for k in PLANE_ORDER if k not in ("pBlockError", "pBitsPerPixel", "pBlockIndex")]
         planes = self.alloc_planes(h, w, names) if planes is None else planes
         s = self._planes_struct(planes)
-        self._ck(self.lib.limgcu_host_encode3d(self.h, _vp(img), w, h, int(has_alpha), C.byref(s), int(error_factor), int(fast_bit_crushing)), "limg_encode3d_test")
+        self.lib.limgcu_set_pool_threads(self.h, int(pool_threads))
+        try:
+            self._ck(self.lib.limgcu_host_encode3d(self.h, _vp(img), w, h, int(has_alpha), C.byref(s), int(error_factor), int(fast_bit_crushing)), "limg_encode3d_test")
+        finally:
+            self.lib.limgcu_set_pool_threads(self.h, 0)
         return planes
 
     def encode_stream(self, img, has_alpha: bool, error_factor: int = 100, fast_bit_crushing: bool = True, no_merge: bool = False, decoded: bool = False) -> dict:

@@ -158,7 +158,8 @@ bool host_has_aesni()
 // Walks the chain over `count` areas in emission order. noise: one byte per pixel of every dithered plane (0 < shift < 8), planes of an area in
 // the order A, B, C; planeOff[3 k + p]: offset of that plane's bytes (~0 for planes that do not consume the chain); before / after: the
 // 64-bit chain state around every area. Returns the number of noise bytes written (<= 3 * pixels). forceSoftware: test hook.
-uint64_t aes_dither_chain_host(const limgcu_area *areas, uint32_t count, uint64_t seed, uint8_t *noise, uint64_t *planeOff, uint64_t *before, uint64_t *after, bool forceSoftware)
+uint64_t aes_dither_chain_host(const limgcu_area *areas, uint32_t count, uint64_t seed, uint8_t *noise, uint64_t *planeOff, uint64_t *before, uint64_t *after, bool forceSoftware,
+                               uint32_t bandAreas, uint32_t bandCount)
 {
   static const AesTables tables;
   const bool ni = !forceSoftware && host_has_aesni();
@@ -167,6 +168,11 @@ uint64_t aes_dither_chain_host(const limgcu_area *areas, uint32_t count, uint64_
   for (uint32_t k = 0; k < count; k++)
   {
     const size_t n = (size_t)areas[k].px_w * areas[k].px_h;
+
+    // non-merged encoder with a thread pool: the chain restarts at the top of every y-band (limg.cpp:1893, 2108-2137)
+    if (bandAreas && k % bandAreas == 0 && k / bandAreas < bandCount)
+      h = seed;
+
     before[k] = h;
 
     for (int p = 0; p < 3; p++)

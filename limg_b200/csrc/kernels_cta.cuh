@@ -148,7 +148,7 @@ struct WaveCluster
 // dynamic shared memory of k_merge_cta in 32-bit words
 __host__ __device__ inline size_t merge_cta_smem_words(int BY, int wordsPerRow) { return (size_t)BY * wordsPerRow + 2 * (size_t)BY + 4 + LIMG_CTA_WARPS * 32; }
 
-// One cluster (gridDim.x == cluster size), LIMG_CTA_WARPS warps per CTA. `attempt`: runs only if flags[0] == attempt (uniform over the cluster).
+// One cluster (gridDim.x == cluster size), up to LIMG_CTA_WARPS warps per CTA (blockDim.x / 32). `attempt`: runs only if flags[0] == attempt (uniform over the cluster).
 template <int CH>
 __global__ void __launch_bounds__(LIMG_CTA_WARPS * 32) k_merge_cta(const __grid_constant__ WaveArgs a, int attempt)
 {

@@ -127,14 +127,22 @@ __global__ void __launch_bounds__(256) k_set_dither_states(limgcu_area *areas, c
   areas[k].ditherAfter = after[k];
 }
 
-__global__ void __launch_bounds__(256) k_dither_states(limgcu_area *areas, const uint32_t *areaCount, const uint64_t *demand, const unsigned long long *before, LcgJumpTable jt)
+// bandAreas > 0 (non-merged encoder with a thread pool, limg.cpp:1893, 2108-2137): the reference restarts the chain at the top of every
+// y-band, i.e. every `bandAreas` areas (areas = blocks in raster order there); the last of the `bandCount` bands takes the rest.
+__global__ void __launch_bounds__(256) k_dither_states(limgcu_area *areas, const uint32_t *areaCount, const uint64_t *demand, const unsigned long long *before, LcgJumpTable jt,
+                                                       uint32_t bandAreas, uint32_t bandCount)
 {
   const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
 
   if (k >= *areaCount)
     return;
 
-  const uint64_t s0 = lcg_jump(LIMG_DITHER_SEED, before[k], jt);
+  unsigned long long steps = before[k];
+
+  if (bandAreas)
+    steps -= before[min(k / bandAreas, bandCount - 1u) * bandAreas];
+
+  const uint64_t s0 = lcg_jump(LIMG_DITHER_SEED, steps, jt);
   areas[k].ditherBefore = s0;
   areas[k].ditherAfter = lcg_jump(s0, demand[k], jt);
 }

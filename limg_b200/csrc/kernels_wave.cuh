@@ -79,7 +79,7 @@ struct WaveArgs
   int symMaxL, symMaxR, symMaxD; // size caps of a centre bitmap built on the fly (same as the plan's)
   int stageGap;              // block rows stage 1 stays behind stage 0
   int specAhead;             // a seed is expanded speculatively once the rows above are within this many columns of where they have to be
-  int experiment;            // LIMGCU_SCAN_EXPERIMENT (measurement only, never set by default): 1 no acquire fence before the final look, 2 claims fenced at CTA scope only, 4 re-speculate on every poll
+  int experiment;            // LIMGCU_SCAN_EXPERIMENT (measurement only, never set by default): 1 no acquire fence before the final look, 2 claims fenced at CTA scope only
 };
 
 __device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t *p)
@@ -563,32 +563,21 @@ struct WaveScan
     return prefetch_bitmaps(prefetch_links(x, y, stage), y, stage);
   }
 
-  // ---- growth from run lengths -----------------------------------------------------------------------------------------------
-  // A growing rectangle only ever contains blocks that matched and were free, so "the next strip joins" is a statement about how
-  // far the run of available blocks of every row reaches: the rectangle grows right while the shortest run of its rows reaches the
-  // new column, and a row joins below (or above) if its run covers the rectangle's width. With one run length per row, four bits
-  // each, packed into a 64-bit word that every lane holds, a strip test is a few uniform integer operations on registers: no ballot,
-  // no shuffle, no loop over the strip (the ballot version spent ~130 cycles per test; a single warp issues one dependent
-  // instruction every 5-6 cycles). Same sequence of tests, same results as grow() (limg.cpp:1315-1383); both functions return false,
-  // with nothing decided, when a test would leave the known part of the bitmap or the 16 rows / 15 columns the packing holds.
-
-  // nibble i of the result = v (0..15) of lane first + i, for 16 lanes
-  __device__ __forceinline__ unsigned long long pack_nibbles16(uint32_t v, int first) const
+  // Right/down growth of a seed decided INSIDE its 8x8 match word (85 % of the stage-0 seeds and 97 % of the stage-1 seeds on photo
+  // content, tools/scan_stats.py): the word and the in-use bits of the 8x8 blocks are two 64-bit values every lane holds, so a strip
+  // test is a handful of uniform integer operations, no ballot or shuffle. Same sequence of tests as grow() (limg.cpp:1315-1343).
+  // Returns false, with nothing decided, if the growth asks for a block outside the word. (A variant that packs one run length per
+  // row into nibbles, for the seed growth and the four-way growth alike, was measured and is slower: the packing costs more
+  // warp reductions than the short growths of real content save, profiles/README.md r2_f.)
+  __device__ __forceinline__ bool grow_in_window(const SeedPre &pre, const Snapshot &sn, int x, int y, int minSide, int &rx, int &ry) const
   {
-    const int i = lane - first;
-    const uint32_t lo = __reduce_or_sync(0xFFFFFFFFu, (i >= 0 && i < 8) ? v << (4 * i) : 0u);
-    const uint32_t hi = __reduce_or_sync(0xFFFFFFFFu, (i >= 8 && i < 16) ? v << (4 * (i - 8)) : 0u);
-    return (unsigned long long)lo | ((unsigned long long)hi << 32);
-  }
-
-  static __device__ __forceinline__ int nibble(unsigned long long packed, int i) { return (int)((packed >> (4 * i)) & 15ull); }
-
-  // right/down growth of seed (x, y). availRow: lane = block row y + lane, bit = column x + bit (matches the seed and is free);
-  // known part [0, kx) x [0, ky).
-  __device__ __forceinline__ bool grow_seed_runs(uint32_t availRow, int kx, int ky, int x, int y, int minSide, int &rx, int &ry) const
-  {
-    const unsigned long long runs = pack_nibbles16((uint32_t)min(__ffs((int)~availRow) - 1 & 63, 15), 0); // ~0 -> ffs 0 -> 63 -> 15
-    int shortest = nibble(runs, 0);
+    // lane 8 + r holds block row y + r of the snapshot (r0 = y - 8)
+    const int sh = x - sn.w0 * 32; // < 40
+    const uint32_t bits8 = (sh < 32 ? __funnelshift_r(sn.w[0], sn.w[1], sh) : __funnelshift_r(sn.w[1], sn.w[2], sh - 32)) & 0xFFu;
+    const uint32_t uLo = __reduce_or_sync(0xFFFFFFFFu, (lane >= 8 && lane < 12) ? bits8 << (8 * (lane - 8)) : 0u);
+    const uint32_t uHi = __reduce_or_sync(0xFFFFFFFFu, (lane >= 12 && lane < 16) ? bits8 << (8 * (lane - 12)) : 0u);
+    const unsigned long long avail = ((unsigned long long)pre.w0 | ((unsigned long long)pre.w1 << 32)) & ~((unsigned long long)uLo | ((unsigned long long)uHi << 32));
+    const unsigned long long column = 0x0101010101010101ull;
     bool right = true, down = true;
     rx = 1;
     ry = 1;
@@ -601,10 +590,11 @@ struct WaveScan
 
         if (ok)
         {
-          if (rx >= kx || rx >= 15)
+          if (rx >= 8)
             return false;
 
-          ok = shortest > rx;
+          const unsigned long long m = (column << rx) & (ry >= 8 ? ~0ull : ((1ull << (8 * ry)) - 1ull));
+          ok = (avail & m) == m;
         }
 
         if (ok) rx++; else right = false;
@@ -616,14 +606,11 @@ struct WaveScan
 
         if (ok)
         {
-          if (ry >= ky || ry >= 16)
+          if (ry >= 8)
             return false;
 
-          const int run = nibble(runs, ry);
-          ok = run >= rx;
-
-          if (ok)
-            shortest = min(shortest, run);
+          const unsigned long long m = ((1ull << rx) - 1ull) << (8 * ry);
+          ok = (avail & m) == m;
         }
 
         if (ok) ry++; else down = false;
@@ -633,129 +620,6 @@ struct WaveScan
         break;
     }
 
-    return true;
-  }
-
-  // four-way growth around centre (cx, cy) from the untested start rectangle [cx, cx + rx) x [cy, cy + ry) (limg.cpp:1428-1433).
-  // avail: lane = block row cy - 8 + lane, bit = column cx - 8 + bit; hdr: known part. Runs are measured from the start rectangle's
-  // edges outwards (its own blocks are never tested); a row that joins must also be available across the start rectangle's columns.
-  __device__ __forceinline__ bool grow_centre_runs(uint32_t avail, uint32_t hdr, int cx, int cy, int &ox, int &oy, int &rx, int &ry) const
-  {
-    const int B = LIMG_SYM_BACK;
-    const int vx0 = (int)(hdr & 0xFF), vy0 = (int)((hdr >> 8) & 0xFF), vx1 = (int)((hdr >> 16) & 0xFF), vy1 = (int)(hdr >> 24);
-    const int sx = rx, sy = ry; // start size
-
-    if (sx > 7 || sy > 7 || !hdr)
-      return false;
-
-    const uint32_t beyond = avail >> (B + sx);   // bit 0 = first column right of the start rectangle
-    const uint32_t before = avail << (32 - B);   // bit 31 = first column left of it
-    const unsigned long long runsR = pack_nibbles16((uint32_t)min(__ffs((int)~beyond) - 1, 15), 0);
-    const unsigned long long runsL = pack_nibbles16((uint32_t)__clz((int)~before), 0); // <= 8
-    const uint32_t across = (1u << sx) - 1u;
-    const uint32_t middle = __ballot_sync(0xFFFFFFFFu, ((avail >> B) & across) == across);
-    int shortR = 15, shortL = 15;
-
-    for (int i = 0; i < sy; i++)
-    {
-      shortR = min(shortR, nibble(runsR, B + i));
-      shortL = min(shortL, nibble(runsL, B + i));
-    }
-
-    // rectangle in bitmap coordinates: columns [c0, c0 + w), rows [r0, r0 + h)
-    int c0 = B, r0 = B, w = sx, h = sy;
-    const int ax = cx - B, ay = cy - B;
-    bool right = true, down = true, up = true, left = true;
-
-    auto row_joins = [&](int r) -> bool {
-      return ((middle >> r) & 1u) && nibble(runsL, r) >= B - c0 && nibble(runsR, r) >= c0 + w - (B + sx);
-    };
-
-    while (right || down || up || left)
-    {
-      if (right)
-      {
-        bool ok = ax + c0 + w + 1 < a.BX;
-
-        if (ok)
-        {
-          const int need = c0 + w - (B + sx) + 1;
-
-          if (c0 + w >= vx1 || need > 15)
-            return false;
-
-          ok = shortR >= need;
-        }
-
-        if (ok) w++; else right = false;
-      }
-
-      if (down)
-      {
-        bool ok = ay + r0 + h + 1 < a.BY;
-
-        if (ok)
-        {
-          const int r = r0 + h;
-
-          if (r >= vy1 || r >= 16 || c0 + w - (B + sx) > 15)
-            return false;
-
-          ok = row_joins(r);
-
-          if (ok)
-          {
-            shortR = min(shortR, nibble(runsR, r));
-            shortL = min(shortL, nibble(runsL, r));
-          }
-        }
-
-        if (ok) h++; else down = false;
-      }
-
-      if (up)
-      {
-        bool ok = ay + r0 > 0;
-
-        if (ok)
-        {
-          const int r = r0 - 1;
-
-          if (r < vy0 || c0 + w - (B + sx) > 15)
-            return false;
-
-          ok = row_joins(r);
-
-          if (ok)
-          {
-            shortR = min(shortR, nibble(runsR, r));
-            shortL = min(shortL, nibble(runsL, r));
-          }
-        }
-
-        if (ok) { r0--; h++; } else up = false;
-      }
-
-      if (left)
-      {
-        bool ok = ax + c0 > 0;
-
-        if (ok)
-        {
-          if (c0 - 1 < vx0)
-            return false;
-
-          ok = shortL >= B - (c0 - 1);
-        }
-
-        if (ok) { c0--; w++; } else left = false;
-      }
-    }
-
-    ox = ax + c0;
-    oy = ay + r0;
-    rx = w;
-    ry = h;
     return true;
   }
 
@@ -941,11 +805,11 @@ struct WaveScan
 
     const long long ts0 = wave_clock();
 
-    g.avail = pre.rowBits & ~region_used(sn, x, y, pre.vy1);
 
-    if (!grow_seed_runs(g.avail, pre.vx1, pre.vy1, x, y, stage == 0 ? 3 : 0, r.rx, r.ry))
+    if (!grow_in_window(pre, sn, x, y, stage == 0 ? 3 : 0, r.rx, r.ry))
     {
       const long long ts1 = wave_clock();
+      g.avail = pre.rowBits & ~region_used(sn, x, y, pre.vy1);
       int ox = x, oy = y;
       r.rx = 1;
       r.ry = 1;
@@ -1033,10 +897,7 @@ struct WaveScan
         const int centre = coy * a.BX + cox;
         const long long tg0 = wave_clock();
         tRegion += tg0 - tr0;
-
-        if (!grow_centre_runs(c.avail, symHdr, cox, coy, cox, coy, crx, cry))
-          grow(centre, c, true, 0, cox, coy, crx, cry);
-
+        grow(centre, c, true, 0, cox, coy, crx, cry);
         tGrow4 += wave_clock() - tg0;
         r.cox = cox; r.coy = coy; r.crx = crx; r.cry = cry;
         r.attempted = 1;
@@ -1433,19 +1294,6 @@ __device__ void wave_scan_rows(const WaveArgs &a, const Backend &be, int attempt
           // The fence orders the mask reads below behind the progress read above (PTX does not order two loads by a branch between
           // them); it is only paid for when this look at the mask can be the final one.
           const bool final = have ? p >= min(r.boxR + a.margin, a.BX) : p >= min(x + 1 + a.margin + 8, a.BX);
-
-          if (have && !final && !(a.experiment & 4))
-          {
-            // the speculative result stands until the look that can make it final: a poll is two shared-memory reads, not a snapshot and a comparison
-            tWait += wave_clock() - tc;
-
-            if (spins > LIMG_WAVE_SPIN_LIMIT) { a.flags[3] = 1; break; }
-
-            look_ahead(r.kind == 1 ? x + r.rx : x + 1);
-            rowPolls++;
-            if (p + 64 < x) __nanosleep(200);
-            continue;
-          }
 
           if (final && !(a.experiment & 1))
             be.acquire_fence();

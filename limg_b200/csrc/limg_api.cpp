@@ -101,7 +101,7 @@ limg_result limg_encode_test(const uint32_t *, const size_t, const size_t, const
   return limg_error_Generic; // legacy one-factor codec: out of scope
 }
 
-limg_result limg_encode3d_test(const uint32_t *pIn, const size_t sizeX, const size_t sizeY, const bool hasAlpha, limg_encode3d_info *pInfo, const uint32_t errorFactor, limg_thread_pool *, const bool fastBitCrushing)
+limg_result limg_encode3d_test(const uint32_t *pIn, const size_t sizeX, const size_t sizeY, const bool hasAlpha, limg_encode3d_info *pInfo, const uint32_t errorFactor, limg_thread_pool *pThreadPool, const bool fastBitCrushing)
 {
   if (pIn == nullptr || pInfo == nullptr)
     return limg_error_ArgumentNull;
@@ -117,7 +117,11 @@ limg_result limg_encode3d_test(const uint32_t *pIn, const size_t sizeX, const si
   p.pColAMin = pInfo->pColAMin; p.pColAMax = pInfo->pColAMax; p.pColBMin = pInfo->pColBMin; p.pColBMax = pInfo->pColBMax;
   p.pColCMin = pInfo->pColCMin; p.pColCMax = pInfo->pColCMax;
   p.pFactorsA = pInfo->pFactorsA; p.pFactorsB = pInfo->pFactorsB; p.pFactorsC = pInfo->pFactorsC;
-  return to_result(limgcu_host_encode3d(ctx, pIn, sizeX, sizeY, hasAlpha ? 1 : 0, &p, errorFactor, fastBitCrushing ? 1 : 0));
+  // the reference's result depends on the pool size (one dither chain per y-band of the pool, limg.cpp:1893, 2108-2137): reproduce it
+  limgcu_set_pool_threads(ctx, pThreadPool ? (int)pThreadPool->threads : 0);
+  const int rc = limgcu_host_encode3d(ctx, pIn, sizeX, sizeY, hasAlpha ? 1 : 0, &p, errorFactor, fastBitCrushing ? 1 : 0);
+  limgcu_set_pool_threads(ctx, 0);
+  return to_result(rc);
 }
 
 limg_result limg_encode3d_test_perf(const uint32_t *pIn, const size_t sizeX, const size_t sizeY, const bool hasAlpha, const uint32_t errorFactor, limg_thread_pool *, const bool fastBitCrushing)

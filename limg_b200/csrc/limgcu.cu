@@ -22,7 +22,8 @@ using namespace limg;
 namespace limg
 {
 // dither_aes_host.cpp
-uint64_t aes_dither_chain_host(const limgcu_area *areas, uint32_t count, uint64_t seed, uint8_t *noise, uint64_t *planeOff, uint64_t *before, uint64_t *after, bool forceSoftware);
+uint64_t aes_dither_chain_host(const limgcu_area *areas, uint32_t count, uint64_t seed, uint8_t *noise, uint64_t *planeOff, uint64_t *before, uint64_t *after, bool forceSoftware,
+                               uint32_t bandAreas, uint32_t bandCount);
 bool host_has_aesni();
 }
 
@@ -94,8 +95,11 @@ struct limgcu_ctx
 
   int mergeExt = 1;                  // LIMGCU_MERGE_EXT=0 disables the speculative match bitmaps (everything beyond the 8x8 window on demand)
   int mergeMode = 0;                 // LIMGCU_MERGE_MODE: 0 wave (pipelined rows + verification), 1 seq (rows strictly in sequence)
-  int scanCluster = 8;               // LIMGCU_SCAN_CLUSTER: CTAs of the cluster that runs the scan with its state in shared memory (k_merge_cta); 0 = scan over the mask in global memory (k_merge_wave)
+  int scanCluster = 8;               // LIMGCU_SCAN_CLUSTER: CTAs of the cluster that runs the scan with its state in shared memory (k_merge_cta); 0 = scan over the mask in global memory (k_merge_wave); unset: 8, or 16 for 8K-class frames
+  bool scanClusterSet = false;
+  int poolThreads = 0;               // limgcu_set_pool_threads: the non-merged encoder restarts its dither chain per y-band of a pool of this many threads, as the reference does (0: pool-less)
   int scanExperiment = 0;            // LIMGCU_SCAN_EXPERIMENT: measurement switches of the scan (WaveArgs::experiment), 0 in production
+  int scanWarps = LIMG_CTA_WARPS;    // LIMGCU_SCAN_WARPS: warps (block rows in flight) per CTA of that cluster, 1..8; 255 registers per thread, so 8 warps take an SM's whole register file, 4 leave half of it to other kernels
   int scanSmemLimit = 0;             // bytes of dynamic shared memory a CTA may opt in to (the mask replica has to fit)
   int planExtW = 16, planSymL = 6, planSymR = 12, planSymD = 16; // LIMGCU_PLAN_EXTW / SYML / SYMR / SYMD: size caps of the speculative bitmaps
   int mergeGap = 16;                 // LIMGCU_MERGE_GAP: block rows stage 1 stays behind stage 0
@@ -351,8 +355,9 @@ extern "C" int limgcu_create(int device, limgcu_ctx **out)
   if (const char *v = getenv("LIMGCU_MERGE_EXT")) ctx->mergeExt = atoi(v);
 
   if (const char *v = getenv("LIMGCU_MERGE_MODE")) ctx->mergeMode = !strcmp(v, "seq") ? 1 : 0;
+  if (const char *v = getenv("LIMGCU_SCAN_WARPS")) ctx->scanWarps = atoi(v) < 1 ? 1 : (atoi(v) > LIMG_CTA_WARPS ? LIMG_CTA_WARPS : atoi(v));
   if (const char *v = getenv("LIMGCU_SCAN_EXPERIMENT")) ctx->scanExperiment = atoi(v);
-  if (const char *v = getenv("LIMGCU_SCAN_CLUSTER")) ctx->scanCluster = atoi(v) < 0 ? 0 : (atoi(v) > 16 ? 16 : atoi(v));
+  if (const char *v = getenv("LIMGCU_SCAN_CLUSTER")) { ctx->scanCluster = atoi(v) < 0 ? 0 : (atoi(v) > 16 ? 16 : atoi(v)); ctx->scanClusterSet = true; }
   if (const char *v = getenv("LIMGCU_MERGE_MARGIN")) ctx->mergeMargin = atoi(v) < 0 ? 0 : atoi(v);
   if (const char *v = getenv("LIMGCU_PLAN_EXTW")) ctx->planExtW = atoi(v) < 8 ? 8 : (atoi(v) > 32 ? 32 : atoi(v));
   if (const char *v = getenv("LIMGCU_PLAN_SYML")) ctx->planSymL = atoi(v) < 1 ? 1 : (atoi(v) > 8 ? 8 : atoi(v));
@@ -694,16 +699,20 @@ static int launch_merge(limgcu_ctx *ctx, const limgcu_decomp *dTable, size_t W, 
       // memory of its CTAs (k_merge_cta), if a replica fits; the scan over global memory is for larger images and for the sequential try.
       const size_t ctaSmem = merge_cta_smem_words(BY, wordsPerRow) * sizeof(uint32_t);
 
-      if (!sequential && ctx->scanCluster > 0 && ctaSmem <= (size_t)ctx->scanSmemLimit)
+      // 8 CTAs x 8 warps = 64 block rows in flight cover the wavefront of a 4K frame (BX / lag rows) and leave the rest of the GPU to other frames'
+      // kernels; an 8K-class frame has twice the columns, so its wavefront is twice as deep: 16 CTAs (a non-portable cluster size, 10 % faster there).
+      const int clusterSize = ctx->scanClusterSet ? ctx->scanCluster : (blocks >= 200000 ? 16 : 8);
+
+      if (!sequential && clusterSize > 0 && ctaSmem <= (size_t)ctx->scanSmemLimit)
       {
         cudaLaunchConfig_t cfg = {};
         cudaLaunchAttribute attr[1];
-        cfg.gridDim = dim3((unsigned)ctx->scanCluster);
-        cfg.blockDim = dim3(LIMG_CTA_WARPS * 32);
+        cfg.gridDim = dim3((unsigned)clusterSize);
+        cfg.blockDim = dim3((unsigned)ctx->scanWarps * 32);
         cfg.dynamicSmemBytes = ctaSmem;
         cfg.stream = ctx->stream;
         attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = (unsigned)ctx->scanCluster;
+        attr[0].val.clusterDim.x = (unsigned)clusterSize;
         attr[0].val.clusterDim.y = 1;
         attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
@@ -870,6 +879,13 @@ extern "C" int limgcu_set_dither_mode(limgcu_ctx *ctx, int aes)
   return LIMGCU_SUCCESS;
 }
 
+extern "C" int limgcu_set_pool_threads(limgcu_ctx *ctx, int threads)
+{
+  NEED(ctx);
+  ctx->poolThreads = threads < 0 ? 0 : threads;
+  return LIMGCU_SUCCESS;
+}
+
 extern "C" int limgcu_host_has_aesni(void)
 {
   return host_has_aesni() ? 1 : 0;
@@ -944,6 +960,28 @@ static int launch_dither_finalize(limgcu_ctx *ctx, const uint32_t *d_src, size_t
   struct { int BY; } e = { (H + 7) / 8 };
   const bool ditherAes = (flags & LIMGCU_FLAG_DITHER_AES) != 0;
 
+  // The non-merged encoder with a thread pool (limg_encode3d_test, limg.cpp:2108-2137) cuts the image into pool * 4 y-bands of whole block rows
+  // (pool bands if that leaves less than a block row per band) and restarts the dither chain at the top of each (limg.cpp:1893): areas are the
+  // blocks in raster order there, so a band is a fixed number of areas and the last band takes the rest.
+  uint32_t bandAreas = 0, bandCount = 0;
+
+  if ((flags & LIMGCU_FLAG_NO_MERGE) && ctx->poolThreads > 0)
+  {
+    size_t bands = (size_t)ctx->poolThreads * 4, rows = (sizeY / 8) / bands;
+
+    if (rows == 0)
+    {
+      bands = (size_t)ctx->poolThreads;
+      rows = (sizeY / 8) / bands;
+    }
+
+    if (rows > 0 && bands > 1)
+    {
+      bandAreas = (uint32_t)(rows * (size_t)BX);
+      bandCount = (uint32_t)bands;
+    }
+  }
+
   if (ditherAes)
   {
     // The AES-round chain cannot be jumped: bring the area table (shifts, pixel rectangles) to the host, walk the chain there
@@ -960,7 +998,8 @@ static int launch_dither_finalize(limgcu_ctx *ctx, const uint32_t *d_src, size_t
     CK(cudaMemcpyAsync(ctx->hAreas, dAreas, (size_t)count * sizeof(limgcu_area), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     const uint64_t noiseBytes = aes_dither_chain_host(ctx->hAreas, count, LIMG_DITHER_SEED, ctx->hNoise, reinterpret_cast<uint64_t *>(ctx->hNoiseOff),
-                                                      reinterpret_cast<uint64_t *>(ctx->hStates), reinterpret_cast<uint64_t *>(ctx->hStates) + count, ctx->aesForceSoftware != 0);
+                                                      reinterpret_cast<uint64_t *>(ctx->hStates), reinterpret_cast<uint64_t *>(ctx->hStates) + count, ctx->aesForceSoftware != 0,
+                                                      bandAreas, bandCount);
     CK(cudaMemcpyAsync(ctx->dNoise, ctx->hNoise, (size_t)noiseBytes, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->dNoiseOff, ctx->hNoiseOff, 3 * (size_t)count * sizeof(unsigned long long), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->dStates, ctx->hStates, 2 * (size_t)count * sizeof(unsigned long long), cudaMemcpyHostToDevice, ctx->stream));
@@ -975,7 +1014,7 @@ static int launch_dither_finalize(limgcu_ctx *ctx, const uint32_t *d_src, size_t
   {
     k_dither_scan<<<1, 1024, 0, ctx->stream>>>(ctx->dCounters + 1, ctx->dDemand, ctx->dDitherBefore, 0);
     CKL("k_dither_scan");
-    k_dither_states<<<(unsigned)((((size_t)BX * e.BY) + 255) / 256), 256, 0, ctx->stream>>>(dAreas, ctx->dCounters + 1, ctx->dDemand, ctx->dDitherBefore, ctx->jt);
+    k_dither_states<<<(unsigned)((((size_t)BX * e.BY) + 255) / 256), 256, 0, ctx->stream>>>(dAreas, ctx->dCounters + 1, ctx->dDemand, ctx->dDitherBefore, ctx->jt, bandAreas, bandCount);
     CKL("k_dither_states");
   }
 

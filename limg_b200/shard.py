@@ -64,14 +64,21 @@ def gather_to_rank0(obj, rank: int, world: int):
 # whole-image-exact row bands (C ABI: limgcu_pass1 / limgcu_merge / limgcu_encode_areas / limgcu_finalize_rows)
 # ---------------------------------------------------------------------------------------------------------------------------------
 
+def padded_block_rows(height: int, world: int) -> int:
+    """Block rows of the table / source when every rank's band is padded to the same size (what an all-gather needs): world * ceil(blockY / world)."""
+    block_rows = (height + BLOCK - 1) // BLOCK
+    return world * ((block_rows + world - 1) // world)
+
+
 class RowBandExact:
     """One rank of the exact row-band encode: the same stream as ONE encode of the whole image (areas may cross the bands, one dither chain).
 
-    The exchange steps are SUM all-reduces over buffers that are zero wherever another rank contributes (pass-1 table: 64 B per block;
-    per-area results: 80 B per area), so that bands of unequal height need no padding; with integer views the sum is exact. The scan runs
-    redundantly on every rank (it is deterministic), the per-area refit + shift search and the per-pixel finalize are sharded.
-    Phases: pass1() -> [all-reduce table] -> merge_and_encode() -> [all-reduce results] -> finalize(). `encode_rowbands_exact` drives them
-    with torch.distributed; the tests drive several ranks on one GPU by hand."""
+    Exchange steps: the source bands and the pass-1 table (64 B per block) are ALL-GATHERED (every rank's band is the same number of block rows,
+    the last ones padded, so the chunks are equal and the gather runs in place); the per-area results (80 B per area, zero wherever another rank
+    encodes the area) are SUM all-reduced with an integer view, which is exact. The scan runs redundantly on every rank (it is deterministic), the
+    per-area refit + shift search and the per-pixel finalize are sharded.
+    Phases: pass1() -> [all-gather table] -> merge_and_encode() -> [all-reduce results] -> finalize(). `encode_rowbands_exact` drives them with
+    torch.distributed on the codec's own stream (no host synchronisation between the phases); the tests drive several ranks on one GPU by hand."""
 
     def __init__(self, codec, d_src, width: int, height: int, has_alpha: bool, rank: int, world: int, error_factor: int = 100, fast_bit_crushing: bool = True):
         import torch
@@ -82,10 +89,12 @@ class RowBandExact:
         self.bx, self.by = (width + 7) // 8, (height + 7) // 8
         self.y0, self.y1 = row_bands(height, world)[rank]
         self.row_lo, self.row_hi = band_block_rows(self.y0, self.y1)
+        self.rows_per_rank = padded_block_rows(height, world) // world
         dev = d_src.device
         blocks = self.bx * self.by
         words = int(codec.lib.limgcu_area_result_words())
-        self.table = torch.zeros(blocks * 16, dtype=torch.int32, device=dev)      # limgcu_decomp[blocks], 64 B each
+        # limgcu_decomp[padded block rows][bx], 64 B each; chunk r = block rows [r * rows_per_rank, (r + 1) * rows_per_rank)
+        self.table = torch.zeros(world * self.rows_per_rank * self.bx * 16, dtype=torch.int32, device=dev)
         self.results = torch.zeros(blocks * words, dtype=torch.int32, device=dev)
         self.areas = torch.zeros(blocks * AREA_DTYPE.itemsize, dtype=torch.uint8, device=dev)
         self.count = torch.zeros(1, dtype=torch.int32, device=dev)
@@ -97,25 +106,29 @@ class RowBandExact:
     def _ck(self, rc, what):
         self.codec._ck(rc, what)
 
+    def table_chunk(self):
+        """this rank's equal-sized chunk of the table (the input of the in-place all-gather)"""
+        n = self.rows_per_rank * self.bx * 16
+        return self.table[self.rank * n:(self.rank + 1) * n]
+
     def pass1(self):
-        """three-factor fit of the blocks of this rank's band -> its rows of the table (the rest stays zero)"""
+        """three-factor fit of the blocks of this rank's band -> its rows of the table; stream ordered, no synchronisation"""
         if self.y1 > self.y0:
             lib, c = self.codec.lib, self.codec
             self._ck(lib.limgcu_pass1(c.h, self.src.data_ptr() + self.y0 * self.w * 4, self.w, self.y1 - self.y0, int(self.alpha), self.table.data_ptr() + self.row_lo * self.bx * 64), "limgcu_pass1")
-        self.codec.sync()
         return self.table
 
     def merge_and_encode(self):
-        """the identical scan on the complete table, then refit + shift search of the areas that start in this rank's block rows"""
+        """the identical scan on the complete table, then refit + shift search of the areas that start in this rank's block rows; stream ordered
+        (a scan that timed out or overflowed is reported by finalize(), on every rank alike: they all run the same scan)"""
         lib, c = self.codec.lib, self.codec
         self._ck(lib.limgcu_merge(c.h, self.table.data_ptr(), self.w, self.h, int(self.alpha), self.areas.data_ptr(), self.count.data_ptr(), self.block_to_area.data_ptr()), "limgcu_merge")
         self._ck(lib.limgcu_encode_areas(c.h, self.src.data_ptr(), self.w, self.h, int(self.alpha), self.ef, self.flags, self.table.data_ptr(), self.areas.data_ptr(), self.row_lo, self.row_hi,
                                          self.results.data_ptr()), "limgcu_encode_areas")
-        self.codec.status()  # synchronises; a timed-out or truncated scan must not be shared with the other ranks
         return self.results
 
     def finalize(self):
-        """complete per-area results -> area table, dither chain, codes of this rank's pixel rows"""
+        """complete per-area results -> area table, dither chain, codes of this rank's pixel rows. Synchronises (and checks the scan's hard-error flags)."""
         from ._lib import Stream
         import ctypes as C
         lib, c = self.codec.lib, self.codec
@@ -133,18 +146,24 @@ class RowBandExact:
         return np.frombuffer(self.areas.cpu().numpy().tobytes(), dtype=AREA_DTYPE, count=n).copy()
 
 
-def encode_rowbands_exact(codec, d_src, width: int, height: int, has_alpha: bool, rank: int, world: int, error_factor: int = 100, fast_bit_crushing: bool = True) -> RowBandExact:
-    """All ranks call this with the whole source in device memory (all-gather it first if every rank holds only its band). Returns the rank's
-    RowBandExact: the complete area table and the codes of its own pixel rows."""
+def encode_rowbands_exact(codec, d_src, width: int, height: int, has_alpha: bool, rank: int, world: int, error_factor: int = 100, fast_bit_crushing: bool = True,
+                          band: "RowBandExact | None" = None) -> RowBandExact:
+    """All ranks call this with the whole source in device memory (all-gather it first if every rank holds only its band, see bench.py). Returns the
+    rank's RowBandExact: the complete area table and the codes of its own pixel rows. The collectives are issued on the codec's stream, so the only
+    host synchronisation is the one at the end of finalize(). `band`: a RowBandExact to reuse (its buffers are allocated and zeroed once)."""
     import torch
-    r = RowBandExact(codec, d_src, width, height, has_alpha, rank, world, error_factor, fast_bit_crushing)
-    table = r.pass1()
-    if world > 1:
-        import torch.distributed as dist
-        dist.all_reduce(table)
-        torch.cuda.synchronize(d_src.device)
-    results = r.merge_and_encode()
-    if world > 1:
-        dist.all_reduce(results)
-        torch.cuda.synchronize(d_src.device)
+    r = band if band is not None else RowBandExact(codec, d_src, width, height, has_alpha, rank, world, error_factor, fast_bit_crushing)
+    r.src = d_src
+    if world == 1:
+        r.pass1()
+        r.merge_and_encode()
+        return r.finalize()
+    import torch.distributed as dist
+    with torch.cuda.stream(torch.cuda.ExternalStream(codec.stream, device=d_src.device)):
+        if band is not None:
+            r.results.zero_()  # areas of other ranks must contribute zeros to the sum
+        r.pass1()
+        dist.all_gather_into_tensor(r.table, r.table_chunk())
+        r.merge_and_encode()
+        dist.all_reduce(r.results)
     return r.finalize()

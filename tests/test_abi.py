@@ -38,7 +38,7 @@ def test_header_symbols_exported(lib):
 def test_cxx_dropin_symbols_exported():
     out = subprocess.run(["nm", "-DC", os.path.join(ROOT, "limg_b200", "liblimgcu.so")], capture_output=True, text=True, check=True).stdout
     for n in ("limg_blocked_encode3d_test(", "limg_encode3d_test(", "limg_encode3d_test_perf(", "limg_compare(", "limg_encode_test(",
-              "limg_thread_pool_new(", "limg_thread_pool_destroy(", "limg_threading_max_threads("):
+              "limg_thread_pool_new(", "limg_thread_pool_destroy(", "limg_threading_max_threads(", "limg_b200_set_device(", "limg_b200_set_dither_mode("):
         assert n in out, n
 
 

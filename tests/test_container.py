@@ -250,12 +250,20 @@ def test_gpu_exact_row_bands_equal_the_whole_image_encode(codec, case):
     codecs = [Codec(0) for _ in range(world)]
     try:
         ranks = [shard.RowBandExact(c, d_src, w, h, alpha, r, world) for r, c in enumerate(codecs)]
-        table = sum(r.pass1() for r in ranks)          # the SUM all-reduce
+        for r in ranks:
+            r.pass1()                                   # stream ordered on the rank's own codec stream
+            r.codec.sync()
+        table = sum(r.table for r in ranks)             # the all-gather: every chunk of the table is zero except on the rank that owns it
         for r in ranks:
             r.table.copy_(table)
-        results = sum(r.merge_and_encode() for r in ranks)
+        torch.cuda.synchronize()
+        for r in ranks:
+            r.merge_and_encode()
+            r.codec.sync()
+        results = sum(r.results for r in ranks)         # the SUM all-reduce
         for r in ranks:
             r.results.copy_(results)
+        torch.cuda.synchronize()
         codes = [np.zeros((h, w), np.uint8) for _ in range(3)]
         for r in ranks:
             r.finalize()

@@ -116,6 +116,54 @@ def test_blocked_encode_golden(codec, name):
     assert abs(psnr - float(g["psnr"])) < 1e-9 and abs(mse - float(g["mse"])) < 1e-9
 
 
+@pytest.mark.parametrize("name", ["rgb_photo_96x64", "rgb_photo_96x64_aes", "rgba_photo_64x64"])
+def test_cxx_dropin_symbols_reproduce_the_reference(name):
+    """The reference's own C++ entry points (limg.h:46 limg_blocked_encode3d_test, limg.h:48 limg_compare), called by their mangled
+    names as the reference CLI binds them (main.cpp:255), through limg_api.cpp: all 13 host planes equal the golden run of the real
+    reference, with the dither generator that run used."""
+    import ctypes as C
+    from limg_b200 import _lib
+    lib = _lib.load()
+    g = H.load_golden(name)
+    img = np.ascontiguousarray(g["img"], dtype=np.uint32)
+    h, w = img.shape
+    alpha = bool(g["has_alpha"])
+    order = ("pDecoded", "pFactorsA", "pFactorsB", "pFactorsC", "pBlockError", "pBitsPerPixel", "pShiftABCX", "pColAMin", "pColAMax", "pColBMin", "pColBMax",
+             "pColCMin", "pColCMax", "pBlockIndex")  # limg_blocked_encode3d_info, limg.h:39-44
+    u8 = ("pFactorsA", "pFactorsB", "pFactorsC", "pBlockError", "pBitsPerPixel")
+
+    class Info(C.Structure):
+        _fields_ = [(k, C.c_void_p) for k in order]
+
+    planes = {k: np.zeros((h, w), np.uint8 if k in u8 else np.uint32) for k in order}
+    info = Info(**{k: v.ctypes.data for k, v in planes.items()})
+    encode = getattr(lib, "_Z26limg_blocked_encode3d_testPKjmmbP26limg_blocked_encode3d_infojP16limg_thread_poolb")
+    encode.restype = C.c_int
+    encode.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_bool, C.c_void_p, C.c_uint32, C.c_void_p, C.c_bool]
+    set_dither = getattr(lib, "_Z25limg_b200_set_dither_modei")
+    set_dither.restype = C.c_int
+    pool_new = getattr(lib, "_Z20limg_thread_pool_newm")
+    pool_new.restype = C.c_void_p
+    pool_new.argtypes = [C.c_size_t]
+    pool = C.c_void_p(pool_new(4))  # a token: the GPU path ignores it, as the reference's blocked encoder's result does not depend on it
+    assert set_dither(1 if bool(g["aes"]) else 0) == (1 if bool(g["aes"]) else 0)
+    try:
+        assert encode(img.ctypes.data, w, h, alpha, C.byref(info), int(g["error_factor"]), pool, bool(g["fast"])) == 0
+    finally:
+        set_dither(-1)
+    for k in H.PLANES:
+        assert np.array_equal(planes[k], g["plane_" + k]), k
+    assert not planes["pBlockError"].any()
+    compare = getattr(lib, "_Z12limg_comparePKjS0_mmbPdS1_")
+    compare.restype = C.c_double
+    compare.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_bool, C.c_void_p, C.c_void_p]
+    mse, mx = C.c_double(), C.c_double()
+    psnr = compare(img.ctypes.data, planes["pDecoded"].ctypes.data, w, h, alpha, C.byref(mse), C.byref(mx))
+    assert abs(psnr - float(g["psnr"])) < 1e-9 and abs(mse.value - float(g["mse"])) < 1e-9
+    # null arguments are rejected, not dereferenced
+    assert encode(None, w, h, alpha, C.byref(info), 100, None, True) == 102  # limg_error_ArgumentNull
+
+
 def test_aes_golden_shares_everything_but_the_noise(codec):
     """The AES-NI dither of the reference changes factor bytes only: area map, shifts, endpoints must still match."""
     g = H.load_golden("rgb_photo_96x64_aes")
@@ -123,12 +171,24 @@ def test_aes_golden_shares_everything_but_the_noise(codec):
     assert_areas_equal(st["areas"], golden_areas(g), dither=False)
 
 
+@pytest.mark.parametrize("threads", [0, 2])
 @pytest.mark.parametrize("name", [n for n in H.golden_image_cases() if "enc3d_t0_pDecoded" in H.load_golden(n).files])
-def test_unmerged_encoder_golden(codec, name):
+def test_unmerged_encoder_golden(codec, name, threads):
+    """limg_encode3d_test pool-less and with a 2-thread pool (8 y-bands, each restarting the dither chain: limg.cpp:1893, 2108-2137)."""
     g = H.load_golden(name)
-    p = codec.encode3d_test(g["img"], bool(g["has_alpha"]), None, 100, True)
+    p = codec.encode3d_test(g["img"], bool(g["has_alpha"]), None, 100, True, pool_threads=threads)
     for k, v in p.items():
-        assert np.array_equal(v, g["enc3d_t0_" + k]), k
+        assert np.array_equal(v, g["enc3d_t%d_%s" % (threads, k)]), k
+
+
+def test_unmerged_encoder_pool_bands_vs_oracle(codec, lo):
+    """pool sizes and heights where the band rule changes (pool * 4 bands, pool bands, or no restart at all), against the C oracle's model"""
+    for (w, h, threads) in ((96, 200, 3), (64, 40, 4), (120, 16, 8), (72, 131, 1)):
+        img = synth.photo_like(w, h, 7 + threads, 3)
+        got = codec.encode3d_test(img, False, None, 100, True, pool_threads=threads)
+        want = lo.encode3d(img, False, 100, True, pool_threads=threads)
+        for k in ("pDecoded", "pFactorsA", "pFactorsB", "pFactorsC"):
+            assert np.array_equal(got[k], want[k]), (k, w, h, threads)
 
 
 # ---- (b) the C oracle on seeded inputs ----------------------------------------------------------------------------

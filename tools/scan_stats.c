@@ -23,7 +23,45 @@ void scan_stats(const lo_decomp *table, int BX, int BY, int CH, double *out /* [
   memset(m.memoKey, 0xFF, cap * 8);
   m.owner = (uint32_t *)malloc((size_t)BX * BY * 4);
   memset(m.owner, 0xFF, (size_t)BX * BY * 4);
+  /* plan filter model: which stage-0 candidates are probably still alive when the scan reaches them? cover[b] = smallest raster index of a
+   * candidate whose mask-free rectangle covers block b; a candidate is "alive" if no earlier candidate covers its 3x3 corner; second round
+   * with the alive candidates of the first round only. */
+  uint32_t *cover = (uint32_t *)malloc((size_t)BX * BY * 4);
+  uint8_t *alive = (uint8_t *)calloc((size_t)BX * BY, 1), *cand0 = (uint8_t *)calloc((size_t)BX * BY, 1);
+  uint8_t *r0x = (uint8_t *)calloc((size_t)BX * BY, 1), *r0y = (uint8_t *)calloc((size_t)BX * BY, 1);
+  for (int y = 0; y < BY; y++)
+    for (int x = 0; x < BX; x++)
+      if (is_cand(&m, x, y, 0))
+      {
+        const Result r0 = expand(&m, x, y, 0, 0u);
+        cand0[y * BX + x] = 1; r0x[y * BX + x] = (uint8_t)(r0.rx > 8 ? 8 : r0.rx); r0y[y * BX + x] = (uint8_t)(r0.ry > 8 ? 8 : r0.ry);
+      }
+  for (int round = 0; round < (int)out[63] + 1; round++)
+  {
+    memset(cover, 0xFF, (size_t)BX * BY * 4);
+    for (int s = 0; s < BX * BY; s++)
+      if (cand0[s] && (round == 0 || alive[s]))
+      {
+        const int x = s % BX, y = s / BX;
+        for (int dy = 0; dy < r0y[s]; dy++)
+          for (int dx = 0; dx < r0x[s]; dx++)
+            if (cover[(y + dy) * BX + x + dx] > (uint32_t)s) cover[(y + dy) * BX + x + dx] = (uint32_t)s;
+      }
+    for (int s = 0; s < BX * BY; s++)
+      if (cand0[s])
+      {
+        const int x = s % BX, y = s / BX;
+        int ok = 1;
+        for (int dy = 0; dy < 3; dy++)
+          for (int dx = 0; dx < 3; dx++)
+            if (cover[(y + dy) * BX + x + dx] < (uint32_t)s) ok = 0;
+        alive[s] = (uint8_t)ok;
+      }
+  }
+  const int rounds = (int)out[63] + 1;
   memset(out, 0, 64 * sizeof(double));
+  out[62] = rounds;
+  for (int s = 0; s < BX * BY; s++) { out[60] += cand0[s]; out[61] += alive[s]; }
 
   for (int stage = 0; stage < 2; stage++)
   {
@@ -41,6 +79,7 @@ void scan_stats(const lo_decomp *table, int BX, int BY, int CH, double *out /* [
           const Result r0 = expand(&m, x, y, stage, 0u);
           o[0]++;                                           /* expansions */
           if (r.kind == 0) { o[1]++; break; }               /* nothing emitted */
+          if (stage == 0 && !alive[y * BX + x]) o[14]++;    /* an emitting seed the filter declared dead */
           const int sameR = r.rx == r0.rx && r.ry == r0.ry;
           const int freeR0 = rect_free(&m, x, y, r0.rx, r0.ry);
           o[2] += sameR; o[3] += freeR0;
