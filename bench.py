@@ -803,10 +803,12 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     t = torch.tensor([total_ms, sum(enc_ms), sum(dec_ms), e2e_s * 1e3], dtype=torch.float64, device=dev)
     px_all = torch.tensor([float(npx)], dtype=torch.float64, device=dev)
     parity_all = torch.tensor([band_parity], dtype=torch.float64, device=dev)
+    fails_all = torch.tensor([float(counters[24])], dtype=torch.float64, device=dev)  # tries of the scan that failed their verification (last encode)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(px_all, op=dist.ReduceOp.SUM)
         dist.all_reduce(parity_all, op=dist.ReduceOp.MIN)
+        dist.all_reduce(fails_all, op=dist.ReduceOp.MAX)
     total_ms, enc_total, dec_total, e2e_ms = [float(x) for x in t.tolist()]
     px_job = float(px_all.item())  # pixels all ranks process per step
 
@@ -851,7 +853,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                                      "kernel": "all kernels of limgcu_blocked_encode3d, 7 algorithmic B/px"},
             "unmerged_encode": {"encode_ms": unmerged_ms, "encode_mpixel_s": npx / 1e6 / (unmerged_ms * 1e-3), "hbm_frac": 7.0 * npx / (unmerged_ms * 1e-3) / 1e9 / peak,
                                 "what": "limgcu_blocked_encode3d with LIMGCU_FLAG_NO_MERGE (the path of limg_encode3d_test / _perf: every 8x8 block its own area), per GPU"},
-            "merge": {"failed_first_tries": int(counters[24]), "areas": int(counters[1]), "merged_rectangles": int(counters[0])},
+            "merge": {"failed_first_tries": int(counters[24]), "failed_first_tries_max_over_ranks": int(fails_all.item()), "areas": int(counters[1]), "merged_rectangles": int(counters[0])},
             "roofline_decode": {"bound": "hbm", "achieved": dec_gbs, "peak": peak, "unit": "GB/s", "frac": dec_gbs / peak, "traffic": None,
                                 "kernel": "k_decode_tile, 7 algorithmic B/px"},
         }

@@ -529,7 +529,10 @@ __global__ void __launch_bounds__(256) k_plan_seeds(PlanArgs a)
     const uint32_t slot = atomicAdd(&a.counters[0], 1u);
 
     if (slot < a.extCap)
-      a.extSeed[slot] = seed; // k_plan_extend publishes extSlot[seed] once the bitmap exists (the scan may already be running)
+    {
+      a.extSeed[slot] = seed;                // k_plan_extend publishes extSlot[seed] once the bitmap exists (the scan may already be running)
+      a.extSlot[seed] = LIMG_SLOT_PENDING;   // also tells k_plan_centres that the seed's mask-free rectangle is not final yet
+    }
   }
 }
 
@@ -619,7 +622,9 @@ __global__ void __launch_bounds__(LIMG_PLAN_WARPS * 32) k_plan_extend(PlanArgs a
 
 // which blocks will the four-way regrowth probably start from? (limg.cpp:1426-1433 with the mask-free rectangle, and up to three
 // blocks to the left of that: a mask shrinks the rectangle's width far more often than its height)
-__global__ void __launch_bounds__(256) k_plan_centres(PlanArgs a)
+// phase 0: the candidates whose growth stays inside their 8x8 word (their mask-free rectangle is final after k_plan_seeds): their centre
+// bitmaps can be built at once, before the (slower) extension bitmaps; phase 1: the others, after k_plan_extend.
+__global__ void __launch_bounds__(256) k_plan_centres(PlanArgs a, int phase)
 {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
 
@@ -627,6 +632,10 @@ __global__ void __launch_bounds__(256) k_plan_centres(PlanArgs a)
     return;
 
   const int seed = (int)a.candList[i];
+
+  if ((*(volatile uint32_t *)&a.extSlot[seed] != LIMG_NO_SLOT) != (phase != 0))
+    return;
+
   const int y = seed / a.BX, x = seed - y * a.BX;
   const uint32_t u = a.unmasked[seed];
   const int rx = u & 0xFF, ry = u >> 8;
@@ -650,6 +659,12 @@ __global__ void __launch_bounds__(256) k_plan_centres(PlanArgs a)
         a.symSeed[slot] = (uint32_t)c; // symSlot[c] stays "pending" until k_plan_sym has written the bitmap
     }
   }
+}
+
+// between the two phases of the centre bitmaps: phase 1 starts where phase 0 stopped
+__global__ void k_plan_mark(PlanArgs a)
+{
+  a.counters[2] = a.counters[3];
 }
 
 // After the bitmaps exist: every stage-0 candidate remembers the slots of the four centres k_plan_centres asked for on its behalf,
@@ -768,15 +783,20 @@ __device__ uint32_t build_centre_bitmap(const PredRec *__restrict__ rec, const u
   return mine;
 }
 
+// phase 0: slots [0, count); it leaves `count` in counters[2] for phase 1, which handles the slots requested since: [counters[2], count)
 template <int CH>
-__global__ void __launch_bounds__(LIMG_PLAN_WARPS * 32) k_plan_sym(PlanArgs a)
+__global__ void __launch_bounds__(LIMG_PLAN_WARPS * 32) k_plan_sym(PlanArgs a, int phase)
 {
   __shared__ uint32_t sRows[LIMG_PLAN_WARPS][32];
   const uint32_t count = min(a.counters[1], a.symCap);
+  const uint32_t first = phase ? min(a.counters[2], count) : 0u;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t warpsTotal = gridDim.x * LIMG_PLAN_WARPS;
 
-  for (uint32_t slot = blockIdx.x * LIMG_PLAN_WARPS + warp; slot < count; slot += warpsTotal)
+  if (phase == 0 && blockIdx.x == 0 && threadIdx.x == 0)
+    a.counters[3] = count; // (copied to counters[2] by the phase-1 k_plan_centres launch's predecessor: see k_plan_mark)
+
+  for (uint32_t slot = first + blockIdx.x * LIMG_PLAN_WARPS + warp; slot < count; slot += warpsTotal)
   {
     const int c = (int)a.symSeed[slot];
     const uint32_t start = a.symStart[c];
@@ -794,6 +814,110 @@ __global__ void __launch_bounds__(LIMG_PLAN_WARPS * 32) k_plan_sym(PlanArgs a)
       *(volatile uint32_t *)&a.symSlot[c] = slot;
 
     __syncwarp();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// How far LEFT of its seed can a stage-0 seed's centre-third regrowth reach? (limg.cpp:1426-1433, 1363-1376)
+//
+// The row-pipelined scan lets a block row decide a seed once the rows above have passed everything the seed probed. A rectangle
+// grown right/down from a seed of a row above starts at that seed's column, but its four-way regrowth also grows LEFT, so an
+// undecided seed further right can still claim blocks the row below has looked at. The regrowth's rectangle always contains its
+// centre's block row, so it cannot pass the first block left of the centre that does not match the centre (mask-free bound; in-use
+// blocks only stop it earlier), and the centre lies inside the seed's right/down rectangle, i.e. at most (run along the seed's
+// row) / 3 columns and (run along its column) / 3 rows from the seed. k_pred_leftrun measures the run of matches left of every block;
+// k_plan_safe turns it, per block row, into the SAFE column of every position: no undecided candidate at or right of that position
+// can touch anything left of the safe column. A row publishes min(own progress, safe column) and the rows below need no margin on
+// top of it. Where the bound is unknown (a run that leaves the 8x8 window, a left run longer than the cap) the old assumption
+// stands in: such a regrowth reaches at most LIMG_SAFE_DEFAULT_REACH columns left of its seed; the verification pass covers the rest.
+// ---------------------------------------------------------------------------------------------
+
+#define LIMG_LEFTRUN_CAP 24
+#define LIMG_LEFTRUN_UNKNOWN 255
+#define LIMG_SAFE_DEFAULT_REACH 8
+
+template <int CH>
+__global__ void __launch_bounds__(128) k_pred_leftrun(const PredRec *__restrict__ rec, int BX, int BY, uint8_t *__restrict__ leftRun)
+{
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+
+  if (b >= BX * BY)
+    return;
+
+  const int y = b / BX, x = b - y * BX;
+  const PredRec s = rec[b];
+  int run = 0;
+
+  while (run < LIMG_LEFTRUN_CAP && x - run - 1 >= 0 && predicate_thread<CH>(s, rec[b - run - 1]))
+    run++;
+
+  // (a run that ends at the grid edge is exact)
+  leftRun[b] = (uint8_t)((run == LIMG_LEFTRUN_CAP && x - run - 1 >= 0) ? LIMG_LEFTRUN_UNKNOWN : run);
+}
+
+// one warp per block row; safe[y * BX + x] = safe column of position x (low 16 bits: candidates at or right of x, i.e. while the candidate at x
+// is undecided; high 16 bits: candidates right of x only, i.e. once x is decided)
+__global__ void __launch_bounds__(32) k_plan_safe(const uint32_t *__restrict__ window, const uint32_t *__restrict__ candBits0, const uint8_t *__restrict__ leftRun, int BX, int BY,
+                                                  int wordsPerRow, uint32_t *__restrict__ safe)
+{
+  const int y = blockIdx.x, lane = threadIdx.x;
+  const int chunks = (BX + 31) >> 5;
+  int carry = 0xFFFF; // safe column of everything right of the current chunk
+
+  for (int c = chunks - 1; c >= 0; c--)
+  {
+    const int x = c * 32 + lane;
+    int mine = 0xFFFF; // leftmost column the regrowth of the candidate at x can touch
+
+    if (x < BX && ((candBits0[(size_t)y * wordsPerRow + c] >> lane) & 1u))
+    {
+      const size_t seed = (size_t)y * BX + x;
+      const uint32_t w0 = window[seed * 2], w1 = window[seed * 2 + 1];
+      // runs along the seed's row and column inside its 8x8 word (the seed itself counts)
+      const int rowRun = __ffs((int)(~(w0 & 0xFFu) & 0x1FFu)) - 1;
+      const uint32_t col = (w0 & 1u) | ((w0 >> 7) & 2u) | ((w0 >> 14) & 4u) | ((w0 >> 21) & 8u) | ((w1 & 1u) << 4) | ((w1 >> 3) & 32u) | ((w1 >> 10) & 64u) | ((w1 >> 17) & 128u);
+      const int colRun = __ffs((int)(~col & 0x1FFu)) - 1;
+
+      if ((rowRun == 8 && x + 8 < BX) || (colRun == 8 && y + 8 < BY))
+      {
+        mine = max(x - LIMG_SAFE_DEFAULT_REACH, 0); // the runs leave the word: where the centre can be is not known here
+      }
+      else
+      {
+        for (int dy = 1; dy <= colRun / 3; dy++)
+          for (int dx = 1; dx <= rowRun / 3; dx++)
+          {
+            const int cx = x + dx, cy = y + dy;
+
+            if (cx >= BX || cy >= BY)
+              continue;
+
+            const int run = leftRun[(size_t)cy * BX + cx];
+            mine = min(mine, run == LIMG_LEFTRUN_UNKNOWN ? max(x - LIMG_SAFE_DEFAULT_REACH, 0) : cx - run);
+          }
+
+        mine = min(mine, x);
+      }
+    }
+
+    // suffix minimum over the lanes (inclusive), then the columns right of this chunk
+    int incl = mine;
+
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1)
+    {
+      const int t = __shfl_down_sync(0xFFFFFFFFu, incl, o);
+      if (lane + o < 32) incl = min(incl, t);
+    }
+
+    int after = __shfl_down_sync(0xFFFFFFFFu, incl, 1);
+    after = min(lane < 31 ? after : 0xFFFF, carry);
+    const int from = min(mine, after);
+
+    if (x < BX)
+      safe[(size_t)y * BX + x] = (uint32_t)from | ((uint32_t)after << 16);
+
+    carry = min(carry, __shfl_sync(0xFFFFFFFFu, incl, 0));
   }
 }
 

@@ -59,6 +59,7 @@ struct WaveArgs
   const uint32_t *symSlot, *symBits, *symHdr;
   const uint16_t *unmasked;
   const uint4 *seedSym;      // per stage-0 candidate: bitmap slots of its predicted centre and the three to its left (nullptr: look them up)
+  const uint32_t *safe;      // [blocks] safe columns of stage 0 (k_plan_safe): low 16 bits while the candidate at the position is undecided, high 16 bits once it is decided; nullptr: none
   const uint32_t *candBits;  // [2][BY][wordsPerRow]: mask-free necessary condition for a seed to emit in stage 0 / 1
   const uint32_t *candList;  // [2][blocks]
   const uint32_t *candCount; // [2]
@@ -237,6 +238,7 @@ struct SeedLinks
   uint32_t u;     // unmasked rx | ry << 8
   uint32_t w0, w1; // the seed's 8x8 match word (warp uniform)
   uint4 links;    // bitmap slots of the predicted centre and the three to its left
+  uint32_t safe;  // safe columns of the candidate's position (stage 0; WaveArgs::safe)
 };
 
 // everything about a seed that does not depend on the mask: loaded while the row waits for the rows above
@@ -504,6 +506,7 @@ struct WaveScan
     l.w0 = w.x;
     l.w1 = w.y;
     l.links = (a.seedSym && stage == 0) ? __ldg(&a.seedSym[seed]) : make_uint4(LIMG_NO_SLOT, LIMG_NO_SLOT, LIMG_NO_SLOT, LIMG_NO_SLOT);
+    l.safe = (a.safe && stage == 0) ? __ldg(&a.safe[seed]) : 0xFFFFFFFFu;
     return l;
   }
 
@@ -1229,12 +1232,18 @@ __device__ void wave_scan_rows(const WaveArgs &a, const Backend &be, int attempt
         ahead.x = -2;
     };
 
-    // the row's own progress: every seed left of `own` is decided, and its claims were fenced when they were made
+    // What the row promises the rows below: every seed left of the published column is decided (its claims were fenced when they were made)
+    // and no seed that is still undecided can touch anything left of it. `rowSafe` is the safe column (k_plan_safe) of the row's undecided
+    // candidates: a stage-0 regrowth also grows to the left of its seed.
+    int rowSafe = (stage == 0 && a.safe) ? (int)(__ldg(&a.safe[(size_t)y * a.BX]) & 0xFFFFu) : LIMG_WAVE_DONE;
+
     auto publish = [&](int own) {
-      if (own > published)
+      const int v = own == LIMG_WAVE_DONE ? own : min(own, rowSafe);
+
+      if (v > published)
       {
-        be.publish(stage, y, own, lane);
-        published = own;
+        be.publish(stage, y, v, lane);
+        published = v;
       }
     };
 
@@ -1252,8 +1261,17 @@ __device__ void wave_scan_rows(const WaveArgs &a, const Backend &be, int attempt
       tc = wave_clock();
       cSeedStart = tc;
       // the seed's links were loaded while the row decided the seed before, if the guess of the next candidate was right
-      SeedPre pre = scan.prefetch_bitmaps(ahead.x == x ? ahead : scan.prefetch_links(x, y, stage), y, stage);
+      const SeedLinks links = ahead.x == x ? ahead : scan.prefetch_links(x, y, stage);
+      SeedPre pre = scan.prefetch_bitmaps(links, y, stage);
       ahead.x = -1;
+
+      if (stage == 0 && a.safe)
+      {
+        rowSafe = (int)(links.safe & 0xFFFFu); // the dead candidates the row skipped no longer count
+        publish(x);
+      }
+
+      const int safeAfter = (stage == 0 && a.safe) ? (int)(links.safe >> 16) : LIMG_WAVE_DONE;
       tPre += wave_clock() - tc;
       cPre = wave_clock() - tc; cWait = 0; cExp = 0; cClaim = 0; cIters = 0;
       const uint32_t first = count;
@@ -1366,7 +1384,10 @@ __device__ void wave_scan_rows(const WaveArgs &a, const Backend &be, int attempt
 
         // hand over to the rows below as early as possible: a right/down rectangle decides every seed up to its right edge
         if (r.kind == 1 && x + r.rx < a.BX)
+        {
+          rowSafe = safeAfter;
           publish(x + r.rx);
+        }
 
         // bookkeeping nobody waits for (read after the kernel): owner times, the row's list
         for (int e = lane; e < erx * ery; e += 32)
@@ -1414,6 +1435,7 @@ __device__ void wave_scan_rows(const WaveArgs &a, const Backend &be, int attempt
       }
 
       x = nextX;
+      rowSafe = safeAfter; // the seed at the old x is decided
 
       if (rowT && lane == 0)
       {

@@ -37,7 +37,7 @@ struct limgcu_ctx
   cudaEvent_t evFork = nullptr, evJoin = nullptr, evFork2 = nullptr, evJoin2 = nullptr, evBand[4] = { nullptr, nullptr, nullptr, nullptr };
   const uint32_t *hostSrc = nullptr; // set by host_encode: limgcu_blocked_encode3d uploads d_src from here in bands, pass 1 of band i under the upload of band i + 1
   int planAsync = 1;                // LIMGCU_PLAN_ASYNC: 0 plan kernels on the main stream, 1 both on the second stream concurrently with the scan, 2 only k_plan_sym
-  int planAsyncCtas = 2;            // LIMGCU_PLAN_CTAS: CTAs per SM of an asynchronous plan kernel (the scan needs room next to them)
+  int planAsyncCtas = 6;            // LIMGCU_PLAN_CTAS: CTAs per SM of an asynchronous plan kernel (the scan is one cluster on 8 or 16 SMs, so they can fill the others: 2 -> 6 is 2 % of a 4K encode)
   char err[512] = { 0 };
   uint64_t launches = 0;
   int smCount = 148;
@@ -68,6 +68,8 @@ struct limgcu_ctx
   uint4 *dSeedSym = nullptr;
   uint32_t *dSymSlot = nullptr, *dSymSeed = nullptr, *dSymBits = nullptr, *dSymHdr = nullptr, *dSymStart = nullptr;
   uint16_t *dUnmasked = nullptr;
+  uint8_t *dLeftRun = nullptr;  // per block: matches to its left (k_pred_leftrun)
+  uint32_t *dSafe = nullptr;    // per block: safe columns of the scan's stage 0 (k_plan_safe)
   uint32_t extCap = 0, symCap = 0;
   uint32_t *dScratchPx = nullptr, *dScratchFac = nullptr;
   uint32_t *dCounters = nullptr; // [32]: 0 merged, 1 areaCount, 2 smallCount, 3 largeCount (fits shared memory), 4 workSmall, 5 workLarge, 6 scratchTop, 7 hugeCount, 8.. stats, 24..28 + 31 scan flags, 29 bigCount, 30 work counter of the huge areas
@@ -106,7 +108,9 @@ struct limgcu_ctx
   int mergeWideMargin = 64;          // margin (and stage gap) of the second try
   int mergeSpec = 8;                 // LIMGCU_MERGE_SPEC: columns of lookahead for the speculative expansion
   int decodeVariant = 20;            // LIMGCU_DECODE_VARIANT: 0 generic k_decode; 2 / 4 / 8 = rows per thread of k_decode_tile (width % 8 == 0)
-  int mergeMargin = 8;               // LIMGCU_MERGE_MARGIN: columns a row stays behind the rows above, beyond what its seed probed
+  int mergeMargin = 0;               // LIMGCU_MERGE_MARGIN: columns a row stays behind the rows above, beyond what its seed probed (the rows above publish SAFE columns, so
+                                     // this is slack, not the protection against leftward regrowth it was before k_plan_safe: 8 then)
+  int mergeSafe = 1;                 // LIMGCU_MERGE_SAFE=0: rows publish their plain progress (no safe columns; use with LIMGCU_MERGE_MARGIN=8)
   bool timing = false;
   cudaEvent_t ev[PHASE_COUNT + 1] = { nullptr };
   float phaseMs[PHASE_COUNT] = { 0 };
@@ -185,6 +189,8 @@ static int ensure_capacity(limgcu_ctx *ctx, size_t W, size_t H)
     ctx->extCap = (uint32_t)(blocks / 2 > 1024 ? blocks / 2 : 1024);
     ctx->symCap = (uint32_t)(blocks > 1024 ? blocks : 1024);
     CK(regrow(ctx->dUnmasked, blocks));
+    CK(regrow(ctx->dLeftRun, blocks));
+    CK(regrow(ctx->dSafe, blocks));
     CK(regrow(ctx->dExtSlot, blocks));
     CK(regrow(ctx->dExtSeed, (size_t)ctx->extCap));
     CK(regrow(ctx->dExtBits, (size_t)ctx->extCap * 32));
@@ -355,6 +361,7 @@ extern "C" int limgcu_create(int device, limgcu_ctx **out)
   if (const char *v = getenv("LIMGCU_MERGE_EXT")) ctx->mergeExt = atoi(v);
 
   if (const char *v = getenv("LIMGCU_MERGE_MODE")) ctx->mergeMode = !strcmp(v, "seq") ? 1 : 0;
+  if (const char *v = getenv("LIMGCU_MERGE_SAFE")) ctx->mergeSafe = atoi(v);
   if (const char *v = getenv("LIMGCU_SCAN_WARPS")) ctx->scanWarps = atoi(v) < 1 ? 1 : (atoi(v) > LIMG_CTA_WARPS ? LIMG_CTA_WARPS : atoi(v));
   if (const char *v = getenv("LIMGCU_SCAN_EXPERIMENT")) ctx->scanExperiment = atoi(v);
   if (const char *v = getenv("LIMGCU_SCAN_CLUSTER")) { ctx->scanCluster = atoi(v) < 0 ? 0 : (atoi(v) > 16 ? 16 : atoi(v)); ctx->scanClusterSet = true; }
@@ -404,7 +411,7 @@ extern "C" void limgcu_destroy(limgcu_ctx *ctx)
 
   void *ptrs[] = { ctx->dLut, ctx->dTable, ctx->dRec, ctx->dWindow, ctx->dAreas, ctx->dBlockToArea, ctx->dWork, ctx->dSmallList, ctx->dLargeList, ctx->dDemand,
                    ctx->dUsed, ctx->dScratchPx, ctx->dScratchFac, ctx->dCounters, ctx->dCompare, ctx->dSrc,
-                   ctx->dExtSlot, ctx->dExtSeed, ctx->dExtBits, ctx->dExtHdr, ctx->dPlanCounters, ctx->dSymSlot, ctx->dSymSeed, ctx->dSymBits, ctx->dSymHdr, ctx->dSymStart, ctx->dSeedSym, ctx->dUnmasked,
+                   ctx->dExtSlot, ctx->dExtSeed, ctx->dExtBits, ctx->dExtHdr, ctx->dPlanCounters, ctx->dSymSlot, ctx->dSymSeed, ctx->dSymBits, ctx->dSymHdr, ctx->dSymStart, ctx->dSeedSym, ctx->dUnmasked, ctx->dLeftRun, ctx->dSafe,
                    ctx->dWaveZero, ctx->dTau, ctx->dCandList, ctx->dRowLists, ctx->dWaveDbg, ctx->dWaveRows, ctx->dRowMeta, ctx->dReplayList, ctx->dReplayCount, ctx->dPayload, ctx->dPayloadOff, ctx->dDitherBefore };
 
   for (void *p : ptrs)
@@ -585,6 +592,12 @@ static int launch_merge(limgcu_ctx *ctx, const limgcu_decomp *dTable, size_t W, 
       CKL("k_pred_records");
       k_pred_window<4><<<(blocks * 2 + 7) / 8, 256, 0, ctx->stream>>>(ctx->dRec, BX, BY, ctx->dWindow);
       CKL("k_pred_window");
+
+      if (ctx->mergeSafe)
+      {
+        k_pred_leftrun<4><<<(blocks + 127) / 128, 128, 0, ctx->stream>>>(ctx->dRec, BX, BY, ctx->dLeftRun);
+        CKL("k_pred_leftrun");
+      }
     }
     else
     {
@@ -592,17 +605,42 @@ static int launch_merge(limgcu_ctx *ctx, const limgcu_decomp *dTable, size_t W, 
       CKL("k_pred_records");
       k_pred_window<3><<<(blocks * 2 + 7) / 8, 256, 0, ctx->stream>>>(ctx->dRec, BX, BY, ctx->dWindow);
       CKL("k_pred_window");
+
+      if (ctx->mergeSafe)
+      {
+        k_pred_leftrun<3><<<(blocks + 127) / 128, 128, 0, ctx->stream>>>(ctx->dRec, BX, BY, ctx->dLeftRun);
+        CKL("k_pred_leftrun");
+      }
     }
 
     k_plan_seeds<<<(blocks + 255) / 256, 256, 0, ctx->stream>>>(pl);
     CKL("k_plan_seeds");
 
-    if (extendAsync)
+    if (ctx->mergeSafe)
+    {
+      k_plan_safe<<<BY, 32, 0, ctx->stream>>>(ctx->dWindow, wCandBits, ctx->dLeftRun, BX, BY, wordsPerRow, ctx->dSafe);
+      CKL("k_plan_safe");
+    }
+
+    if (async)
     {
       CK(cudaEventRecord(ctx->evFork, ctx->stream));
       CK(cudaStreamWaitEvent(ctx->streamAux, ctx->evFork, 0));
     }
 
+    // Order: the centre bitmaps of the candidates whose mask-free growth stays inside their 8x8 word first (85 % of them on photo content: the scan's
+    // top rows need them at once), then the extension bitmaps, then the centre bitmaps of the candidates that needed an extension.
+    k_plan_centres<<<(blocks + 255) / 256, 256, 0, planStream>>>(pl, 0);
+    CKL("k_plan_centres");
+
+    if (hasAlpha)
+      k_plan_sym<4><<<planGrid, LIMG_PLAN_WARPS * 32, 0, planStream>>>(pl, 0);
+    else
+      k_plan_sym<3><<<planGrid, LIMG_PLAN_WARPS * 32, 0, planStream>>>(pl, 0);
+
+    CKL("k_plan_sym");
+
+    // (planAsync == 2: the extension bitmaps run on the main stream, in front of the scan and next to the first centre bitmaps)
     if (hasAlpha)
       k_plan_extend<4><<<extendGrid, LIMG_PLAN_WARPS * 32, 0, extendStream>>>(pl);
     else
@@ -616,13 +654,15 @@ static int launch_merge(limgcu_ctx *ctx, const limgcu_decomp *dTable, size_t W, 
       CK(cudaStreamWaitEvent(ctx->streamAux, ctx->evFork, 0));
     }
 
-    k_plan_centres<<<(blocks + 255) / 256, 256, 0, planStream>>>(pl);
+    k_plan_mark<<<1, 1, 0, planStream>>>(pl);
+    CKL("k_plan_mark");
+    k_plan_centres<<<(blocks + 255) / 256, 256, 0, planStream>>>(pl, 1);
     CKL("k_plan_centres");
 
     if (hasAlpha)
-      k_plan_sym<4><<<planGrid, LIMG_PLAN_WARPS * 32, 0, planStream>>>(pl);
+      k_plan_sym<4><<<planGrid, LIMG_PLAN_WARPS * 32, 0, planStream>>>(pl, 1);
     else
-      k_plan_sym<3><<<planGrid, LIMG_PLAN_WARPS * 32, 0, planStream>>>(pl);
+      k_plan_sym<3><<<planGrid, LIMG_PLAN_WARPS * 32, 0, planStream>>>(pl, 1);
 
     CKL("k_plan_sym");
 
@@ -643,7 +683,7 @@ static int launch_merge(limgcu_ctx *ctx, const limgcu_decomp *dTable, size_t W, 
 
     WaveArgs w;
     w.rec = ctx->dRec; w.window = ctx->dWindow; w.extSlot = ctx->dExtSlot; w.extBits = ctx->dExtBits; w.extHdr = ctx->dExtHdr;
-    w.symSlot = ctx->dSymSlot; w.symBits = ctx->dSymBits; w.symHdr = ctx->dSymHdr; w.unmasked = ctx->dUnmasked; w.seedSym = async ? nullptr : ctx->dSeedSym;
+    w.symSlot = ctx->dSymSlot; w.symBits = ctx->dSymBits; w.symHdr = ctx->dSymHdr; w.unmasked = ctx->dUnmasked; w.seedSym = async ? nullptr : ctx->dSeedSym; w.safe = ctx->mergeSafe ? ctx->dSafe : nullptr;
     w.candBits = wCandBits; w.candList = ctx->dCandList; w.candCount = wCandCount;
     w.BX = BX; w.BY = BY; w.wordsPerRow = wordsPerRow;
     w.used = ctx->dUsed; w.tau = ctx->dTau; w.progress = wProgress; w.ticket = wTicket;
