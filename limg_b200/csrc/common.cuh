@@ -94,6 +94,48 @@ __device__ __forceinline__ f4 px_to_f4(uint32_t px)
 }
 
 // ---------------------------------------------------------------------------------------------
+// bulk-copy (TMA) plumbing: mbarriers, 1-D bulk copies, 2-D tensor-map tile loads
+// ---------------------------------------------------------------------------------------------
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
+
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+  asm volatile("{\n"
+               ".reg .pred p;\n"
+               "LIMG_WAIT_%=:\n"
+               "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+               "@p bra LIMG_DONE_%=;\n"
+               "bra LIMG_WAIT_%=;\n"
+               "LIMG_DONE_%=:\n"
+               "}" ::"r"(bar), "r"(parity) : "memory");
+}
+
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+{
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+// one tile of a 2-D tensor map (cuTensorMapEncodeTiled on the host): innermost coordinate x, then y; elements outside the tensor arrive as zeros
+__device__ __forceinline__ void tensor_g2s_2d(uint32_t dst, const void *tensorMap, int x, int y, uint32_t bar)
+{
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+               :: "r"(dst), "l"(tensorMap), "r"(x), "r"(y), "r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void fence_mbarrier_init()
+{
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
 // integer reconstruction (limg_decode.h:39-236, limg_bit_crush_simd.h:315-810)
 // ---------------------------------------------------------------------------------------------
 

@@ -23,8 +23,6 @@ namespace limg
 
 #define LIMG_CTA_WARPS 8
 
-__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
 __device__ __forceinline__ uint32_t lds_volatile(uint32_t addr)
 {
   uint32_t v;
@@ -166,7 +164,7 @@ __global__ void __launch_bounds__(LIMG_CTA_WARPS * 32) k_merge_cta(const __grid_
   // nobody writes into a replica before it is initialised
   cluster.sync();
 
-  const WaveCluster be{ a, smem_addr(sUsed), smem_addr(sProgress), smem_addr(sMisc), cluster_size() };
+  const WaveCluster be{ a, smem_u32(sUsed), smem_u32(sProgress), smem_u32(sMisc), cluster_size() };
   wave_scan_rows<CH>(a, be, attempt, 0, sScratch + (threadIdx.x >> 5) * 32);
 
   // every row is done (its claims were fenced when they were made) and no CTA leaves while another may still write into it

@@ -187,32 +187,6 @@ __global__ void __launch_bounds__(CTA, 1024 / CTA) k_decode_tile(const limgcu_ar
 // (in registers). One thread reconstructs a whole 8x8 block, so the 90-instruction set-up is paid once per 64 pixels.
 // Needs sizeX % 16 == 0 and 16-byte aligned planes (bulk copies move multiples of 16 bytes).
 
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
-
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
-{
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
-{
-  asm volatile("{\n"
-               ".reg .pred p;\n"
-               "LIMG_WAIT_%=:\n"
-               "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-               "@p bra LIMG_DONE_%=;\n"
-               "bra LIMG_WAIT_%=;\n"
-               "LIMG_DONE_%=:\n"
-               "}" ::"r"(bar), "r"(parity) : "memory");
-}
-
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
-{
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-
 struct AreaRaw // the 52 bytes of an area record the reconstruction needs
 {
   uint2 aMin, aMax, bOff, bMag, cOff, cMag;

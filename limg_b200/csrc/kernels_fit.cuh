@@ -4,6 +4,8 @@
 
 #include "group.cuh"
 
+#include <cuda.h> // CUtensorMap (the driver entry point that encodes it is looked up at run time: no link dependency)
+
 namespace limg
 {
 
@@ -72,6 +74,87 @@ __global__ void __launch_bounds__(256) k_pass1(const uint32_t *__restrict__ src,
       store_decomp(&table[b], d);
 
     __syncwarp();
+  }
+}
+
+// The same fit with the pixels staged by the TMA: every warp runs its own two-deep pipeline of 2-D tensor-map tile loads (cp.async.bulk.tensor, one
+// 8 x 8 pixel box = 256 bytes per block, completion counted in bytes on the warp's mbarrier): lane 0 requests the warp's NEXT block before the warp
+// waits for the current one, so the load is in flight during the ~1400 instructions of a fit and no warp waits for another. A box arrives row by row,
+// 8 pixels each, which IS the reference's pixel order of a full block (limg.cpp:1106-1107); pixels right of or below the image arrive as zeros, so ragged
+// edge blocks need no address arithmetic, only a repack to their rx * ry pixels. Needs a row pitch that is a multiple of 16 bytes (sizeX % 4 == 0);
+// k_pass1 above is the path for the other widths.
+template <int CH>
+__global__ void __launch_bounds__(256) k_pass1_tma(const __grid_constant__ CUtensorMap srcMap, int W, int H, int BX, int BY, const uint16_t *__restrict__ gLut, limgcu_decomp *__restrict__ table)
+{
+  __shared__ __align__(128) uint32_t sTile[8][2][LIMG_BLOCK * LIMG_BLOCK];
+  __shared__ __align__(8) unsigned long long sBar[8][2];
+  __shared__ uint16_t sLut[2048];
+  __shared__ uint32_t sPx[8][64];
+  __shared__ float4 sStage[8][64];
+  __shared__ GroupScratch<1> sGs[8];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr uint32_t kTileBytes = sizeof(uint32_t) * LIMG_BLOCK * LIMG_BLOCK;
+
+  if (lane == 0)
+  {
+    mbar_init(smem_u32(&sBar[warp][0]), 1);
+    mbar_init(smem_u32(&sBar[warp][1]), 1);
+    fence_mbarrier_init();
+  }
+
+  load_lut(sLut, gLut);
+  __syncthreads();
+
+  auto request = [&](int b, int slot) {
+    const int by = b / BX, bx = b - by * BX;
+    mbar_expect_tx(smem_u32(&sBar[warp][slot]), kTileBytes);
+    tensor_g2s_2d(smem_u32(&sTile[warp][slot][0]), &srcMap, bx * LIMG_BLOCK, by * LIMG_BLOCK, smem_u32(&sBar[warp][slot]));
+  };
+
+  const int stride = (int)gridDim.x * 8;
+  int b = (int)blockIdx.x * 8 + warp;
+
+  if (lane == 0 && b < BX * BY)
+    request(b, 0);
+
+  uint32_t parity = 0;
+
+  for (int it = 0; b < BX * BY; b += stride, it++)
+  {
+    const int slot = it & 1;
+
+    // the other slot is free: the warp finished the block it held (the __syncwarp at the end of the previous iteration)
+    if (lane == 0 && b + stride < BX * BY)
+      request(b + stride, slot ^ 1);
+
+    mbar_wait(smem_u32(&sBar[warp][slot]), (uint32_t)((it >> 1) & 1));
+
+    const int by = b / BX, bx = b - by * BX;
+    const int w = min(LIMG_BLOCK, W - bx * LIMG_BLOCK), h = min(LIMG_BLOCK, H - by * LIMG_BLOCK);
+    const uint32_t n = (uint32_t)(w * h);
+    const uint32_t *px = sTile[warp][slot];
+
+    if (w != LIMG_BLOCK)
+    {
+      // ragged in x: the box's rows are 8 pixels apart, the block's rows w
+      for (uint32_t i = lane; i < n; i += 32)
+      {
+        const int row = (int)i / w, col = (int)i - row * w;
+        sPx[warp][i] = sTile[warp][slot][row * LIMG_BLOCK + col];
+      }
+
+      __syncwarp();
+      px = sPx[warp];
+    }
+
+    limgcu_decomp d;
+    group_fit<CH, 1>(px, n, sLut, sStage[warp], 64, &sGs[warp], parity, d);
+
+    if (lane == 0)
+      store_decomp(&table[b], d);
+
+    __syncwarp(); // the slot can be refilled
   }
 }
 

@@ -459,10 +459,12 @@ struct WaveScan
       }
     };
 
-    add(x, y, x + r.rx + 1, y + r.ry + 1);
+    // Only the blocks of the rectangles themselves count: a strip that did NOT join (a mismatch, or a block already in use) can never join later,
+    // because in-use bits are only ever set; a strip that joined stays joined exactly as long as its blocks stay free.
+    add(x, y, x + r.rx, y + r.ry);
 
     if (r.attempted)
-      add(r.cox - 1, r.coy - 1, r.cox + r.crx + 1, r.coy + r.cry + 1);
+      add(r.cox, r.coy, r.cox + r.crx, r.coy + r.cry);
 
     const bool same = ((p.w[0] ^ q.w[0]) & m[0]) == 0 && ((p.w[1] ^ q.w[1]) & m[1]) == 0 && ((p.w[2] ^ q.w[2]) & m[2]) == 0;
     return __all_sync(0xFFFFFFFFu, same);
@@ -829,7 +831,7 @@ struct WaveScan
     r.kind = 0;
     r.cox = r.coy = r.crx = r.cry = 0;
     r.attempted = 0;
-    r.boxR = min(x + r.rx + 1, a.BX);
+    r.boxR = x + r.rx; // the rows above have to be past the rectangle's blocks, not past the strip that stopped it (see same_where_probed)
 
     if (stage == 0)
     {
@@ -905,7 +907,7 @@ struct WaveScan
         r.cox = cox; r.coy = coy; r.crx = crx; r.cry = cry;
         r.attempted = 1;
         r.kind = (crx * cry > r.rx * r.ry) ? 2 : 1;
-        r.boxR = max(r.boxR, min(cox + crx + 1, a.BX));
+        r.boxR = max(r.boxR, cox + crx);
         tFour += wave_clock() - t0;
         cause = 0;
       }
@@ -920,7 +922,7 @@ struct WaveScan
       return max(by0, 0) >= sn.r0 && min(by1, a.BY) <= sn.r0 + 32 && max(bx0, 0) >= sn.w0 * 32 && min(bx1, a.BX) <= sn.w0 * 32 + 96;
     };
 
-    volatileReads = !inside(x, y, x + r.rx + 1, y + r.ry + 1) || (r.attempted && !inside(r.cox - 1, r.coy - 1, r.cox + r.crx + 1, r.coy + r.cry + 1));
+    volatileReads = !inside(x, y, x + r.rx, y + r.ry) || (r.attempted && !inside(r.cox, r.coy, r.cox + r.crx, r.coy + r.cry));
     return r;
   }
 };
@@ -1265,13 +1267,37 @@ __device__ void wave_scan_rows(const WaveArgs &a, const Backend &be, int attempt
       SeedPre pre = scan.prefetch_bitmaps(links, y, stage);
       ahead.x = -1;
 
+      const int safeAfter = (stage == 0 && a.safe) ? (int)(links.safe >> 16) : LIMG_WAVE_DONE;
+
       if (stage == 0 && a.safe)
       {
-        rowSafe = (int)(links.safe & 0xFFFFu); // the dead candidates the row skipped no longer count
+        // The static safe column of this candidate is a mask-free bound. The regrowth's rectangle spans its centre's block row from the centre
+        // (right of the seed) leftwards without a gap, so it also stops at the nearest block at or left of the seed column that is in use NOW in
+        // that row (in-use bits never clear): usually the rectangle the row emitted just before. The centre's row is 1 .. (run along the seed's
+        // column) / 3 rows below the seed.
+        const uint32_t col = (links.w0 & 1u) | ((links.w0 >> 7) & 2u) | ((links.w0 >> 14) & 4u) | ((links.w0 >> 21) & 8u) | ((links.w1 & 1u) << 4) | ((links.w1 >> 3) & 32u) |
+                             ((links.w1 >> 10) & 64u) | ((links.w1 >> 17) & 128u);
+        const int colRun = __ffs((int)(~col & 0x1FFu)) - 1;
+        int blocked = 0x7FFF; // leftmost column the regrowth can reach in this lane's candidate centre row
+
+        if (!(colRun == 8 && y + 8 < a.BY) && lane < colRun / 3 && y + 1 + lane < a.BY)
+        {
+          const int cy = y + 1 + lane, w = x >> 5;
+          uint32_t bits = be.used_word(cy, w) & (0xFFFFFFFFu >> (31 - (x & 31)));
+          blocked = -1; // nothing in use within reach of the two words: no bound from the mask
+
+          if (bits)
+            blocked = w * 32 + 32 - __clz((int)bits);
+          else if (w > 0 && (bits = be.used_word(cy, w - 1)) != 0)
+            blocked = (w - 1) * 32 + 32 - __clz((int)bits);
+        }
+
+        const int dyn = __reduce_min_sync(0xFFFFFFFFu, blocked);
+        const int mine = max((int)(links.safe & 0xFFFFu), dyn == 0x7FFF ? -1 : dyn);
+        rowSafe = min(mine, safeAfter); // (the dead candidates the row skipped no longer count either)
         publish(x);
       }
 
-      const int safeAfter = (stage == 0 && a.safe) ? (int)(links.safe >> 16) : LIMG_WAVE_DONE;
       tPre += wave_clock() - tc;
       cPre = wave_clock() - tc; cWait = 0; cExp = 0; cClaim = 0; cIters = 0;
       const uint32_t first = count;
@@ -1340,6 +1366,10 @@ __device__ void wave_scan_rows(const WaveArgs &a, const Backend &be, int attempt
             if (LIMG_WAVE_PROFILE && a.dbg && lane == 0)
               atomicAdd(&a.dbg[stage * 16 + min(15, 63 - __clzll((dt >> 8) | 1))], 1u);
           }
+
+          // A seed that emits nothing now never will (in-use bits are only ever set, so its rectangle can only shrink): no need to wait for the rows above.
+          if (r.kind == 0)
+            break;
 
           if (final && p >= min(r.boxR + a.margin, a.BX))
           {

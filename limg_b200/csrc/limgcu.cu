@@ -99,6 +99,7 @@ struct limgcu_ctx
   int mergeMode = 0;                 // LIMGCU_MERGE_MODE: 0 wave (pipelined rows + verification), 1 seq (rows strictly in sequence)
   int scanCluster = 8;               // LIMGCU_SCAN_CLUSTER: CTAs of the cluster that runs the scan with its state in shared memory (k_merge_cta); 0 = scan over the mask in global memory (k_merge_wave); unset: 8, or 16 for 8K-class frames
   bool scanClusterSet = false;
+  int pass1Tma = 1;                  // LIMGCU_PASS1_TMA=0: pass 1 stages its pixels with plain loads (k_pass1) instead of tensor-map tile loads (k_pass1_tma)
   int poolThreads = 0;               // limgcu_set_pool_threads: the non-merged encoder restarts its dither chain per y-band of a pool of this many threads, as the reference does (0: pool-less)
   int scanExperiment = 0;            // LIMGCU_SCAN_EXPERIMENT: measurement switches of the scan (WaveArgs::experiment), 0 in production
   int scanWarps = LIMG_CTA_WARPS;    // LIMGCU_SCAN_WARPS: warps (block rows in flight) per CTA of that cluster, 1..8; 255 registers per thread, so 8 warps take an SM's whole register file, 4 leave half of it to other kernels
@@ -361,6 +362,7 @@ extern "C" int limgcu_create(int device, limgcu_ctx **out)
   if (const char *v = getenv("LIMGCU_MERGE_EXT")) ctx->mergeExt = atoi(v);
 
   if (const char *v = getenv("LIMGCU_MERGE_MODE")) ctx->mergeMode = !strcmp(v, "seq") ? 1 : 0;
+  if (const char *v = getenv("LIMGCU_PASS1_TMA")) ctx->pass1Tma = atoi(v);
   if (const char *v = getenv("LIMGCU_MERGE_SAFE")) ctx->mergeSafe = atoi(v);
   if (const char *v = getenv("LIMGCU_SCAN_WARPS")) ctx->scanWarps = atoi(v) < 1 ? 1 : (atoi(v) > LIMG_CTA_WARPS ? LIMG_CTA_WARPS : atoi(v));
   if (const char *v = getenv("LIMGCU_SCAN_EXPERIMENT")) ctx->scanExperiment = atoi(v);
@@ -520,9 +522,56 @@ static int check_image(limgcu_ctx *ctx, size_t W, size_t H)
   return LIMGCU_SUCCESS;
 }
 
+// 2-D tensor map over the source (uint32 pixels, row pitch sizeX * 4 bytes) with 8 x 8 pixel boxes: what k_pass1_tma's tile loads address.
+// The encoder is a driver entry point, looked up once (no link dependency on libcuda).
+static bool make_source_map(const uint32_t *dSrc, size_t W, size_t H, CUtensorMap *map)
+{
+  typedef CUresult (*EncodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeTiled encode = nullptr;
+  static bool looked = false;
+
+  if (!looked)
+  {
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      encode = reinterpret_cast<EncodeTiled>(fn);
+    else
+      cudaGetLastError();
+
+    looked = true;
+  }
+
+  if (encode == nullptr || (W % 4) != 0 || (reinterpret_cast<uintptr_t>(dSrc) & 15) != 0)
+    return false;
+
+  const cuuint64_t dims[2] = { (cuuint64_t)W, (cuuint64_t)H }, strides[1] = { (cuuint64_t)W * sizeof(uint32_t) };
+  const cuuint32_t box[2] = { LIMG_BLOCK, LIMG_BLOCK }, elem[2] = { 1, 1 };
+  return encode(map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<uint32_t *>(dSrc), dims, strides, box, elem, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 static int launch_pass1(limgcu_ctx *ctx, const uint32_t *dSrc, size_t W, size_t H, int hasAlpha, limgcu_decomp *dTable)
 {
   const int BX = (int)((W + 7) / 8), BY = (int)((H + 7) / 8);
+  CUtensorMap map;
+
+  // pixels staged by the TMA (one 8 x 8 tile load per block, two in flight per warp) where the row pitch allows it; LIMGCU_PASS1_TMA=0: the plain loads
+  if (ctx->pass1Tma && make_source_map(dSrc, W, H, &map))
+  {
+    const int gridT = (BX * BY + 7) / 8 < ctx->smCount * 8 ? (BX * BY + 7) / 8 : ctx->smCount * 8;
+
+    if (hasAlpha)
+      k_pass1_tma<4><<<gridT, 256, 0, ctx->stream>>>(map, (int)W, (int)H, BX, BY, ctx->dLut, dTable);
+    else
+      k_pass1_tma<3><<<gridT, 256, 0, ctx->stream>>>(map, (int)W, (int)H, BX, BY, ctx->dLut, dTable);
+
+    CKL("k_pass1_tma");
+    return LIMGCU_SUCCESS;
+  }
+
   const int grid = (BX * BY + 7) / 8 < ctx->smCount * 8 ? (BX * BY + 7) / 8 : ctx->smCount * 8;
 
   if (hasAlpha)
