@@ -834,7 +834,7 @@ __global__ void __launch_bounds__(LIMG_PLAN_WARPS * 32) k_plan_sym(PlanArgs a, i
 
 #define LIMG_LEFTRUN_CAP 24
 #define LIMG_LEFTRUN_UNKNOWN 255
-#define LIMG_SAFE_DEFAULT_REACH 8
+#define LIMG_SAFE_DEFAULT_REACH 10
 
 template <int CH>
 __global__ void __launch_bounds__(128) k_pred_leftrun(const PredRec *__restrict__ rec, int BX, int BY, uint8_t *__restrict__ leftRun)

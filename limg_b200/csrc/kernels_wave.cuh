@@ -227,6 +227,7 @@ struct WaveResult
   int cox, coy, crx, cry; // four-way regrowth (valid when attempted)
   int attempted;          // the centre-third regrowth ran
   int boxR;               // exclusive right edge of every column whose in-use bits were consulted
+  int boxD;               // exclusive bottom edge of the rectangles it would emit
 };
 
 // first level of a seed's immutable data: what is indexed by the seed itself. Loaded one candidate ahead (the loads are in flight
@@ -831,6 +832,7 @@ struct WaveScan
     r.kind = 0;
     r.cox = r.coy = r.crx = r.cry = 0;
     r.attempted = 0;
+    r.boxD = y + r.ry;
     r.boxR = x + r.rx; // the rows above have to be past the rectangle's blocks, not past the strip that stopped it (see same_where_probed)
 
     if (stage == 0)
@@ -908,6 +910,7 @@ struct WaveScan
         r.attempted = 1;
         r.kind = (crx * cry > r.rx * r.ry) ? 2 : 1;
         r.boxR = max(r.boxR, cox + crx);
+        r.boxD = max(r.boxD, coy + cry);
         tFour += wave_clock() - t0;
         cause = 0;
       }
@@ -1003,7 +1006,7 @@ __device__ __forceinline__ void fence_sc_gpu() { asm volatile("fence.sc.gpu;" ::
 
 // common part of the back ends' take_row(): lane 0 decides, the warp gets (stage, row) or false when nothing is left
 template <class Backend>
-__device__ __forceinline__ bool wave_take_row(const Backend &be, int BY, int gap, int sequential, int lane, int &stage, int &y)
+__device__ __forceinline__ bool wave_take_row(const Backend &be, int BY, int gap, int sequential, int lane, int maxStage1, int &stage, int &y)
 {
   int packed = -1;
 
@@ -1011,7 +1014,9 @@ __device__ __forceinline__ bool wave_take_row(const Backend &be, int BY, int gap
   {
     const int next1 = (int)be.peek_next(1);
 
-    if (next1 < BY && (int)be.done_rows(0) >= (sequential ? BY : min(next1 + gap + 1, BY)))
+    // (at most maxStage1 stage-1 rows in flight while stage-0 rows are left to hand out: a stage-1 seed with a tall rectangle waits for
+    // stage-0 rows further down, which therefore must always find a warp)
+    if (next1 < BY && (int)be.done_rows(0) >= (sequential ? BY : min(next1 + gap + 1, BY)) && ((int)be.peek_next(0) >= BY || next1 - (int)be.done_rows(1) < maxStage1))
     {
       const int k = (int)be.take_next(1);
 
@@ -1161,7 +1166,7 @@ __device__ void wave_scan_rows(const WaveArgs &a, const Backend &be, int attempt
   {
     int stage, y;
 
-    if (!wave_take_row(be, a.BY, a.stageGap, sequential, lane, stage, y))
+    if (!wave_take_row(be, a.BY, a.stageGap, sequential, lane, max(1, (int)(gridDim.x * (blockDim.x >> 5)) / 2), stage, y))
       break;
 
     const uint32_t *cand = a.candBits + (size_t)stage * a.BY * a.wordsPerRow;
@@ -1323,6 +1328,10 @@ __device__ void wave_scan_rows(const WaveArgs &a, const Backend &be, int attempt
           if (y > 0 && !sequential)
             p = wave_rows_above(be, stage, y, lane);
 
+          // A stage-1 rectangle reaches down into rows whose stage-0 seeds must all be decided first (its row started when stage 0
+          // was done stageGap rows below the seed; a taller rectangle waits for the same distance below its last rows).
+          const int below = (stage == 1 && !sequential) ? (int)be.done_rows(0) : a.BY;
+
           if (p < min(x + 1 + a.margin - a.specAhead, a.BX))
           {
             // the rows above are still far away: whatever the mask shows now is not worth expanding against
@@ -1337,7 +1346,7 @@ __device__ void wave_scan_rows(const WaveArgs &a, const Backend &be, int attempt
 
           // The fence orders the mask reads below behind the progress read above (PTX does not order two loads by a branch between
           // them); it is only paid for when this look at the mask can be the final one.
-          const bool final = have ? p >= min(r.boxR + a.margin, a.BX) : p >= min(x + 1 + a.margin + 8, a.BX);
+          const bool final = have ? p >= min(r.boxR + a.margin, a.BX) && below >= min(r.boxD + a.stageGap / 2, a.BY) : p >= min(x + 1 + a.margin + 8, a.BX);
 
           if (final && !(a.experiment & 1))
             be.acquire_fence();
@@ -1371,7 +1380,7 @@ __device__ void wave_scan_rows(const WaveArgs &a, const Backend &be, int attempt
           if (r.kind == 0)
             break;
 
-          if (final && p >= min(r.boxR + a.margin, a.BX))
+          if (final && p >= min(r.boxR + a.margin, a.BX) && below >= min(r.boxD + a.stageGap / 2, a.BY))
           {
             if (LIMG_WAVE_PROFILE && a.dbg && lane == 0 && stage == 0)
             {
@@ -1390,7 +1399,7 @@ __device__ void wave_scan_rows(const WaveArgs &a, const Backend &be, int attempt
           // the seed has to wait: the next candidate's links can be on their way meanwhile
           look_ahead(r.kind == 1 ? x + r.rx : x + 1);
 
-          if (p >= min(r.boxR + a.margin, a.BX))
+          if (p >= min(r.boxR + a.margin, a.BX) && below >= min(r.boxD + a.stageGap / 2, a.BY))
             continue; // far enough, but this look was not fenced: look again at once
 
           rowPolls++;
