@@ -946,8 +946,9 @@ __device__ __forceinline__ uint2 pack_rect(int ox, int oy, int rx, int ry)
 // its whole 3 x 3 corner must be free (limg.cpp:1424 keeps nothing smaller), in stage 1 the block and its right or lower neighbour.
 // In-use bits at columns >= x of these rows only ever come from logically earlier rectangles, so skipping is exact. BX if none.
 // `used(dy, w)` returns in-use word w of block row y + dy (rows are padded by two zero words).
-template <class UsedWord>
-__device__ __forceinline__ int wave_next_candidate(const uint32_t *candRow, UsedWord used, int nWords, int x, int BX, int stage, int lane)
+// `dead(w)`: further candidates of word w to pass over (decided out of order, or owned by another warp of the row's team).
+template <class UsedWord, class DeadWord>
+__device__ __forceinline__ int wave_next_candidate(const uint32_t *candRow, UsedWord used, DeadWord dead, int nWords, int x, int BX, int stage, int lane)
 {
   for (int w0 = x >> 5; w0 < nWords; w0 += 32)
   {
@@ -958,7 +959,7 @@ __device__ __forceinline__ int wave_next_candidate(const uint32_t *candRow, Used
     {
       // rows are padded with zero words, and candidates never sit in the last block rows (their 3 x 3 corner / lower neighbour is inside the grid)
       const unsigned long long u0 = used(0, w) | ((unsigned long long)used(0, w + 1) << 32);
-      bits = __ldg(candRow + w);
+      bits = __ldg(candRow + w) & ~dead(w);
 
       if (stage == 0 && bits) // a candidate bit in this word: block rows y + 1 and y + 2 exist
       {
@@ -988,6 +989,12 @@ __device__ __forceinline__ int wave_next_candidate(const uint32_t *candRow, Used
   }
 
   return BX;
+}
+
+template <class UsedWord>
+__device__ __forceinline__ int wave_next_candidate(const uint32_t *candRow, UsedWord used, int nWords, int x, int BX, int stage, int lane)
+{
+  return wave_next_candidate(candRow, used, [](int) { return 0u; }, nWords, x, BX, stage, lane);
 }
 
 #define LIMG_WAVE_SPIN_LIMIT (1u << 22) // watchdog: a wait that long (seconds) is a bug; flag it instead of hanging the GPU
@@ -1222,7 +1229,7 @@ __device__ void wave_scan_rows(const WaveArgs &a, const Backend &be, int attempt
     const uint32_t *candRow = cand + (size_t)y * a.wordsPerRow;
     uint2 *list = lists + (size_t)y * a.listCap;
     uint32_t count = 0;
-    int x = 0, published = 0, nEvents = 0, xEvent = 0;
+    int x = (stage == 1 && (a.experiment & 8)) ? a.BX : 0, published = 0, nEvents = 0, xEvent = 0; // (experiment 8: timing of stage 0 alone, stage 1 emits nothing)
     SeedLinks ahead;
     ahead.x = -1;
 
