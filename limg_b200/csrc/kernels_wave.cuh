@@ -946,9 +946,8 @@ __device__ __forceinline__ uint2 pack_rect(int ox, int oy, int rx, int ry)
 // its whole 3 x 3 corner must be free (limg.cpp:1424 keeps nothing smaller), in stage 1 the block and its right or lower neighbour.
 // In-use bits at columns >= x of these rows only ever come from logically earlier rectangles, so skipping is exact. BX if none.
 // `used(dy, w)` returns in-use word w of block row y + dy (rows are padded by two zero words).
-// `dead(w)`: further candidates of word w to pass over (decided out of order, or owned by another warp of the row's team).
-template <class UsedWord, class DeadWord>
-__device__ __forceinline__ int wave_next_candidate(const uint32_t *candRow, UsedWord used, DeadWord dead, int nWords, int x, int BX, int stage, int lane)
+template <class UsedWord>
+__device__ __forceinline__ int wave_next_candidate(const uint32_t *candRow, UsedWord used, int nWords, int x, int BX, int stage, int lane)
 {
   for (int w0 = x >> 5; w0 < nWords; w0 += 32)
   {
@@ -959,7 +958,7 @@ __device__ __forceinline__ int wave_next_candidate(const uint32_t *candRow, Used
     {
       // rows are padded with zero words, and candidates never sit in the last block rows (their 3 x 3 corner / lower neighbour is inside the grid)
       const unsigned long long u0 = used(0, w) | ((unsigned long long)used(0, w + 1) << 32);
-      bits = __ldg(candRow + w) & ~dead(w);
+      bits = __ldg(candRow + w);
 
       if (stage == 0 && bits) // a candidate bit in this word: block rows y + 1 and y + 2 exist
       {
@@ -989,12 +988,6 @@ __device__ __forceinline__ int wave_next_candidate(const uint32_t *candRow, Used
   }
 
   return BX;
-}
-
-template <class UsedWord>
-__device__ __forceinline__ int wave_next_candidate(const uint32_t *candRow, UsedWord used, int nWords, int x, int BX, int stage, int lane)
-{
-  return wave_next_candidate(candRow, used, [](int) { return 0u; }, nWords, x, BX, stage, lane);
 }
 
 #define LIMG_WAVE_SPIN_LIMIT (1u << 22) // watchdog: a wait that long (seconds) is a bug; flag it instead of hanging the GPU
@@ -1229,7 +1222,7 @@ __device__ void wave_scan_rows(const WaveArgs &a, const Backend &be, int attempt
     const uint32_t *candRow = cand + (size_t)y * a.wordsPerRow;
     uint2 *list = lists + (size_t)y * a.listCap;
     uint32_t count = 0;
-    int x = (stage == 1 && (a.experiment & 8)) ? a.BX : 0, published = 0, nEvents = 0, xEvent = 0; // (experiment 8: timing of stage 0 alone, stage 1 emits nothing)
+    int x = 0, published = 0, nEvents = 0, xEvent = 0;
     SeedLinks ahead;
     ahead.x = -1;
 
@@ -1675,6 +1668,8 @@ __global__ void __launch_bounds__(256) k_merge_verify(const __grid_constant__ Wa
     const uint2 *rec = lists + (size_t)y * a.listCap + start;
     uint32_t e = 0;
     bool ok = true;
+    int reason = 0; // diagnostics: which check failed (tools/fail_sweep.py)
+    uint2 wantRect = make_uint2(0u, 0u);
     bool havePre = false;
     SeedPre pre;
 
@@ -1706,7 +1701,7 @@ __global__ void __launch_bounds__(256) k_merge_verify(const __grid_constant__ Wa
           busy = !rightFree && !downFree;
         }
 
-        if (busy) { ok = e == have; break; }
+        if (busy) { ok = e == have; reason = 1; break; }
       }
 
       if (!havePre) { pre = scan.prefetch(x, y, stage); havePre = true; }
@@ -1714,27 +1709,47 @@ __global__ void __launch_bounds__(256) k_merge_verify(const __grid_constant__ Wa
       const Snapshot sn = scan.snapshot(x, y);
       const WaveResult r = scan.expand(x, y, stage, pre, sn);
 
-      if (r.kind == 0) { ok = e == have; break; }
+      if (r.kind == 0) { ok = e == have; reason = 2; break; }
 
       const int eox = r.kind == 2 ? r.cox : x, eoy = r.kind == 2 ? r.coy : y;
       const int erx = r.kind == 2 ? r.crx : r.rx, ery = r.kind == 2 ? r.cry : r.ry;
 
-      if (e >= have) { ok = false; break; }
+      if (e >= have) { ok = false; reason = 3; wantRect = pack_rect(eox, eoy, erx, ery); break; }
 
       const uint2 want = pack_rect(eox, eoy, erx, ery), got = rec[e];
       e++;
 
-      if (want.x != got.x || want.y != got.y) { ok = false; break; }
+      if (want.x != got.x || want.y != got.y) { ok = false; reason = 4; wantRect = want; break; }
 
       // every block of the rectangle is owned by it (no overlap with another rectangle)
       bool foreign = false;
 
+      uint32_t foreignOwner = 0;
+
       for (int b = lane; b < erx * ery; b += 32)
-        foreign |= __ldg(&a.tau[(size_t)(eoy + b / erx) * a.BX + eox + b % erx]) != T;
+      {
+        const uint32_t owner = __ldg(&a.tau[(size_t)(eoy + b / erx) * a.BX + eox + b % erx]);
 
-      if (__any_sync(0xFFFFFFFFu, foreign)) { ok = false; break; }
+        if (owner != T)
+        {
+          foreign = true;
+          foreignOwner = owner;
+        }
+      }
 
-      if (r.kind == 1) { ok = e == have; break; }
+      if (__any_sync(0xFFFFFFFFu, foreign))
+      {
+        // diagnostics: the other owner's first rectangle
+        const uint32_t other = __reduce_max_sync(0xFFFFFFFFu, foreignOwner);
+        const uint32_t oseed = (other & (LIMG_TAU_STAGE1 - 1u)) >> 3;
+        const int ostage = other >= LIMG_TAU_STAGE1 ? 1 : 0;
+        const uint32_t oinfo = a.emitInfo[(size_t)ostage * a.BX * a.BY + oseed];
+        const uint2 orect = (a.rowLists + ((size_t)ostage * a.BY + oseed / a.BX) * a.listCap)[oinfo >> 8];
+        ok = false; reason = 5; wantRect = make_uint2(other, orect.x); e = orect.y;
+        break;
+      }
+
+      if (r.kind == 1) { ok = e == have; reason = 6; break; }
     }
 
     if (!ok && lane == 0)
@@ -1750,7 +1765,8 @@ __global__ void __launch_bounds__(256) k_merge_verify(const __grid_constant__ Wa
         {
           uint32_t *o = a.dbg + 104 + slot * 8;
           o[0] = (uint32_t)stage | ((uint32_t)attempt << 8); o[1] = (uint32_t)x; o[2] = (uint32_t)y; o[3] = have; o[4] = e;
-          o[5] = have ? rec[0].x : 0u; o[6] = have ? rec[0].y : 0u;
+          o[5] = have ? rec[0].x : 0u; o[6] = have ? rec[0].y : 0u; o[7] = (uint32_t)reason;
+          a.dbg[232 + slot * 2] = wantRect.x; a.dbg[233 + slot * 2] = wantRect.y; // (what the replay wanted / who else owns a block)
         }
       }
     }

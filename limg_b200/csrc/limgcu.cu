@@ -102,7 +102,6 @@ struct limgcu_ctx
   int pass1Tma = 1;                  // LIMGCU_PASS1_TMA=0: pass 1 stages its pixels with plain loads (k_pass1) instead of tensor-map tile loads (k_pass1_tma)
   int poolThreads = 0;               // limgcu_set_pool_threads: the non-merged encoder restarts its dither chain per y-band of a pool of this many threads, as the reference does (0: pool-less)
   int scanExperiment = 0;            // LIMGCU_SCAN_EXPERIMENT: measurement switches of the scan (WaveArgs::experiment), 0 in production
-  int scanTeam = 1;                  // LIMGCU_SCAN_TEAM: warps that share a block row (kernels_cta.cuh wave_scan_team), 1, 2, 4 or 8
   int scanWarps = LIMG_CTA_WARPS;    // LIMGCU_SCAN_WARPS: warps (block rows in flight) per CTA of that cluster, 1..8; 255 registers per thread, so 8 warps take an SM's whole register file, 4 leave half of it to other kernels
   int scanSmemLimit = 0;             // bytes of dynamic shared memory a CTA may opt in to (the mask replica has to fit)
   int planExtW = 16, planSymL = 6, planSymR = 12, planSymD = 16; // LIMGCU_PLAN_EXTW / SYML / SYMR / SYMD: size caps of the speculative bitmaps
@@ -365,7 +364,6 @@ extern "C" int limgcu_create(int device, limgcu_ctx **out)
   if (const char *v = getenv("LIMGCU_MERGE_MODE")) ctx->mergeMode = !strcmp(v, "seq") ? 1 : 0;
   if (const char *v = getenv("LIMGCU_PASS1_TMA")) ctx->pass1Tma = atoi(v);
   if (const char *v = getenv("LIMGCU_MERGE_SAFE")) ctx->mergeSafe = atoi(v);
-  if (const char *v = getenv("LIMGCU_SCAN_TEAM")) ctx->scanTeam = atoi(v) < 1 ? 1 : atoi(v);
   if (const char *v = getenv("LIMGCU_SCAN_WARPS")) ctx->scanWarps = atoi(v) < 1 ? 1 : (atoi(v) > LIMG_CTA_WARPS ? LIMG_CTA_WARPS : atoi(v));
   if (const char *v = getenv("LIMGCU_SCAN_EXPERIMENT")) ctx->scanExperiment = atoi(v);
   if (const char *v = getenv("LIMGCU_SCAN_CLUSTER")) { ctx->scanCluster = atoi(v) < 0 ? 0 : (atoi(v) > 16 ? 16 : atoi(v)); ctx->scanClusterSet = true; }
@@ -784,9 +782,6 @@ static int launch_merge(limgcu_ctx *ctx, const limgcu_decomp *dTable, size_t W, 
 
     for (int attempt = 0; attempt < 3; attempt++)
     {
-      if ((ctx->scanExperiment & 8) && attempt > 0)
-        break; // timing experiment: one try, whatever it produced
-
       WaveArgs wa = w;
       const int sequential = attempt == 2 ? 1 : 0;
 
@@ -812,8 +807,6 @@ static int launch_merge(limgcu_ctx *ctx, const limgcu_decomp *dTable, size_t W, 
 
       if (!sequential && clusterSize > 0 && ctaSmem <= (size_t)ctx->scanSmemLimit)
       {
-        // warps that share a block row (wave_scan_team); one warp per row where the team's bitmaps do not cover the row
-        const int teamWarps = (ctx->scanTeam > 1 && BX <= 1024 && ctx->scanWarps % ctx->scanTeam == 0 && ctx->scanWarps / ctx->scanTeam <= LIMG_CTA_WARPS / 2) ? ctx->scanTeam : 1;
         cudaLaunchConfig_t cfg = {};
         cudaLaunchAttribute attr[1];
         cfg.gridDim = dim3((unsigned)clusterSize);
@@ -828,9 +821,9 @@ static int launch_merge(limgcu_ctx *ctx, const limgcu_decomp *dTable, size_t W, 
         cfg.numAttrs = 1;
 
         if (hasAlpha)
-          CK(cudaLaunchKernelEx(&cfg, k_merge_cta<4>, wa, attempt, teamWarps));
+          CK(cudaLaunchKernelEx(&cfg, k_merge_cta<4>, wa, attempt));
         else
-          CK(cudaLaunchKernelEx(&cfg, k_merge_cta<3>, wa, attempt, teamWarps));
+          CK(cudaLaunchKernelEx(&cfg, k_merge_cta<3>, wa, attempt));
 
         CKL("k_merge_cta");
       }

@@ -32,7 +32,22 @@ for name, make, alpha in cases:
         c.sync()
         fails.append(int(c.debug_counters()[24]))
         if fails[-1] and o is None:
-            o = c.debug_wave()[104:112]
+            dbg = c.debug_wave()
+            o = dbg[104:112]
+            why = {1: "corner busy but count differs", 2: "replay emits nothing", 3: "replay emits more", 4: "different rectangle", 5: "a block of the rectangle has another owner", 6: "recorded more"}
+            for k in range(min(int(dbg[100]), 8)):
+                q = dbg[104 + 8 * k: 112 + 8 * k]
+                wx, wy = dbg[232 + 2 * k], dbg[233 + 2 * k]
+                if int(q[7]) == 5:
+                    bx = (w + 7) // 8
+                    own = int(wx)
+                    st1 = own >= 0x40000000
+                    sd = ((own & 0x3FFFFFFF) >> 3)
+                    print("     stage %d seed (%d, %d) rectangle (%d,%d %dx%d): a block is owned by stage %d seed (%d, %d) attempt %d whose first rectangle is (%d,%d %dx%d)" % (
+                        q[0] & 255, q[1], q[2], q[5] & 0xFFFF, q[5] >> 16, q[6] & 0xFFFF, q[6] >> 16, int(st1), sd % bx, sd // bx, own & 7, wy & 0xFFFF, wy >> 16, q[4] & 0xFFFF, q[4] >> 16))
+                    continue
+                print("     stage %d seed (%d, %d) recorded %d replayed %d first recorded (%d,%d %dx%d) replay wants (%d,%d %dx%d): %s" % (
+                    q[0] & 255, q[1], q[2], q[3], q[4], q[5] & 0xFFFF, q[5] >> 16, q[6] & 0xFFFF, q[6] >> 16, wx & 0xFFFF, wx >> 16, wy & 0xFFFF, wy >> 16, why.get(int(q[7]), "?")))
     total += sum(1 for f in fails if f)
     if any(fails):
         print("FAIL %s: tries %s; first failing seed: stage %d (%d, %d) recorded %d rect0 ox %d oy %d rx %d ry %d" % (name, fails, o[0] & 255, o[1], o[2], o[3], o[5] & 0xFFFF, o[5] >> 16, o[6] & 0xFFFF, o[6] >> 16))
