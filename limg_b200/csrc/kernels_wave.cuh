@@ -1585,10 +1585,12 @@ __global__ void __launch_bounds__(LIMG_WAVE_WARPS * 32) k_merge_wave(const __gri
 // Verification, part 1 (one THREAD per candidate seed): most candidates were in use before their turn came, or could not emit
 // any more (stage 0: a block of the 3 x 3 corner taken, stage 1: both neighbours taken). Those must not have emitted anything;
 // the others go on the replay list.
-__global__ void __launch_bounds__(256) k_merge_verify_filter(WaveArgs a, int stage, int attempt, uint32_t *replayList, uint32_t *replayCount)
+__global__ void __launch_bounds__(256) k_merge_verify_filter(WaveArgs a, int attempt, uint32_t *replayList, uint32_t *replayCount)
 {
   if (a.flags[0] != (uint32_t)attempt)
     return;
+
+  const int stage = (int)blockIdx.y;
 
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t blocks = (uint32_t)(a.BX * a.BY);
@@ -1645,11 +1647,12 @@ __global__ void __launch_bounds__(256) k_merge_verify_filter(WaveArgs a, int sta
 // Verification, part 2 (one WARP per remaining seed): replays the seed against the mask at its logical time and compares with the
 // wave's record.
 template <int CH>
-__global__ void __launch_bounds__(256) k_merge_verify(const __grid_constant__ WaveArgs a, int stage, int attempt, const uint32_t *replayList, const uint32_t *replayCount)
+__global__ void __launch_bounds__(256) k_merge_verify(const __grid_constant__ WaveArgs a, int attempt, const uint32_t *replayList, const uint32_t *replayCount)
 {
   if (a.flags[0] != (uint32_t)attempt)
     return; // this try did not run, or already failed
 
+  const int stage = (int)blockIdx.y; // both stages in one launch: each is a few seeds per warp, i.e. as long as its slowest replay
   __shared__ uint32_t sScratchV[8][32];
   const int lane = threadIdx.x & 31;
   const uint32_t n = replayCount[stage];

@@ -652,27 +652,37 @@ static int launch_merge(limgcu_ctx *ctx, const limgcu_decomp *dTable, size_t W, 
     {
       k_pred_records<4><<<(blocks + 255) / 256, 256, 0, ctx->stream>>>(dTable, blocks, ctx->dRec);
       CKL("k_pred_records");
-      k_pred_window<4><<<(blocks * 2 + 7) / 8, 256, 0, ctx->stream>>>(ctx->dRec, BX, BY, ctx->dWindow);
-      CKL("k_pred_window");
 
       if (ctx->mergeSafe)
       {
-        k_pred_leftrun<4><<<(blocks + 127) / 128, 128, 0, ctx->stream>>>(ctx->dRec, BX, BY, ctx->dLeftRun);
+        // (one thread per block and a chain of predicates each: latency bound, so it runs beside the window kernel on the second stream)
+        CK(cudaEventRecord(ctx->evFork2, ctx->stream));
+        CK(cudaStreamWaitEvent(ctx->streamAux, ctx->evFork2, 0));
+        k_pred_leftrun<4><<<(blocks + 127) / 128, 128, 0, ctx->streamAux>>>(ctx->dRec, BX, BY, ctx->dLeftRun);
         CKL("k_pred_leftrun");
+        CK(cudaEventRecord(ctx->evJoin2, ctx->streamAux));
       }
+
+      k_pred_window<4><<<(blocks * 2 + 7) / 8, 256, 0, ctx->stream>>>(ctx->dRec, BX, BY, ctx->dWindow);
+      CKL("k_pred_window");
     }
     else
     {
       k_pred_records<3><<<(blocks + 255) / 256, 256, 0, ctx->stream>>>(dTable, blocks, ctx->dRec);
       CKL("k_pred_records");
-      k_pred_window<3><<<(blocks * 2 + 7) / 8, 256, 0, ctx->stream>>>(ctx->dRec, BX, BY, ctx->dWindow);
-      CKL("k_pred_window");
 
       if (ctx->mergeSafe)
       {
-        k_pred_leftrun<3><<<(blocks + 127) / 128, 128, 0, ctx->stream>>>(ctx->dRec, BX, BY, ctx->dLeftRun);
+        // (one thread per block and a chain of predicates each: latency bound, so it runs beside the window kernel on the second stream)
+        CK(cudaEventRecord(ctx->evFork2, ctx->stream));
+        CK(cudaStreamWaitEvent(ctx->streamAux, ctx->evFork2, 0));
+        k_pred_leftrun<3><<<(blocks + 127) / 128, 128, 0, ctx->streamAux>>>(ctx->dRec, BX, BY, ctx->dLeftRun);
         CKL("k_pred_leftrun");
+        CK(cudaEventRecord(ctx->evJoin2, ctx->streamAux));
       }
+
+      k_pred_window<3><<<(blocks * 2 + 7) / 8, 256, 0, ctx->stream>>>(ctx->dRec, BX, BY, ctx->dWindow);
+      CKL("k_pred_window");
     }
 
     k_plan_seeds<<<(blocks + 255) / 256, 256, 0, ctx->stream>>>(pl);
@@ -680,6 +690,7 @@ static int launch_merge(limgcu_ctx *ctx, const limgcu_decomp *dTable, size_t W, 
 
     if (ctx->mergeSafe)
     {
+      CK(cudaStreamWaitEvent(ctx->stream, ctx->evJoin2, 0)); // the left runs
       k_plan_safe<<<BY, 32, 0, ctx->stream>>>(ctx->dWindow, wCandBits, ctx->dLeftRun, BX, BY, wordsPerRow, ctx->dSafe);
       CKL("k_plan_safe");
     }
@@ -844,21 +855,15 @@ static int launch_merge(limgcu_ctx *ctx, const limgcu_decomp *dTable, size_t W, 
       {
         CK(cudaMemsetAsync(ctx->dReplayCount, 0, 2 * sizeof(uint32_t), ctx->stream));
 
-        for (int stage = 0; stage < 2; stage++)
-        {
-          k_merge_verify_filter<<<(blocks + 255) / 256, 256, 0, ctx->stream>>>(wa, stage, attempt, ctx->dReplayList, ctx->dReplayCount);
-          CKL("k_merge_verify_filter");
-        }
+        k_merge_verify_filter<<<dim3((blocks + 255) / 256, 2), 256, 0, ctx->stream>>>(wa, attempt, ctx->dReplayList, ctx->dReplayCount);
+        CKL("k_merge_verify_filter");
 
-        for (int stage = 0; stage < 2; stage++)
-        {
-          if (hasAlpha)
-            k_merge_verify<4><<<ctx->smCount * 4, 256, 0, ctx->stream>>>(wa, stage, attempt, ctx->dReplayList, ctx->dReplayCount);
-          else
-            k_merge_verify<3><<<ctx->smCount * 4, 256, 0, ctx->stream>>>(wa, stage, attempt, ctx->dReplayList, ctx->dReplayCount);
+        if (hasAlpha)
+          k_merge_verify<4><<<dim3(ctx->smCount * 4, 2), 256, 0, ctx->stream>>>(wa, attempt, ctx->dReplayList, ctx->dReplayCount);
+        else
+          k_merge_verify<3><<<dim3(ctx->smCount * 4, 2), 256, 0, ctx->stream>>>(wa, attempt, ctx->dReplayList, ctx->dReplayCount);
 
-          CKL("k_merge_verify");
-        }
+        CKL("k_merge_verify");
 
         k_merge_judge<<<1, 1, 0, ctx->stream>>>(wa, attempt);
         CKL("k_merge_judge");
