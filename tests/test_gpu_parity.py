@@ -411,6 +411,22 @@ def test_failed_speculation_is_repaired(monkeypatch, lo, name):
         c.close()
 
 
+def test_tall_stage1_rectangles_pass_the_first_try(codec, lo):
+    """A smooth gradient leaves stage-1 rectangles taller than the gap stage 1 keeps behind stage 0 (16 block rows): such a seed has to
+    wait for stage 0 below its rectangle, or it takes blocks that are free only because stage 0 has not got there yet (this frame failed
+    every first try before that rule, profiles/README.md r2_n). The area table must equal the reference's order and no try may fail."""
+    img = synth.gradient_noise(1024, 768, 403, sigma=11.0)
+    h, w = img.shape
+    table = codec.pass1(img, False)
+    want, _ = lo.merge(table, (w + 7) // 8, (h + 7) // 8, False)
+    assert int(want["ry"][want["stage"] == 1].max()) > 16  # the frame does have such rectangles
+    for _ in range(3):
+        areas = codec.merge(table, w, h, False)
+        assert int(codec.debug_counters()[24]) == 0
+        for k in ("ox", "oy", "rx", "ry", "stage"):
+            assert np.array_equal(areas[k], want[k]), k
+
+
 @pytest.mark.parametrize("cfg", ["c1_512_gradient", "c5_1080p_frame0", "c2_4k_photo", "c4_4k_flatui", "c3_8k_rgba"])
 def test_predicate_shortcut_never_disagrees(codec, cfg):
     """The guard-banded shortcut of the merge predicate decides only where the reference-order 27-sample score decides the same."""
