@@ -548,7 +548,7 @@ __device__ __forceinline__ int run_end(uint32_t bits, int from)
 #define LIMG_PLAN_WARPS 8
 
 template <int CH>
-__global__ void __launch_bounds__(LIMG_PLAN_WARPS * 32) k_plan_extend(PlanArgs a)
+__global__ void __launch_bounds__(LIMG_PLAN_WARPS * 32) k_plan_extend(PlanArgs a, int rowLo, int rowHi /* seeds of block rows [rowLo, rowHi) only */)
 {
   __shared__ uint32_t sRows[LIMG_PLAN_WARPS][32];
   const uint32_t count = min(a.counters[0], a.extCap);
@@ -560,6 +560,10 @@ __global__ void __launch_bounds__(LIMG_PLAN_WARPS * 32) k_plan_extend(PlanArgs a
   {
     const int seed = (int)a.extSeed[slot];
     const int y = seed / a.BX, x = seed - y * a.BX;
+
+    if (y < rowLo || y >= rowHi)
+      continue;
+
     const PredRec s = a.rec[seed];
     const uint32_t w0 = a.window[(size_t)seed * 2], w1 = a.window[(size_t)seed * 2 + 1];
     const uint32_t win = lane < 8 ? ((lane < 4 ? w0 >> (8 * lane) : w1 >> (8 * (lane - 4))) & 0xFFu) : 0u; // lane = row of the 8x8 window
@@ -624,7 +628,8 @@ __global__ void __launch_bounds__(LIMG_PLAN_WARPS * 32) k_plan_extend(PlanArgs a
 // blocks to the left of that: a mask shrinks the rectangle's width far more often than its height)
 // phase 0: the candidates whose growth stays inside their 8x8 word (their mask-free rectangle is final after k_plan_seeds): their centre
 // bitmaps can be built at once, before the (slower) extension bitmaps; phase 1: the others, after k_plan_extend.
-__global__ void __launch_bounds__(256) k_plan_centres(PlanArgs a, int phase)
+// Candidates of block rows [rowLo, rowHi) only: the bitmaps are built top-down in bands of block rows, the order in which the scan wants them.
+__global__ void __launch_bounds__(256) k_plan_centres(PlanArgs a, int phase, int rowLo, int rowHi)
 {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
 
@@ -637,6 +642,10 @@ __global__ void __launch_bounds__(256) k_plan_centres(PlanArgs a, int phase)
     return;
 
   const int y = seed / a.BX, x = seed - y * a.BX;
+
+  if (y < rowLo || y >= rowHi)
+    return;
+
   const uint32_t u = a.unmasked[seed];
   const int rx = u & 0xFF, ry = u >> 8;
 
@@ -661,7 +670,7 @@ __global__ void __launch_bounds__(256) k_plan_centres(PlanArgs a, int phase)
   }
 }
 
-// between the two phases of the centre bitmaps: phase 1 starts where phase 0 stopped
+// behind every k_plan_sym launch: the next one starts where this one stopped
 __global__ void k_plan_mark(PlanArgs a)
 {
   a.counters[2] = a.counters[3];
@@ -783,18 +792,19 @@ __device__ uint32_t build_centre_bitmap(const PredRec *__restrict__ rec, const u
   return mine;
 }
 
-// phase 0: slots [0, count); it leaves `count` in counters[2] for phase 1, which handles the slots requested since: [counters[2], count)
+// The slots requested since the last launch: [counters[2], count). It leaves `count` in counters[3]; k_plan_mark, launched behind it, copies that
+// to counters[2] (not this kernel: other CTAs of the launch still read it).
 template <int CH>
-__global__ void __launch_bounds__(LIMG_PLAN_WARPS * 32) k_plan_sym(PlanArgs a, int phase)
+__global__ void __launch_bounds__(LIMG_PLAN_WARPS * 32) k_plan_sym(PlanArgs a)
 {
   __shared__ uint32_t sRows[LIMG_PLAN_WARPS][32];
   const uint32_t count = min(a.counters[1], a.symCap);
-  const uint32_t first = phase ? min(a.counters[2], count) : 0u;
+  const uint32_t first = min(a.counters[2], count);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t warpsTotal = gridDim.x * LIMG_PLAN_WARPS;
 
-  if (phase == 0 && blockIdx.x == 0 && threadIdx.x == 0)
-    a.counters[3] = count; // (copied to counters[2] by the phase-1 k_plan_centres launch's predecessor: see k_plan_mark)
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+    a.counters[3] = count;
 
   for (uint32_t slot = first + blockIdx.x * LIMG_PLAN_WARPS + warp; slot < count; slot += warpsTotal)
   {

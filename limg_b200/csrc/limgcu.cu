@@ -102,6 +102,7 @@ struct limgcu_ctx
   int pass1Tma = 1;                  // LIMGCU_PASS1_TMA=0: pass 1 stages its pixels with plain loads (k_pass1) instead of tensor-map tile loads (k_pass1_tma)
   int poolThreads = 0;               // limgcu_set_pool_threads: the non-merged encoder restarts its dither chain per y-band of a pool of this many threads, as the reference does (0: pool-less)
   int scanExperiment = 0;            // LIMGCU_SCAN_EXPERIMENT: measurement switches of the scan (WaveArgs::experiment), 0 in production
+  int planBands = 8;                 // LIMGCU_PLAN_BANDS: bands of block rows the extension bitmaps and the centre bitmaps behind them are built in, top-down
   int scanWarps = LIMG_CTA_WARPS;    // LIMGCU_SCAN_WARPS: warps (block rows in flight) per CTA of that cluster, 1..8; 255 registers per thread, so 8 warps take an SM's whole register file, 4 leave half of it to other kernels
   int scanSmemLimit = 0;             // bytes of dynamic shared memory a CTA may opt in to (the mask replica has to fit)
   int planExtW = 16, planSymL = 6, planSymR = 12, planSymD = 16; // LIMGCU_PLAN_EXTW / SYML / SYMR / SYMD: size caps of the speculative bitmaps
@@ -364,6 +365,7 @@ extern "C" int limgcu_create(int device, limgcu_ctx **out)
   if (const char *v = getenv("LIMGCU_MERGE_MODE")) ctx->mergeMode = !strcmp(v, "seq") ? 1 : 0;
   if (const char *v = getenv("LIMGCU_PASS1_TMA")) ctx->pass1Tma = atoi(v);
   if (const char *v = getenv("LIMGCU_MERGE_SAFE")) ctx->mergeSafe = atoi(v);
+  if (const char *v = getenv("LIMGCU_PLAN_BANDS")) ctx->planBands = atoi(v) < 1 ? 1 : (atoi(v) > 64 ? 64 : atoi(v));
   if (const char *v = getenv("LIMGCU_SCAN_WARPS")) ctx->scanWarps = atoi(v) < 1 ? 1 : (atoi(v) > LIMG_CTA_WARPS ? LIMG_CTA_WARPS : atoi(v));
   if (const char *v = getenv("LIMGCU_SCAN_EXPERIMENT")) ctx->scanExperiment = atoi(v);
   if (const char *v = getenv("LIMGCU_SCAN_CLUSTER")) { ctx->scanCluster = atoi(v) < 0 ? 0 : (atoi(v) > 16 ? 16 : atoi(v)); ctx->scanClusterSet = true; }
@@ -701,43 +703,47 @@ static int launch_merge(limgcu_ctx *ctx, const limgcu_decomp *dTable, size_t W, 
       CK(cudaStreamWaitEvent(ctx->streamAux, ctx->evFork, 0));
     }
 
-    // Order: the centre bitmaps of the candidates whose mask-free growth stays inside their 8x8 word first (85 % of them on photo content: the scan's
-    // top rows need them at once), then the extension bitmaps, then the centre bitmaps of the candidates that needed an extension.
-    k_plan_centres<<<(blocks + 255) / 256, 256, 0, planStream>>>(pl, 0);
-    CKL("k_plan_centres");
+    // The bitmaps are built TOP-DOWN in bands of block rows (LIMGCU_PLAN_BANDS, default 8), per band: the centres of the candidates whose mask-free growth stays
+    // inside their 8x8 word are requested (85 % on photo content: their rectangle, hence their predicted centre, is final after k_plan_seeds), the extension bitmaps
+    // are built, the centres of the candidates that needed one are requested, and one k_plan_sym launch builds all centre bitmaps requested since the last one.
+    // The scan spends its first millisecond in the top rows (block row 0 runs on its own, every row below follows it 10 us behind the one above), and a seed whose
+    // bitmap is not there yet grows with on-demand predicates and builds its centre bitmap itself (20 us on the row's chain): with the three kernels over the
+    // whole image one after the other, the centre bitmap of a top-row seed that needed an extension appeared 0.5 ms after the scan's start (4K: 5.11 -> 4.79 ms,
+    // 8K RGBA 16.8 -> 14.9, profiles/README.md r2_x). The bitmaps are built 2.7 x faster than the scan consumes rows, so top-down order keeps them ahead of it.
+    // (planAsync == 2: the extension bitmaps run on the main stream, in front of the scan: one band)
+    const int planBands = (extendAsync && BY >= 8 * ctx->planBands) ? ctx->planBands : 1;
 
-    if (hasAlpha)
-      k_plan_sym<4><<<planGrid, LIMG_PLAN_WARPS * 32, 0, planStream>>>(pl, 0);
-    else
-      k_plan_sym<3><<<planGrid, LIMG_PLAN_WARPS * 32, 0, planStream>>>(pl, 0);
-
-    CKL("k_plan_sym");
-
-    // (planAsync == 2: the extension bitmaps run on the main stream, in front of the scan and next to the first centre bitmaps)
-    if (hasAlpha)
-      k_plan_extend<4><<<extendGrid, LIMG_PLAN_WARPS * 32, 0, extendStream>>>(pl);
-    else
-      k_plan_extend<3><<<extendGrid, LIMG_PLAN_WARPS * 32, 0, extendStream>>>(pl);
-
-    CKL("k_plan_extend");
-
-    if (async && !extendAsync)
+    for (int band = 0; band < planBands; band++)
     {
-      CK(cudaEventRecord(ctx->evFork, ctx->stream));
-      CK(cudaStreamWaitEvent(ctx->streamAux, ctx->evFork, 0));
+      const int rowLo = (int)((long long)BY * band / planBands), rowHi = (int)((long long)BY * (band + 1) / planBands);
+      k_plan_centres<<<(blocks + 255) / 256, 256, 0, planStream>>>(pl, 0, rowLo, rowHi);
+      CKL("k_plan_centres");
+
+      if (hasAlpha)
+        k_plan_extend<4><<<extendGrid, LIMG_PLAN_WARPS * 32, 0, extendStream>>>(pl, rowLo, rowHi);
+      else
+        k_plan_extend<3><<<extendGrid, LIMG_PLAN_WARPS * 32, 0, extendStream>>>(pl, rowLo, rowHi);
+
+      CKL("k_plan_extend");
+
+      if (async && !extendAsync)
+      {
+        CK(cudaEventRecord(ctx->evFork, ctx->stream));
+        CK(cudaStreamWaitEvent(ctx->streamAux, ctx->evFork, 0));
+      }
+
+      k_plan_centres<<<(blocks + 255) / 256, 256, 0, planStream>>>(pl, 1, rowLo, rowHi);
+      CKL("k_plan_centres");
+
+      if (hasAlpha)
+        k_plan_sym<4><<<planGrid, LIMG_PLAN_WARPS * 32, 0, planStream>>>(pl);
+      else
+        k_plan_sym<3><<<planGrid, LIMG_PLAN_WARPS * 32, 0, planStream>>>(pl);
+
+      CKL("k_plan_sym");
+      k_plan_mark<<<1, 1, 0, planStream>>>(pl);
+      CKL("k_plan_mark");
     }
-
-    k_plan_mark<<<1, 1, 0, planStream>>>(pl);
-    CKL("k_plan_mark");
-    k_plan_centres<<<(blocks + 255) / 256, 256, 0, planStream>>>(pl, 1);
-    CKL("k_plan_centres");
-
-    if (hasAlpha)
-      k_plan_sym<4><<<planGrid, LIMG_PLAN_WARPS * 32, 0, planStream>>>(pl, 1);
-    else
-      k_plan_sym<3><<<planGrid, LIMG_PLAN_WARPS * 32, 0, planStream>>>(pl, 1);
-
-    CKL("k_plan_sym");
 
     if (async)
     {
