@@ -711,7 +711,7 @@ static int launch_merge(limgcu_ctx *ctx, const limgcu_decomp *dTable, size_t W, 
     // whole image one after the other, the centre bitmap of a top-row seed that needed an extension appeared 0.5 ms after the scan's start (4K: 5.11 -> 4.79 ms,
     // 8K RGBA 16.8 -> 14.9, profiles/README.md r2_x). The bitmaps are built 2.7 x faster than the scan consumes rows, so top-down order keeps them ahead of it.
     // (planAsync == 2: the extension bitmaps run on the main stream, in front of the scan: one band)
-    const int planBands = (extendAsync && BY >= 8 * ctx->planBands) ? ctx->planBands : 1;
+    const int planBands = (extendAsync && BY >= 16 * ctx->planBands) ? ctx->planBands : 1; // (a band is four launches: not worth it below ~16 block rows per band)
 
     for (int band = 0; band < planBands; band++)
     {
