@@ -690,17 +690,18 @@ static int launch_merge(limgcu_ctx *ctx, const limgcu_decomp *dTable, size_t W, 
     k_plan_seeds<<<(blocks + 255) / 256, 256, 0, ctx->stream>>>(pl);
     CKL("k_plan_seeds");
 
+    // (the bitmap kernels need nothing after this: they start beside the safe columns, the scan behind them)
+    if (async)
+    {
+      CK(cudaEventRecord(ctx->evFork, ctx->stream));
+      CK(cudaStreamWaitEvent(ctx->streamAux, ctx->evFork, 0));
+    }
+
     if (ctx->mergeSafe)
     {
       CK(cudaStreamWaitEvent(ctx->stream, ctx->evJoin2, 0)); // the left runs
       k_plan_safe<<<BY, 32, 0, ctx->stream>>>(ctx->dWindow, wCandBits, ctx->dLeftRun, BX, BY, wordsPerRow, ctx->dSafe);
       CKL("k_plan_safe");
-    }
-
-    if (async)
-    {
-      CK(cudaEventRecord(ctx->evFork, ctx->stream));
-      CK(cudaStreamWaitEvent(ctx->streamAux, ctx->evFork, 0));
     }
 
     // The bitmaps are built TOP-DOWN in bands of block rows (LIMGCU_PLAN_BANDS, default 8), per band: the centres of the candidates whose mask-free growth stays
